@@ -1,0 +1,67 @@
+"""TEST INFRASTRUCTURE ONLY -- loader for the *unmodified* reference (masabdi/LSPS).
+
+Only usable where /root/reference is mounted (the build container).  It is used by
+`oracle/make_golden.py` to pin the oracle port (`oracle/lsps_oracle.py`) and to
+generate the committed fixtures under tests/golden/.  Nothing in the product
+package (`lsps_b200/`) may import this file.
+
+Recipe: copy /root/reference/src to a scratch dir, expand tabs
+(python-2 tab semantics, tab stop 8 -- `src/trainers/lsps_trainer.py:58` mixes tabs
+and spaces), stub `matplotlib`, and make `.cuda()` a no-op on CPU.  No arithmetic
+is edited.
+"""
+import os
+import shutil
+import sys
+import tempfile
+import types
+
+REFERENCE_ROOT = os.environ.get("LSPS_REFERENCE_ROOT", "/root/reference")
+
+
+def reference_available():
+    return os.path.isdir(os.path.join(REFERENCE_ROOT, "src", "trainers"))
+
+
+_scratch = None
+
+
+def load_reference(cpu_shim=True):
+    """Returns the imported `trainers` package of the reference."""
+    global _scratch
+    import torch
+
+    if "trainers" in sys.modules and getattr(sys.modules["trainers"], "_lsps_ref", False):
+        return sys.modules["trainers"]
+    if not reference_available():
+        raise RuntimeError("reference sources not mounted at %s" % REFERENCE_ROOT)
+    _scratch = tempfile.mkdtemp(prefix="lsps_ref_")
+    dst = os.path.join(_scratch, "src")
+    shutil.copytree(os.path.join(REFERENCE_ROOT, "src"), dst,
+                    ignore=shutil.ignore_patterns("*.pyc"))
+    for root, _, files in os.walk(dst):
+        for f in files:
+            if f.endswith(".py"):
+                p = os.path.join(root, f)
+                with open(p, "r", encoding="utf-8", errors="replace") as fh:
+                    text = fh.read()
+                with open(p, "w", encoding="utf-8") as fh:
+                    fh.write(text.expandtabs(8))
+    sys.path.insert(0, dst)
+    for m in ("matplotlib", "matplotlib.pyplot"):
+        if m not in sys.modules:
+            sys.modules[m] = types.ModuleType(m)
+    if cpu_shim and not torch.cuda.is_available():
+        torch.Tensor.cuda = lambda self, *a, **k: self
+        torch.nn.Module.cuda = lambda self, *a, **k: self
+    import trainers  # noqa: the reference package
+
+    trainers._lsps_ref = True
+    return trainers
+
+
+def load_hyperparameters(name="nnyu"):
+    import yaml
+
+    with open(os.path.join(REFERENCE_ROOT, "exps", name + ".yaml")) as fh:
+        return yaml.safe_load(fh)["train"]["hyperparameters"]
