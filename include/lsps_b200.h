@@ -1,0 +1,138 @@
+/* lsps_b200 -- C ABI of the B200 (sm_100a) kernel library behind the LSPS training step.
+ *
+ * The reference (masabdi/LSPS) has no native layer: its "L0" is torch.nn / ATen called implicitly from
+ *   src/trainers/common_net.py:160-181,221-268   (LeakyINSResBlock, LeakyReLUConv2d, LeakyReLUConvTranspose2d, ...)
+ *   src/trainers/lsps_nets.py:34-83,86-160,164-272 (poseVAE, SharedDis, SharedResGen)
+ *   src/trainers/lsps_trainer.py:55-262           (losses, Adam steps)
+ * Each entry point below names the reference op site(s) it replaces.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller (16-byte aligned); nothing is retained after the call
+ *     except cached TMA descriptors keyed by (pointer, shape);
+ *   - activations are NHWC; "bf16" tensors are __nv_bfloat16, everything else is float32 unless stated;
+ *   - conv weights are "packed": [tap = r*3+s][Cout][Cin] (forward operand) and [tap][Cin][Cout] (dgrad operand),
+ *     taps indexed in the FORWARD op's kernel coordinates (for ConvTranspose2d: its own (r,s));
+ *   - all work is asynchronous on the given stream (capturable in a CUDA graph); no host synchronisation;
+ *   - return value 0 = ok, <0 = LSPS_E_*; text via lsps_last_error().  One ctx per (process, device).
+ */
+#ifndef LSPS_B200_H
+#define LSPS_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct lsps_ctx lsps_ctx;
+typedef void* lsps_stream; /* cudaStream_t */
+
+enum { LSPS_OK = 0, LSPS_E_ARG = -1, LSPS_E_SHAPE = -2, LSPS_E_ARCH = -3, LSPS_E_CUDA = -4 };
+
+/* conv kinds: 3x3 stride-1 pad-1 Conv2d | 3x3 stride-2 pad-1 Conv2d | 3x3 stride-2 pad-1 output_padding-1 ConvTranspose2d */
+enum { LSPS_CONV_S1 = 0, LSPS_CONV_S2 = 1, LSPS_DECONV_S2 = 2 };
+/* epilogue flags of the implicit-GEMM kernels, applied in this order: +bias, LeakyReLU, *lrelu'(mask), +add */
+enum { LSPS_EP_BIAS = 1, LSPS_EP_LRELU = 2, LSPS_EP_MASK = 4, LSPS_EP_ADD = 8 };
+
+/* n images; h,w = INPUT spatial size of the FORWARD op; cin/cout of the forward op (multiples of 64). */
+typedef struct { int kind, n, h, w, cin, cout; } lsps_conv_shape;
+
+int lsps_ctx_create(lsps_ctx** out, int device);
+void lsps_ctx_destroy(lsps_ctx* ctx);
+const char* lsps_last_error(lsps_ctx* ctx);
+int lsps_abi_version(void);
+/* number of kernels this ctx has launched so far (bench.py's gpu_launches) */
+long long lsps_launch_count(lsps_ctx* ctx);
+
+/* ---- tcgen05 implicit-GEMM convolutions (nn.Conv2d / nn.ConvTranspose2d forward, common_net.py:246-268,160-175) */
+/* y = epilogue(conv(x, w) [+ bias]) ; x bf16 [n,h,w,cin] ; y bf16 [n,ho,wo,cout] */
+int lsps_conv_fwd(lsps_ctx*, const lsps_conv_shape*, const void* x, const void* w_fwd, const float* bias, void* y,
+                  int flags, float slope, lsps_stream);
+/* dx = epilogue(conv_backward_data(dy, w)) ; mask/add: bf16 tensors shaped like dx (flags MASK / ADD) */
+int lsps_conv_dgrad(lsps_ctx*, const lsps_conv_shape*, const void* dy, const void* w_dgrad, void* dx,
+                    const void* mask, const void* add, int flags, float slope, lsps_stream);
+/* dw[tap][cout][cin] += conv_backward_weight(x, dy)   (fp32, accumulating; split-K over pixels with red.add) */
+int lsps_conv_wgrad(lsps_ctx*, const lsps_conv_shape*, const void* x, const void* dy, float* dw, lsps_stream);
+/* db[c] += sum over rows of dy[rows][c]   (bias gradients; dy bf16) */
+int lsps_colsum_bf16(lsps_ctx*, const void* dy, long long rows, int c, float* db, lsps_stream);
+
+/* ---- Cin=1 7x7 stems (lsps_nets.py:104,186) : img f32 [n,h,w]; y bf16 [n,h/stride,w/stride,64]; w f32 [64][49] */
+int lsps_stem_fwd(lsps_ctx*, const float* img, const float* w, const float* bias, void* y, int n, int h, int wd,
+                  int stride, float slope, lsps_stream);
+/* dy must already carry the LeakyReLU mask.  dw[64][49] += ..., db[64] += ... */
+int lsps_stem_wgrad(lsps_ctx*, const float* img, const void* dy, float* dw, float* db, int n, int h, int wd,
+                    int stride, lsps_stream);
+/* dimg (+)= conv_backward_data(dy, w); accumulate != 0 adds into dimg */
+int lsps_stem_dgrad(lsps_ctx*, const void* dy, const float* w, float* dimg, int n, int h, int wd, int stride,
+                    int accumulate, lsps_stream);
+
+/* ---- decoder head ConvTranspose2d(64,1,1)+Tanh (lsps_nets.py:226-229): x bf16 [npix,64] -> out f32 [npix] */
+int lsps_head_fwd(lsps_ctx*, const void* x, const float* w, const float* bias, float* out, long long npix, lsps_stream);
+/* dpre = dout*(1-out^2); dx = dpre*w*lrelu'(x) (bf16); dw[64] += sum dpre*x ; db += sum dpre */
+int lsps_head_bwd(lsps_ctx*, const void* x, const float* w, const float* out, const float* dout, void* dx, float* dw,
+                  float* db, long long npix, float slope, lsps_stream);
+
+/* ---- InstanceNorm2d(affine=False) fused with what follows it in LeakyINSResBlock (common_net.py:160-181) */
+/* mode 0: y = lrelu(IN(h)) ; mode 1: y = res + IN(h).  h,y,res bf16 [n,hw,c]; stats f32 [n,c,2] = (mean, rstd) out */
+int lsps_instnorm_fwd(lsps_ctx*, const void* h, const void* res, void* y, float* stats, int n, int hw, int c, int mode,
+                      float eps, float slope, lsps_stream);
+/* dh = IN_backward(g) with g = dy (mode 1) or dy*lrelu'(IN(h)) (mode 0) */
+int lsps_instnorm_bwd(lsps_ctx*, const void* dy, const void* h, const float* stats, void* dh, int n, int hw, int c,
+                      int mode, float slope, lsps_stream);
+
+/* ---- GaussianNoiseLayer + KL term (common_net.py:36-40; lsps_trainer.py:55-58): z = x + noise, acc[0] += sum z^2 */
+int lsps_noise_kl_fwd(lsps_ctx*, const void* x, const float* noise, void* z, float* acc, long long n, lsps_stream);
+/* out = a + alpha * b  (bf16 tensors; a may be NULL) */
+int lsps_axpy_bf16(lsps_ctx*, const void* a, const void* b, float alpha, void* out, long long n, lsps_stream);
+
+/* ---- losses.  All `acc` arguments are single float accumulators (sum, not mean) in device memory. */
+/* L1 (nn.L1Loss, lsps_trainer.py:42,118-121): acc += sum|x-t| ; dx (+)= scale*sign(x-t) */
+int lsps_l1_f32(lsps_ctx*, const float* x, const float* t, float* dx, float scale, int accumulate, float* acc,
+                long long n, lsps_stream);
+/* feature matching L1 on bf16 trunk features (lsps_trainer.py:171-177,241-243):
+   acc += sum|a-b| ; da += scale*sign(a-b) ; db -= scale*sign(a-b)  (da/db f32, may be NULL) */
+int lsps_l1_feat(lsps_ctx*, const void* a, const void* b, float* da, float* db, float scale, float* acc, long long n,
+                 lsps_stream);
+/* D head Conv2d(2048,1,1) (lsps_nets.py:124,157): logits[r] = f[r,:] . w + b ; f bf16 [rows,c] */
+int lsps_dhead_fwd(lsps_ctx*, const void* f, const float* w, const float* bias, float* logits, long long rows, int c,
+                   lsps_stream);
+/* sigmoid + binary_cross_entropy vs constant target (lsps_trainer.py:107-112,179-192), torch semantics (log clamp -100):
+   acc[0] += sum bce ; acc[1] += #(sigmoid >= .5 if target==1 else <= .5) ; dlogits = scale*(p - target) */
+int lsps_bce_logits(lsps_ctx*, const float* logits, float target, float scale, float* dlogits, float* acc,
+                    long long rows, lsps_stream);
+/* df[r,:] += dlogits[r]*w (f32) ; dw[c] += sum_r dlogits[r]*f[r,c] ; db += sum dlogits  (dw/db may be NULL) */
+int lsps_dhead_bwd(lsps_ctx*, const void* f, const float* w, const float* dlogits, float* df, float* dw, float* db,
+                   long long rows, int c, lsps_stream);
+/* trunk-feature gradient f32 -> bf16 with the LeakyReLU mask of the features: out = df * lrelu'(f) */
+int lsps_mask_to_bf16(lsps_ctx*, const float* df, const void* f, void* out, float slope, long long n, lsps_stream);
+
+/* ---- small dense layers (Post head = FC 8192->20, lsps_nets.py:123,135-145; poseVAE MLP, lsps_nets.py:34-83) */
+/* y[m,n] = act(x[m,k] . w[n,k]^T + b[n]) ; act 0 none, 1 lrelu, 2 softplus.  x is bf16 if x_bf16 else f32 */
+int lsps_linear_fwd(lsps_ctx*, const void* x, int x_bf16, const float* w, const float* b, float* y, int m, int n, int k,
+                    int act, float slope, lsps_stream);
+/* dy is the gradient w.r.t. the pre-activation.  dx[m,k] (+)= dy.w ; dw[n,k] += dy^T.x ; db[n] += sum dy. NULL skips. */
+int lsps_linear_bwd(lsps_ctx*, const void* x, int x_bf16, const float* w, const float* dy, float* dx, int dx_accumulate,
+                    float* dw, float* db, int m, int n, int k, lsps_stream);
+/* dy_pre = dy * act'(y) in place on a [n] vector (act as above, y = post-activation output) */
+int lsps_act_bwd(lsps_ctx*, float* dy, const float* y, int act, float slope, long long n, lsps_stream);
+/* acc += sum (p-e)^2 ; dp = scale*(p-e) */
+int lsps_mse(lsps_ctx*, const float* p, const float* e, float* dp, float scale, float* acc, long long n, lsps_stream);
+/* poseVAE reparameterisation + KL (lsps_nets.py:72-78; lsps_trainer.py:59-60):
+   z = mu + sd*noise ; acc += sum(mu^2 + sd^2 - log sd^2) */
+int lsps_vae_reparam(lsps_ctx*, const float* mu, const float* sd, const float* noise, float* z, float* acc, long long n,
+                     lsps_stream);
+/* dmu = dz + kl_scale*2*mu ; dsd = dz*noise + kl_scale*(2*sd - 2/sd) */
+int lsps_vae_reparam_bwd(lsps_ctx*, const float* mu, const float* sd, const float* noise, const float* dz, float* dmu,
+                         float* dsd, float kl_scale, long long n, lsps_stream);
+
+/* ---- optimiser (torch.optim.Adam with L2 weight decay, lsps_trainer.py:26-34) on a flat fp32 segment.
+   g += wd*p ; m,v update ; p -= lr * mhat/(sqrt(vhat)+eps) ; optionally refresh the bf16 copy w16 (may be NULL). */
+int lsps_adam(lsps_ctx*, float* p, const float* g, float* m, float* v, void* w16, long long n, float lr, float beta1,
+              float beta2, float eps, float wd, int step, float grad_scale, lsps_stream);
+/* wt[tap][cin][cout] (bf16) = transpose of w[tap][cout][cin] (f32 master) : the dgrad operand */
+int lsps_pack_dgrad(lsps_ctx*, const float* w, void* wt, int taps, int cout, int cin, lsps_stream);
+int lsps_f32_to_bf16(lsps_ctx*, const float* x, void* y, long long n, lsps_stream);
+int lsps_bf16_to_f32(lsps_ctx*, const void* x, float* y, long long n, lsps_stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,916 @@
+// HBM-/latency-bound kernels around the tcgen05 convolutions: Cin=1 stems, decoder head, InstanceNorm,
+// noise/KL, losses, discriminator heads, small dense layers (Post head, pose-VAE), Adam, weight repacking.
+// None of these is a tensor-core shape (K=49, N=1, reductions, elementwise); they are written for coalesced
+// 16-byte accesses over NHWC bf16 data and fp32 accumulation.
+//
+// Reference op sites: /root/reference/src/trainers/lsps_nets.py:34-83,102-126,186-229 ;
+//                     /root/reference/src/trainers/common_net.py:32-40,160-181 ;
+//                     /root/reference/src/trainers/lsps_trainer.py:26-34,42-60,107-121,171-192,241-250
+#include "common.h"
+#include "ptx.cuh"
+
+using namespace lsps;
+typedef __nv_bfloat16 bf16;
+
+namespace {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+// block-wide sum (blockDim.x <= 1024, multiple of 32); result valid in thread 0
+__device__ __forceinline__ float block_sum(float v, float* sm) {
+  v = warp_sum(v);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) sm[w] = v;
+  __syncthreads();
+  float r = 0.f;
+  if (w == 0) {
+    r = l < (blockDim.x >> 5) ? sm[l] : 0.f;
+    r = warp_sum(r);
+  }
+  __syncthreads();
+  return r;
+}
+__device__ __forceinline__ void unpack8(const uint4& u, float* f) {
+  f[0] = bf16lo(u.x); f[1] = bf16hi(u.x); f[2] = bf16lo(u.y); f[3] = bf16hi(u.y);
+  f[4] = bf16lo(u.z); f[5] = bf16hi(u.z); f[6] = bf16lo(u.w); f[7] = bf16hi(u.w);
+}
+__device__ __forceinline__ uint4 pack8(const float* f) {
+  uint4 u;
+  u.x = pack_bf16x2(f[0], f[1]); u.y = pack_bf16x2(f[2], f[3]);
+  u.z = pack_bf16x2(f[4], f[5]); u.w = pack_bf16x2(f[6], f[7]);
+  return u;
+}
+inline int grid_for(long long n, int block, int cap) {
+  long long g = (n + block - 1) / block;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+// =============================================================================================== stems (7x7, Cin=1)
+constexpr int ST = 16;  // output tile edge
+
+template <int S>
+__global__ void __launch_bounds__(256) stem_fwd_kernel(const float* __restrict__ img, const float* __restrict__ w,
+                                                      const float* __restrict__ bias, bf16* __restrict__ y, int h,
+                                                      int wd, float slope) {
+  constexpr int PE = (ST - 1) * S + 7;
+  __shared__ float ws[49][64];
+  __shared__ float patch[PE][PE + 1];
+  const int ho = h / S, wo = wd / S;
+  const int n = blockIdx.z, oy0 = blockIdx.y * ST, ox0 = blockIdx.x * ST;
+  for (int i = threadIdx.x; i < 49 * 64; i += 256) ws[i % 49][i / 49] = w[i];  // w is [co][tap]
+  const float* im = img + (long long)n * h * wd;
+  for (int i = threadIdx.x; i < PE * PE; i += 256) {
+    const int py = i / PE, px = i % PE;
+    const int iy = oy0 * S - 3 + py, ix = ox0 * S - 3 + px;
+    patch[py][px] = (iy >= 0 && iy < h && ix >= 0 && ix < wd) ? im[iy * wd + ix] : 0.f;
+  }
+  __syncthreads();
+  const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
+  float acc[64];
+#pragma unroll
+  for (int c = 0; c < 64; ++c) acc[c] = 0.f;
+  for (int r = 0; r < 7; ++r)
+    for (int c = 0; c < 7; ++c) {
+      const float v = patch[ty * S + r][tx * S + c];
+      const float4* w4 = reinterpret_cast<const float4*>(ws[r * 7 + c]);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const float4 q = w4[j];
+        acc[4 * j] += v * q.x; acc[4 * j + 1] += v * q.y; acc[4 * j + 2] += v * q.z; acc[4 * j + 3] += v * q.w;
+      }
+    }
+  const int oy = oy0 + ty, ox = ox0 + tx;
+  if (oy < ho && ox < wo) {
+    uint4* o = reinterpret_cast<uint4*>(y + (((long long)n * ho + oy) * wo + ox) * 64);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float f[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        float t = acc[8 * j + k] + __ldg(bias + 8 * j + k);
+        f[k] = t > 0.f ? t : t * slope;
+      }
+      o[j] = pack8(f);
+    }
+  }
+}
+
+// dW[co][tap] += sum dy[pix][co] * img[pix @ tap]; db[co] += sum dy.  Persistent over 16x16 output tiles.
+template <int S>
+__global__ void __launch_bounds__(256) stem_wgrad_kernel(const float* __restrict__ img, const bf16* __restrict__ dy,
+                                                        float* __restrict__ dw, float* __restrict__ db, int n, int h,
+                                                        int wd) {
+  constexpr int PE = (ST - 1) * S + 7;
+  __shared__ __align__(16) bf16 dys[ST * ST][64];
+  __shared__ float patch[PE][PE + 1];
+  const int ho = h / S, wo = wd / S;
+  const int tiles_x = wo / ST, tiles_y = ho / ST;
+  const int total = tiles_x * tiles_y * n;
+  const int co = threadIdx.x & 63, tg = threadIdx.x >> 6;
+  float acc[13], accb = 0.f;
+#pragma unroll
+  for (int j = 0; j < 13; ++j) acc[j] = 0.f;
+  for (int t = blockIdx.x; t < total; t += gridDim.x) {
+    const int tx = t % tiles_x, ty = (t / tiles_x) % tiles_y, im_i = t / (tiles_x * tiles_y);
+    const int oy0 = ty * ST, ox0 = tx * ST;
+    __syncthreads();
+    const float* im = img + (long long)im_i * h * wd;
+    for (int i = threadIdx.x; i < PE * PE; i += 256) {
+      const int py = i / PE, px = i % PE;
+      const int iy = oy0 * S - 3 + py, ix = ox0 * S - 3 + px;
+      patch[py][px] = (iy >= 0 && iy < h && ix >= 0 && ix < wd) ? im[iy * wd + ix] : 0.f;
+    }
+    for (int i = threadIdx.x; i < ST * ST * 8; i += 256) {
+      const int px = i >> 3, j = i & 7;
+      const int oy = oy0 + (px >> 4), ox = ox0 + (px & 15);
+      reinterpret_cast<uint4*>(dys[px])[j] =
+          __ldg(reinterpret_cast<const uint4*>(dy + (((long long)im_i * ho + oy) * wo + ox) * 64) + j);
+    }
+    __syncthreads();
+    for (int px = 0; px < ST * ST; ++px) {
+      const float d = __bfloat162float(dys[px][co]);
+      const int py_ = (px >> 4) * S, px_ = (px & 15) * S;
+      if (tg == 0) accb += d;
+#pragma unroll
+      for (int j = 0; j < 13; ++j) {
+        const int tap = tg + 4 * j;
+        if (tap < 49) acc[j] += d * patch[py_ + tap / 7][px_ + tap % 7];
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 13; ++j) {
+    const int tap = tg + 4 * j;
+    if (tap < 49) atomicAdd(dw + co * 49 + tap, acc[j]);
+  }
+  if (tg == 0 && db) atomicAdd(db + co, accb);
+}
+
+// dimg[y][x] (+)= sum_{r,c,co} dy[(y+3-r)/S][(x+3-c)/S][co] * w[co][r][c]
+template <int S>
+__global__ void __launch_bounds__(256) stem_dgrad_kernel(const bf16* __restrict__ dy, const float* __restrict__ w,
+                                                        float* __restrict__ dimg, int h, int wd, int accumulate) {
+  constexpr int DE = S == 1 ? ST + 6 : (ST + 6) / 2 + 1;  // dy patch edge (output pixels touching a 16x16 input tile)
+  extern __shared__ __align__(16) uint8_t dsm[];
+  float(*ws)[64] = reinterpret_cast<float(*)[64]>(dsm);                // [49][64]
+  uint4* dys = reinterpret_cast<uint4*>(dsm + 49 * 64 * sizeof(float));  // [DE*DE][8] chunks, xor-swizzled
+  const int ho = h / S, wo = wd / S;
+  const int n = blockIdx.z, y0 = blockIdx.y * ST, x0 = blockIdx.x * ST;
+  for (int i = threadIdx.x; i < 49 * 64; i += 256) ws[i % 49][i / 49] = w[i];
+  // first output row/col that can touch this tile: oy >= ceil((y0 + 3 - 6)/S)
+  const int oyb = S == 1 ? y0 - 3 : (y0 - 3 + 1) >> 1, oxb = S == 1 ? x0 - 3 : (x0 - 3 + 1) >> 1;
+  for (int i = threadIdx.x; i < DE * DE * 8; i += 256) {
+    const int px = i >> 3, j = i & 7;
+    const int oy = oyb + px / DE, ox = oxb + px % DE;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (oy >= 0 && oy < ho && ox >= 0 && ox < wo)
+      v = __ldg(reinterpret_cast<const uint4*>(dy + (((long long)n * ho + oy) * wo + ox) * 64) + j);
+    dys[px * 8 + (j ^ (px & 7))] = v;
+  }
+  __syncthreads();
+  const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
+  const int y = y0 + ty, x = x0 + tx;
+  float acc = 0.f;
+  for (int r = 0; r < 7; ++r) {
+    const int ny = y + 3 - r;
+    if (S == 2 && (ny & 1)) continue;
+    const int oy = ny / S - oyb;
+    if (ny < 0 || ny / S >= ho) continue;
+    for (int c = 0; c < 7; ++c) {
+      const int nx = x + 3 - c;
+      if (S == 2 && (nx & 1)) continue;
+      if (nx < 0 || nx / S >= wo) continue;
+      const int ox = nx / S - oxb;
+      const int px = oy * DE + ox;
+      const float4* w4 = reinterpret_cast<const float4*>(ws[r * 7 + c]);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float f[8];
+        unpack8(dys[px * 8 + (j ^ (px & 7))], f);
+        const float4 a = w4[2 * j], b = w4[2 * j + 1];
+        acc += f[0] * a.x + f[1] * a.y + f[2] * a.z + f[3] * a.w + f[4] * b.x + f[5] * b.y + f[6] * b.z + f[7] * b.w;
+      }
+    }
+  }
+  if (y < h && x < wd) {
+    float* o = dimg + ((long long)n * h + y) * wd + x;
+    *o = accumulate ? *o + acc : acc;
+  }
+}
+
+// =============================================================================================== decoder head
+__global__ void __launch_bounds__(256) head_fwd_kernel(const bf16* __restrict__ x, const float* __restrict__ w,
+                                                      const float* __restrict__ bias, float* __restrict__ out,
+                                                      long long npix) {
+  const int oct = threadIdx.x & 7;
+  float wr[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) wr[k] = __ldg(w + oct * 8 + k);
+  const float b = __ldg(bias);
+  for (long long p = (long long)blockIdx.x * 32 + (threadIdx.x >> 3); p < npix; p += (long long)gridDim.x * 32) {
+    float f[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(x + p * 64) + oct), f);
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += f[k] * wr[k];
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    s += __shfl_xor_sync(0xffffffffu, s, 4);
+    if (oct == 0) out[p] = tanhf(s + b);
+  }
+}
+
+__global__ void __launch_bounds__(256) head_bwd_kernel(const bf16* __restrict__ x, const float* __restrict__ w,
+                                                      const float* __restrict__ out, const float* __restrict__ dout,
+                                                      bf16* __restrict__ dx, float* __restrict__ dw,
+                                                      float* __restrict__ db, long long npix, float slope) {
+  __shared__ float red[32][64];
+  __shared__ float redb[8];
+  const int oct = threadIdx.x & 7, pl = threadIdx.x >> 3;
+  float wr[8], aw[8], ab = 0.f;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { wr[k] = __ldg(w + oct * 8 + k); aw[k] = 0.f; }
+  for (long long p = (long long)blockIdx.x * 32 + pl; p < npix; p += (long long)gridDim.x * 32) {
+    const float o = __ldg(out + p);
+    const float dpre = __ldg(dout + p) * (1.f - o * o);
+    float f[8], g[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(x + p * 64) + oct), f);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      aw[k] += dpre * f[k];
+      g[k] = dpre * wr[k] * (f[k] > 0.f ? 1.f : slope);
+    }
+    reinterpret_cast<uint4*>(dx + p * 64)[oct] = pack8(g);
+    if (oct == 0) ab += dpre;
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) red[pl][oct * 8 + k] = aw[k];
+  const float bs = block_sum(ab, redb);  // contains __syncthreads
+  if (threadIdx.x < 64) {
+    float s = 0.f;
+    for (int i = 0; i < 32; ++i) s += red[i][threadIdx.x];
+    atomicAdd(dw + threadIdx.x, s);
+  }
+  if (threadIdx.x == 0) atomicAdd(db, bs);
+}
+
+// =============================================================================================== InstanceNorm
+// one CTA per (image, 64-channel group); thread = (8-channel octet, pixel lane)
+__device__ __forceinline__ void in_reduce64(const float* v8, float (*red)[64], float* outc) {
+  const int oct = threadIdx.x & 7, pl = threadIdx.x >> 3;
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 8; ++k) red[pl][oct * 8 + k] = v8[k];
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    float s = 0.f;
+#pragma unroll 8
+    for (int i = 0; i < 32; ++i) s += red[i][threadIdx.x];
+    outc[threadIdx.x] = s;
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(256) instnorm_fwd_kernel(const bf16* __restrict__ h, const bf16* __restrict__ res,
+                                                          bf16* __restrict__ y, float* __restrict__ stats, int hw,
+                                                          int c, int mode, float eps, float slope) {
+  __shared__ float red[32][64];
+  __shared__ float s_mean[64], s_var[64];
+  const int n = blockIdx.y, cg = blockIdx.x;
+  const int oct = threadIdx.x & 7, pl = threadIdx.x >> 3;
+  const long long base = (long long)n * hw * c + cg * 64 + oct * 8;
+  float a[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) a[k] = 0.f;
+  for (int p = pl; p < hw; p += 32) {
+    float f[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(h + base + (long long)p * c)), f);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) a[k] += f[k];
+  }
+  in_reduce64(a, red, s_mean);
+  float mean[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { mean[k] = s_mean[oct * 8 + k] / hw; a[k] = 0.f; }
+  for (int p = pl; p < hw; p += 32) {
+    float f[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(h + base + (long long)p * c)), f);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { const float d = f[k] - mean[k]; a[k] += d * d; }
+  }
+  in_reduce64(a, red, s_var);
+  float rstd[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) rstd[k] = rsqrtf(s_var[oct * 8 + k] / hw + eps);
+  if (pl == 0) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      float* s = stats + ((long long)n * c + cg * 64 + oct * 8 + k) * 2;
+      s[0] = mean[k]; s[1] = rstd[k];
+    }
+  }
+  for (int p = pl; p < hw; p += 32) {
+    float f[8], r[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(h + base + (long long)p * c)), f);
+    if (mode == 1) unpack8(__ldg(reinterpret_cast<const uint4*>(res + base + (long long)p * c)), r);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float v = (f[k] - mean[k]) * rstd[k];
+      f[k] = mode == 1 ? r[k] + v : (v > 0.f ? v : v * slope);
+    }
+    *reinterpret_cast<uint4*>(y + base + (long long)p * c) = pack8(f);
+  }
+}
+
+__global__ void __launch_bounds__(256) instnorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ h,
+                                                          const float* __restrict__ stats, bf16* __restrict__ dh,
+                                                          int hw, int c, int mode, float slope) {
+  __shared__ float red[32][64];
+  __shared__ float s_a[64], s_b[64];
+  const int n = blockIdx.y, cg = blockIdx.x;
+  const int oct = threadIdx.x & 7, pl = threadIdx.x >> 3;
+  const long long base = (long long)n * hw * c + cg * 64 + oct * 8;
+  float mean[8], rstd[8], sg[8], sgx[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const float* s = stats + ((long long)n * c + cg * 64 + oct * 8 + k) * 2;
+    mean[k] = s[0]; rstd[k] = s[1]; sg[k] = 0.f; sgx[k] = 0.f;
+  }
+  for (int p = pl; p < hw; p += 32) {
+    float f[8], g[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(h + base + (long long)p * c)), f);
+    unpack8(__ldg(reinterpret_cast<const uint4*>(dy + base + (long long)p * c)), g);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float xh = (f[k] - mean[k]) * rstd[k];
+      const float gg = (mode == 0 && !(xh > 0.f)) ? g[k] * slope : g[k];
+      sg[k] += gg; sgx[k] += gg * xh;
+    }
+  }
+  in_reduce64(sg, red, s_a);
+  in_reduce64(sgx, red, s_b);
+  float mg[8], mgx[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { mg[k] = s_a[oct * 8 + k] / hw; mgx[k] = s_b[oct * 8 + k] / hw; }
+  for (int p = pl; p < hw; p += 32) {
+    float f[8], g[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(h + base + (long long)p * c)), f);
+    unpack8(__ldg(reinterpret_cast<const uint4*>(dy + base + (long long)p * c)), g);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float xh = (f[k] - mean[k]) * rstd[k];
+      const float gg = (mode == 0 && !(xh > 0.f)) ? g[k] * slope : g[k];
+      f[k] = rstd[k] * (gg - mg[k] - xh * mgx[k]);
+    }
+    *reinterpret_cast<uint4*>(dh + base + (long long)p * c) = pack8(f);
+  }
+}
+
+// =============================================================================================== elementwise / losses
+__global__ void __launch_bounds__(256) noise_kl_kernel(const bf16* __restrict__ x, const float* __restrict__ noise,
+                                                      bf16* __restrict__ z, float* __restrict__ acc, long long n8) {
+  __shared__ float sm[8];
+  float s = 0.f;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n8; i += (long long)gridDim.x * 256) {
+    float f[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(x) + i), f);
+    const float4 a = __ldg(reinterpret_cast<const float4*>(noise) + 2 * i);
+    const float4 b = __ldg(reinterpret_cast<const float4*>(noise) + 2 * i + 1);
+    f[0] += a.x; f[1] += a.y; f[2] += a.z; f[3] += a.w; f[4] += b.x; f[5] += b.y; f[6] += b.z; f[7] += b.w;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += f[k] * f[k];
+    reinterpret_cast<uint4*>(z)[i] = pack8(f);
+  }
+  const float t = block_sum(s, sm);
+  if (threadIdx.x == 0) atomicAdd(acc, t);
+}
+
+__global__ void __launch_bounds__(256) axpy_bf16_kernel(const bf16* __restrict__ a, const bf16* __restrict__ b,
+                                                       float alpha, bf16* __restrict__ out, long long n8) {
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n8; i += (long long)gridDim.x * 256) {
+    float f[8], g[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(b) + i), g);
+    if (a) unpack8(__ldg(reinterpret_cast<const uint4*>(a) + i), f);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) f[k] = (a ? f[k] : 0.f) + alpha * g[k];
+    reinterpret_cast<uint4*>(out)[i] = pack8(f);
+  }
+}
+
+__global__ void __launch_bounds__(256) l1_f32_kernel(const float* __restrict__ x, const float* __restrict__ t,
+                                                    float* __restrict__ dx, float scale, int accumulate,
+                                                    float* __restrict__ acc, long long n) {
+  __shared__ float sm[8];
+  float s = 0.f;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
+    const float d = x[i] - t[i];
+    s += fabsf(d);
+    if (dx) {
+      const float g = d > 0.f ? scale : (d < 0.f ? -scale : 0.f);
+      dx[i] = accumulate ? dx[i] + g : g;
+    }
+  }
+  const float r = block_sum(s, sm);
+  if (threadIdx.x == 0) atomicAdd(acc, r);
+}
+
+__global__ void __launch_bounds__(256) l1_feat_kernel(const bf16* __restrict__ a, const bf16* __restrict__ b,
+                                                     float* __restrict__ da, float* __restrict__ db, float scale,
+                                                     float* __restrict__ acc, long long n) {
+  __shared__ float sm[8];
+  float s = 0.f;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
+    const float d = __bfloat162float(a[i]) - __bfloat162float(b[i]);
+    s += fabsf(d);
+    const float g = d > 0.f ? scale : (d < 0.f ? -scale : 0.f);
+    if (da) da[i] += g;
+    if (db) db[i] -= g;
+  }
+  const float r = block_sum(s, sm);
+  if (threadIdx.x == 0) atomicAdd(acc, r);
+}
+
+// one warp per row
+__global__ void __launch_bounds__(256) dhead_fwd_kernel(const bf16* __restrict__ f, const float* __restrict__ w,
+                                                       const float* __restrict__ bias, float* __restrict__ logits,
+                                                       long long rows, int c) {
+  const int lane = threadIdx.x & 31;
+  const long long r = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (r >= rows) return;
+  float s = 0.f;
+  for (int j = lane; j < c / 8; j += 32) {
+    float v[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(f + r * c) + j), v);
+    const float4 a = __ldg(reinterpret_cast<const float4*>(w) + 2 * j), b = __ldg(reinterpret_cast<const float4*>(w) + 2 * j + 1);
+    s += v[0] * a.x + v[1] * a.y + v[2] * a.z + v[3] * a.w + v[4] * b.x + v[5] * b.y + v[6] * b.z + v[7] * b.w;
+  }
+  s = warp_sum(s);
+  if (lane == 0) logits[r] = s + __ldg(bias);
+}
+
+__global__ void __launch_bounds__(256) bce_logits_kernel(const float* __restrict__ logits, float target, float scale,
+                                                        float* __restrict__ dlogits, float* __restrict__ acc,
+                                                        long long rows) {
+  __shared__ float sm[8];
+  float s = 0.f, cnt = 0.f;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < rows; i += (long long)gridDim.x * 256) {
+    const float z = logits[i];
+    const float p = 1.f / (1.f + expf(-z));
+    const float lp = fmaxf(logf(p), -100.f), lq = fmaxf(logf(1.f - p), -100.f);
+    s += -(target * lp + (1.f - target) * lq);
+    cnt += target > 0.5f ? (p >= 0.5f ? 1.f : 0.f) : (p <= 0.5f ? 1.f : 0.f);
+    if (dlogits) dlogits[i] = scale * (p - target);
+  }
+  const float r = block_sum(s, sm);
+  const float c2 = block_sum(cnt, sm);
+  if (threadIdx.x == 0) { atomicAdd(acc, r); atomicAdd(acc + 1, c2); }
+}
+
+// thread per column, block.y = row chunk
+__global__ void __launch_bounds__(256) dhead_bwd_kernel(const bf16* __restrict__ f, const float* __restrict__ w,
+                                                       const float* __restrict__ dl, float* __restrict__ df,
+                                                       float* __restrict__ dw, float* __restrict__ db, long long rows,
+                                                       int c, int rows_per_block) {
+  const int col = blockIdx.x * 256 + threadIdx.x;
+  if (col >= c) return;
+  const long long r0 = (long long)blockIdx.y * rows_per_block;
+  const long long r1 = r0 + rows_per_block < rows ? r0 + rows_per_block : rows;
+  const float wc = __ldg(w + col);
+  float aw = 0.f, ab = 0.f;
+  for (long long r = r0; r < r1; ++r) {
+    const float d = __ldg(dl + r);
+    if (df) df[r * c + col] += d * wc;
+    aw += d * __bfloat162float(f[r * c + col]);
+    ab += d;
+  }
+  if (dw) atomicAdd(dw + col, aw);
+  if (db && col == 0) atomicAdd(db, ab);
+}
+
+__global__ void __launch_bounds__(256) mask_to_bf16_kernel(const float* __restrict__ df, const bf16* __restrict__ f,
+                                                          bf16* __restrict__ out, float slope, long long n) {
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
+    const float v = __bfloat162float(f[i]);
+    out[i] = __float2bfloat16(df[i] * (v > 0.f ? 1.f : slope));
+  }
+}
+
+__global__ void __launch_bounds__(256) colsum_kernel(const bf16* __restrict__ dy, long long rows, int c,
+                                                    float* __restrict__ db, int row_lanes) {
+  const int octs = c / 8;
+  const int oct = blockIdx.y * (256 / row_lanes) + threadIdx.x % (256 / row_lanes);
+  const int rl = threadIdx.x / (256 / row_lanes);
+  if (oct >= octs) return;
+  float a[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) a[k] = 0.f;
+  for (long long r = (long long)blockIdx.x * row_lanes + rl; r < rows; r += (long long)gridDim.x * row_lanes) {
+    float f[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(dy + r * c) + oct), f);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) a[k] += f[k];
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) atomicAdd(db + oct * 8 + k, a[k]);
+}
+
+// =============================================================================================== small dense layers
+template <bool XBF16>
+__global__ void __launch_bounds__(256) linear_fwd_kernel(const void* __restrict__ x_, const float* __restrict__ w,
+                                                        const float* __restrict__ b, float* __restrict__ y, int m,
+                                                        int n, int k, int act, float slope) {
+  const int lane = threadIdx.x & 31;
+  const long long o = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (o >= (long long)m * n) return;
+  const int i = (int)(o / n), j = (int)(o % n);
+  float s = 0.f;
+  for (int q = lane; q < k; q += 32) {
+    const float xv = XBF16 ? __bfloat162float(static_cast<const bf16*>(x_)[(long long)i * k + q])
+                           : static_cast<const float*>(x_)[(long long)i * k + q];
+    s += xv * __ldg(w + (long long)j * k + q);
+  }
+  s = warp_sum(s);
+  if (lane == 0) {
+    s += b ? __ldg(b + j) : 0.f;
+    if (act == 1) s = s > 0.f ? s : s * slope;
+    else if (act == 2) s = s > 20.f ? s : log1pf(expf(s));
+    y[o] = s;
+  }
+}
+
+template <bool XBF16>
+__global__ void __launch_bounds__(256) linear_bwd_dw_kernel(const void* __restrict__ x_, const float* __restrict__ dy,
+                                                           float* __restrict__ dw, int m, int n, int k) {
+  const long long o = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (o >= (long long)n * k) return;
+  const int j = (int)(o / k), q = (int)(o % k);
+  float s = 0.f;
+  for (int i = 0; i < m; ++i) {
+    const float xv = XBF16 ? __bfloat162float(static_cast<const bf16*>(x_)[(long long)i * k + q])
+                           : static_cast<const float*>(x_)[(long long)i * k + q];
+    s += __ldg(dy + (long long)i * n + j) * xv;
+  }
+  dw[o] += s;
+}
+__global__ void __launch_bounds__(256) linear_bwd_dx_kernel(const float* __restrict__ w, const float* __restrict__ dy,
+                                                           float* __restrict__ dx, int accumulate, int m, int n, int k) {
+  const long long o = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (o >= (long long)m * k) return;
+  const int i = (int)(o / k), q = (int)(o % k);
+  float s = 0.f;
+  for (int j = 0; j < n; ++j) s += __ldg(dy + (long long)i * n + j) * __ldg(w + (long long)j * k + q);
+  dx[o] = accumulate ? dx[o] + s : s;
+}
+__global__ void linear_bwd_db_kernel(const float* __restrict__ dy, float* __restrict__ db, int m, int n) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  float s = 0.f;
+  for (int i = 0; i < m; ++i) s += dy[(long long)i * n + j];
+  db[j] += s;
+}
+
+__global__ void act_bwd_kernel(float* __restrict__ dy, const float* __restrict__ y, int act, float slope, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float v = y[i];
+  if (act == 1) dy[i] *= v > 0.f ? 1.f : slope;
+  else if (act == 2) dy[i] *= v > 20.f ? 1.f : 1.f - expf(-v);  // softplus' = sigmoid(pre) = 1 - exp(-softplus)
+}
+
+__global__ void __launch_bounds__(256) mse_kernel(const float* __restrict__ p, const float* __restrict__ e,
+                                                 float* __restrict__ dp, float scale, float* __restrict__ acc,
+                                                 long long n) {
+  __shared__ float sm[8];
+  float s = 0.f;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
+    const float d = p[i] - e[i];
+    s += d * d;
+    if (dp) dp[i] = scale * d;
+  }
+  const float r = block_sum(s, sm);
+  if (threadIdx.x == 0) atomicAdd(acc, r);
+}
+
+__global__ void __launch_bounds__(256) vae_reparam_kernel(const float* __restrict__ mu, const float* __restrict__ sd,
+                                                         const float* __restrict__ noise, float* __restrict__ z,
+                                                         float* __restrict__ acc, long long n) {
+  __shared__ float sm[8];
+  float s = 0.f;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
+    const float m = mu[i], d = sd[i];
+    z[i] = m + d * noise[i];
+    s += m * m + d * d - logf(d * d);
+  }
+  const float r = block_sum(s, sm);
+  if (threadIdx.x == 0 && acc) atomicAdd(acc, r);
+}
+__global__ void vae_reparam_bwd_kernel(const float* __restrict__ mu, const float* __restrict__ sd,
+                                       const float* __restrict__ noise, const float* __restrict__ dz,
+                                       float* __restrict__ dmu, float* __restrict__ dsd, float kl_scale, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float d = sd[i];
+  dmu[i] = dz[i] + kl_scale * 2.f * mu[i];
+  dsd[i] = dz[i] * noise[i] + kl_scale * (2.f * d - 2.f / d);
+}
+
+// =============================================================================================== optimiser / packing
+__global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g,
+                                                  float* __restrict__ m, float* __restrict__ v, bf16* __restrict__ w16,
+                                                  long long n, float step_size, float beta1, float beta2, float eps,
+                                                  float wd, float inv_sqrt_bc2, float grad_scale) {
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
+    const float pv = p[i];
+    const float gr = g[i] * grad_scale + wd * pv;
+    const float mm = beta1 * m[i] + (1.f - beta1) * gr;
+    const float vv = beta2 * v[i] + (1.f - beta2) * gr * gr;
+    m[i] = mm; v[i] = vv;
+    const float np = pv - step_size * mm / (sqrtf(vv) * inv_sqrt_bc2 + eps);
+    p[i] = np;
+    if (w16) w16[i] = __float2bfloat16(np);
+  }
+}
+
+__global__ void pack_dgrad_kernel(const float* __restrict__ w, bf16* __restrict__ wt, int cout, int cin) {
+  __shared__ float tile[32][33];
+  const int tap = blockIdx.z;
+  const int ci0 = blockIdx.x * 32, co0 = blockIdx.y * 32;
+  const float* src = w + (long long)tap * cout * cin;
+  bf16* dst = wt + (long long)tap * cout * cin;
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int co = co0 + r, ci = ci0 + threadIdx.x;
+    tile[r][threadIdx.x] = (co < cout && ci < cin) ? src[(long long)co * cin + ci] : 0.f;
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int ci = ci0 + r, co = co0 + threadIdx.x;
+    if (ci < cin && co < cout) dst[(long long)ci * cout + co] = __float2bfloat16(tile[threadIdx.x][r]);
+  }
+}
+
+__global__ void f32_to_bf16_kernel(const float* __restrict__ x, bf16* __restrict__ y, long long n) {
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256)
+    y[i] = __float2bfloat16(x[i]);
+}
+__global__ void bf16_to_f32_kernel(const bf16* __restrict__ x, float* __restrict__ y, long long n) {
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256)
+    y[i] = __bfloat162float(x[i]);
+}
+
+}  // namespace
+
+#define ST_(s) static_cast<cudaStream_t>(s)
+#define REQUIRE(ctx, cond, code, msg) \
+  do { if (!(cond)) return lsps_set_error(ctx, code, msg); } while (0)
+
+// =============================================================================================== C ABI
+extern "C" int lsps_stem_fwd(lsps_ctx* ctx, const float* img, const float* w, const float* bias, void* y, int n, int h,
+                             int wd, int stride, float slope, lsps_stream st) {
+  REQUIRE(ctx, img && w && bias && y, LSPS_E_ARG, "stem_fwd: null");
+  REQUIRE(ctx, (stride == 1 || stride == 2) && h % (ST * stride) == 0 && wd % (ST * stride) == 0 && n > 0, LSPS_E_SHAPE,
+          "stem_fwd: h,w must be multiples of 16*stride");
+  dim3 grid(wd / stride / ST, h / stride / ST, n);
+  if (stride == 1) stem_fwd_kernel<1><<<grid, 256, 0, ST_(st)>>>(img, w, bias, static_cast<bf16*>(y), h, wd, slope);
+  else stem_fwd_kernel<2><<<grid, 256, 0, ST_(st)>>>(img, w, bias, static_cast<bf16*>(y), h, wd, slope);
+  LSPS_CHECK_LAUNCH(ctx, "stem_fwd");
+  return LSPS_OK;
+}
+
+extern "C" int lsps_stem_wgrad(lsps_ctx* ctx, const float* img, const void* dy, float* dw, float* db, int n, int h,
+                               int wd, int stride, lsps_stream st) {
+  REQUIRE(ctx, img && dy && dw, LSPS_E_ARG, "stem_wgrad: null");
+  REQUIRE(ctx, (stride == 1 || stride == 2) && h % (ST * stride) == 0 && wd % (ST * stride) == 0 && n > 0, LSPS_E_SHAPE,
+          "stem_wgrad: shape");
+  const int total = (wd / stride / ST) * (h / stride / ST) * n;
+  const int grid = total < 4 * ctx->num_sms ? total : 4 * ctx->num_sms;
+  if (stride == 1) stem_wgrad_kernel<1><<<grid, 256, 0, ST_(st)>>>(img, static_cast<const bf16*>(dy), dw, db, n, h, wd);
+  else stem_wgrad_kernel<2><<<grid, 256, 0, ST_(st)>>>(img, static_cast<const bf16*>(dy), dw, db, n, h, wd);
+  LSPS_CHECK_LAUNCH(ctx, "stem_wgrad");
+  return LSPS_OK;
+}
+
+extern "C" int lsps_stem_dgrad(lsps_ctx* ctx, const void* dy, const float* w, float* dimg, int n, int h, int wd,
+                               int stride, int accumulate, lsps_stream st) {
+  REQUIRE(ctx, dy && w && dimg, LSPS_E_ARG, "stem_dgrad: null");
+  REQUIRE(ctx, (stride == 1 || stride == 2) && h % (ST * stride) == 0 && wd % (ST * stride) == 0 && n > 0, LSPS_E_SHAPE,
+          "stem_dgrad: shape");
+  dim3 grid(wd / ST, h / ST, n);
+  const int de = stride == 1 ? ST + 6 : (ST + 6) / 2 + 1;
+  const int smem = 49 * 64 * 4 + de * de * 128;
+  if (stride == 1) {
+    static bool cfg = false;
+    if (!cfg) { cudaFuncSetAttribute(stem_dgrad_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); cfg = true; }
+    stem_dgrad_kernel<1><<<grid, 256, smem, ST_(st)>>>(static_cast<const bf16*>(dy), w, dimg, h, wd, accumulate);
+  } else {
+    stem_dgrad_kernel<2><<<grid, 256, smem, ST_(st)>>>(static_cast<const bf16*>(dy), w, dimg, h, wd, accumulate);
+  }
+  LSPS_CHECK_LAUNCH(ctx, "stem_dgrad");
+  return LSPS_OK;
+}
+
+extern "C" int lsps_head_fwd(lsps_ctx* ctx, const void* x, const float* w, const float* bias, float* out,
+                             long long npix, lsps_stream st) {
+  REQUIRE(ctx, x && w && bias && out && npix > 0, LSPS_E_ARG, "head_fwd: null");
+  head_fwd_kernel<<<grid_for(npix, 32, 16 * ctx->num_sms), 256, 0, ST_(st)>>>(static_cast<const bf16*>(x), w, bias, out, npix);
+  LSPS_CHECK_LAUNCH(ctx, "head_fwd");
+  return LSPS_OK;
+}
+extern "C" int lsps_head_bwd(lsps_ctx* ctx, const void* x, const float* w, const float* out, const float* dout,
+                             void* dx, float* dw, float* db, long long npix, float slope, lsps_stream st) {
+  REQUIRE(ctx, x && w && out && dout && dx && dw && db && npix > 0, LSPS_E_ARG, "head_bwd: null");
+  head_bwd_kernel<<<grid_for(npix, 32, 8 * ctx->num_sms), 256, 0, ST_(st)>>>(static_cast<const bf16*>(x), w, out, dout,
+                                                                           static_cast<bf16*>(dx), dw, db, npix, slope);
+  LSPS_CHECK_LAUNCH(ctx, "head_bwd");
+  return LSPS_OK;
+}
+
+extern "C" int lsps_instnorm_fwd(lsps_ctx* ctx, const void* h, const void* res, void* y, float* stats, int n, int hw,
+                                 int c, int mode, float eps, float slope, lsps_stream st) {
+  REQUIRE(ctx, h && y && stats && (mode == 0 || res), LSPS_E_ARG, "instnorm_fwd: null");
+  REQUIRE(ctx, n > 0 && hw > 0 && c % 64 == 0, LSPS_E_SHAPE, "instnorm_fwd: c must be a multiple of 64");
+  instnorm_fwd_kernel<<<dim3(c / 64, n), 256, 0, ST_(st)>>>(static_cast<const bf16*>(h), static_cast<const bf16*>(res),
+                                                          static_cast<bf16*>(y), stats, hw, c, mode, eps, slope);
+  LSPS_CHECK_LAUNCH(ctx, "instnorm_fwd");
+  return LSPS_OK;
+}
+extern "C" int lsps_instnorm_bwd(lsps_ctx* ctx, const void* dy, const void* h, const float* stats, void* dh, int n,
+                                 int hw, int c, int mode, float slope, lsps_stream st) {
+  REQUIRE(ctx, dy && h && stats && dh, LSPS_E_ARG, "instnorm_bwd: null");
+  REQUIRE(ctx, n > 0 && hw > 0 && c % 64 == 0, LSPS_E_SHAPE, "instnorm_bwd: c must be a multiple of 64");
+  instnorm_bwd_kernel<<<dim3(c / 64, n), 256, 0, ST_(st)>>>(static_cast<const bf16*>(dy), static_cast<const bf16*>(h),
+                                                          stats, static_cast<bf16*>(dh), hw, c, mode, slope);
+  LSPS_CHECK_LAUNCH(ctx, "instnorm_bwd");
+  return LSPS_OK;
+}
+
+extern "C" int lsps_noise_kl_fwd(lsps_ctx* ctx, const void* x, const float* noise, void* z, float* acc, long long n,
+                                 lsps_stream st) {
+  REQUIRE(ctx, x && noise && z && acc, LSPS_E_ARG, "noise_kl: null");
+  REQUIRE(ctx, n > 0 && n % 8 == 0, LSPS_E_SHAPE, "noise_kl: n % 8");
+  noise_kl_kernel<<<grid_for(n / 8, 256, 8 * ctx->num_sms), 256, 0, ST_(st)>>>(static_cast<const bf16*>(x), noise,
+                                                                             static_cast<bf16*>(z), acc, n / 8);
+  LSPS_CHECK_LAUNCH(ctx, "noise_kl");
+  return LSPS_OK;
+}
+extern "C" int lsps_axpy_bf16(lsps_ctx* ctx, const void* a, const void* b, float alpha, void* out, long long n,
+                              lsps_stream st) {
+  REQUIRE(ctx, b && out, LSPS_E_ARG, "axpy: null");
+  REQUIRE(ctx, n > 0 && n % 8 == 0, LSPS_E_SHAPE, "axpy: n % 8");
+  axpy_bf16_kernel<<<grid_for(n / 8, 256, 8 * ctx->num_sms), 256, 0, ST_(st)>>>(
+      static_cast<const bf16*>(a), static_cast<const bf16*>(b), alpha, static_cast<bf16*>(out), n / 8);
+  LSPS_CHECK_LAUNCH(ctx, "axpy");
+  return LSPS_OK;
+}
+extern "C" int lsps_l1_f32(lsps_ctx* ctx, const float* x, const float* t, float* dx, float scale, int accumulate,
+                           float* acc, long long n, lsps_stream st) {
+  REQUIRE(ctx, x && t && acc && n > 0, LSPS_E_ARG, "l1_f32: null");
+  l1_f32_kernel<<<grid_for(n, 256, 4 * ctx->num_sms), 256, 0, ST_(st)>>>(x, t, dx, scale, accumulate, acc, n);
+  LSPS_CHECK_LAUNCH(ctx, "l1_f32");
+  return LSPS_OK;
+}
+extern "C" int lsps_l1_feat(lsps_ctx* ctx, const void* a, const void* b, float* da, float* db, float scale, float* acc,
+                            long long n, lsps_stream st) {
+  REQUIRE(ctx, a && b && acc && n > 0, LSPS_E_ARG, "l1_feat: null");
+  l1_feat_kernel<<<grid_for(n, 256, 4 * ctx->num_sms), 256, 0, ST_(st)>>>(static_cast<const bf16*>(a),
+                                                                        static_cast<const bf16*>(b), da, db, scale, acc, n);
+  LSPS_CHECK_LAUNCH(ctx, "l1_feat");
+  return LSPS_OK;
+}
+extern "C" int lsps_dhead_fwd(lsps_ctx* ctx, const void* f, const float* w, const float* bias, float* logits,
+                              long long rows, int c, lsps_stream st) {
+  REQUIRE(ctx, f && w && bias && logits && rows > 0, LSPS_E_ARG, "dhead_fwd: null");
+  REQUIRE(ctx, c % 8 == 0, LSPS_E_SHAPE, "dhead_fwd: c % 8");
+  dhead_fwd_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, ST_(st)>>>(static_cast<const bf16*>(f), w, bias, logits, rows, c);
+  LSPS_CHECK_LAUNCH(ctx, "dhead_fwd");
+  return LSPS_OK;
+}
+extern "C" int lsps_bce_logits(lsps_ctx* ctx, const float* logits, float target, float scale, float* dlogits,
+                               float* acc, long long rows, lsps_stream st) {
+  REQUIRE(ctx, logits && acc && rows > 0, LSPS_E_ARG, "bce: null");
+  bce_logits_kernel<<<grid_for(rows, 256, ctx->num_sms), 256, 0, ST_(st)>>>(logits, target, scale, dlogits, acc, rows);
+  LSPS_CHECK_LAUNCH(ctx, "bce_logits");
+  return LSPS_OK;
+}
+extern "C" int lsps_dhead_bwd(lsps_ctx* ctx, const void* f, const float* w, const float* dlogits, float* df, float* dw,
+                              float* db, long long rows, int c, lsps_stream st) {
+  REQUIRE(ctx, f && w && dlogits && rows > 0, LSPS_E_ARG, "dhead_bwd: null");
+  const int rpb = 32;
+  dim3 grid((c + 255) / 256, (unsigned)((rows + rpb - 1) / rpb));
+  dhead_bwd_kernel<<<grid, 256, 0, ST_(st)>>>(static_cast<const bf16*>(f), w, dlogits, df, dw, db, rows, c, rpb);
+  LSPS_CHECK_LAUNCH(ctx, "dhead_bwd");
+  return LSPS_OK;
+}
+extern "C" int lsps_mask_to_bf16(lsps_ctx* ctx, const float* df, const void* f, void* out, float slope, long long n,
+                                 lsps_stream st) {
+  REQUIRE(ctx, df && f && out && n > 0, LSPS_E_ARG, "mask_to_bf16: null");
+  mask_to_bf16_kernel<<<grid_for(n, 256, 8 * ctx->num_sms), 256, 0, ST_(st)>>>(df, static_cast<const bf16*>(f),
+                                                                             static_cast<bf16*>(out), slope, n);
+  LSPS_CHECK_LAUNCH(ctx, "mask_to_bf16");
+  return LSPS_OK;
+}
+extern "C" int lsps_colsum_bf16(lsps_ctx* ctx, const void* dy, long long rows, int c, float* db, lsps_stream st) {
+  REQUIRE(ctx, dy && db && rows > 0, LSPS_E_ARG, "colsum: null");
+  REQUIRE(ctx, c % 8 == 0 && (c / 8 >= 256 ? (c / 8) % 256 == 0 : 256 % (c / 8) == 0), LSPS_E_SHAPE, "colsum: c");
+  const int octs = c / 8;
+  const int row_lanes = octs >= 256 ? 1 : 256 / octs;
+  const int gy = octs >= 256 ? octs / 256 : 1;
+  long long gx = (rows + row_lanes - 1) / row_lanes;
+  const long long cap = (4LL * ctx->num_sms + gy - 1) / gy;
+  if (gx > cap) gx = cap;
+  colsum_kernel<<<dim3((unsigned)gx, gy), 256, 0, ST_(st)>>>(static_cast<const bf16*>(dy), rows, c, db, row_lanes);
+  LSPS_CHECK_LAUNCH(ctx, "colsum");
+  return LSPS_OK;
+}
+
+extern "C" int lsps_linear_fwd(lsps_ctx* ctx, const void* x, int x_bf16, const float* w, const float* b, float* y, int m,
+                               int n, int k, int act, float slope, lsps_stream st) {
+  REQUIRE(ctx, x && w && y && m > 0 && n > 0 && k > 0, LSPS_E_ARG, "linear_fwd: arg");
+  const unsigned grid = (unsigned)(((long long)m * n + 7) / 8);
+  if (x_bf16) linear_fwd_kernel<true><<<grid, 256, 0, ST_(st)>>>(x, w, b, y, m, n, k, act, slope);
+  else linear_fwd_kernel<false><<<grid, 256, 0, ST_(st)>>>(x, w, b, y, m, n, k, act, slope);
+  LSPS_CHECK_LAUNCH(ctx, "linear_fwd");
+  return LSPS_OK;
+}
+extern "C" int lsps_linear_bwd(lsps_ctx* ctx, const void* x, int x_bf16, const float* w, const float* dy, float* dx,
+                               int dx_accumulate, float* dw, float* db, int m, int n, int k, lsps_stream st) {
+  REQUIRE(ctx, dy && m > 0 && n > 0 && k > 0, LSPS_E_ARG, "linear_bwd: arg");
+  if (dw) {
+    REQUIRE(ctx, x, LSPS_E_ARG, "linear_bwd: dw needs x");
+    const unsigned grid = (unsigned)(((long long)n * k + 255) / 256);
+    if (x_bf16) linear_bwd_dw_kernel<true><<<grid, 256, 0, ST_(st)>>>(x, dy, dw, m, n, k);
+    else linear_bwd_dw_kernel<false><<<grid, 256, 0, ST_(st)>>>(x, dy, dw, m, n, k);
+    LSPS_CHECK_LAUNCH(ctx, "linear_bwd_dw");
+  }
+  if (dx) {
+    REQUIRE(ctx, w, LSPS_E_ARG, "linear_bwd: dx needs w");
+    linear_bwd_dx_kernel<<<(unsigned)(((long long)m * k + 255) / 256), 256, 0, ST_(st)>>>(w, dy, dx, dx_accumulate, m, n, k);
+    LSPS_CHECK_LAUNCH(ctx, "linear_bwd_dx");
+  }
+  if (db) {
+    linear_bwd_db_kernel<<<(n + 127) / 128, 128, 0, ST_(st)>>>(dy, db, m, n);
+    LSPS_CHECK_LAUNCH(ctx, "linear_bwd_db");
+  }
+  return LSPS_OK;
+}
+extern "C" int lsps_act_bwd(lsps_ctx* ctx, float* dy, const float* y, int act, float slope, long long n, lsps_stream st) {
+  REQUIRE(ctx, dy && y && n > 0, LSPS_E_ARG, "act_bwd: arg");
+  act_bwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ST_(st)>>>(dy, y, act, slope, n);
+  LSPS_CHECK_LAUNCH(ctx, "act_bwd");
+  return LSPS_OK;
+}
+extern "C" int lsps_mse(lsps_ctx* ctx, const float* p, const float* e, float* dp, float scale, float* acc, long long n,
+                        lsps_stream st) {
+  REQUIRE(ctx, p && e && acc && n > 0, LSPS_E_ARG, "mse: arg");
+  mse_kernel<<<grid_for(n, 256, ctx->num_sms), 256, 0, ST_(st)>>>(p, e, dp, scale, acc, n);
+  LSPS_CHECK_LAUNCH(ctx, "mse");
+  return LSPS_OK;
+}
+extern "C" int lsps_vae_reparam(lsps_ctx* ctx, const float* mu, const float* sd, const float* noise, float* z,
+                                float* acc, long long n, lsps_stream st) {
+  REQUIRE(ctx, mu && sd && noise && z && n > 0, LSPS_E_ARG, "vae_reparam: arg");
+  vae_reparam_kernel<<<grid_for(n, 256, ctx->num_sms), 256, 0, ST_(st)>>>(mu, sd, noise, z, acc, n);
+  LSPS_CHECK_LAUNCH(ctx, "vae_reparam");
+  return LSPS_OK;
+}
+extern "C" int lsps_vae_reparam_bwd(lsps_ctx* ctx, const float* mu, const float* sd, const float* noise,
+                                    const float* dz, float* dmu, float* dsd, float kl_scale, long long n,
+                                    lsps_stream st) {
+  REQUIRE(ctx, mu && sd && noise && dz && dmu && dsd && n > 0, LSPS_E_ARG, "vae_reparam_bwd: arg");
+  vae_reparam_bwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ST_(st)>>>(mu, sd, noise, dz, dmu, dsd, kl_scale, n);
+  LSPS_CHECK_LAUNCH(ctx, "vae_reparam_bwd");
+  return LSPS_OK;
+}
+
+extern "C" int lsps_adam(lsps_ctx* ctx, float* p, const float* g, float* m, float* v, void* w16, long long n, float lr,
+                         float beta1, float beta2, float eps, float wd, int step, float grad_scale, lsps_stream st) {
+  REQUIRE(ctx, p && g && m && v && n > 0 && step > 0, LSPS_E_ARG, "adam: arg");
+  const double bc1 = 1.0 - pow((double)beta1, step), bc2 = 1.0 - pow((double)beta2, step);
+  adam_kernel<<<grid_for(n, 256, 8 * ctx->num_sms), 256, 0, ST_(st)>>>(p, g, m, v, static_cast<bf16*>(w16), n,
+                                                                     (float)(lr / bc1), beta1, beta2, eps, wd,
+                                                                     (float)(1.0 / sqrt(bc2)), grad_scale);
+  LSPS_CHECK_LAUNCH(ctx, "adam");
+  return LSPS_OK;
+}
+extern "C" int lsps_pack_dgrad(lsps_ctx* ctx, const float* w, void* wt, int taps, int cout, int cin, lsps_stream st) {
+  REQUIRE(ctx, w && wt && taps > 0 && cout > 0 && cin > 0, LSPS_E_ARG, "pack_dgrad: arg");
+  pack_dgrad_kernel<<<dim3((cin + 31) / 32, (cout + 31) / 32, taps), dim3(32, 8), 0, ST_(st)>>>(w, static_cast<bf16*>(wt), cout, cin);
+  LSPS_CHECK_LAUNCH(ctx, "pack_dgrad");
+  return LSPS_OK;
+}
+extern "C" int lsps_f32_to_bf16(lsps_ctx* ctx, const float* x, void* y, long long n, lsps_stream st) {
+  REQUIRE(ctx, x && y && n > 0, LSPS_E_ARG, "f32_to_bf16: arg");
+  f32_to_bf16_kernel<<<grid_for(n, 256, 8 * ctx->num_sms), 256, 0, ST_(st)>>>(x, static_cast<bf16*>(y), n);
+  LSPS_CHECK_LAUNCH(ctx, "f32_to_bf16");
+  return LSPS_OK;
+}
+extern "C" int lsps_bf16_to_f32(lsps_ctx* ctx, const void* x, float* y, long long n, lsps_stream st) {
+  REQUIRE(ctx, x && y && n > 0, LSPS_E_ARG, "bf16_to_f32: arg");
+  bf16_to_f32_kernel<<<grid_for(n, 256, 8 * ctx->num_sms), 256, 0, ST_(st)>>>(static_cast<const bf16*>(x), y, n);
+  LSPS_CHECK_LAUNCH(ctx, "bf16_to_f32");
+  return LSPS_OK;
+}

@@ -1,0 +1,646 @@
+// Implicit-GEMM convolutions on the 5th-generation tensor cores (tcgen05 + TMEM), operands staged by TMA.
+//
+//   conv_igemm_kernel : y[pixels, Cout] = sum over taps, Cin of x[pixel shifted by tap, Cin] * W[tap][Cout][Cin]
+//                       covers Conv2d 3x3 s1/s2 forward, their data gradients and the stride-2 ConvTranspose2d
+//                       (forward = 4 sub-pixel phases, no zero insertion, no col2im atomics).
+//   wgrad_kernel      : dW[tap][Cout, Cin] += sum over pixels dy[pixel, Cout]^T * x[pixel shifted by tap, Cin]
+//                       (both operands MN-major straight out of NHWC, split-K over pixel tiles, fp32 red.add).
+//
+// There is no im2col buffer: every (tap, 64-channel chunk) K-step is ONE 5-D TMA box out of the NHWC activation
+// tensor; TMA's out-of-bounds zero fill *is* the conv padding.  Stride-2 access never uses elementStrides: the
+// tensor is viewed as [N][H/2][2][W/2][2C] ("pair view") so that a stride-2 tap is a plain box at a parity index.
+//
+// Replaces the cuDNN calls under nn.Conv2d / nn.ConvTranspose2d at
+//   /root/reference/src/trainers/common_net.py:160-181 (LeakyINSResBlock), :246-268 (LeakyReLUConv2d / ConvTranspose2d)
+#include <stdarg.h>
+#include <stdio.h>
+
+#include "common.h"
+#include "ptx.cuh"
+
+using namespace lsps;
+
+// ------------------------------------------------------------------------------------------------ ctx
+int lsps_set_error(lsps_ctx* ctx, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  if (ctx) ctx->err = buf;
+  return code;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+extern "C" int lsps_abi_version(void) { return 1; }
+
+extern "C" int lsps_ctx_create(lsps_ctx** out, int device) {
+  if (!out) return LSPS_E_ARG;
+  *out = nullptr;
+  cudaError_t e = cudaSetDevice(device);
+  if (e != cudaSuccess) return LSPS_E_CUDA;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return LSPS_E_CUDA;
+  if (prop.major != 10) return LSPS_E_ARCH;  // sm_100a only: no fallback path exists
+  lsps_ctx* ctx = new lsps_ctx();
+  ctx->device = device;
+  ctx->num_sms = prop.multiProcessorCount;
+  cudaDriverEntryPointQueryResult q;
+  void* fn = nullptr;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || !fn) {
+    delete ctx;
+    return LSPS_E_CUDA;
+  }
+  ctx->encode_fn = fn;
+  *out = ctx;
+  return LSPS_OK;
+}
+extern "C" void lsps_ctx_destroy(lsps_ctx* ctx) { delete ctx; }
+extern "C" const char* lsps_last_error(lsps_ctx* ctx) { return ctx ? ctx->err.c_str() : "null ctx"; }
+extern "C" long long lsps_launch_count(lsps_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int lsps_get_tmap(lsps_ctx* ctx, const void* ptr, int rank, const uint32_t* dims, const uint32_t* box,
+                  CUtensorMap* out) {
+  TmapKey key{};
+  key.ptr = ptr;
+  key.rank = rank;
+  for (int i = 0; i < rank; ++i) { key.dims[i] = dims[i]; key.box[i] = box[i]; }
+  auto it = ctx->tmaps.find(key);
+  if (it != ctx->tmaps.end()) { *out = it->second; return LSPS_OK; }
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0) return lsps_set_error(ctx, LSPS_E_ARG, "tensor not 16-byte aligned");
+  cuuint64_t gdim[5], gstr[4];
+  cuuint32_t bdim[5], estr[5];
+  uint64_t stride = 2;  // bf16
+  for (int i = 0; i < rank; ++i) {
+    gdim[i] = dims[i];
+    bdim[i] = box[i];
+    estr[i] = 1;
+    stride *= dims[i];
+    if (i < rank - 1) gstr[i] = stride;
+  }
+  CUtensorMap tm;
+  CUresult r = reinterpret_cast<EncodeTiledFn>(ctx->encode_fn)(
+      &tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(ptr), gdim, gstr, bdim, estr,
+      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return lsps_set_error(ctx, LSPS_E_CUDA, "cuTensorMapEncodeTiled failed (%d) rank %d dims %u %u %u %u %u box %u %u %u %u %u",
+                          (int)r, rank, dims[0], dims[1], rank > 2 ? dims[2] : 0, rank > 3 ? dims[3] : 0,
+                          rank > 4 ? dims[4] : 0, box[0], box[1], rank > 2 ? box[2] : 0, rank > 3 ? box[3] : 0,
+                          rank > 4 ? box[4] : 0);
+  if (ctx->tmaps.size() > 4096) ctx->tmaps.clear();
+  ctx->tmaps.emplace(key, tm);
+  *out = tm;
+  return LSPS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ plans
+struct Tap {       // coordinate offsets of one filter tap in the A-operand tensor map
+  short ac, ax, ap, ay;  // channel offset (pair view: parity of x), x, row-parity index, y
+  int brow;              // first row of this tap's [N][K] weight slice
+};
+struct Phase { short tap0, ntaps, oa, ob; };  // output sub-pixel phase (oa, ob) and its tap list
+struct IgemmParams {
+  int tiles_x, tiles_y, tiles_i, tiles_n, nphases;
+  int twl, thl, nb;   // M tile = 2^twl x 2^thl pixels x nb images = 128 rows
+  int nimg, kchunks;  // kchunks = K channels / 64
+  long long o_n, o_y, o_x;  // output strides (elements)
+  int o_sy, o_sx;           // output pixel = (y*o_sy + oa, x*o_sx + ob)
+  __nv_bfloat16* out;
+  const float* bias;
+  const __nv_bfloat16* mask;
+  const __nv_bfloat16* add;
+  float slope;
+  int flags;
+  Phase ph[4];
+  Tap taps[9];
+};
+
+constexpr int A_STAGE_BYTES = 128 * 128;  // 128 rows x 64 bf16
+
+template <int BN>
+struct IgemmCfg {
+  static constexpr int STAGES = BN == 256 ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int B_STAGE_BYTES = BN * 128;
+  static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
+  static constexpr int SMEM_BYTES = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 1024 + 256;
+};
+
+// warp 0: TMA producer | warp 1: TMEM owner + MMA issuer | warps 2-5: epilogue (TMEM -> regs -> global)
+template <int BN>
+__global__ void __launch_bounds__(192, 1)
+conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                  const __grid_constant__ IgemmParams p) {
+  using Cfg = IgemmCfg<BN>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = base;
+  uint8_t* sB = base + STAGES * A_STAGE_BYTES;
+  uint64_t* full = reinterpret_cast<uint64_t*>(base + STAGES * (A_STAGE_BYTES + Cfg::B_STAGE_BYTES));
+  uint64_t* empty = full + STAGES;
+  uint64_t* tfull = empty + STAGES;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
+    fence_barrier_init();
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1) { tmem_alloc(tmem_slot, Cfg::TMEM_COLS); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int tiles_m = p.tiles_x * p.tiles_y * p.tiles_i;
+  const int per_phase = tiles_m * p.tiles_n;
+  const int total = per_phase * p.nphases;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0; uint32_t ph = 0;
+      for (int t = blockIdx.x; t < total; t += gridDim.x) {
+        const int pi = t / per_phase, r = t - pi * per_phase;
+        const int nt = r / tiles_m, mt = r - nt * tiles_m;
+        const int tx = mt % p.tiles_x, ty = (mt / p.tiles_x) % p.tiles_y, ti = mt / (p.tiles_x * p.tiles_y);
+        const int x0 = tx << p.twl, y0 = ty << p.thl, n0 = ti * p.nb;
+        const Phase P = p.ph[pi];
+        for (int tp = 0; tp < P.ntaps; ++tp) {
+          const Tap T = p.taps[P.tap0 + tp];
+          for (int kc = 0; kc < p.kchunks; ++kc) {
+            mbar_wait(&empty[stage], ph ^ 1);
+            mbar_expect_tx(&full[stage], A_STAGE_BYTES + Cfg::B_STAGE_BYTES);
+            tma_load_5d(sA + stage * A_STAGE_BYTES, &tmA, &full[stage], kc * 64 + T.ac, x0 + T.ax, T.ap, y0 + T.ay, n0);
+            tma_load_2d(sB + stage * Cfg::B_STAGE_BYTES, &tmB, &full[stage], kc * 64, T.brow + nt * BN);
+            if (++stage == STAGES) { stage = 0; ph ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(128, BN, 0, 0);
+      int stage = 0; uint32_t ph = 0; int it = 0;
+      for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
+        const int pi = t / per_phase;
+        const int nk = p.ph[pi].ntaps * p.kchunks;
+        const int acc = it & 1; const uint32_t accph = (it >> 1) & 1;
+        mbar_wait(&tempty[acc], accph ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int ks = 0; ks < nk; ++ks) {
+          mbar_wait(&full[stage], ph);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(sA + stage * A_STAGE_BYTES);
+          const uint32_t b_addr = smem_u32(sB + stage * Cfg::B_STAGE_BYTES);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_bf16(d_tmem, umma_smem_desc(a_addr + k * 32, 0, 1024), umma_smem_desc(b_addr + k * 32, 0, 1024), idesc,
+                      (ks | k) != 0 ? 1u : 0u);
+          umma_commit(&empty[stage]);
+          if (++stage == STAGES) { stage = 0; ph ^= 1; }
+        }
+        umma_commit(&tfull[acc]);
+      }
+    }
+  } else {
+    const int q = warp & 3;  // TMEM lane quarter this warp may read
+    const int row = q * 32 + lane;
+    const int tw_mask = (1 << p.twl) - 1, th_mask = (1 << p.thl) - 1;
+    const int xl = row & tw_mask, yl = (row >> p.twl) & th_mask, nl = row >> (p.twl + p.thl);
+    int it = 0;
+    for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
+      const int pi = t / per_phase, r = t - pi * per_phase;
+      const int nt = r / tiles_m, mt = r - nt * tiles_m;
+      const int tx = mt % p.tiles_x, ty = (mt / p.tiles_x) % p.tiles_y, ti = mt / (p.tiles_x * p.tiles_y);
+      const int x0 = tx << p.twl, y0 = ty << p.thl, n = ti * p.nb + nl;
+      const Phase P = p.ph[pi];
+      const bool valid = n < p.nimg;
+      const long long off = (long long)n * p.o_n + (long long)((y0 + yl) * p.o_sy + P.oa) * p.o_y +
+                            (long long)((x0 + xl) * p.o_sx + P.ob) * p.o_x + nt * BN;
+      const int acc = it & 1; const uint32_t accph = (it >> 1) & 1;
+      mbar_wait(&tfull[acc], accph);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(taddr + c0, v);
+        tmem_ld_wait();
+        if (valid) {
+          float f[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+          if (p.flags & LSPS_EP_BIAS) {
+            const float4* b4 = reinterpret_cast<const float4*>(p.bias + nt * BN + c0);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 b = __ldg(b4 + j);
+              f[4 * j] += b.x; f[4 * j + 1] += b.y; f[4 * j + 2] += b.z; f[4 * j + 3] += b.w;
+            }
+          }
+          if (p.flags & LSPS_EP_LRELU) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = f[j] > 0.f ? f[j] : f[j] * p.slope;
+          }
+          if (p.flags & LSPS_EP_MASK) {
+            const uint4* m4 = reinterpret_cast<const uint4*>(p.mask + off + c0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint4 m = __ldg(m4 + j);
+              const uint32_t w[4] = {m.x, m.y, m.z, m.w};
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                if (!(bf16lo(w[k]) > 0.f)) f[8 * j + 2 * k] *= p.slope;
+                if (!(bf16hi(w[k]) > 0.f)) f[8 * j + 2 * k + 1] *= p.slope;
+              }
+            }
+          }
+          if (p.flags & LSPS_EP_ADD) {
+            const uint4* a4 = reinterpret_cast<const uint4*>(p.add + off + c0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint4 m = __ldg(a4 + j);
+              const uint32_t w[4] = {m.x, m.y, m.z, m.w};
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                f[8 * j + 2 * k] += bf16lo(w[k]);
+                f[8 * j + 2 * k + 1] += bf16hi(w[k]);
+              }
+            }
+          }
+          uint4* o4 = reinterpret_cast<uint4*>(p.out + off + c0);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint4 o;
+            o.x = pack_bf16x2(f[8 * j], f[8 * j + 1]);
+            o.y = pack_bf16x2(f[8 * j + 2], f[8 * j + 3]);
+            o.z = pack_bf16x2(f[8 * j + 4], f[8 * j + 5]);
+            o.w = pack_bf16x2(f[8 * j + 6], f[8 * j + 7]);
+            o4[j] = o;
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[acc]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+}
+
+// ------------------------------------------------------------------------------------------------ wgrad
+struct WTap { short mc, mx, mp, my, nc, nx, np, ny; };  // tap offsets in the dy (M side) / x (N side) maps
+struct WgradParams {
+  int tiles_x, tiles_y, tiles_i;
+  int twl, thl, nb;  // K tile = 64 pixels
+  int ntaps, co_tiles, ci_tiles, splits;
+  int cout, cin;
+  float* dw;
+  WTap taps[9];
+};
+constexpr int W_BOX_BYTES = 64 * 128;  // 64 pixels x 64 bf16
+
+template <int BN>
+struct WgradCfg {
+  static constexpr int STAGE_BYTES = (2 + BN / 64) * W_BOX_BYTES;
+  static constexpr int STAGES = (196608 / STAGE_BYTES) > 8 ? 8 : (196608 / STAGE_BYTES);
+  static constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(192, 1)
+wgrad_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ CUtensorMap tmN,
+             const __grid_constant__ WgradParams p) {
+  using Cfg = WgradCfg<BN>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full = reinterpret_cast<uint64_t*>(base + STAGES * Cfg::STAGE_BYTES);
+  uint64_t* empty = full + STAGES;
+  uint64_t* tfull = empty + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tfull + 1);
+
+  int b = blockIdx.x;
+  const int split = b % p.splits; b /= p.splits;
+  const int cit = b % p.ci_tiles; b /= p.ci_tiles;
+  const int cot = b % p.co_tiles;
+  const int tap = b / p.co_tiles;
+  const int ptiles = p.tiles_x * p.tiles_y * p.tiles_i;
+  const int pt0 = (int)((long long)ptiles * split / p.splits);
+  const int pt1 = (int)((long long)ptiles * (split + 1) / p.splits);
+  if (pt0 >= pt1) return;
+  const int nA = min(2, (p.cout - cot * 128) / 64);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    mbar_init(tfull, 1);
+    fence_barrier_init();
+    tma_prefetch_desc(&tmM);
+    tma_prefetch_desc(&tmN);
+  }
+  if (warp == 1) { tmem_alloc(tmem_slot, Cfg::TMEM_COLS); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const WTap T = p.taps[tap];
+      int stage = 0; uint32_t ph = 0;
+      for (int pt = pt0; pt < pt1; ++pt) {
+        const int tx = pt % p.tiles_x, ty = (pt / p.tiles_x) % p.tiles_y, ti = pt / (p.tiles_x * p.tiles_y);
+        const int x0 = tx << p.twl, y0 = ty << p.thl, n0 = ti * p.nb;
+        uint8_t* s = base + stage * Cfg::STAGE_BYTES;
+        mbar_wait(&empty[stage], ph ^ 1);
+        mbar_expect_tx(&full[stage], (nA + BN / 64) * W_BOX_BYTES);
+        for (int j = 0; j < nA; ++j)
+          tma_load_5d(s + j * W_BOX_BYTES, &tmM, &full[stage], cot * 128 + j * 64 + T.mc, x0 + T.mx, T.mp, y0 + T.my, n0);
+#pragma unroll
+        for (int j = 0; j < BN / 64; ++j)
+          tma_load_5d(s + (2 + j) * W_BOX_BYTES, &tmN, &full[stage], cit * BN + j * 64 + T.nc, x0 + T.nx, T.np,
+                      y0 + T.ny, n0);
+        if (++stage == STAGES) { stage = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(128, BN, 1, 1);
+      int stage = 0; uint32_t ph = 0;
+      for (int pt = pt0; pt < pt1; ++pt) {
+        mbar_wait(&full[stage], ph);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(base + stage * Cfg::STAGE_BYTES);
+        const uint32_t b_addr = a_addr + 2 * W_BOX_BYTES;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)  // 16 pixels per MMA = 16 rows of 128 B
+          umma_bf16(tmem_base, umma_smem_desc(a_addr + k * 2048, W_BOX_BYTES, 1024),
+                    umma_smem_desc(b_addr + k * 2048, W_BOX_BYTES, 1024), idesc, (pt > pt0 || k > 0) ? 1u : 0u);
+        umma_commit(&empty[stage]);
+        if (++stage == STAGES) { stage = 0; ph ^= 1; }
+      }
+      umma_commit(tfull);
+    }
+  } else {
+    const int q = warp & 3;
+    const int co = cot * 128 + q * 32 + lane;
+    mbar_wait(tfull, 0);
+    tc_fence_after();
+    float* dst = p.dw + ((long long)tap * p.cout + co) * p.cin + cit * BN;
+    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      uint32_t v[32];
+      tmem_ld32(taddr + c0, v);
+      tmem_ld_wait();
+      if (co < p.cout) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + c0 + 4 * j),
+                       "f"(__uint_as_float(v[4 * j])), "f"(__uint_as_float(v[4 * j + 1])),
+                       "f"(__uint_as_float(v[4 * j + 2])), "f"(__uint_as_float(v[4 * j + 3]))
+                       : "memory");
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+namespace {
+
+struct Geo { int tw, th, nb, twl, thl; };
+inline int ilog2(int v) { int l = 0; while ((1 << l) < v) ++l; return l; }
+inline bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
+Geo geo_for(int hg, int wg, int pixels) {
+  Geo g;
+  g.tw = wg < pixels ? wg : pixels;
+  g.th = hg < pixels / g.tw ? hg : pixels / g.tw;
+  g.nb = pixels / (g.tw * g.th);
+  g.twl = ilog2(g.tw);
+  g.thl = ilog2(g.th);
+  return g;
+}
+
+// activation tensor map: plain view (C, W, 1, H, N) or pair view (2C, W/2, 2, H/2, N); box = (64, tw, 1, th, nb)
+int act_tmap(lsps_ctx* ctx, const void* ptr, int n, int h, int w, int c, bool pair, const Geo& g, CUtensorMap* tm) {
+  uint32_t dims[5], box[5] = {64, (uint32_t)g.tw, 1, (uint32_t)g.th, (uint32_t)g.nb};
+  if (pair) { dims[0] = 2 * c; dims[1] = w / 2; dims[2] = 2; dims[3] = h / 2; dims[4] = n; }
+  else      { dims[0] = c;     dims[1] = w;     dims[2] = 1; dims[3] = h;     dims[4] = n; }
+  return lsps_get_tmap(ctx, ptr, 5, dims, box, tm);
+}
+
+// taps of a stride-2 access along one axis, forward-conv indexing: input index 2*o + r - 1
+//   r=0 -> pair o-1, parity 1 ; r=1 -> pair o, parity 0 ; r=2 -> pair o, parity 1
+inline void s2_axis(int r, int* d, int* par) { *d = (r == 0) ? -1 : 0; *par = (r == 1) ? 0 : 1; }
+// taps of a transposed stride-2 access along one axis for output parity a: list of (r, input offset d)
+inline int t2_axis(int a, int* rs, int* ds) {
+  if (a == 0) { rs[0] = 1; ds[0] = 0; return 1; }
+  rs[0] = 0; ds[0] = 1; rs[1] = 2; ds[1] = 0; return 2;
+}
+
+enum Dir { FWD = 0, DGRAD = 1 };
+
+template <int BN>
+int launch_igemm(lsps_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tmB, const IgemmParams& p, cudaStream_t st) {
+  using Cfg = IgemmCfg<BN>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(conv_igemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) return lsps_set_error(ctx, LSPS_E_CUDA, "igemm smem attr: %s", cudaGetErrorString(e));
+    configured = true;
+  }
+  const int total = p.tiles_x * p.tiles_y * p.tiles_i * p.tiles_n * p.nphases;
+  const int grid = total < ctx->num_sms ? total : ctx->num_sms;
+  conv_igemm_kernel<BN><<<grid, 192, Cfg::SMEM_BYTES, st>>>(tmA, tmB, p);
+  LSPS_CHECK_LAUNCH(ctx, "conv_igemm");
+  return LSPS_OK;
+}
+
+// Builds the plan for forward / data-gradient of any of the three conv kinds and launches it.
+//   in : the tensor the GEMM reads (x for FWD, dy for DGRAD); out: what it writes (y / dx)
+int run_igemm(lsps_ctx* ctx, const lsps_conv_shape* s, Dir dir, const void* in, const void* wpk, const float* bias,
+              void* out, const void* mask, const void* add, int flags, float slope, cudaStream_t st) {
+  if (!ctx || !s || !in || !wpk || !out) return lsps_set_error(ctx, LSPS_E_ARG, "null argument");
+  const int kind = s->kind, n = s->n, h = s->h, w = s->w, cin = s->cin, cout = s->cout;
+  if (kind < 0 || kind > 2 || n <= 0 || !is_pow2(h) || !is_pow2(w) || cin % 64 || cout % 64 || cin <= 0 || cout <= 0)
+    return lsps_set_error(ctx, LSPS_E_SHAPE, "conv shape kind %d n %d h %d w %d cin %d cout %d", kind, n, h, w, cin, cout);
+  if (kind != LSPS_CONV_S1 && (h < 2 || w < 2)) return lsps_set_error(ctx, LSPS_E_SHAPE, "stride-2 op needs h,w >= 2");
+  if ((flags & LSPS_EP_BIAS) && !bias) return lsps_set_error(ctx, LSPS_E_ARG, "bias flag without bias");
+  if ((flags & LSPS_EP_MASK) && !mask) return lsps_set_error(ctx, LSPS_E_ARG, "mask flag without mask");
+  if ((flags & LSPS_EP_ADD) && !add) return lsps_set_error(ctx, LSPS_E_ARG, "add flag without add");
+
+  // forward-op output dims
+  const int ho = kind == LSPS_CONV_S1 ? h : (kind == LSPS_CONV_S2 ? h / 2 : 2 * h);
+  const int wo = kind == LSPS_CONV_S1 ? w : (kind == LSPS_CONV_S2 ? w / 2 : 2 * w);
+  // GEMM dims: K channels (of `in`), N channels (of `out`)
+  const int kc = dir == FWD ? cin : cout, nc = dir == FWD ? cout : cin;
+  // `in` / `out` tensor dims
+  const int ih = dir == FWD ? h : ho, iw = dir == FWD ? w : wo;
+  const int oh = dir == FWD ? ho : h, ow = dir == FWD ? wo : w;
+  // classify the access pattern
+  //   plain  : out grid == in grid, 9 shifted taps                       (S1 fwd, S1 dgrad)
+  //   down   : out grid = in grid / 2, pair view on `in`                 (S2 fwd, DECONV dgrad)
+  //   up     : out grid = 2 * in grid, 4 phases, strided store           (DECONV fwd, S2 dgrad)
+  const bool plain = kind == LSPS_CONV_S1;
+  const bool down = (kind == LSPS_CONV_S2 && dir == FWD) || (kind == LSPS_DECONV_S2 && dir == DGRAD);
+  const int hg = down ? ih / 2 : ih, wg = down ? iw / 2 : iw;  // GEMM pixel grid
+  const Geo g = geo_for(hg, wg, 128);
+
+  IgemmParams p{};
+  p.tiles_x = wg / g.tw; p.tiles_y = hg / g.th; p.tiles_i = (n + g.nb - 1) / g.nb;
+  p.twl = g.twl; p.thl = g.thl; p.nb = g.nb;
+  p.nimg = n; p.kchunks = kc / 64;
+  p.o_n = (long long)oh * ow * nc; p.o_y = (long long)ow * nc; p.o_x = nc;
+  p.out = static_cast<__nv_bfloat16*>(out); p.bias = bias;
+  p.mask = static_cast<const __nv_bfloat16*>(mask); p.add = static_cast<const __nv_bfloat16*>(add);
+  p.slope = slope; p.flags = flags;
+
+  int nt = 0;
+  if (plain) {
+    p.nphases = 1; p.o_sy = p.o_sx = 1;
+    p.ph[0] = Phase{0, 9, 0, 0};
+    for (int r = 0; r < 3; ++r)
+      for (int c = 0; c < 3; ++c) {
+        Tap& T = p.taps[nt++];
+        T.ac = 0; T.ap = 0;
+        T.ay = dir == FWD ? r - 1 : 1 - r;
+        T.ax = dir == FWD ? c - 1 : 1 - c;
+        T.brow = (r * 3 + c) * nc;
+      }
+  } else if (down) {
+    p.nphases = 1; p.o_sy = p.o_sx = 1;
+    p.ph[0] = Phase{0, 9, 0, 0};
+    for (int r = 0; r < 3; ++r)
+      for (int c = 0; c < 3; ++c) {
+        Tap& T = p.taps[nt++];
+        int dy, py, dx, px;
+        s2_axis(r, &dy, &py);
+        s2_axis(c, &dx, &px);
+        T.ay = dy; T.ap = py; T.ax = dx; T.ac = px * kc;
+        T.brow = (r * 3 + c) * nc;
+      }
+  } else {  // up: heaviest phase first
+    p.nphases = 4; p.o_sy = p.o_sx = 2;
+    const int order[4][2] = {{1, 1}, {1, 0}, {0, 1}, {0, 0}};
+    for (int i = 0; i < 4; ++i) {
+      const int a = order[i][0], b = order[i][1];
+      int rs[2], dys[2], cs[2], dxs[2];
+      const int nr = t2_axis(a, rs, dys), ncs = t2_axis(b, cs, dxs);
+      p.ph[i] = Phase{(short)nt, (short)(nr * ncs), (short)a, (short)b};
+      for (int ri = 0; ri < nr; ++ri)
+        for (int ci = 0; ci < ncs; ++ci) {
+          Tap& T = p.taps[nt++];
+          T.ac = 0; T.ap = 0; T.ay = dys[ri]; T.ax = dxs[ci];
+          T.brow = (rs[ri] * 3 + cs[ci]) * nc;
+        }
+    }
+  }
+
+  const int bn = nc % 256 == 0 ? 256 : (nc % 128 == 0 ? 128 : 64);
+  p.tiles_n = nc / bn;
+  CUtensorMap tmA, tmB;
+  int rc = act_tmap(ctx, in, n, ih, iw, kc, down, g, &tmA);
+  if (rc) return rc;
+  uint32_t wd[2] = {(uint32_t)kc, (uint32_t)(9 * nc)}, wb[2] = {64, (uint32_t)bn};
+  rc = lsps_get_tmap(ctx, wpk, 2, wd, wb, &tmB);
+  if (rc) return rc;
+  if (bn == 256) return launch_igemm<256>(ctx, tmA, tmB, p, st);
+  if (bn == 128) return launch_igemm<128>(ctx, tmA, tmB, p, st);
+  return launch_igemm<64>(ctx, tmA, tmB, p, st);
+}
+
+template <int BN>
+int launch_wgrad(lsps_ctx* ctx, const CUtensorMap& tmM, const CUtensorMap& tmN, const WgradParams& p, cudaStream_t st) {
+  using Cfg = WgradCfg<BN>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(wgrad_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) return lsps_set_error(ctx, LSPS_E_CUDA, "wgrad smem attr: %s", cudaGetErrorString(e));
+    configured = true;
+  }
+  const int grid = p.ntaps * p.co_tiles * p.ci_tiles * p.splits;
+  wgrad_kernel<BN><<<grid, 192, Cfg::SMEM_BYTES, st>>>(tmM, tmN, p);
+  LSPS_CHECK_LAUNCH(ctx, "wgrad");
+  return LSPS_OK;
+}
+
+}  // namespace
+
+extern "C" int lsps_conv_fwd(lsps_ctx* ctx, const lsps_conv_shape* s, const void* x, const void* w_fwd,
+                             const float* bias, void* y, int flags, float slope, lsps_stream st) {
+  return run_igemm(ctx, s, FWD, x, w_fwd, bias, y, nullptr, nullptr, flags & (LSPS_EP_BIAS | LSPS_EP_LRELU), slope,
+                   static_cast<cudaStream_t>(st));
+}
+
+extern "C" int lsps_conv_dgrad(lsps_ctx* ctx, const lsps_conv_shape* s, const void* dy, const void* w_dgrad, void* dx,
+                               const void* mask, const void* add, int flags, float slope, lsps_stream st) {
+  return run_igemm(ctx, s, DGRAD, dy, w_dgrad, nullptr, dx, mask, add, flags & (LSPS_EP_MASK | LSPS_EP_ADD), slope,
+                   static_cast<cudaStream_t>(st));
+}
+
+extern "C" int lsps_conv_wgrad(lsps_ctx* ctx, const lsps_conv_shape* s, const void* x, const void* dy, float* dw,
+                               lsps_stream st_) {
+  cudaStream_t st = static_cast<cudaStream_t>(st_);
+  if (!ctx || !s || !x || !dy || !dw) return lsps_set_error(ctx, LSPS_E_ARG, "null argument");
+  const int kind = s->kind, n = s->n, h = s->h, w = s->w, cin = s->cin, cout = s->cout;
+  if (kind < 0 || kind > 2 || n <= 0 || !is_pow2(h) || !is_pow2(w) || cin % 64 || cout % 64 || cin <= 0 || cout <= 0)
+    return lsps_set_error(ctx, LSPS_E_SHAPE, "wgrad shape kind %d n %d h %d w %d cin %d cout %d", kind, n, h, w, cin, cout);
+  const int ho = kind == LSPS_CONV_S1 ? h : (kind == LSPS_CONV_S2 ? h / 2 : 2 * h);
+  const int wo = kind == LSPS_CONV_S1 ? w : (kind == LSPS_CONV_S2 ? w / 2 : 2 * w);
+  // reduction grid: the coarser of the two spatial grids
+  const int hg = kind == LSPS_CONV_S2 ? ho : h, wg = kind == LSPS_CONV_S2 ? wo : w;
+  const Geo g = geo_for(hg, wg, 64);
+  WgradParams p{};
+  p.tiles_x = wg / g.tw; p.tiles_y = hg / g.th; p.tiles_i = (n + g.nb - 1) / g.nb;
+  p.twl = g.twl; p.thl = g.thl; p.nb = g.nb;
+  p.ntaps = 9; p.cout = cout; p.cin = cin; p.dw = dw;
+  p.co_tiles = (cout + 127) / 128;
+  const int bn = cin % 256 == 0 ? 256 : (cin % 128 == 0 ? 128 : 64);
+  p.ci_tiles = cin / bn;
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 3; ++c) {
+      WTap& T = p.taps[r * 3 + c];
+      T = WTap{0, 0, 0, 0, 0, 0, 0, 0};
+      if (kind == LSPS_CONV_S1) { T.ny = r - 1; T.nx = c - 1; }
+      else if (kind == LSPS_CONV_S2) {
+        int dy_, py, dx_, px;
+        s2_axis(r, &dy_, &py); s2_axis(c, &dx_, &px);
+        T.ny = dy_; T.np = py; T.nx = dx_; T.nc = px * cin;
+      } else {  // deconv: dy pair view at parity (a,b); x shifted by (di,dj)
+        const int a = r == 1 ? 0 : 1, b = c == 1 ? 0 : 1;
+        T.mp = a; T.mc = b * cout;
+        T.ny = r == 0 ? 1 : 0; T.nx = c == 0 ? 1 : 0;
+      }
+    }
+  const int ptiles = p.tiles_x * p.tiles_y * p.tiles_i;
+  const int work = p.ntaps * p.co_tiles * p.ci_tiles;
+  int splits = ctx->num_sms / work;
+  if (splits < 1) splits = 1;
+  if (splits > ptiles) splits = ptiles;
+  p.splits = splits;
+  CUtensorMap tmM, tmN;
+  // M side: dy (cout channels) ; N side: x (cin channels)
+  int rc = act_tmap(ctx, dy, n, ho, wo, cout, kind == LSPS_DECONV_S2, g, &tmM);
+  if (rc) return rc;
+  rc = act_tmap(ctx, x, n, h, w, cin, kind == LSPS_CONV_S2, g, &tmN);
+  if (rc) return rc;
+  if (bn == 256) return launch_wgrad<256>(ctx, tmM, tmN, p, st);
+  if (bn == 128) return launch_wgrad<128>(ctx, tmM, tmN, p, st);
+  return launch_wgrad<64>(ctx, tmM, tmN, p, st);
+}
