@@ -1,0 +1,262 @@
+#!/usr/bin/env python
+"""bench.py -- train-step depth-images/sec of the LSPS pretrain step (dis_update + gen_update) on B200.
+
+  python bench.py --gpus N --steps K --warmup W          (N>1: launched by torch.distributed.run, one rank per GPU)
+  python bench.py --impl reference ...                   (the reference's CPU path = the oracle port, host cores)
+
+Workload (BASELINE.json configs[1]): depth_train.py --mode pretrain, exps/nnyu.yaml, synthetic 128x128 depth
+crops, batch 64 per domain per GPU (weak scaling: the per-GPU batch is fixed as N grows).  One step = one
+dis_update + one gen_update (src/depth_train.py:158-161) = 2*64 depth images per GPU.
+
+Prints ONE JSON line.  `value`: inputs already resident in HBM.  `e2e`: same calls with pinned HOST inputs, the
+host->device copies and the per-update device->host loss read inside the timed region.  `roofline`: the dominant
+kernel (3x3 s1 256->256 implicit GEMM on tcgen05, the K1 shape of SURVEY.md 2.2) timed per launch with CUDA events
+in an extra instrumented step.  `cpu_baseline`: the oracle port timed on this box's host cores on a bounded sample.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "train-step depth-images/sec at 128x128 (pretrain: dis_update+gen_update, nnyu)"
+UNIT = "images/s"
+BATCH = int(os.environ.get("LSPS_BENCH_BATCH", "64"))          # per domain per GPU
+CPU_SAMPLE_BATCH = int(os.environ.get("LSPS_BENCH_CPU_BATCH", "2"))
+# algorithmic work, SURVEY.md section 8d: 195.4 GMAC per (a,b) image pair per pretrain step
+GFLOP_PER_PAIR = 390.7
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as fh:
+            d = json.load(fh)
+        return dict(hbm=d["hbm_gbs"], tf=d["bf16_tflops"], tf_sustained=d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                    src="measured (MEASURED_PEAKS.json)")
+    return dict(hbm=6650.0, tf=1590.0, tf_sustained=1400.0, src="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag, self.proc = index, [], False, None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([c.strip() for c in line.split(",")])
+                if self.stop_flag:
+                    break
+        except Exception:  # noqa
+            pass
+
+    def finish(self):
+        self.stop_flag = True
+        time.sleep(0.15)
+        if self.proc:
+            self.proc.terminate()
+        sm, reasons, smax = [], set(), None
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); smax = float(r[1])
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:  # noqa
+                continue
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def cpu_reference_rate(steps, warmup, batch):
+    """The reference's own CPU path of this workload (oracle port of LSPSTrainer) on all host cores."""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import lsps_oracle as O
+    import yaml
+    with open(os.path.join(ROOT, "exps", "nnyu.yaml")) as fh:
+        hp = yaml.safe_load(fh)["train"]["hyperparameters"]
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    tr = O.OracleTrainer(hp, seed=0)
+    g = torch.Generator().manual_seed(1234)
+    ia, ib, la, lb = O.synthetic_batch(batch, 108, g, "hand")
+    times = []
+    for s in range(warmup + steps):
+        t0 = time.perf_counter()
+        tr.dis_update(ia, la, ib, lb, None, None, hp)
+        tr.gen_update(ia, la, ib, lb, hp)
+        if s >= warmup:
+            times.append(time.perf_counter() - t0)
+    sec = sum(times) / len(times)
+    return 2 * batch / sec, sec, cores
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps, warmup = max(1, min(args.steps, 3)), max(1, min(args.warmup, 1))
+    rate, sec, cores = cpu_reference_rate(steps, warmup, CPU_SAMPLE_BATCH)
+    sample = "pretrain step (dis_update+gen_update) at batch %d per domain, %d timed steps, oracle port of " \
+             "LSPSTrainer on torch CPU fp32" % (CPU_SAMPLE_BATCH, steps)
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "pretrain nnyu 128x128, CPU sample batch %d/domain" % CPU_SAMPLE_BATCH},
+        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    import lsps_b200
+    from lsps_b200 import engine as _engine
+    hp = lsps_b200.load_hyperparameters("nnyu")
+    tr = lsps_b200.LSPSTrainerB200(hp, device=local, seed=0, noise="device")
+    B = BATCH
+    g = torch.Generator().manual_seed(1234 + rank)
+    ia_h, ib_h, la_h, lb_h = (t.pin_memory() for t in lsps_b200.synthetic_batch(B, 108, g, "hand"))
+    ia, ib, la, lb = (t.cuda(non_blocking=True) for t in (ia_h, ib_h, la_h, lb_h))
+
+    def step_dev():
+        tr.dis_update(ia, la, ib, lb, None, None, hp)
+        tr.gen_update(ia, la, ib, lb, hp)
+
+    def step_e2e():
+        a, b_, c, d = (t.cuda(non_blocking=True) for t in (ia_h, ib_h, la_h, lb_h))
+        tr.dis_update(a, c, b_, d, None, None, hp)
+        tr.gen_update(a, c, b_, d, hp)
+
+    def timed(fn, k):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(k):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+            dist.barrier()
+        return ms.item()
+
+    W, K = max(3, args.warmup), args.steps
+    for _ in range(W):
+        step_dev()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    l0 = tr.ops.ctx.launch_count()
+    ms = timed(step_dev, K)
+    launches = tr.ops.ctx.launch_count() - l0
+    clocks = sampler.finish() if sampler else None
+    value = world * 2 * B * K / (ms / 1e3)
+    for _ in range(2):
+        step_e2e()
+    ms_e2e = timed(step_e2e, K)
+    e2e = world * 2 * B * K / (ms_e2e / 1e3)
+    h2d = sum(t.numel() * t.element_size() for t in (ia_h, ib_h, la_h, lb_h))
+    d2h = (8 + 16) * 4
+
+    # ---- roofline of the dominant kernel: every launch of the K1 shape in one instrumented step
+    roof = None
+    if rank == 0:
+        pk = _peaks()
+        ev = []
+        orig_f, orig_d = _engine.Ops.conv_fwd, _engine.Ops.conv_dgrad
+
+        def wrap(orig, is_fwd):
+            def f(self, S, key, kind, x, *a, **kw):
+                shp = x.shape if is_fwd else a[0]
+                k1 = kind == 0 and shp[1] == 32 and shp[3] == 256
+                if k1:
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                out = orig(self, S, key, kind, x, *a, **kw)
+                if k1:
+                    e1.record()
+                    ev.append((e0, e1, shp[0]))
+                return out
+            return f
+        _engine.Ops.conv_fwd, _engine.Ops.conv_dgrad = wrap(orig_f, True), wrap(orig_d, False)
+        step_dev()
+        torch.cuda.synchronize()
+        _engine.Ops.conv_fwd, _engine.Ops.conv_dgrad = orig_f, orig_d
+        tot_ms = sum(a.elapsed_time(b_) for a, b_, _ in ev)
+        tot_flop = sum(2.0 * n * 1024 * 256 * 2304 for _, _, n in ev)
+        ach = tot_flop / (tot_ms * 1e-3) / 1e12
+        roof = {"bound": "tensor", "kernel": "conv_igemm_kernel<256> (3x3 s1 256->256 @32x32, fwd+dgrad)",
+                "achieved": ach, "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": ach / pk["tf_sustained"],
+                "traffic": None, "launches": len(ev), "avg_launch_ms": tot_ms / max(1, len(ev)),
+                "share_of_step": tot_ms / (ms / K), "peak_source": pk["src"] + ", sustained bf16"}
+
+    if world > 1:
+        dist.barrier()
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        rate, sec, cores = cpu_reference_rate(2, 1, CPU_SAMPLE_BATCH)
+        cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": "pretrain step at batch %d per domain, 1 warm-up + 2 timed steps (%.1f s/step), oracle port "
+                         "of the reference LSPSTrainer on torch CPU fp32" % (CPU_SAMPLE_BATCH, sec)}
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+        "data": "synthetic",
+        "config": {"workload": "depth_train.py --mode pretrain, exps/nnyu.yaml, 128x128 synthetic depth, batch %d per "
+                               "domain per GPU (dis_update + gen_update)" % B,
+                   "global_batch_per_domain": B * world, "parallelism": "dp%d" % world,
+                   "noise": "device Philox (host-RNG parity mode is not the timed mode)",
+                   "l2": "working set >> 126 MB L2 (activations of one step are several GB); no explicit flush",
+                   "algorithmic_tflop_per_step_per_gpu": GFLOP_PER_PAIR * B / 1e3},
+        "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": ms_e2e / K},
+        "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
+        "step_tflops": GFLOP_PER_PAIR * B / 1e3 / (ms / K / 1e3) * world,
+    }
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

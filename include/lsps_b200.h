@@ -29,7 +29,7 @@ enum { LSPS_OK = 0, LSPS_E_ARG = -1, LSPS_E_SHAPE = -2, LSPS_E_ARCH = -3, LSPS_E
 
 /* conv kinds: 3x3 stride-1 pad-1 Conv2d | 3x3 stride-2 pad-1 Conv2d | 3x3 stride-2 pad-1 output_padding-1 ConvTranspose2d */
 enum { LSPS_CONV_S1 = 0, LSPS_CONV_S2 = 1, LSPS_DECONV_S2 = 2 };
-/* epilogue flags of the implicit-GEMM kernels, applied in this order: +bias, LeakyReLU, *lrelu'(mask), +add */
+/* epilogue flags of the implicit-GEMM kernels, applied in this order: +bias, LeakyReLU, +add, *lrelu'(mask) */
 enum { LSPS_EP_BIAS = 1, LSPS_EP_LRELU = 2, LSPS_EP_MASK = 4, LSPS_EP_ADD = 8 };
 
 /* n images; h,w = INPUT spatial size of the FORWARD op; cin/cout of the forward op (multiples of 64). */
@@ -46,7 +46,7 @@ long long lsps_launch_count(lsps_ctx* ctx);
 /* y = epilogue(conv(x, w) [+ bias]) ; x bf16 [n,h,w,cin] ; y bf16 [n,ho,wo,cout] */
 int lsps_conv_fwd(lsps_ctx*, const lsps_conv_shape*, const void* x, const void* w_fwd, const float* bias, void* y,
                   int flags, float slope, lsps_stream);
-/* dx = epilogue(conv_backward_data(dy, w)) ; mask/add: bf16 tensors shaped like dx (flags MASK / ADD) */
+/* dx = (conv_backward_data(dy, w) + add) * lrelu'(mask) ; mask/add: bf16 tensors shaped like dx (flags ADD / MASK) */
 int lsps_conv_dgrad(lsps_ctx*, const lsps_conv_shape*, const void* dy, const void* w_dgrad, void* dx,
                     const void* mask, const void* add, int flags, float slope, lsps_stream);
 /* dw[tap][cout][cin] += conv_backward_weight(x, dy)   (fp32, accumulating; split-K over pixels with red.add) */

@@ -251,19 +251,6 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 #pragma unroll
             for (int j = 0; j < 32; ++j) f[j] = f[j] > 0.f ? f[j] : f[j] * p.slope;
           }
-          if (p.flags & LSPS_EP_MASK) {
-            const uint4* m4 = reinterpret_cast<const uint4*>(p.mask + off + c0);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const uint4 m = __ldg(m4 + j);
-              const uint32_t w[4] = {m.x, m.y, m.z, m.w};
-#pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                if (!(bf16lo(w[k]) > 0.f)) f[8 * j + 2 * k] *= p.slope;
-                if (!(bf16hi(w[k]) > 0.f)) f[8 * j + 2 * k + 1] *= p.slope;
-              }
-            }
-          }
           if (p.flags & LSPS_EP_ADD) {
             const uint4* a4 = reinterpret_cast<const uint4*>(p.add + off + c0);
 #pragma unroll
@@ -274,6 +261,19 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               for (int k = 0; k < 4; ++k) {
                 f[8 * j + 2 * k] += bf16lo(w[k]);
                 f[8 * j + 2 * k + 1] += bf16hi(w[k]);
+              }
+            }
+          }
+          if (p.flags & LSPS_EP_MASK) {
+            const uint4* m4 = reinterpret_cast<const uint4*>(p.mask + off + c0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint4 m = __ldg(m4 + j);
+              const uint32_t w[4] = {m.x, m.y, m.z, m.w};
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                if (!(bf16lo(w[k]) > 0.f)) f[8 * j + 2 * k] *= p.slope;
+                if (!(bf16hi(w[k]) > 0.f)) f[8 * j + 2 * k + 1] *= p.slope;
               }
             }
           }

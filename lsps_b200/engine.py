@@ -1,0 +1,498 @@
+"""Hand-scheduled forward/backward of the LSPS networks on the lsps_b200 kernels.
+
+There is no autograd: every update of the reference trainer (/root/reference/src/trainers/lsps_trainer.py:62-262)
+is a static schedule over the C-ABI kernels -- forward passes keep exactly the activations
+their backward needs, gradients that the reference computes and then discards (generator backward inside
+dis_update, discriminator wgrad inside gen_update) are never computed.
+
+Layouts: images fp32 [n,128,128]; activations bf16 NHWC; InstanceNorm statistics, loss sums and all parameter
+gradients fp32.  Network structure follows lsps_nets.py:86-160 (SharedDis) and :164-272 (SharedResGen).
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import CONV_S1, CONV_S2, DECONV_S2, EP_BIAS, EP_LRELU, EP_MASK, EP_ADD, ConvShape
+
+SLOPE = 0.01   # nn.LeakyReLU() default (common_net.py:169,251)
+IN_EPS = 1e-5  # nn.InstanceNorm2d default
+
+
+def _shape(kind, n, h, w, cin, cout):
+    return C.byref(ConvShape(kind, n, h, w, cin, cout))
+
+
+class Ops:
+    """Typed wrappers: torch tensors in, kernels out."""
+
+    def __init__(self, device):
+        self.device = torch.device(device)
+        self.ctx = _lib.context(self.device.index)
+
+    def empty(self, *shape, dtype=torch.bfloat16):
+        return torch.empty(shape, dtype=dtype, device=self.device)
+
+    def zeros(self, *shape, dtype=torch.float32):
+        return torch.zeros(shape, dtype=dtype, device=self.device)
+
+    # ---- 3x3 convs on tcgen05
+    @staticmethod
+    def _io(S, key, kind):
+        sh = S.entries[key + ".weight"].shape
+        return (sh[1], sh[0]) if kind != DECONV_S2 else (sh[0], sh[1])  # (cin, cout)
+
+    def conv_fwd(self, S, key, kind, x, lrelu, out=None):
+        n, h, w, cin = x.shape
+        ci, co = self._io(S, key, kind)
+        assert ci == cin, (key, ci, cin)
+        ho, wo = (h, w) if kind == CONV_S1 else ((h // 2, w // 2) if kind == CONV_S2 else (2 * h, 2 * w))
+        y = out if out is not None else self.empty(n, ho, wo, co)
+        self.ctx.conv_fwd(_shape(kind, n, h, w, ci, co), x.data_ptr(), S.W16(key + ".weight").data_ptr(),
+                          S.W(key + ".bias").data_ptr(), y.data_ptr(), EP_BIAS | (EP_LRELU if lrelu else 0), SLOPE)
+        return y
+
+    def conv_dgrad(self, S, key, kind, dy, x_shape, mask=None, add=None, out=None):
+        n, h, w, cin = x_shape
+        ci, co = self._io(S, key, kind)
+        dx = out if out is not None else self.empty(n, h, w, ci)
+        flags = (EP_MASK if mask is not None else 0) | (EP_ADD if add is not None else 0)
+        self.ctx.conv_dgrad(_shape(kind, n, h, w, ci, co), dy.data_ptr(), S.W16T(key + ".weight").data_ptr(),
+                            dx.data_ptr(), _lib.ptr(mask), _lib.ptr(add), flags, SLOPE)
+        return dx
+
+    def conv_wgrad(self, S, key, kind, x, dy):
+        n, h, w, cin = x.shape
+        ci, co = self._io(S, key, kind)
+        self.ctx.conv_wgrad(_shape(kind, n, h, w, ci, co), x.data_ptr(), dy.data_ptr(), S.G(key + ".weight").data_ptr())
+        self.ctx.colsum_bf16(dy.data_ptr(), dy.numel() // co, co, S.G(key + ".bias").data_ptr())
+
+    # ---- InstanceNorm
+    def in_fwd(self, h, mode, res=None, out=None):
+        n, hh, ww, c = h.shape
+        stats = self.empty(n, c, 2, dtype=torch.float32)
+        y = out if out is not None else torch.empty_like(h)
+        self.ctx.instnorm_fwd(h.data_ptr(), _lib.ptr(res), y.data_ptr(), stats.data_ptr(), n, hh * ww, c, mode, IN_EPS,
+                              SLOPE)
+        return y, stats
+
+    def in_bwd(self, dy, h, stats, mode):
+        n, hh, ww, c = h.shape
+        dh = torch.empty_like(h)
+        self.ctx.instnorm_bwd(dy.data_ptr(), h.data_ptr(), stats.data_ptr(), dh.data_ptr(), n, hh * ww, c, mode, SLOPE)
+        return dh
+
+    # ---- LeakyINSResBlock (common_net.py:160-181)
+    def res_fwd(self, S, key, x, save, out=None):
+        h1 = self.conv_fwd(S, key + ".model.0", CONV_S1, x, False)
+        a1, st1 = self.in_fwd(h1, 0)
+        h2 = self.conv_fwd(S, key + ".model.3", CONV_S1, a1, False)
+        y, st2 = self.in_fwd(h2, 1, res=x, out=out)
+        if save is not None:
+            save.append((key, x, h1, st1, a1, h2, st2))
+        return y
+
+    def res_bwd(self, S, saved, dout, wgrad=True, mask=None, out=None):
+        key, x, h1, st1, a1, h2, st2 = saved
+        dh2 = self.in_bwd(dout, h2, st2, 1)
+        if wgrad:
+            self.conv_wgrad(S, key + ".model.3", CONV_S1, a1, dh2)
+        da1 = self.conv_dgrad(S, key + ".model.3", CONV_S1, dh2, a1.shape)
+        dh1 = self.in_bwd(da1, h1, st1, 0)
+        if wgrad:
+            self.conv_wgrad(S, key + ".model.0", CONV_S1, x, dh1)
+        return self.conv_dgrad(S, key + ".model.0", CONV_S1, dh1, x.shape, mask=mask, add=dout, out=out)
+
+    # ---- stems / head
+    def stem_fwd(self, S, key, img, stride, out=None):
+        n, h, w = img.shape
+        y = out if out is not None else self.empty(n, h // stride, w // stride, 64)
+        self.ctx.stem_fwd(img.data_ptr(), S.W(key + ".weight").data_ptr(), S.W(key + ".bias").data_ptr(), y.data_ptr(),
+                          n, h, w, stride, SLOPE)
+        return y
+
+    def stem_wgrad(self, S, key, img, dy, stride):
+        n, h, w = img.shape
+        self.ctx.stem_wgrad(img.data_ptr(), dy.data_ptr(), S.G(key + ".weight").data_ptr(),
+                            S.G(key + ".bias").data_ptr(), n, h, w, stride)
+
+    def stem_dgrad(self, S, key, dy, dimg, stride, accumulate):
+        n, h, w = dimg.shape
+        self.ctx.stem_dgrad(dy.data_ptr(), S.W(key + ".weight").data_ptr(), dimg.data_ptr(), n, h, w, stride,
+                            1 if accumulate else 0)
+
+
+class Generator:
+    """SharedResGen forward/backward (lsps_nets.py:164-272)."""
+
+    def __init__(self, ops, store, hp):
+        self.ops, self.S, self.p = ops, store, hp
+        assert hp["n_enc_front_blk"] == 3 and hp["n_gen_front_blk"] == 3 and hp["ch"] == 64, \
+            "kernel set covers the reference configs (exps/nnyu.yaml, nicvl.yaml): 3 front blocks, ch=64"
+        self.training = True  # the reference drivers never call gen.eval()
+
+    # -- encoder: 7x7 s1 stem, two 3x3 s2 convs, n_enc_res_blk res blocks
+    def enc_fwd(self, dom, img, save, out=None):
+        o, S, e = self.ops, self.S, "encode_%s" % dom
+        f0 = o.stem_fwd(S, e + ".0.model.0", img, 1)
+        f1 = o.conv_fwd(S, e + ".1.model.0", CONV_S2, f0, True)
+        f2 = o.conv_fwd(S, e + ".2.model.0", CONV_S2, f1, True)
+        blocks = [] if save is not None else None
+        x, nres = f2, self.p["n_enc_res_blk"]
+        for i in range(nres):
+            x = o.res_fwd(S, "%s.%d" % (e, 3 + i), x, blocks, out=out if i == nres - 1 else None)
+        if save is not None:
+            save.append(dict(dom=dom, img=img, f0=f0, f1=f1, f2=f2, blocks=blocks))
+        return x
+
+    def enc_bwd(self, sv, dx, dimg=None):
+        o, S, e = self.ops, self.S, "encode_%s" % sv["dom"]
+        blocks = sv["blocks"]
+        for i in range(len(blocks) - 1, -1, -1):
+            dx = o.res_bwd(S, blocks[i], dx, mask=sv["f2"] if i == 0 else None)
+        if not blocks:
+            raise NotImplementedError("n_enc_res_blk == 0")
+        o.conv_wgrad(S, e + ".2.model.0", CONV_S2, sv["f1"], dx)
+        d1 = o.conv_dgrad(S, e + ".2.model.0", CONV_S2, dx, sv["f1"].shape, mask=sv["f1"])
+        o.conv_wgrad(S, e + ".1.model.0", CONV_S2, sv["f0"], d1)
+        d0 = o.conv_dgrad(S, e + ".1.model.0", CONV_S2, d1, sv["f0"].shape, mask=sv["f0"])
+        o.stem_wgrad(S, e + ".0.model.0", sv["img"], d0, 1)
+        if dimg is not None:
+            o.stem_dgrad(S, e + ".0.model.0", d0, dimg, 1, accumulate=True)
+
+    # -- shared latent: res blocks + GaussianNoiseLayer (+ KL sum of the noised latent) ; then dec_shared
+    def shared_fwd(self, x, noise, kl_acc, save):
+        o, S = self.ops, self.S
+        eb = [] if save is not None else None
+        for i in range(self.p["n_enc_shared_blk"]):
+            x = o.res_fwd(S, "enc_shared.%d" % i, x, eb)
+        if noise is not None:
+            z = torch.empty_like(x)
+            o.ctx.noise_kl_fwd(x.data_ptr(), noise.data_ptr(), z.data_ptr(), kl_acc.data_ptr(), x.numel())
+        else:
+            z = x
+        db = [] if save is not None else None
+        y = z
+        for i in range(self.p["n_gen_shared_blk"]):
+            y = o.res_fwd(S, "dec_shared.%d" % i, y, db)
+        if save is not None:
+            save.append(dict(eb=eb, db=db, z=z))
+        return y, z
+
+    def shared_bwd(self, sv, dy, kl_alpha):
+        """kl_alpha = d(loss)/d(sum z^2): the KL term contributes 2*kl_alpha*z to dz."""
+        o, S = self.ops, self.S
+        for blk in reversed(sv["db"]):
+            dy = o.res_bwd(S, blk, dy)
+        z = sv["z"]
+        dz = torch.empty_like(z)
+        o.ctx.axpy_bf16(dy.data_ptr(), z.data_ptr(), 2.0 * kl_alpha, dz.data_ptr(), z.numel())
+        for blk in reversed(sv["eb"]):
+            dz = o.res_bwd(S, blk, dz)
+        return dz
+
+    # -- decoder: res blocks, two transposed 3x3 s2 convs, 1x1 head + tanh
+    def dec_fwd(self, dom, x, save, out=None):
+        o, S, d = self.ops, self.S, "decode_%s" % dom
+        blocks = [] if save is not None else None
+        nres = self.p["n_gen_res_blk"]
+        for i in range(nres):
+            x = o.res_fwd(S, "%s.%d" % (d, i), x, blocks)
+        g1 = o.conv_fwd(S, "%s.%d.model.0" % (d, nres), DECONV_S2, x, True)
+        g2 = o.conv_fwd(S, "%s.%d.model.0" % (d, nres + 1), DECONV_S2, g1, True)
+        n = g2.shape[0]
+        img = out if out is not None else o.empty(n, g2.shape[1], g2.shape[2], dtype=torch.float32)
+        hk = "%s.%d" % (d, nres + 2)
+        o.ctx.head_fwd(g2.data_ptr(), S.W(hk + ".weight").data_ptr(), S.W(hk + ".bias").data_ptr(), img.data_ptr(),
+                       img.numel())
+        if save is not None:
+            save.append(dict(dom=dom, blocks=blocks, x3=x, g1=g1, g2=g2, out=img))
+        return img
+
+    def dec_bwd(self, sv, dout, out=None):
+        o, S, d = self.ops, self.S, "decode_%s" % sv["dom"]
+        nres = self.p["n_gen_res_blk"]
+        g2, g1, x3 = sv["g2"], sv["g1"], sv["x3"]
+        hk = "%s.%d" % (d, nres + 2)
+        dg2 = torch.empty_like(g2)
+        o.ctx.head_bwd(g2.data_ptr(), S.W(hk + ".weight").data_ptr(), sv["out"].data_ptr(), dout.data_ptr(),
+                       dg2.data_ptr(), S.G(hk + ".weight").data_ptr(), S.G(hk + ".bias").data_ptr(), dout.numel(), SLOPE)
+        k4, k3 = "%s.%d.model.0" % (d, nres + 1), "%s.%d.model.0" % (d, nres)
+        o.conv_wgrad(S, k4, DECONV_S2, g1, dg2)
+        dg1 = o.conv_dgrad(S, k4, DECONV_S2, dg2, g1.shape, mask=g1)
+        o.conv_wgrad(S, k3, DECONV_S2, x3, dg1)
+        nb = len(sv["blocks"])
+        dx = o.conv_dgrad(S, k3, DECONV_S2, dg1, x3.shape, out=out if nb == 0 else None)
+        for i in range(nb - 1, -1, -1):
+            dx = o.res_bwd(S, sv["blocks"][i], dx, out=out if i == 0 else None)
+        return dx
+
+    # -- full forward (lsps_nets.py:250-258): returns images (x_aa|x_ba) and (x_ab|x_bb) as [2n,128,128] tensors
+    def forward(self, xa, xb, noise, kl_acc, save=None):
+        """xa [na,128,128] / xb [nb,128,128] (either may be None).  Returns decode_A and decode_B of ALL na+nb
+        latents: oa = (x_aa | x_ba), ob = (x_ab | x_bb), plus the noised shared latent."""
+        o = self.ops
+        na = xa.shape[0] if xa is not None else 0
+        nb = xb.shape[0] if xb is not None else 0
+        h = o.empty(na + nb, 32, 32, 4 * self.p["ch"])
+        se = [] if save is not None else None
+        if na:
+            self.enc_fwd("A", xa, se, out=h[:na])
+        if nb:
+            self.enc_fwd("B", xb, se, out=h[na:])
+        ss = [] if save is not None else None
+        y, z = self.shared_fwd(h, noise, kl_acc, ss)
+        sd = [] if save is not None else None
+        oa = self.dec_fwd("A", y, sd)
+        ob = self.dec_fwd("B", y, sd)
+        if save is not None:
+            save.update(enc=se, shared=ss[0], dec=sd, na=na, nb=nb)
+        return oa, ob, z
+
+    def backward(self, save, doa, dob, kl_alpha):
+        """doa/dob: fp32 gradients w.r.t. the [na+nb,128,128] outputs of decode_A / decode_B."""
+        na, nb = save["na"], save["nb"]
+        dy = self.dec_bwd(save["dec"][0], doa)
+        dy2 = self.dec_bwd(save["dec"][1], dob)
+        self.ops.ctx.axpy_bf16(dy.data_ptr(), dy2.data_ptr(), 1.0, dy.data_ptr(), dy.numel())
+        dh = self.shared_bwd(save["shared"], dy, kl_alpha)
+        i = 0
+        if na:
+            self.enc_bwd(save["enc"][i], dh[:na])
+            i += 1
+        if nb:
+            self.enc_bwd(save["enc"][i], dh[na:])
+
+    # -- cycle passes (lsps_nets.py:260-272), batched: first half a2b (encode_A -> decode_B), second half b2a
+    def forward_cycle(self, x_ba, x_ab, noise, kl_acc_bab, kl_acc_aba, save=None):
+        o = self.ops
+        n = x_ba.shape[0]
+        h = o.empty(2 * n, 32, 32, 4 * self.p["ch"])
+        se = [] if save is not None else None
+        self.enc_fwd("A", x_ba, se, out=h[:n])
+        self.enc_fwd("B", x_ab, se, out=h[n:])
+        ss = [] if save is not None else None
+        # two KL sums (bab / aba halves): run the noise kernel per half via shared_fwd's single call on a split
+        y, z = self._shared_fwd_split(h, noise, kl_acc_bab, kl_acc_aba, n, ss)
+        sd = [] if save is not None else None
+        x_bab = self.dec_fwd("B", y[:n], sd)
+        x_aba = self.dec_fwd("A", y[n:], sd)
+        if save is not None:
+            save.update(enc=se, shared=ss[0], dec=sd, n=n)
+        return x_bab, x_aba
+
+    def _shared_fwd_split(self, x, noise, acc0, acc1, n, save):
+        o, S = self.ops, self.S
+        eb = [] if save is not None else None
+        for i in range(self.p["n_enc_shared_blk"]):
+            x = o.res_fwd(S, "enc_shared.%d" % i, x, eb)
+        z = torch.empty_like(x)
+        half = x[:n].numel()
+        o.ctx.noise_kl_fwd(x[:n].data_ptr(), noise[:n].data_ptr(), z[:n].data_ptr(), acc0.data_ptr(), half)
+        o.ctx.noise_kl_fwd(x[n:].data_ptr(), noise[n:].data_ptr(), z[n:].data_ptr(), acc1.data_ptr(), half)
+        db = [] if save is not None else None
+        y = z
+        for i in range(self.p["n_gen_shared_blk"]):
+            y = o.res_fwd(S, "dec_shared.%d" % i, y, db)
+        if save is not None:
+            save.append(dict(eb=eb, db=db, z=z))
+        return y, z
+
+    def backward_cycle(self, save, d_bab, d_aba, kl_alpha, dimg_ba, dimg_ab):
+        n = save["n"]
+        dy = self.ops.empty(2 * n, 32, 32, 4 * self.p["ch"])
+        self.dec_bwd(save["dec"][0], d_bab, out=dy[:n])
+        self.dec_bwd(save["dec"][1], d_aba, out=dy[n:])
+        dh = self.shared_bwd(save["shared"], dy, kl_alpha)
+        self.enc_bwd(save["enc"][0], dh[:n], dimg=dimg_ba)
+        self.enc_bwd(save["enc"][1], dh[n:], dimg=dimg_ab)
+
+
+class Discriminator:
+    """SharedDis forward/backward (lsps_nets.py:86-160)."""
+
+    def __init__(self, ops, store, hp):
+        self.ops, self.S, self.p = ops, store, hp
+        assert hp["n_front_layer"] == 2 and hp["ch"] == 64, "kernel set covers the reference configs"
+        self.training = True
+
+    def train(self, mode=True):
+        self.training = mode
+        return self
+
+    def eval(self):
+        return self.train(False)
+
+    def front_fwd(self, dom, img, save, out=None):
+        o, S, m = self.ops, self.S, "model_%s" % dom
+        f0 = o.stem_fwd(S, m + ".0.model.0", img, 2)
+        f1 = o.conv_fwd(S, m + ".1.model.0", CONV_S2, f0, True, out=out)
+        if save is not None:
+            save.append(dict(dom=dom, img=img, f0=f0))
+        return f1
+
+    def front_bwd(self, sv, d1, wgrad, dimg=None, f1=None):
+        o, S, m = self.ops, self.S, "model_%s" % sv["dom"]
+        f0 = sv["f0"]
+        if wgrad:
+            o.conv_wgrad(S, m + ".1.model.0", CONV_S2, f0, d1)
+        d0 = o.conv_dgrad(S, m + ".1.model.0", CONV_S2, d1, f0.shape, mask=f0)
+        if wgrad:
+            o.stem_wgrad(S, m + ".0.model.0", sv["img"], d0, 2)
+        if dimg is not None:
+            o.stem_dgrad(S, m + ".0.model.0", d0, dimg, 2, accumulate=False)
+
+    def trunk_fwd(self, x, save):
+        o, S = self.ops, self.S
+        acts = [x]
+        for i in range(self.p["n_shared_layer"]):
+            x = o.conv_fwd(S, "model_S.%d.model.0" % i, CONV_S2, x, True)
+            acts.append(x)
+        if save is not None:
+            save["acts"] = acts
+        return x
+
+    def trunk_bwd(self, acts, d, wgrad):
+        """d: gradient w.r.t. the trunk features already multiplied by their LeakyReLU mask.  Returns the gradient
+        w.r.t. the pre-activation of the last front conv (masked)."""
+        o, S = self.ops, self.S
+        for i in range(self.p["n_shared_layer"] - 1, -1, -1):
+            key = "model_S.%d.model.0" % i
+            if wgrad:
+                o.conv_wgrad(S, key, CONV_S2, acts[i], d)
+            d = o.conv_dgrad(S, key, CONV_S2, d, acts[i].shape, mask=acts[i])
+        return d
+
+    def features(self, imgs_a, imgs_b, save=None):
+        """model_A / model_B fronts on their image batches, concatenated along batch, shared trunk."""
+        o = self.ops
+        na = imgs_a.shape[0] if imgs_a is not None else 0
+        nb = imgs_b.shape[0] if imgs_b is not None else 0
+        x = o.empty(na + nb, 32, 32, 2 * self.p["ch"])
+        fr = [] if save is not None else None
+        if na:
+            self.front_fwd("A", imgs_a, fr, out=x[:na])
+        if nb:
+            self.front_fwd("B", imgs_b, fr, out=x[na:])
+        if save is not None:
+            save.update(fronts=fr, na=na, nb=nb)
+        return self.trunk_fwd(x, save)
+
+    def features_bwd(self, save, dF_masked, wgrad, dimg_a=None, dimg_b=None):
+        d = self.trunk_bwd(save["acts"], dF_masked, wgrad)
+        na, i = save["na"], 0
+        if na:
+            self.front_bwd(save["fronts"][i], d[:na], wgrad, dimg=dimg_a)
+            i += 1
+        if save["nb"]:
+            self.front_bwd(save["fronts"][i], d[na:], wgrad, dimg=dimg_b)
+
+    def logits(self, F):
+        o, S = self.ops, self.S
+        rows = F.numel() // F.shape[-1]
+        lg = o.empty(rows, dtype=torch.float32)
+        o.ctx.dhead_fwd(F.data_ptr(), S.W("D.weight").data_ptr(), S.W("D.bias").data_ptr(), lg.data_ptr(), rows,
+                        F.shape[-1])
+        return lg
+
+    def post(self, F):
+        """Post = Conv2d(2048, post_dim, 2) on the 2x2 map == FC 8192 -> post_dim (lsps_nets.py:123,135-145)."""
+        o, S = self.ops, self.S
+        n = F.shape[0]
+        k = F.numel() // n
+        pd = self.p["post_dim"]
+        out = o.empty(n, pd, dtype=torch.float32)
+        o.ctx.linear_fwd(F.data_ptr(), 1, S.W("Post.weight").data_ptr(), S.W("Post.bias").data_ptr(), out.data_ptr(),
+                         n, pd, k, 0, SLOPE)
+        return out
+
+    # public inference API used by the drivers (depth_train.py:197-206)
+    def _regress(self, dom, x):
+        img = x.reshape(x.shape[0], x.shape[-2], x.shape[-1]).contiguous().float()
+        F = self.features(img if dom == "A" else None, img if dom == "B" else None)
+        p = self.post(F).squeeze()
+        return p, p, p
+
+    def regress_a(self, x):
+        return self._regress("A", x)
+
+    def regress_b(self, x):
+        return self._regress("B", x)
+
+    def state_dict(self):
+        return self.S.state_dict()
+
+    def load_state_dict(self, sd, strict=True):
+        self.S.load_state_dict(sd, strict)
+
+
+class PoseVAE:
+    """poseVAE MLP (lsps_nets.py:34-83) on the small dense kernels."""
+
+    def __init__(self, ops, store, hp, noise_fn):
+        self.ops, self.S, self.p, self.noise_fn = ops, store, hp, noise_fn
+
+    def _lin(self, key, x, act):
+        o, S = self.ops, self.S
+        w = S.entries[key + ".weight"].shape
+        y = o.empty(x.shape[0], w[0], dtype=torch.float32)
+        o.ctx.linear_fwd(x.data_ptr(), 0, S.W(key + ".weight").data_ptr(), S.W(key + ".bias").data_ptr(), y.data_ptr(),
+                         x.shape[0], w[0], w[1], act, SLOPE)
+        return y
+
+    def _lin_bwd(self, key, x, dy, need_dx, acc_into=None):
+        o, S = self.ops, self.S
+        w = S.entries[key + ".weight"].shape
+        dx = acc_into if acc_into is not None else (o.empty(x.shape[0], w[1], dtype=torch.float32) if need_dx else None)
+        o.ctx.linear_bwd(x.data_ptr(), 0, S.W(key + ".weight").data_ptr(), dy.data_ptr(), _lib.ptr(dx),
+                         1 if acc_into is not None else 0,
+                         S.G(key + ".weight").data_ptr(), S.G(key + ".bias").data_ptr(), x.shape[0], w[0], w[1])
+        return dx
+
+    def encode(self, y, kl_acc=None, save=None):
+        o = self.ops
+        y = y.contiguous().float()
+        h = self._lin("en_fc1", y, _lib.ACT_LRELU)
+        mu = self._lin("en_mu", h, _lib.ACT_NONE)
+        sd = self._lin("en_sigma", h, _lib.ACT_SOFTPLUS)
+        noise = self.noise_fn(tuple(mu.shape))
+        z = torch.empty_like(mu)
+        o.ctx.vae_reparam(mu.data_ptr(), sd.data_ptr(), noise.data_ptr(), z.data_ptr(), _lib.ptr(kl_acc), mu.numel())
+        if save is not None:
+            save.update(y=y, h=h, mu=mu, sd=sd, noise=noise, z=z)
+        return z, mu, sd
+
+    def decode(self, z, save=None):
+        z = z.contiguous().float()
+        if z.dim() == 1:
+            z = z[None]
+        h = self._lin("de_fc1.model.0", z, _lib.ACT_LRELU)
+        out = self._lin("de_fc2", h, _lib.ACT_NONE)
+        if save is not None:
+            save.update(dz_in=z, dh=h)
+        return out
+
+    def forward(self, y, kl_acc=None, save=None):
+        z, mu, sd = self.encode(y, kl_acc, save)
+        return self.decode(z, save), z, mu, sd
+
+    def backward(self, sv, ddec, kl_scale):
+        """ddec: gradient w.r.t. the decoder output; kl_scale = d(loss)/d(KL sum)."""
+        o = self.ops
+        dh = self._lin_bwd("de_fc2", sv["dh"], ddec, True)
+        o.ctx.act_bwd(dh.data_ptr(), sv["dh"].data_ptr(), _lib.ACT_LRELU, SLOPE, dh.numel())
+        dz = self._lin_bwd("de_fc1.model.0", sv["dz_in"], dh, True)
+        dmu, dsd = torch.empty_like(dz), torch.empty_like(dz)
+        o.ctx.vae_reparam_bwd(sv["mu"].data_ptr(), sv["sd"].data_ptr(), sv["noise"].data_ptr(), dz.data_ptr(),
+                              dmu.data_ptr(), dsd.data_ptr(), kl_scale, dz.numel())
+        o.ctx.act_bwd(dsd.data_ptr(), sv["sd"].data_ptr(), _lib.ACT_SOFTPLUS, SLOPE, dsd.numel())
+        dh1 = self._lin_bwd("en_mu", sv["h"], dmu, True)
+        self._lin_bwd("en_sigma", sv["h"], dsd, True, acc_into=dh1)
+        o.ctx.act_bwd(dh1.data_ptr(), sv["h"].data_ptr(), _lib.ACT_LRELU, SLOPE, dh1.numel())
+        self._lin_bwd("en_fc1", sv["y"], dh1, False)
+
+    def state_dict(self):
+        return self.S.state_dict()
+
+    def load_state_dict(self, sd, strict=True):
+        self.S.load_state_dict(sd, strict)

@@ -1,0 +1,31 @@
+"""Batch sharding rules of the data-parallel step (pure host logic, importable without CUDA).
+
+The path shards over batch: rank r owns samples [r*B, (r+1)*B) of BOTH domains.  Tensors the
+reference builds by concatenating `groups` per-domain blocks along batch (e.g. the (2B,256,32,32) latent noise of
+gen.forward = [domain-a block | domain-b block]) are sharded block-wise so that every rank sees exactly the rows
+of its own samples."""
+import torch
+
+
+def shard_rows(t, groups, world, rank):
+    """t: [groups * world * per, ...] global tensor -> [groups * per, ...] rows of `rank`."""
+    if world == 1:
+        return t
+    assert t.shape[0] % (groups * world) == 0, (t.shape, groups, world)
+    per = t.shape[0] // (groups * world)
+    return torch.cat([t[g * per * world + rank * per: g * per * world + (rank + 1) * per] for g in range(groups)], 0)
+
+
+def source_assignment(n_a, n_b, world, rank):
+    """post_update modes >= 2 run the generator on the GLOBAL first 4 samples of each domain
+    (/root/reference/src/trainers/lsps_trainer.py:238).  Source image a_i goes to rank i % world, b_i to rank
+    (n_a + i) % world; InstanceNorm is per-sample, so the split is exact."""
+    ka = [i for i in range(n_a) if i % world == rank]
+    kb = [i for i in range(n_b) if (n_a + i) % world == rank]
+    return ka, kb
+
+
+def global_count(local, world):
+    """Every loss mean is normalised by the global element count so that sum-allreduced gradients equal the
+    single-process gradients of the global batch."""
+    return local * world

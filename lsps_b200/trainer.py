@@ -1,0 +1,378 @@
+"""LSPSTrainerB200 -- drop-in for the reference's `LSPSTrainer` (src/trainers/lsps_trainer.py:15-347).
+
+Same constructor argument (the YAML `hyperparameters` dict), same update methods and return values, same loss /
+accuracy attribute names (read by common.py:71-80 `write_loss`), same state_dict keys -- but every update is a
+static kernel schedule on sm_100a (engine.py) and each update does ONE device->host read for all of its scalars.
+
+Multi-GPU: one process per GPU (torch.distributed, NCCL).  Each rank calls the update with ITS shard of the
+batch; the only exchange is one sum-allreduce of the flat gradient buffer (loss sums ride in its tail) per update.
+Every loss is normalised by the GLOBAL element count so that the summed gradient equals the single-GPU one.
+"""
+import os
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import _lib
+from .engine import Ops, Generator, Discriminator, PoseVAE, SLOPE
+from .sharding import shard_rows, source_assignment
+from .params import ParamStore, MultiStepLR, Optimizer, gen_entries, dis_entries, vae_entries
+
+_LATENT = 256 * 32 * 32
+_NPIX = 128 * 128
+
+
+def _world():
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_world_size(), dist.get_rank()
+    return 1, 0
+
+
+def _img(t, dev):
+    """(B,1,128,128) any device -> contiguous fp32 [B,128,128] on dev."""
+    t = t.detach()
+    return t.reshape(t.shape[0], t.shape[-2], t.shape[-1]).to(device=dev, dtype=torch.float32).contiguous()
+
+
+class LSPSTrainerB200(object):
+    def __init__(self, hyperparameters, device=None, seed=0, noise="host"):
+        hp = hyperparameters
+        if hp.get("train_map", False):
+            raise NotImplementedError("train_map=True (Mapping net) is a SURVEY section 8f 'next' row")
+        if device is None:
+            device = torch.cuda.current_device() if torch.cuda.is_available() else 0
+        self.device = torch.device("cuda", device if isinstance(device, int) else torch.device(device).index)
+        self.gpu = self.device.index
+        self.hp = hp
+        self.noise_mode = noise  # "host": reference RNG stream (CPU torch.randn, same draw order); "device": Philox
+        torch.cuda.set_device(self.device)
+        self.ops = Ops(self.device)
+        lr = hp["lr"]
+        # lsps_trainer.py:26-31 -- Adam betas (0.5, 0.999); weight decay 1e-4 (dis, gen) / 1e-3 (vae); vae lr = 10*lr
+        self.gen_store = ParamStore(gen_entries(hp["gen"]), self.device, lr, 1e-4)
+        self.dis_store = ParamStore(dis_entries(hp["dis"]), self.device, lr, 1e-4)
+        self.vae_store = ParamStore(vae_entries(hp["vae"]), self.device, lr * 10.0, 1e-3)
+        self.gen_store.init_(seed + 1)
+        self.dis_store.init_(seed + 2)
+        self.vae_store.init_(seed + 3)
+        self.gen = Generator(self.ops, self.gen_store, hp["gen"])
+        self.dis = Discriminator(self.ops, self.dis_store, hp["dis"])
+        self.vae = PoseVAE(self.ops, self.vae_store, hp["vae"], self._vae_noise)
+        self.gen.state_dict, self.gen.load_state_dict = self.gen_store.state_dict, self.gen_store.load_state_dict
+        self.map = None
+        self.dis_opt, self.gen_opt, self.vae_opt = Optimizer(self.dis_store), Optimizer(self.gen_store), Optimizer(self.vae_store)
+        # lsps_trainer.py:32-34
+        self.dis_sch = MultiStepLR(self.dis_store, [200, 300, 400, 450], 0.5)
+        self.gen_sch = MultiStepLR(self.gen_store, [200, 300, 400, 450], 0.5)
+        self.vae_sch = MultiStepLR(self.vae_store, [125, 175], 0.1)
+        self._scratch = torch.zeros(8, dtype=torch.float32, device=self.device)
+        self.last_outputs = None
+
+    # ------------------------------------------------------------------ plumbing
+    def cuda(self, gpu=None):
+        if gpu is not None and gpu != self.gpu:
+            raise RuntimeError("LSPSTrainerB200 lives on cuda:%d; construct it with device=%d" % (self.gpu, gpu))
+        return self
+
+    def _latent_noise(self, n, groups=1, shard=True):
+        """GaussianNoiseLayer draw (common_net.py:36-40): the reference draws N(0,1) of shape (n,256,32,32) on the HOST.
+        "host" mode reproduces that stream (same global draw on every rank, each rank keeps the rows of its samples:
+        the global batch is `groups` blocks of world*n/groups rows, rank r owns the r-th slice of every block)."""
+        world, rank = _world()
+        if self.noise_mode == "host":
+            if world == 1 or not shard:
+                t = torch.randn(n, 256, 32, 32)
+            else:
+                t = shard_rows(torch.randn(n * world, 256, 32, 32), groups, world, rank)
+            return t.to(self.device).permute(0, 2, 3, 1).contiguous()
+        return torch.randn(n, 32, 32, 256, device=self.device)
+
+    def _vae_noise(self, shape):
+        """poseVAE.encode draw (lsps_nets.py:77): torch.normal(zeros, std=0.05) on the host."""
+        world, rank = _world()
+        if self.noise_mode == "host":
+            if world == 1:
+                return torch.normal(torch.zeros(shape), std=0.05).to(self.device)
+            t = torch.normal(torch.zeros((shape[0] * world,) + tuple(shape[1:])), std=0.05)
+            return shard_rows(t, 1, world, rank).to(self.device)
+        return torch.randn(shape, device=self.device) * 0.05
+
+    def _allreduce(self, store):
+        world, _ = _world()
+        if world > 1:
+            dist.all_reduce(store.gbuf, op=dist.ReduceOp.SUM)
+
+    def _p(self, t):
+        return t.data_ptr()
+
+    # ------------------------------------------------------------------ vae_update (lsps_trainer.py:62-74)
+    def vae_update(self, y, hyperparameters=None):
+        hp = hyperparameters or self.hp
+        S, ctx = self.vae_store, self.ops.ctx
+        world, _ = _world()
+        y = y.detach().to(device=self.device, dtype=torch.float32).contiguous()
+        rows, dim = y.shape[0] * world, y.shape[1]
+        S.zero_grad()
+        sv = {}
+        dec, z, mu, sd = self.vae.forward(y, kl_acc=S.acc[0:], save=sv)
+        ddec = torch.empty_like(dec)
+        ctx.l1_f32(dec.data_ptr(), y.data_ptr(), ddec.data_ptr(), hp["ll_loss_vae"] / float(rows * dim), 0,
+                   S.acc[1:].data_ptr(), dec.numel())
+        self.vae.backward(sv, ddec, hp["kl_loss_vae"] / float(rows))
+        self._allreduce(S)
+        S.adam_step()
+        acc = S.acc[:2].cpu().numpy().astype(np.float64)
+        self.vae_total_loss = np.float32(hp["kl_loss_vae"] * acc[0] / rows + hp["ll_loss_vae"] * acc[1] / (rows * dim))
+        return dec
+
+    # ------------------------------------------------------------------ dis_update (lsps_trainer.py:143-218)
+    def dis_update(self, images_a, labels_a, images_b, labels_b, com_a=None, com_b=None, hyperparameters=None,
+                   feat_mat=True):
+        hp = hyperparameters or self.hp
+        D, ctx, dis = self.dis_store, self.ops.ctx, self.dis
+        world, _ = _world()
+        ia, ib = _img(images_a, self.device), _img(images_b, self.device)
+        B = ia.shape[0]
+        Bg = B * world
+        D.zero_grad()
+        noise = self._latent_noise(2 * B, groups=2)
+        oa, ob, _ = self.gen.forward(ia, ib, noise, self._scratch)           # no activations kept: gen gets no grads
+        x_aa, x_ba, x_ab, x_bb = oa[:B], oa[B:], ob[:B], ob[B:]
+        if feat_mat:
+            imgs_a, imgs_b, ndiv = torch.cat((ia, x_ba, x_aa), 0), torch.cat((ib, x_ab, x_bb), 0), 3
+        else:
+            imgs_a, imgs_b, ndiv = torch.cat((ia, x_ba), 0), torch.cat((ib, x_ab), 0), 2
+        sv = {}
+        F = dis.features(imgs_a, imgs_b, sv)                                 # [2*ndiv*B, 2, 2, 2048]
+        cf = F.shape[-1]
+        lg = dis.logits(F)
+        dlg = torch.zeros_like(lg)
+        r = 4 * B                                                            # logits per group
+        scale = hp["gan_w"] / float(4 * Bg)
+        for off in (0, ndiv * r):                                            # domain a, domain b
+            ctx.bce_logits(lg[off:].data_ptr(), 1.0, scale, dlg[off:].data_ptr(), D.acc[0:].data_ptr(), r)
+            ctx.bce_logits(lg[off + r:].data_ptr(), 0.0, scale, dlg[off + r:].data_ptr(), D.acc[2:].data_ptr(), r)
+        dF = torch.zeros(F.numel(), dtype=torch.float32, device=self.device)
+        ctx.dhead_bwd(F.data_ptr(), D.W("D.weight").data_ptr(), dlg.data_ptr(), dF.data_ptr(),
+                      D.G("D.weight").data_ptr(), D.G("D.bias").data_ptr(), lg.numel(), cf)
+        if feat_mat:
+            fs = B * 4 * cf
+            Ff = F.reshape(-1)
+            fscale = hp["feature_w"] / float(Bg * 4 * cf)
+            # mean|F_b(x_ab) - F_a(x_aa)| + mean|F_a(x_ba) - F_b(x_bb)|   groups: a=(ia,x_ba,x_aa) b=(ib,x_ab,x_bb)
+            for ga, gb in ((4, 2), (1, 5)):
+                ctx.l1_feat(Ff[ga * fs:].data_ptr(), Ff[gb * fs:].data_ptr(), dF[ga * fs:].data_ptr(),
+                            dF[gb * fs:].data_ptr(), fscale, D.acc[4:].data_ptr(), fs)
+        dFm = torch.empty_like(F)
+        ctx.mask_to_bf16(dF.data_ptr(), F.data_ptr(), dFm.data_ptr(), SLOPE, F.numel())
+        dis.features_bwd(sv, dFm, wgrad=True)
+        del sv
+        self._allreduce(D)
+        D.adam_step(active=lambda k: not k.startswith("Post."))
+        D.refresh_dgrad_operands()
+        acc = D.acc[:8].cpu().numpy().astype(np.float64)
+        ad = (acc[0] + acc[2]) / (4 * Bg)
+        feat = acc[4] / (Bg * 4 * cf) if feat_mat else 0.0
+        self.dis_ad_loss, self.dis_feat_loss = np.float32(ad), np.float32(feat)
+        self.dis_loss = np.float32(hp["gan_w"] * ad + hp["feature_w"] * feat)
+        self.dis_true_acc = np.float32(acc[1] / (8 * Bg))
+        self.dis_fake_acc = np.float32(acc[3] / (8 * Bg))
+
+    # ------------------------------------------------------------------ gen_update (lsps_trainer.py:76-141)
+    def gen_update(self, images_a, labels_a, images_b, labels_b, hyperparameters=None):
+        hp = hyperparameters or self.hp
+        G, D, ctx, gen, dis = self.gen_store, self.dis_store, self.ops.ctx, self.gen, self.dis
+        world, _ = _world()
+        ia, ib = _img(images_a, self.device), _img(images_b, self.device)
+        B = ia.shape[0]
+        Bg = B * world
+        G.zero_grad()
+        n2 = self._latent_noise(2 * B, groups=2)  # host RNG draw order of the reference: gen(), forward_a2b, forward_b2a
+        n3 = self._latent_noise(B)
+        n4 = self._latent_noise(B)
+        s1 = {}
+        oa, ob, _ = gen.forward(ia, ib, n2, G.acc[2:], s1)
+        x_aa, x_ba, x_ab, x_bb = oa[:B], oa[B:], ob[:B], ob[B:]
+        s2 = {}
+        x_bab, x_aba = gen.forward_cycle(x_ba, x_ab, torch.cat((n3, n4), 0), G.acc[3:], G.acc[4:], s2)
+        del n2, n3, n4
+        # adversarial term through the discriminator (data gradient only)
+        sd = {}
+        F = dis.features(x_ba, x_ab, sd)
+        lg = dis.logits(F)
+        dlg = torch.empty_like(lg)
+        ctx.bce_logits(lg.data_ptr(), 1.0, hp["gan_w"] / float(4 * Bg), dlg.data_ptr(), G.acc[0:].data_ptr(), lg.numel())
+        dF = torch.zeros(F.numel(), dtype=torch.float32, device=self.device)
+        ctx.dhead_bwd(F.data_ptr(), D.W("D.weight").data_ptr(), dlg.data_ptr(), dF.data_ptr(), None, None, lg.numel(),
+                      F.shape[-1])
+        dFm = torch.empty_like(F)
+        ctx.mask_to_bf16(dF.data_ptr(), F.data_ptr(), dFm.data_ptr(), SLOPE, F.numel())
+        doa = torch.empty_like(oa)           # d/d(x_aa | x_ba)
+        dob = torch.empty_like(ob)           # d/d(x_ab | x_bb)
+        dis.features_bwd(sd, dFm, wgrad=False, dimg_a=doa[B:], dimg_b=dob[:B])
+        del sd
+        npx = float(Bg * _NPIX)
+        d_bab, d_aba = torch.empty_like(x_bab), torch.empty_like(x_aba)
+        ctx.l1_f32(x_bab.data_ptr(), ib.data_ptr(), d_bab.data_ptr(), hp["ll_cycle_link_w"] / npx, 0, G.acc[8:].data_ptr(), x_bab.numel())
+        ctx.l1_f32(x_aba.data_ptr(), ia.data_ptr(), d_aba.data_ptr(), hp["ll_cycle_link_w"] / npx, 0, G.acc[7:].data_ptr(), x_aba.numel())
+        gen.backward_cycle(s2, d_bab, d_aba, hp["kl_cycle_link_w"] / float(Bg * _LATENT), doa[B:], dob[:B])
+        del s2
+        ctx.l1_f32(x_aa.data_ptr(), ia.data_ptr(), doa[:B].data_ptr(), hp["ll_direct_link_w"] / npx, 0, G.acc[5:].data_ptr(), x_aa.numel())
+        ctx.l1_f32(x_bb.data_ptr(), ib.data_ptr(), dob[B:].data_ptr(), hp["ll_direct_link_w"] / npx, 0, G.acc[6:].data_ptr(), x_bb.numel())
+        # kl_direct * (enc + enc) with enc = mean over the 2B latents
+        gen.backward(s1, doa, dob, 2.0 * hp["kl_direct_link_w"] / float(2 * Bg * _LATENT))
+        del s1
+        self._allreduce(G)
+        G.adam_step()
+        G.refresh_dgrad_operands()
+        acc = G.acc[:16].cpu().numpy().astype(np.float64)
+        ad = acc[0] / (4 * Bg)
+        enc, enc2 = acc[2] / (2 * Bg * _LATENT), (acc[3] + acc[4]) / (Bg * _LATENT)
+        ll, ll2 = (acc[5] + acc[6]) / npx, (acc[7] + acc[8]) / npx
+        self.gen_enc_loss, self.gen_enc_loss2 = np.float32(enc), np.float32(enc2)
+        self.gen_ad_loss = np.float32(ad)
+        self.gen_ll_loss, self.gen_ll_loss2 = np.float32(ll), np.float32(ll2)
+        self.gen_total_loss = np.float32(hp["gan_w"] * ad + hp["ll_direct_link_w"] * ll + hp["ll_cycle_link_w"] * ll2 +
+                                         hp["kl_direct_link_w"] * 2.0 * enc + hp["kl_cycle_link_w"] * enc2)
+        u = lambda t: t.unsqueeze(1)
+        return (u(x_aa), u(x_ba), u(x_ab), u(x_bb), u(x_aba), u(x_bab), u(x_ba), u(x_ab))
+
+    # ------------------------------------------------------------------ post_update (lsps_trainer.py:220-262)
+    def post_update(self, images_a, labels_a, images_b, labels_b, com_a=None, com_b=None, mode=3, hyperparameters=None):
+        hp = hyperparameters or self.hp
+        D, ctx, dis = self.dis_store, self.ops.ctx, self.dis
+        world, rank = _world()
+        ia, ib = _img(images_a, self.device), _img(images_b, self.device)
+        B = ia.shape[0]
+        Bg = B * world
+        D.zero_grad()
+        reg_a, reg_b, feat = mode != 1, mode in (1, 4), mode >= 2
+        outs = (ia, ia, ib, ib)
+        fa_extra = fb_extra = None
+        nf, n4 = 0, 4
+        if feat:
+            # the reference uses the GLOBAL first 4 samples of each domain (lsps_trainer.py:238); per-sample ops make
+            # it exact to give source image a_i to rank i % world and b_i to rank (4+i) % world
+            src_a, src_b = ia[0:4], ib[0:4]
+            n4 = src_a.shape[0]
+            if world > 1:
+                src_a, src_b = src_a.clone(), src_b.clone()
+                dist.broadcast(src_a, 0)
+                dist.broadcast(src_b, 0)
+            noise = self._latent_noise(src_a.shape[0] + src_b.shape[0], shard=False)
+            ka, kb = source_assignment(src_a.shape[0], src_b.shape[0], world, rank)
+            if ka or kb:
+                xa = src_a[ka] if ka else None
+                xb = src_b[kb] if kb else None
+                nz = noise[ka + [src_a.shape[0] + i for i in kb]].contiguous()
+                oa, ob, _ = self.gen.forward(xa, xb, nz, self._scratch)     # (x_aa|x_ba), (x_ab|x_bb)
+                na, nb = len(ka), len(kb)
+                nf = na + nb
+                fa_extra, fb_extra = oa, ob
+                outs = (oa[:na], oa[na:], ob[:na], ob[na:])
+        imgs_a = [t for t in (fa_extra, ia if reg_a else None) if t is not None]
+        imgs_b = [t for t in (fb_extra, ib if reg_b else None) if t is not None]
+        imgs_a = torch.cat(imgs_a, 0) if len(imgs_a) > 1 else (imgs_a[0] if imgs_a else None)
+        imgs_b = torch.cat(imgs_b, 0) if len(imgs_b) > 1 else (imgs_b[0] if imgs_b else None)
+        sv = {}
+        F = dis.features(imgs_a, imgs_b, sv)
+        cf = F.shape[-1]
+        per = 4 * cf
+        n_a = imgs_a.shape[0] if imgs_a is not None else 0
+        Ff = F.reshape(F.shape[0], per)
+        dF = torch.zeros(F.shape[0], per, dtype=torch.float32, device=self.device)
+        pd = hp["dis"]["post_dim"]
+        preds = []
+        for dom, on, row0, labels, slot in (("a", reg_a, nf, labels_a, 5), ("b", reg_b, n_a + nf, labels_b, 6)):
+            if not on:
+                continue
+            Fr = Ff[row0:row0 + B]
+            p = self.ops.empty(B, pd, dtype=torch.float32)
+            ctx.linear_fwd(Fr.data_ptr(), 1, D.W("Post.weight").data_ptr(), D.W("Post.bias").data_ptr(), p.data_ptr(),
+                           B, pd, per, 0, SLOPE)
+            e = self.vae.encode(labels.detach().to(self.device))[0]
+            dp = torch.empty_like(p)
+            ctx.mse(p.data_ptr(), e.data_ptr(), dp.data_ptr(), 2.0 * hp["reg_w"] / float(Bg * pd), D.acc[slot:].data_ptr(),
+                    p.numel())
+            ctx.linear_bwd(Fr.data_ptr(), 1, D.W("Post.weight").data_ptr(), dp.data_ptr(), dF[row0:].data_ptr(), 0,
+                           D.G("Post.weight").data_ptr(), D.G("Post.bias").data_ptr(), B, pd, per)
+            preds.append(p)
+        if nf:
+            na = outs[0].shape[0]
+            nb = nf - na
+            fscale = hp["feature_w_reg"] / float(n4 * per)
+            # rows: FA part = (x_aa[na] | x_ba[nb]) ; FB part (offset n_a) = (x_ab[na] | x_bb[nb])
+            if na:   # mean|f_ab - f_aa|
+                ctx.l1_feat(Ff[n_a:].data_ptr(), Ff[0:].data_ptr(), dF[n_a:].data_ptr(), dF[0:].data_ptr(), fscale,
+                            D.acc[7:].data_ptr(), na * per)
+            if nb:   # mean|f_ba - f_bb|
+                ctx.l1_feat(Ff[na:].data_ptr(), Ff[n_a + na:].data_ptr(), dF[na:].data_ptr(), dF[n_a + na:].data_ptr(),
+                            fscale, D.acc[7:].data_ptr(), nb * per)
+        dFm = torch.empty_like(F)
+        ctx.mask_to_bf16(dF.data_ptr(), F.data_ptr(), dFm.data_ptr(), SLOPE, F.numel())
+        dis.features_bwd(sv, dFm, wgrad=True)
+        del sv
+        self._allreduce(D)
+        skip = ["D."] + ([] if (reg_a or feat) else ["model_A."]) + ([] if (reg_b or feat) else ["model_B."])
+        D.adam_step(active=lambda k: not any(k.startswith(s) for s in skip))
+        D.refresh_dgrad_operands()
+        acc = D.acc[:8].cpu().numpy().astype(np.float64)
+        reg = (acc[5] + acc[6]) / (Bg * pd)
+        fm = acc[7] / (n4 * per) if feat else 0.0
+        self.dis_reg_loss = np.float32(reg)
+        self.dis_total_loss = np.float32(hp["reg_w"] * reg + hp["feature_w_reg"] * fm)
+        self.last_pred_post = preds
+        u = lambda t: t.unsqueeze(1)
+        x_aa, x_ba, x_ab, x_bb = outs
+        return (u(x_aa), u(x_ba), u(x_ab), u(x_bb), u(x_aa), u(x_bb), u(x_aa), u(x_bb))
+
+    # ------------------------------------------------------------------ outputs / snapshots
+    def assemble_outputs(self, images_a, images_b, network_outputs):
+        """lsps_trainer.py:264-276: first sample of each tensor concatenated along width -> (1,1,128,1280)."""
+        f = lambda t: t[0:1].detach().to(self.device).reshape(1, 1, t.shape[-2], t.shape[-1]).float()
+        o = network_outputs
+        return torch.cat((f(images_a), f(o[0]), f(o[2]), f(o[4]), f(o[6]), f(images_b), f(o[3]), f(o[1]), f(o[5]),
+                          f(o[7])), 3)
+
+    def save(self, snapshot_prefix, iterations):
+        """lsps_trainer.py:307-319: <prefix>_gen_%08d.pkl / _dis_ ; state_dict keys and shapes of the reference."""
+        torch.save({k: v.cpu() for k, v in self.gen_store.state_dict().items()}, "%s_gen_%08d.pkl" % (snapshot_prefix, iterations + 1))
+        torch.save({k: v.cpu() for k, v in self.dis_store.state_dict().items()}, "%s_dis_%08d.pkl" % (snapshot_prefix, iterations + 1))
+        torch.save({"gen": self._cpu(self.gen_store.opt_state()), "dis": self._cpu(self.dis_store.opt_state())},
+                   "%s_opt_%08d.pkl" % (snapshot_prefix, iterations + 1))
+
+    @staticmethod
+    def _cpu(st):
+        return {k: (v.cpu() if torch.is_tensor(v) else v) for k, v in st.items()}
+
+    def resume(self, snapshot_prefix, idx=-1, load_opt=False, est=False):
+        """lsps_trainer.py:278-305: newest (or idx-th) snapshot; iteration parsed from the file name."""
+        import glob
+        dirname, base = os.path.dirname(snapshot_prefix), os.path.basename(snapshot_prefix)
+        iterations = 0
+        for net, store in (("gen", self.gen_store), ("dis", self.dis_store)):
+            pref = base + ("_est" if (est and net == "dis") else "")
+            files = sorted(glob.glob(os.path.join(dirname, "%s_%s_*.pkl" % (pref, net))))
+            if not files:
+                continue
+            f = files[idx]
+            store.load_state_dict(torch.load(f, map_location="cpu"), strict=False)
+            iterations = int(f[-12:-4])
+            if load_opt:
+                fo = f.replace("_%s_" % net, "_opt_")
+                if os.path.exists(fo):
+                    st = torch.load(fo, map_location="cpu")[net]
+                    store.load_opt_state({k: (v.to(self.device) if torch.is_tensor(v) else v) for k, v in st.items()})
+        return iterations
+
+    def save_vae(self, snapshot_prefix, iterations, frac):
+        torch.save({k: v.cpu() for k, v in self.vae_store.state_dict().items()},
+                   "%s_vae_%.2f_%08d.pkl" % (snapshot_prefix, frac, iterations + 1))
+
+    def load_vae(self, snapshot_prefix, frac):
+        import glob
+        files = sorted(glob.glob("%s_vae_%.2f_*.pkl" % (snapshot_prefix, frac)))
+        if not files:
+            raise IOError("no pose-VAE snapshot for %s" % snapshot_prefix)
+        self.vae_store.load_state_dict(torch.load(files[-1], map_location="cpu"))

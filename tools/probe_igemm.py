@@ -84,9 +84,10 @@ def run(kind, n, h, w, cin, cout, seed=0, time_it=False):
     out["dgrad"] = rel(from_nhwc(dxb), x.grad)
     mask = torch.randn(n, cin, h, w, device=dev, generator=g)
     add = torch.randn(n, cin, h, w, device=dev, generator=g).bfloat16().float()
-    chk(lib.lsps_conv_dgrad(ctx, C.byref(sh), P(dyb), P(wdb), P(dxb), P(nhwc(mask)), P(nhwc(add)), 12, C.c_float(0.01), st))
+    mb, ab = nhwc(mask), nhwc(add)
+    chk(lib.lsps_conv_dgrad(ctx, C.byref(sh), P(dyb), P(wdb), P(dxb), P(mb), P(ab), 12, C.c_float(0.01), st))
     torch.cuda.synchronize()
-    ref = x.grad * torch.where(nhwc(mask).float().permute(0, 3, 1, 2) > 0, 1.0, 0.01) + add
+    ref = (x.grad + add) * torch.where(mb.float().permute(0, 3, 1, 2) > 0, 1.0, 0.01)
     out["dgrad_mask_add"] = rel(from_nhwc(dxb), ref)
     # wgrad
     dw = torch.zeros(9, cout, cin, device=dev)
