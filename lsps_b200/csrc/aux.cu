@@ -101,6 +101,8 @@ __global__ void __launch_bounds__(256) stem_fwd_kernel(const float* __restrict__
 }
 
 // dW[co][tap] += sum dy[pix][co] * img[pix @ tap]; db[co] += sum dy.  Persistent over 16x16 output tiles.
+// thread = (4 consecutive channels, tap set ts: taps ts, ts+16, ts+32, ts+48): one 8-byte dy load + 4 patch loads
+// feed 16 FMAs per pixel.
 template <int S>
 __global__ void __launch_bounds__(256) stem_wgrad_kernel(const float* __restrict__ img, const bf16* __restrict__ dy,
                                                         float* __restrict__ dw, float* __restrict__ db, int n, int h,
@@ -111,10 +113,19 @@ __global__ void __launch_bounds__(256) stem_wgrad_kernel(const float* __restrict
   const int ho = h / S, wo = wd / S;
   const int tiles_x = wo / ST, tiles_y = ho / ST;
   const int total = tiles_x * tiles_y * n;
-  const int co = threadIdx.x & 63, tg = threadIdx.x >> 6;
-  float acc[13], accb = 0.f;
+  const int cq = threadIdx.x & 15, ts = threadIdx.x >> 4;
+  int toff[4];
 #pragma unroll
-  for (int j = 0; j < 13; ++j) acc[j] = 0.f;
+  for (int j = 0; j < 4; ++j) {
+    const int tap = ts + 16 * j;
+    toff[j] = tap < 49 ? (tap / 7) * (PE + 1) + tap % 7 : -1;
+  }
+  float acc[4][4], accb[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) acc[j][k] = 0.f;
+  const float* pflat = &patch[0][0];
   for (int t = blockIdx.x; t < total; t += gridDim.x) {
     const int tx = t % tiles_x, ty = (t / tiles_x) % tiles_y, im_i = t / (tiles_x * tiles_y);
     const int oy0 = ty * ST, ox0 = tx * ST;
@@ -132,23 +143,37 @@ __global__ void __launch_bounds__(256) stem_wgrad_kernel(const float* __restrict
           __ldg(reinterpret_cast<const uint4*>(dy + (((long long)im_i * ho + oy) * wo + ox) * 64) + j);
     }
     __syncthreads();
+#pragma unroll 4
     for (int px = 0; px < ST * ST; ++px) {
-      const float d = __bfloat162float(dys[px][co]);
-      const int py_ = (px >> 4) * S, px_ = (px & 15) * S;
-      if (tg == 0) accb += d;
+      const uint2 u = *reinterpret_cast<const uint2*>(&dys[px][cq * 4]);
+      const float d[4] = {bf16lo(u.x), bf16hi(u.x), bf16lo(u.y), bf16hi(u.y)};
+      const int pbase = (px >> 4) * S * (PE + 1) + (px & 15) * S;
+      if (ts == 0) {
 #pragma unroll
-      for (int j = 0; j < 13; ++j) {
-        const int tap = tg + 4 * j;
-        if (tap < 49) acc[j] += d * patch[py_ + tap / 7][px_ + tap % 7];
+        for (int k = 0; k < 4; ++k) accb[k] += d[k];
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (toff[j] >= 0) {
+          const float v = pflat[pbase + toff[j]];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) acc[j][k] += d[k] * v;
+        }
       }
     }
   }
 #pragma unroll
-  for (int j = 0; j < 13; ++j) {
-    const int tap = tg + 4 * j;
-    if (tap < 49) atomicAdd(dw + co * 49 + tap, acc[j]);
+  for (int j = 0; j < 4; ++j) {
+    const int tap = ts + 16 * j;
+    if (tap < 49) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) atomicAdd(dw + (cq * 4 + k) * 49 + tap, acc[j][k]);
+    }
   }
-  if (tg == 0 && db) atomicAdd(db + co, accb);
+  if (ts == 0 && db) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) atomicAdd(db + cq * 4 + k, accb[k]);
+  }
 }
 
 // dimg[y][x] (+)= sum_{r,c,co} dy[(y+3-r)/S][(x+3-c)/S][co] * w[co][r][c]
@@ -502,21 +527,33 @@ __global__ void __launch_bounds__(256) mask_to_bf16_kernel(const float* __restri
 
 __global__ void __launch_bounds__(256) colsum_kernel(const bf16* __restrict__ dy, long long rows, int c,
                                                     float* __restrict__ db, int row_lanes) {
+  // block = (octets of 8 channels) x (row lanes); grid.x strides over rows, grid.y over 2048-channel slabs
+  __shared__ float red[256 * 8];
+  const int octs_blk = 256 / row_lanes;
   const int octs = c / 8;
-  const int oct = blockIdx.y * (256 / row_lanes) + threadIdx.x % (256 / row_lanes);
-  const int rl = threadIdx.x / (256 / row_lanes);
-  if (oct >= octs) return;
+  const int ol = threadIdx.x % octs_blk, rl = threadIdx.x / octs_blk;
+  const int oct = blockIdx.y * octs_blk + ol;
   float a[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) a[k] = 0.f;
-  for (long long r = (long long)blockIdx.x * row_lanes + rl; r < rows; r += (long long)gridDim.x * row_lanes) {
-    float f[8];
-    unpack8(__ldg(reinterpret_cast<const uint4*>(dy + r * c) + oct), f);
+  if (oct < octs) {
+    for (long long r = (long long)blockIdx.x * row_lanes + rl; r < rows; r += (long long)gridDim.x * row_lanes) {
+      float f[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(dy + r * c) + oct), f);
 #pragma unroll
-    for (int k = 0; k < 8; ++k) a[k] += f[k];
+      for (int k = 0; k < 8; ++k) a[k] += f[k];
+    }
   }
 #pragma unroll
-  for (int k = 0; k < 8; ++k) atomicAdd(db + oct * 8 + k, a[k]);
+  for (int k = 0; k < 8; ++k) red[(rl * octs_blk + ol) * 8 + k] = a[k];
+  __syncthreads();
+  const int nch = octs_blk * 8;  // channels handled by this block
+  for (int ch = threadIdx.x; ch < nch; ch += 256) {
+    float s = 0.f;
+    for (int j = 0; j < row_lanes; ++j) s += red[j * nch + ch];
+    const int gc = blockIdx.y * nch + ch;
+    if (gc < c) atomicAdd(db + gc, s);
+  }
 }
 
 // =============================================================================================== small dense layers
@@ -687,7 +724,7 @@ extern "C" int lsps_stem_wgrad(lsps_ctx* ctx, const float* img, const void* dy, 
   REQUIRE(ctx, (stride == 1 || stride == 2) && h % (ST * stride) == 0 && wd % (ST * stride) == 0 && n > 0, LSPS_E_SHAPE,
           "stem_wgrad: shape");
   const int total = (wd / stride / ST) * (h / stride / ST) * n;
-  const int grid = total < 4 * ctx->num_sms ? total : 4 * ctx->num_sms;
+  const int grid = total < 2 * ctx->num_sms ? total : 2 * ctx->num_sms;
   if (stride == 1) stem_wgrad_kernel<1><<<grid, 256, 0, ST_(st)>>>(img, static_cast<const bf16*>(dy), dw, db, n, h, wd);
   else stem_wgrad_kernel<2><<<grid, 256, 0, ST_(st)>>>(img, static_cast<const bf16*>(dy), dw, db, n, h, wd);
   LSPS_CHECK_LAUNCH(ctx, "stem_wgrad");
@@ -820,7 +857,7 @@ extern "C" int lsps_colsum_bf16(lsps_ctx* ctx, const void* dy, long long rows, i
   const int row_lanes = octs >= 256 ? 1 : 256 / octs;
   const int gy = octs >= 256 ? octs / 256 : 1;
   long long gx = (rows + row_lanes - 1) / row_lanes;
-  const long long cap = (4LL * ctx->num_sms + gy - 1) / gy;
+  const long long cap = (2LL * ctx->num_sms + gy - 1) / gy;
   if (gx > cap) gx = cap;
   colsum_kernel<<<dim3((unsigned)gx, gy), 256, 0, ST_(st)>>>(static_cast<const bf16*>(dy), rows, c, db, row_lanes);
   LSPS_CHECK_LAUNCH(ctx, "colsum");

@@ -358,23 +358,27 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ CU
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
-      const WTap T = p.taps[tap];
-      int stage = 0; uint32_t ph = 0;
-      for (int pt = pt0; pt < pt1; ++pt) {
-        const int tx = pt % p.tiles_x, ty = (pt / p.tiles_x) % p.tiles_y, ti = pt / (p.tiles_x * p.tiles_y);
-        const int x0 = tx << p.twl, y0 = ty << p.thl, n0 = ti * p.nb;
-        uint8_t* s = base + stage * Cfg::STAGE_BYTES;
+    // every box of a stage is issued by its own lane (6 boxes per stage at BN=256: one thread issuing them
+    // back to back would take longer than the 512-cycle MMA budget of the stage)
+    const WTap T = p.taps[tap];
+    int stage = 0; uint32_t ph = 0;
+    const int nboxes = nA + BN / 64;
+    for (int pt = pt0; pt < pt1; ++pt) {
+      const int tx = pt % p.tiles_x, ty = (pt / p.tiles_x) % p.tiles_y, ti = pt / (p.tiles_x * p.tiles_y);
+      const int x0 = tx << p.twl, y0 = ty << p.thl, n0 = ti * p.nb;
+      uint8_t* s = base + stage * Cfg::STAGE_BYTES;
+      if (lane == 0) {
         mbar_wait(&empty[stage], ph ^ 1);
-        mbar_expect_tx(&full[stage], (nA + BN / 64) * W_BOX_BYTES);
-        for (int j = 0; j < nA; ++j)
-          tma_load_5d(s + j * W_BOX_BYTES, &tmM, &full[stage], cot * 128 + j * 64 + T.mc, x0 + T.mx, T.mp, y0 + T.my, n0);
-#pragma unroll
-        for (int j = 0; j < BN / 64; ++j)
-          tma_load_5d(s + (2 + j) * W_BOX_BYTES, &tmN, &full[stage], cit * BN + j * 64 + T.nc, x0 + T.nx, T.np,
-                      y0 + T.ny, n0);
-        if (++stage == STAGES) { stage = 0; ph ^= 1; }
+        mbar_expect_tx(&full[stage], nboxes * W_BOX_BYTES);
       }
+      __syncwarp();
+      if (lane < nA)
+        tma_load_5d(s + lane * W_BOX_BYTES, &tmM, &full[stage], cot * 128 + lane * 64 + T.mc, x0 + T.mx, T.mp, y0 + T.my, n0);
+      else if (lane < nboxes) {
+        const int j = lane - nA;
+        tma_load_5d(s + (2 + j) * W_BOX_BYTES, &tmN, &full[stage], cit * BN + j * 64 + T.nc, x0 + T.nx, T.np, y0 + T.ny, n0);
+      }
+      if (++stage == STAGES) { stage = 0; ph ^= 1; }
     }
   } else if (warp == 1) {
     if (lane == 0) {
