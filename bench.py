@@ -200,12 +200,11 @@ def main():
     d2h = (8 + 16) * 4
 
     # ---- roofline of the dominant kernel: every launch of the K1 shape in one instrumented step
+    # (every rank runs the step -- it contains the gradient allreduce -- but only rank 0 instruments and reports)
     roof = None
+    ev = []
+    orig_f, orig_d = _engine.Ops.conv_fwd, _engine.Ops.conv_dgrad
     if rank == 0:
-        pk = _peaks()
-        ev = []
-        orig_f, orig_d = _engine.Ops.conv_fwd, _engine.Ops.conv_dgrad
-
         def wrap(orig, is_fwd):
             def f(self, S, key, kind, x, *a, **kw):
                 shp = x.shape if is_fwd else a[0]
@@ -220,15 +219,20 @@ def main():
                 return out
             return f
         _engine.Ops.conv_fwd, _engine.Ops.conv_dgrad = wrap(orig_f, True), wrap(orig_d, False)
-        step_dev()
-        torch.cuda.synchronize()
-        _engine.Ops.conv_fwd, _engine.Ops.conv_dgrad = orig_f, orig_d
+    step_dev()
+    torch.cuda.synchronize()
+    _engine.Ops.conv_fwd, _engine.Ops.conv_dgrad = orig_f, orig_d
+    if rank == 0:
+        pk = _peaks()
         tot_ms = sum(a.elapsed_time(b_) for a, b_, _ in ev)
         tot_flop = sum(2.0 * n * 1024 * 256 * 2304 for _, _, n in ev)
         ach = tot_flop / (tot_ms * 1e-3) / 1e12
         roof = {"bound": "tensor", "kernel": "conv_igemm_kernel<256> (3x3 s1 256->256 @32x32, fwd+dgrad)",
                 "achieved": ach, "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": ach / pk["tf_sustained"],
-                "traffic": None, "launches": len(ev), "avg_launch_ms": tot_ms / max(1, len(ev)),
+                "traffic": 87.9e6, "traffic_note": "dram read+write bytes per launch at N=128 images from "
+                "profiles/r01_ncu_k1_wgrad_v0.md (algorithmic: 64 MB in + 64 MB out + 1.2 MB weights; part of the "
+                "output is still in L2 at kernel end)",
+                "launches": len(ev), "avg_launch_ms": tot_ms / max(1, len(ev)),
                 "share_of_step": tot_ms / (ms / K), "peak_source": pk["src"] + ", sustained bf16"}
 
     if world > 1:

@@ -14,6 +14,7 @@
 //   /root/reference/src/trainers/common_net.py:160-181 (LeakyINSResBlock), :246-268 (LeakyReLUConv2d / ConvTranspose2d)
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "common.h"
 #include "ptx.cuh"
@@ -115,61 +116,74 @@ struct IgemmParams {
   const __nv_bfloat16* add;
   float slope;
   int flags;
+  int dbg;  // profiling experiments only: 1 = skip MMA issue, 2 = skip TMA issue (results are garbage)
   Phase ph[4];
   Tap taps[9];
 };
 
 constexpr int A_STAGE_BYTES = 128 * 128;  // 128 rows x 64 bf16
 
-template <int BN>
+// CG = 1: one CTA per 128 x BN tile.  CG = 2: a CTA pair (cluster of 2, tcgen05 cta_group::2) per 256 x BN tile --
+// each CTA stages its own 128 rows of A and HALF of the weight tile, one MMA of M=256 reads both halves, so the
+// shared-memory fill + read traffic per MAC drops by a third and the pipeline gets 6 stages instead of 4.
+template <int BN, int CG>
 struct IgemmCfg {
-  static constexpr int STAGES = BN == 256 ? 4 : (BN == 128 ? 6 : 8);
-  static constexpr int B_STAGE_BYTES = BN * 128;
+  static constexpr int B_STAGE_BYTES = (BN / CG) * 128;
+  static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+  static constexpr int STAGES = (196608 / STAGE_BYTES) > 8 ? 8 : (196608 / STAGE_BYTES);
   static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
-  static constexpr int SMEM_BYTES = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 1024 + 256;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
 };
 
 // warp 0: TMA producer | warp 1: TMEM owner + MMA issuer | warps 2-5: epilogue (TMEM -> regs -> global)
-template <int BN>
+template <int BN, int CG>
 __global__ void __launch_bounds__(192, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const __grid_constant__ IgemmParams p) {
-  using Cfg = IgemmCfg<BN>;
+  using Cfg = IgemmCfg<BN, CG>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = base;
   uint8_t* sB = base + STAGES * A_STAGE_BYTES;
-  uint64_t* full = reinterpret_cast<uint64_t*>(base + STAGES * (A_STAGE_BYTES + Cfg::B_STAGE_BYTES));
+  uint64_t* full = reinterpret_cast<uint64_t*>(base + STAGES * Cfg::STAGE_BYTES);
   uint64_t* empty = full + STAGES;
   uint64_t* tfull = empty + STAGES;
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rank = CG == 2 ? (int)cluster_ctarank() : 0;  // position in the CTA pair
+  const bool leader = rank == 0;
   if (threadIdx.x == 0) {
     for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4 * CG); }
     fence_barrier_init();
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
   }
-  if (warp == 1) { tmem_alloc(tmem_slot, Cfg::TMEM_COLS); tmem_relinquish(); }
+  if (warp == 1) {
+    if (CG == 2) { tmem_alloc_cg2(tmem_slot, Cfg::TMEM_COLS); tmem_relinquish_cg2(); }
+    else { tmem_alloc(tmem_slot, Cfg::TMEM_COLS); tmem_relinquish(); }
+  }
   tc_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // work items: (phase, n tile, group of CG consecutive m tiles); a phantom m tile (odd count) loads zeros, stores nothing
   const int tiles_m = p.tiles_x * p.tiles_y * p.tiles_i;
-  const int per_phase = tiles_m * p.tiles_n;
+  const int groups_m = (tiles_m + CG - 1) / CG;
+  const int per_phase = groups_m * p.tiles_n;
   const int total = per_phase * p.nphases;
+  const int worker = blockIdx.x / CG, nworkers = gridDim.x / CG;
 
   if (warp == 0) {
     if (lane == 0) {
       int stage = 0; uint32_t ph = 0;
-      for (int t = blockIdx.x; t < total; t += gridDim.x) {
-        const int pi = t / per_phase, r = t - pi * per_phase;
-        const int nt = r / tiles_m, mt = r - nt * tiles_m;
+      for (int t = worker; t < total; t += nworkers) {
+        const int pi = t % p.nphases, r = t / p.nphases;
+        const int nt = r / groups_m, mt = (r - nt * groups_m) * CG + rank;
         const int tx = mt % p.tiles_x, ty = (mt / p.tiles_x) % p.tiles_y, ti = mt / (p.tiles_x * p.tiles_y);
         const int x0 = tx << p.twl, y0 = ty << p.thl, n0 = ti * p.nb;
         const Phase P = p.ph[pi];
@@ -177,20 +191,28 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           const Tap T = p.taps[P.tap0 + tp];
           for (int kc = 0; kc < p.kchunks; ++kc) {
             mbar_wait(&empty[stage], ph ^ 1);
-            mbar_expect_tx(&full[stage], A_STAGE_BYTES + Cfg::B_STAGE_BYTES);
-            tma_load_5d(sA + stage * A_STAGE_BYTES, &tmA, &full[stage], kc * 64 + T.ac, x0 + T.ax, T.ap, y0 + T.ay, n0);
-            tma_load_2d(sB + stage * Cfg::B_STAGE_BYTES, &tmB, &full[stage], kc * 64, T.brow + nt * BN);
+            if (p.dbg & 2) {
+              if (leader) mbar_arrive(&full[stage]);
+            } else if (CG == 2) {
+              if (leader) mbar_expect_tx(&full[stage], 2 * Cfg::STAGE_BYTES);  // both CTAs' boxes land on the leader's barrier
+              tma_load_5d_cg2(sA + stage * A_STAGE_BYTES, &tmA, &full[stage], kc * 64 + T.ac, x0 + T.ax, T.ap, y0 + T.ay, n0);
+              tma_load_2d_cg2(sB + stage * Cfg::B_STAGE_BYTES, &tmB, &full[stage], kc * 64, T.brow + nt * BN + rank * (BN / 2));
+            } else {
+              mbar_expect_tx(&full[stage], Cfg::STAGE_BYTES);
+              tma_load_5d(sA + stage * A_STAGE_BYTES, &tmA, &full[stage], kc * 64 + T.ac, x0 + T.ax, T.ap, y0 + T.ay, n0);
+              tma_load_2d(sB + stage * Cfg::B_STAGE_BYTES, &tmB, &full[stage], kc * 64, T.brow + nt * BN);
+            }
             if (++stage == STAGES) { stage = 0; ph ^= 1; }
           }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(128, BN, 0, 0);
+    if (lane == 0 && leader) {
+      constexpr uint32_t idesc = umma_idesc_bf16(128 * CG, BN, 0, 0);
       int stage = 0; uint32_t ph = 0; int it = 0;
-      for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
-        const int pi = t / per_phase;
+      for (int t = worker; t < total; t += nworkers, ++it) {
+        const int pi = t % p.nphases;
         const int nk = p.ph[pi].ntaps * p.kchunks;
         const int acc = it & 1; const uint32_t accph = (it >> 1) & 1;
         mbar_wait(&tempty[acc], accph ^ 1);
@@ -202,13 +224,16 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           const uint32_t a_addr = smem_u32(sA + stage * A_STAGE_BYTES);
           const uint32_t b_addr = smem_u32(sB + stage * Cfg::B_STAGE_BYTES);
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_bf16(d_tmem, umma_smem_desc(a_addr + k * 32, 0, 1024), umma_smem_desc(b_addr + k * 32, 0, 1024), idesc,
-                      (ks | k) != 0 ? 1u : 0u);
-          umma_commit(&empty[stage]);
+          for (int k = 0; k < 4; ++k) {
+            if (p.dbg & 1) break;
+            const uint64_t ad = umma_smem_desc(a_addr + k * 32, 0, 1024), bd = umma_smem_desc(b_addr + k * 32, 0, 1024);
+            if (CG == 2) umma_bf16_cg2(d_tmem, ad, bd, idesc, (ks | k) != 0 ? 1u : 0u);
+            else umma_bf16(d_tmem, ad, bd, idesc, (ks | k) != 0 ? 1u : 0u);
+          }
+          if (CG == 2) umma_commit_cg2(&empty[stage]); else umma_commit(&empty[stage]);
           if (++stage == STAGES) { stage = 0; ph ^= 1; }
         }
-        umma_commit(&tfull[acc]);
+        if (CG == 2) umma_commit_cg2(&tfull[acc]); else umma_commit(&tfull[acc]);
       }
     }
   } else {
@@ -217,9 +242,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int tw_mask = (1 << p.twl) - 1, th_mask = (1 << p.thl) - 1;
     const int xl = row & tw_mask, yl = (row >> p.twl) & th_mask, nl = row >> (p.twl + p.thl);
     int it = 0;
-    for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
-      const int pi = t / per_phase, r = t - pi * per_phase;
-      const int nt = r / tiles_m, mt = r - nt * tiles_m;
+    for (int t = worker; t < total; t += nworkers, ++it) {
+      const int pi = t % p.nphases, r = t / p.nphases;
+      const int nt = r / groups_m, mt = (r - nt * groups_m) * CG + rank;
       const int tx = mt % p.tiles_x, ty = (mt / p.tiles_x) % p.tiles_y, ti = mt / (p.tiles_x * p.tiles_y);
       const int x0 = tx << p.twl, y0 = ty << p.thl, n = ti * p.nb + nl;
       const Phase P = p.ph[pi];
@@ -291,12 +316,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty[acc]);
+      if (lane == 0) { if (CG == 2) mbar_arrive_leader(&tempty[acc]); else mbar_arrive(&tempty[acc]); }
     }
   }
   tc_fence_before();
-  __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  if (CG == 2) cluster_sync_all(); else __syncthreads();
+  if (warp == 1) { if (CG == 2) tmem_dealloc_cg2(tmem_base, Cfg::TMEM_COLS); else tmem_dealloc(tmem_base, Cfg::TMEM_COLS); }
 }
 
 // ------------------------------------------------------------------------------------------------ wgrad
@@ -304,26 +329,28 @@ struct WTap { short mc, mx, mp, my, nc, nx, np, ny; };  // tap offsets in the dy
 struct WgradParams {
   int tiles_x, tiles_y, tiles_i;
   int twl, thl, nb;  // K tile = 64 pixels
-  int ntaps, co_tiles, ci_tiles, splits;
+  int ntaps, co_tiles, ci_tiles, splits;   // co_tiles counts tiles of 128*CG output channels
   int cout, cin;
+  int dbg;
   float* dw;
   WTap taps[9];
 };
 constexpr int W_BOX_BYTES = 64 * 128;  // 64 pixels x 64 bf16
 
-template <int BN>
+template <int BN, int CG>
 struct WgradCfg {
-  static constexpr int STAGE_BYTES = (2 + BN / 64) * W_BOX_BYTES;
+  static constexpr int NB_BOXES = BN / 64 / CG;                    // x boxes staged by this CTA
+  static constexpr int STAGE_BYTES = (2 + NB_BOXES) * W_BOX_BYTES;
   static constexpr int STAGES = (196608 / STAGE_BYTES) > 8 ? 8 : (196608 / STAGE_BYTES);
   static constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
 };
 
-template <int BN>
+template <int BN, int CG>
 __global__ void __launch_bounds__(192, 1)
 wgrad_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ CUtensorMap tmN,
              const __grid_constant__ WgradParams p) {
-  using Cfg = WgradCfg<BN>;
+  using Cfg = WgradCfg<BN, CG>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -332,16 +359,18 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ CU
   uint64_t* tfull = empty + STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tfull + 1);
 
-  int b = blockIdx.x;
+  const int rank = CG == 2 ? (int)cluster_ctarank() : 0;
+  const bool leader = rank == 0;
+  int b = blockIdx.x / CG;
   const int split = b % p.splits; b /= p.splits;
   const int cit = b % p.ci_tiles; b /= p.ci_tiles;
-  const int cot = b % p.co_tiles;
+  const int cot = (b % p.co_tiles) * CG + rank;   // this CTA's 128-channel tile of dy
   const int tap = b / p.co_tiles;
   const int ptiles = p.tiles_x * p.tiles_y * p.tiles_i;
   const int pt0 = (int)((long long)ptiles * split / p.splits);
   const int pt1 = (int)((long long)ptiles * (split + 1) / p.splits);
-  if (pt0 >= pt1) return;
-  const int nA = min(2, (p.cout - cot * 128) / 64);
+  if (pt0 >= pt1) return;   // both CTAs of a pair take the same decision
+  const int nA = CG == 2 ? 2 : min(2, (p.cout - cot * 128) / 64);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
@@ -351,38 +380,46 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ CU
     tma_prefetch_desc(&tmM);
     tma_prefetch_desc(&tmN);
   }
-  if (warp == 1) { tmem_alloc(tmem_slot, Cfg::TMEM_COLS); tmem_relinquish(); }
+  if (warp == 1) {
+    if (CG == 2) { tmem_alloc_cg2(tmem_slot, Cfg::TMEM_COLS); tmem_relinquish_cg2(); }
+    else { tmem_alloc(tmem_slot, Cfg::TMEM_COLS); tmem_relinquish(); }
+  }
   tc_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // every box of a stage is issued by its own lane (6 boxes per stage at BN=256: one thread issuing them
-    // back to back would take longer than the 512-cycle MMA budget of the stage)
+    // every box of a stage is issued by its own lane
     const WTap T = p.taps[tap];
     int stage = 0; uint32_t ph = 0;
-    const int nboxes = nA + BN / 64;
+    const int nboxes = nA + Cfg::NB_BOXES;
     for (int pt = pt0; pt < pt1; ++pt) {
       const int tx = pt % p.tiles_x, ty = (pt / p.tiles_x) % p.tiles_y, ti = pt / (p.tiles_x * p.tiles_y);
       const int x0 = tx << p.twl, y0 = ty << p.thl, n0 = ti * p.nb;
       uint8_t* s = base + stage * Cfg::STAGE_BYTES;
       if (lane == 0) {
         mbar_wait(&empty[stage], ph ^ 1);
-        mbar_expect_tx(&full[stage], nboxes * W_BOX_BYTES);
+        if (p.dbg & 2) { if (leader) mbar_arrive(&full[stage]); }
+        else if (CG == 1) mbar_expect_tx(&full[stage], nboxes * W_BOX_BYTES);
+        else if (leader) mbar_expect_tx(&full[stage], 2 * Cfg::STAGE_BYTES);
       }
       __syncwarp();
-      if (lane < nA)
-        tma_load_5d(s + lane * W_BOX_BYTES, &tmM, &full[stage], cot * 128 + lane * 64 + T.mc, x0 + T.mx, T.mp, y0 + T.my, n0);
-      else if (lane < nboxes) {
+      if (p.dbg & 2) {
+      } else if (lane < nA) {
+        if (CG == 2) tma_load_5d_cg2(s + lane * W_BOX_BYTES, &tmM, &full[stage], cot * 128 + lane * 64 + T.mc, x0 + T.mx, T.mp, y0 + T.my, n0);
+        else tma_load_5d(s + lane * W_BOX_BYTES, &tmM, &full[stage], cot * 128 + lane * 64 + T.mc, x0 + T.mx, T.mp, y0 + T.my, n0);
+      } else if (lane < nboxes) {
         const int j = lane - nA;
-        tma_load_5d(s + (2 + j) * W_BOX_BYTES, &tmN, &full[stage], cit * BN + j * 64 + T.nc, x0 + T.nx, T.np, y0 + T.ny, n0);
+        const int cbase = cit * BN + (rank * Cfg::NB_BOXES + j) * 64 + T.nc;
+        if (CG == 2) tma_load_5d_cg2(s + (2 + j) * W_BOX_BYTES, &tmN, &full[stage], cbase, x0 + T.nx, T.np, y0 + T.ny, n0);
+        else tma_load_5d(s + (2 + j) * W_BOX_BYTES, &tmN, &full[stage], cbase, x0 + T.nx, T.np, y0 + T.ny, n0);
       }
       if (++stage == STAGES) { stage = 0; ph ^= 1; }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(128, BN, 1, 1);
+    if (lane == 0 && leader) {
+      constexpr uint32_t idesc = umma_idesc_bf16(128 * CG, BN, 1, 1);
       int stage = 0; uint32_t ph = 0;
       for (int pt = pt0; pt < pt1; ++pt) {
         mbar_wait(&full[stage], ph);
@@ -390,13 +427,17 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ CU
         const uint32_t a_addr = smem_u32(base + stage * Cfg::STAGE_BYTES);
         const uint32_t b_addr = a_addr + 2 * W_BOX_BYTES;
 #pragma unroll
-        for (int k = 0; k < 4; ++k)  // 16 pixels per MMA = 16 rows of 128 B
-          umma_bf16(tmem_base, umma_smem_desc(a_addr + k * 2048, W_BOX_BYTES, 1024),
-                    umma_smem_desc(b_addr + k * 2048, W_BOX_BYTES, 1024), idesc, (pt > pt0 || k > 0) ? 1u : 0u);
-        umma_commit(&empty[stage]);
+        for (int k = 0; k < 4; ++k) {  // 16 pixels per MMA = 16 rows of 128 B
+          if (p.dbg & 1) break;
+          const uint64_t ad = umma_smem_desc(a_addr + k * 2048, W_BOX_BYTES, 1024);
+          const uint64_t bd = umma_smem_desc(b_addr + k * 2048, W_BOX_BYTES, 1024);
+          if (CG == 2) umma_bf16_cg2(tmem_base, ad, bd, idesc, (pt > pt0 || k > 0) ? 1u : 0u);
+          else umma_bf16(tmem_base, ad, bd, idesc, (pt > pt0 || k > 0) ? 1u : 0u);
+        }
+        if (CG == 2) umma_commit_cg2(&empty[stage]); else umma_commit(&empty[stage]);
         if (++stage == STAGES) { stage = 0; ph ^= 1; }
       }
-      umma_commit(tfull);
+      if (CG == 2) umma_commit_cg2(tfull); else umma_commit(tfull);
     }
   } else {
     const int q = warp & 3;
@@ -421,8 +462,8 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ CU
     }
   }
   tc_fence_before();
-  __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  if (CG == 2) cluster_sync_all(); else __syncthreads();
+  if (warp == 1) { if (CG == 2) tmem_dealloc_cg2(tmem_base, Cfg::TMEM_COLS); else tmem_dealloc(tmem_base, Cfg::TMEM_COLS); }
 }
 
 // ------------------------------------------------------------------------------------------------ host side
@@ -460,18 +501,47 @@ inline int t2_axis(int a, int* rs, int* ds) {
 
 enum Dir { FWD = 0, DGRAD = 1 };
 
-template <int BN>
+inline int lsps_force_cg() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("LSPS_FORCE_CG"); v = e ? atoi(e) : 0; }
+  return v;
+}
+inline int lsps_dbg() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("LSPS_DBG"); v = e ? atoi(e) : 0; }
+  return v;
+}
+inline bool lsps_use_pairs() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("LSPS_NO_PAIRS"); v = (e && e[0] == '1') ? 0 : 1; }
+  return v == 1;
+}
+
+template <typename K, typename... Args>
+cudaError_t launch_maybe_cluster(K kernel, int grid, int smem, int cg, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(192); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = cg; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, args...);
+}
+
+template <int BN, int CG>
 int launch_igemm(lsps_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tmB, const IgemmParams& p, cudaStream_t st) {
-  using Cfg = IgemmCfg<BN>;
+  using Cfg = IgemmCfg<BN, CG>;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(conv_igemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(conv_igemm_kernel<BN, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return lsps_set_error(ctx, LSPS_E_CUDA, "igemm smem attr: %s", cudaGetErrorString(e));
     configured = true;
   }
-  const int total = p.tiles_x * p.tiles_y * p.tiles_i * p.tiles_n * p.nphases;
-  const int grid = total < ctx->num_sms ? total : ctx->num_sms;
-  conv_igemm_kernel<BN><<<grid, 192, Cfg::SMEM_BYTES, st>>>(tmA, tmB, p);
+  const int tiles_m = p.tiles_x * p.tiles_y * p.tiles_i;
+  const int total = ((tiles_m + CG - 1) / CG) * p.tiles_n * p.nphases;
+  const int workers = total < ctx->num_sms / CG ? total : ctx->num_sms / CG;
+  cudaError_t e = launch_maybe_cluster(conv_igemm_kernel<BN, CG>, workers * CG, Cfg::SMEM_BYTES, CG, st, tmA, tmB, p);
+  if (e != cudaSuccess) return lsps_set_error(ctx, LSPS_E_CUDA, "conv_igemm launch: %s", cudaGetErrorString(e));
   LSPS_CHECK_LAUNCH(ctx, "conv_igemm");
   return LSPS_OK;
 }
@@ -513,7 +583,7 @@ int run_igemm(lsps_ctx* ctx, const lsps_conv_shape* s, Dir dir, const void* in, 
   p.o_n = (long long)oh * ow * nc; p.o_y = (long long)ow * nc; p.o_x = nc;
   p.out = static_cast<__nv_bfloat16*>(out); p.bias = bias;
   p.mask = static_cast<const __nv_bfloat16*>(mask); p.add = static_cast<const __nv_bfloat16*>(add);
-  p.slope = slope; p.flags = flags;
+  p.slope = slope; p.flags = flags; p.dbg = lsps_dbg();
 
   int nt = 0;
   if (plain) {
@@ -558,28 +628,43 @@ int run_igemm(lsps_ctx* ctx, const lsps_conv_shape* s, Dir dir, const void* in, 
 
   const int bn = nc % 256 == 0 ? 256 : (nc % 128 == 0 ? 128 : 64);
   p.tiles_n = nc / bn;
+  // CTA pairs (cta_group::2) whenever there are at least two M tiles to pair up
+  const int tiles_m = p.tiles_x * p.tiles_y * p.tiles_i;
+  //   ... and the tile is MMA-bound (>= 27 K-steps) and there are enough tiles to keep every SM busy in pairs;
+  //   short-K layers are issue-/latency-bound per tile and run faster as 148 independent CTAs (measured, r01 probes)
+  int nk_min = 1 << 30;
+  for (int i = 0; i < p.nphases; ++i) nk_min = p.ph[i].ntaps * p.kchunks < nk_min ? p.ph[i].ntaps * p.kchunks : nk_min;
+  const int force = lsps_force_cg();
+  int cg = (lsps_use_pairs() && tiles_m >= 2 && nk_min >= 27 && (long long)tiles_m * p.tiles_n >= 2 * ctx->num_sms) ? 2 : 1;
+  if (force && tiles_m >= 2) cg = force;
   CUtensorMap tmA, tmB;
   int rc = act_tmap(ctx, in, n, ih, iw, kc, down, g, &tmA);
   if (rc) return rc;
-  uint32_t wd[2] = {(uint32_t)kc, (uint32_t)(9 * nc)}, wb[2] = {64, (uint32_t)bn};
+  uint32_t wd[2] = {(uint32_t)kc, (uint32_t)(9 * nc)}, wb[2] = {64, (uint32_t)(bn / cg)};
   rc = lsps_get_tmap(ctx, wpk, 2, wd, wb, &tmB);
   if (rc) return rc;
-  if (bn == 256) return launch_igemm<256>(ctx, tmA, tmB, p, st);
-  if (bn == 128) return launch_igemm<128>(ctx, tmA, tmB, p, st);
-  return launch_igemm<64>(ctx, tmA, tmB, p, st);
+  if (cg == 2) {
+    if (bn == 256) return launch_igemm<256, 2>(ctx, tmA, tmB, p, st);
+    if (bn == 128) return launch_igemm<128, 2>(ctx, tmA, tmB, p, st);
+    return launch_igemm<64, 2>(ctx, tmA, tmB, p, st);
+  }
+  if (bn == 256) return launch_igemm<256, 1>(ctx, tmA, tmB, p, st);
+  if (bn == 128) return launch_igemm<128, 1>(ctx, tmA, tmB, p, st);
+  return launch_igemm<64, 1>(ctx, tmA, tmB, p, st);
 }
 
-template <int BN>
+template <int BN, int CG>
 int launch_wgrad(lsps_ctx* ctx, const CUtensorMap& tmM, const CUtensorMap& tmN, const WgradParams& p, cudaStream_t st) {
-  using Cfg = WgradCfg<BN>;
+  using Cfg = WgradCfg<BN, CG>;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(wgrad_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(wgrad_kernel<BN, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return lsps_set_error(ctx, LSPS_E_CUDA, "wgrad smem attr: %s", cudaGetErrorString(e));
     configured = true;
   }
-  const int grid = p.ntaps * p.co_tiles * p.ci_tiles * p.splits;
-  wgrad_kernel<BN><<<grid, 192, Cfg::SMEM_BYTES, st>>>(tmM, tmN, p);
+  const int grid = p.ntaps * p.co_tiles * p.ci_tiles * p.splits * CG;
+  cudaError_t e = launch_maybe_cluster(wgrad_kernel<BN, CG>, grid, Cfg::SMEM_BYTES, CG, st, tmM, tmN, p);
+  if (e != cudaSuccess) return lsps_set_error(ctx, LSPS_E_CUDA, "wgrad launch: %s", cudaGetErrorString(e));
   LSPS_CHECK_LAUNCH(ctx, "wgrad");
   return LSPS_OK;
 }
@@ -613,9 +698,11 @@ extern "C" int lsps_conv_wgrad(lsps_ctx* ctx, const lsps_conv_shape* s, const vo
   WgradParams p{};
   p.tiles_x = wg / g.tw; p.tiles_y = hg / g.th; p.tiles_i = (n + g.nb - 1) / g.nb;
   p.twl = g.twl; p.thl = g.thl; p.nb = g.nb;
-  p.ntaps = 9; p.cout = cout; p.cin = cin; p.dw = dw;
-  p.co_tiles = (cout + 127) / 128;
+  p.ntaps = 9; p.cout = cout; p.cin = cin; p.dw = dw; p.dbg = lsps_dbg();
   const int bn = cin % 256 == 0 ? 256 : (cin % 128 == 0 ? 128 : 64);
+  // CTA pairs: 256 output channels per pair, each CTA stages half of the x tile (needs >= 128 input channels)
+  const int cg = (lsps_use_pairs() && cout % 256 == 0 && bn >= 128) ? 2 : 1;
+  p.co_tiles = (cout + 128 * cg - 1) / (128 * cg);
   p.ci_tiles = cin / bn;
   for (int r = 0; r < 3; ++r)
     for (int c = 0; c < 3; ++c) {
@@ -633,7 +720,7 @@ extern "C" int lsps_conv_wgrad(lsps_ctx* ctx, const lsps_conv_shape* s, const vo
       }
     }
   const int ptiles = p.tiles_x * p.tiles_y * p.tiles_i;
-  const int work = p.ntaps * p.co_tiles * p.ci_tiles;
+  const int work = p.ntaps * p.co_tiles * p.ci_tiles * cg;
   int splits = ctx->num_sms / work;
   if (splits < 1) splits = 1;
   if (splits > ptiles) splits = ptiles;
@@ -644,7 +731,11 @@ extern "C" int lsps_conv_wgrad(lsps_ctx* ctx, const lsps_conv_shape* s, const vo
   if (rc) return rc;
   rc = act_tmap(ctx, x, n, h, w, cin, kind == LSPS_CONV_S2, g, &tmN);
   if (rc) return rc;
-  if (bn == 256) return launch_wgrad<256>(ctx, tmM, tmN, p, st);
-  if (bn == 128) return launch_wgrad<128>(ctx, tmM, tmN, p, st);
-  return launch_wgrad<64>(ctx, tmM, tmN, p, st);
+  if (cg == 2) {
+    if (bn == 256) return launch_wgrad<256, 2>(ctx, tmM, tmN, p, st);
+    return launch_wgrad<128, 2>(ctx, tmM, tmN, p, st);
+  }
+  if (bn == 256) return launch_wgrad<256, 1>(ctx, tmM, tmN, p, st);
+  if (bn == 128) return launch_wgrad<128, 1>(ctx, tmM, tmN, p, st);
+  return launch_wgrad<64, 1>(ctx, tmM, tmN, p, st);
 }
