@@ -6,6 +6,8 @@
 // Reference op sites: /root/reference/src/trainers/lsps_nets.py:34-83,102-126,186-229 ;
 //                     /root/reference/src/trainers/common_net.py:32-40,160-181 ;
 //                     /root/reference/src/trainers/lsps_trainer.py:26-34,42-60,107-121,171-192,241-250
+#include <stdlib.h>
+
 #include "common.h"
 #include "ptx.cuh"
 
@@ -285,7 +287,8 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(const bf16* __restrict__ 
 }
 
 // =============================================================================================== InstanceNorm
-// one CTA per (image, 64-channel group); thread = (8-channel octet, pixel lane)
+// one CTA (512 threads) per (image, 64-channel group); thread = (8-channel octet, one of 64 pixel lanes); 8 independent
+// 16-byte loads in flight per thread so that each of the three passes is bandwidth- rather than latency-bound
 __device__ __forceinline__ void in_reduce64(const float* v8, float (*red)[64], float* outc) {
   const int oct = threadIdx.x & 7, pl = threadIdx.x >> 3;
   __syncthreads();
@@ -295,16 +298,16 @@ __device__ __forceinline__ void in_reduce64(const float* v8, float (*red)[64], f
   if (threadIdx.x < 64) {
     float s = 0.f;
 #pragma unroll 8
-    for (int i = 0; i < 32; ++i) s += red[i][threadIdx.x];
+    for (int i = 0; i < 64; ++i) s += red[i][threadIdx.x];
     outc[threadIdx.x] = s;
   }
   __syncthreads();
 }
 
-__global__ void __launch_bounds__(256) instnorm_fwd_kernel(const bf16* __restrict__ h, const bf16* __restrict__ res,
+__global__ void __launch_bounds__(512) instnorm_fwd_kernel(const bf16* __restrict__ h, const bf16* __restrict__ res,
                                                           bf16* __restrict__ y, float* __restrict__ stats, int hw,
                                                           int c, int mode, float eps, float slope) {
-  __shared__ float red[32][64];
+  __shared__ float red[64][64];
   __shared__ float s_mean[64], s_var[64];
   const int n = blockIdx.y, cg = blockIdx.x;
   const int oct = threadIdx.x & 7, pl = threadIdx.x >> 3;
@@ -312,7 +315,8 @@ __global__ void __launch_bounds__(256) instnorm_fwd_kernel(const bf16* __restric
   float a[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) a[k] = 0.f;
-  for (int p = pl; p < hw; p += 32) {
+#pragma unroll 8
+  for (int p = pl; p < hw; p += 64) {
     float f[8];
     unpack8(__ldg(reinterpret_cast<const uint4*>(h + base + (long long)p * c)), f);
 #pragma unroll
@@ -322,7 +326,8 @@ __global__ void __launch_bounds__(256) instnorm_fwd_kernel(const bf16* __restric
   float mean[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) { mean[k] = s_mean[oct * 8 + k] / hw; a[k] = 0.f; }
-  for (int p = pl; p < hw; p += 32) {
+#pragma unroll 8
+  for (int p = pl; p < hw; p += 64) {
     float f[8];
     unpack8(__ldg(reinterpret_cast<const uint4*>(h + base + (long long)p * c)), f);
 #pragma unroll
@@ -339,7 +344,8 @@ __global__ void __launch_bounds__(256) instnorm_fwd_kernel(const bf16* __restric
       s[0] = mean[k]; s[1] = rstd[k];
     }
   }
-  for (int p = pl; p < hw; p += 32) {
+#pragma unroll 8
+  for (int p = pl; p < hw; p += 64) {
     float f[8], r[8];
     unpack8(__ldg(reinterpret_cast<const uint4*>(h + base + (long long)p * c)), f);
     if (mode == 1) unpack8(__ldg(reinterpret_cast<const uint4*>(res + base + (long long)p * c)), r);
@@ -352,10 +358,10 @@ __global__ void __launch_bounds__(256) instnorm_fwd_kernel(const bf16* __restric
   }
 }
 
-__global__ void __launch_bounds__(256) instnorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ h,
+__global__ void __launch_bounds__(512) instnorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ h,
                                                           const float* __restrict__ stats, bf16* __restrict__ dh,
                                                           int hw, int c, int mode, float slope) {
-  __shared__ float red[32][64];
+  __shared__ float red[64][64];
   __shared__ float s_a[64], s_b[64];
   const int n = blockIdx.y, cg = blockIdx.x;
   const int oct = threadIdx.x & 7, pl = threadIdx.x >> 3;
@@ -366,7 +372,8 @@ __global__ void __launch_bounds__(256) instnorm_bwd_kernel(const bf16* __restric
     const float* s = stats + ((long long)n * c + cg * 64 + oct * 8 + k) * 2;
     mean[k] = s[0]; rstd[k] = s[1]; sg[k] = 0.f; sgx[k] = 0.f;
   }
-  for (int p = pl; p < hw; p += 32) {
+#pragma unroll 8
+  for (int p = pl; p < hw; p += 64) {
     float f[8], g[8];
     unpack8(__ldg(reinterpret_cast<const uint4*>(h + base + (long long)p * c)), f);
     unpack8(__ldg(reinterpret_cast<const uint4*>(dy + base + (long long)p * c)), g);
@@ -382,7 +389,8 @@ __global__ void __launch_bounds__(256) instnorm_bwd_kernel(const bf16* __restric
   float mg[8], mgx[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) { mg[k] = s_a[oct * 8 + k] / hw; mgx[k] = s_b[oct * 8 + k] / hw; }
-  for (int p = pl; p < hw; p += 32) {
+#pragma unroll 8
+  for (int p = pl; p < hw; p += 64) {
     float f[8], g[8];
     unpack8(__ldg(reinterpret_cast<const uint4*>(h + base + (long long)p * c)), f);
     unpack8(__ldg(reinterpret_cast<const uint4*>(dy + base + (long long)p * c)), g);
@@ -701,6 +709,18 @@ __global__ void bf16_to_f32_kernel(const bf16* __restrict__ x, float* __restrict
 
 }  // namespace
 
+// tensor-core stems (stem_tc.cu); LSPS_STEM_SIMT=1 keeps the direct fp32 kernels of this file
+int lsps_stem_fwd_tc(lsps_ctx* ctx, const float* img, const float* w, const float* bias, void* y, int n, int h, int wd,
+                     int stride, float slope, cudaStream_t st);
+int lsps_stem_wgrad_tc(lsps_ctx* ctx, const float* img, const void* dy, float* dw, float* db, int n, int h, int wd,
+                       int stride, cudaStream_t st);
+static bool stem_use_tc(int wd, int stride) {
+  static int simt = -1;
+  if (simt < 0) { const char* e = getenv("LSPS_STEM_SIMT"); simt = (e && e[0] == '1') ? 1 : 0; }
+  const int wo = wd / stride;
+  return !simt && (wo == 64 || wo == 128);
+}
+
 #define ST_(s) static_cast<cudaStream_t>(s)
 #define REQUIRE(ctx, cond, code, msg) \
   do { if (!(cond)) return lsps_set_error(ctx, code, msg); } while (0)
@@ -711,6 +731,8 @@ extern "C" int lsps_stem_fwd(lsps_ctx* ctx, const float* img, const float* w, co
   REQUIRE(ctx, img && w && bias && y, LSPS_E_ARG, "stem_fwd: null");
   REQUIRE(ctx, (stride == 1 || stride == 2) && h % (ST * stride) == 0 && wd % (ST * stride) == 0 && n > 0, LSPS_E_SHAPE,
           "stem_fwd: h,w must be multiples of 16*stride");
+  if (stem_use_tc(wd, stride) && (h / stride) % (128 / (wd / stride)) == 0)
+    return lsps_stem_fwd_tc(ctx, img, w, bias, y, n, h, wd, stride, slope, ST_(st));
   dim3 grid(wd / stride / ST, h / stride / ST, n);
   if (stride == 1) stem_fwd_kernel<1><<<grid, 256, 0, ST_(st)>>>(img, w, bias, static_cast<bf16*>(y), h, wd, slope);
   else stem_fwd_kernel<2><<<grid, 256, 0, ST_(st)>>>(img, w, bias, static_cast<bf16*>(y), h, wd, slope);
@@ -723,6 +745,8 @@ extern "C" int lsps_stem_wgrad(lsps_ctx* ctx, const float* img, const void* dy, 
   REQUIRE(ctx, img && dy && dw, LSPS_E_ARG, "stem_wgrad: null");
   REQUIRE(ctx, (stride == 1 || stride == 2) && h % (ST * stride) == 0 && wd % (ST * stride) == 0 && n > 0, LSPS_E_SHAPE,
           "stem_wgrad: shape");
+  if (stem_use_tc(wd, stride) && (h / stride) % (128 / (wd / stride)) == 0)
+    return lsps_stem_wgrad_tc(ctx, img, dy, dw, db, n, h, wd, stride, ST_(st));
   const int total = (wd / stride / ST) * (h / stride / ST) * n;
   const int grid = total < 2 * ctx->num_sms ? total : 2 * ctx->num_sms;
   if (stride == 1) stem_wgrad_kernel<1><<<grid, 256, 0, ST_(st)>>>(img, static_cast<const bf16*>(dy), dw, db, n, h, wd);
@@ -770,7 +794,7 @@ extern "C" int lsps_instnorm_fwd(lsps_ctx* ctx, const void* h, const void* res, 
                                  int c, int mode, float eps, float slope, lsps_stream st) {
   REQUIRE(ctx, h && y && stats && (mode == 0 || res), LSPS_E_ARG, "instnorm_fwd: null");
   REQUIRE(ctx, n > 0 && hw > 0 && c % 64 == 0, LSPS_E_SHAPE, "instnorm_fwd: c must be a multiple of 64");
-  instnorm_fwd_kernel<<<dim3(c / 64, n), 256, 0, ST_(st)>>>(static_cast<const bf16*>(h), static_cast<const bf16*>(res),
+  instnorm_fwd_kernel<<<dim3(c / 64, n), 512, 0, ST_(st)>>>(static_cast<const bf16*>(h), static_cast<const bf16*>(res),
                                                           static_cast<bf16*>(y), stats, hw, c, mode, eps, slope);
   LSPS_CHECK_LAUNCH(ctx, "instnorm_fwd");
   return LSPS_OK;
@@ -779,7 +803,7 @@ extern "C" int lsps_instnorm_bwd(lsps_ctx* ctx, const void* dy, const void* h, c
                                  int hw, int c, int mode, float slope, lsps_stream st) {
   REQUIRE(ctx, dy && h && stats && dh, LSPS_E_ARG, "instnorm_bwd: null");
   REQUIRE(ctx, n > 0 && hw > 0 && c % 64 == 0, LSPS_E_SHAPE, "instnorm_bwd: c must be a multiple of 64");
-  instnorm_bwd_kernel<<<dim3(c / 64, n), 256, 0, ST_(st)>>>(static_cast<const bf16*>(dy), static_cast<const bf16*>(h),
+  instnorm_bwd_kernel<<<dim3(c / 64, n), 512, 0, ST_(st)>>>(static_cast<const bf16*>(dy), static_cast<const bf16*>(h),
                                                           stats, static_cast<bf16*>(dh), hw, c, mode, slope);
   LSPS_CHECK_LAUNCH(ctx, "instnorm_bwd");
   return LSPS_OK;

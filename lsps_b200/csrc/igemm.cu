@@ -59,7 +59,10 @@ extern "C" int lsps_ctx_create(lsps_ctx** out, int device) {
   *out = ctx;
   return LSPS_OK;
 }
-extern "C" void lsps_ctx_destroy(lsps_ctx* ctx) { delete ctx; }
+extern "C" void lsps_ctx_destroy(lsps_ctx* ctx) {
+  if (ctx && ctx->ws) cudaFree(ctx->ws);
+  delete ctx;
+}
 extern "C" const char* lsps_last_error(lsps_ctx* ctx) { return ctx ? ctx->err.c_str() : "null ctx"; }
 extern "C" long long lsps_launch_count(lsps_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
@@ -132,7 +135,8 @@ struct IgemmCfg {
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
   static constexpr int STAGES = (196608 / STAGE_BYTES) > 8 ? 8 : (196608 / STAGE_BYTES);
   static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+  static constexpr int BIAS_BYTES = 2048 * 4;  // whole bias vector (Cout <= 2048) staged once per CTA
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256 + BIAS_BYTES;
 };
 
 // warp 0: TMA producer | warp 1: TMEM owner + MMA issuer | warps 2-5: epilogue (TMEM -> regs -> global)
@@ -151,9 +155,14 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   uint64_t* tfull = empty + STAGES;
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  float* sbias = reinterpret_cast<float*>(base + STAGES * Cfg::STAGE_BYTES + 256);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int rank = CG == 2 ? (int)cluster_ctarank() : 0;  // position in the CTA pair
+  if (p.flags & LSPS_EP_BIAS) {
+    const int nc_total = p.tiles_n * BN;
+    for (int i = threadIdx.x; i < nc_total; i += blockDim.x) sbias[i] = p.bias[i];
+  }
   const bool leader = rank == 0;
   if (threadIdx.x == 0) {
     for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
@@ -182,7 +191,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     if (lane == 0) {
       int stage = 0; uint32_t ph = 0;
       for (int t = worker; t < total; t += nworkers) {
-        const int pi = t % p.nphases, r = t / p.nphases;
+        const int pi = t / per_phase, r = t - pi * per_phase;
         const int nt = r / groups_m, mt = (r - nt * groups_m) * CG + rank;
         const int tx = mt % p.tiles_x, ty = (mt / p.tiles_x) % p.tiles_y, ti = mt / (p.tiles_x * p.tiles_y);
         const int x0 = tx << p.twl, y0 = ty << p.thl, n0 = ti * p.nb;
@@ -212,7 +221,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       constexpr uint32_t idesc = umma_idesc_bf16(128 * CG, BN, 0, 0);
       int stage = 0; uint32_t ph = 0; int it = 0;
       for (int t = worker; t < total; t += nworkers, ++it) {
-        const int pi = t % p.nphases;
+        const int pi = t / per_phase;
         const int nk = p.ph[pi].ntaps * p.kchunks;
         const int acc = it & 1; const uint32_t accph = (it >> 1) & 1;
         mbar_wait(&tempty[acc], accph ^ 1);
@@ -243,7 +252,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int xl = row & tw_mask, yl = (row >> p.twl) & th_mask, nl = row >> (p.twl + p.thl);
     int it = 0;
     for (int t = worker; t < total; t += nworkers, ++it) {
-      const int pi = t % p.nphases, r = t / p.nphases;
+      const int pi = t / per_phase, r = t - pi * per_phase;
       const int nt = r / groups_m, mt = (r - nt * groups_m) * CG + rank;
       const int tx = mt % p.tiles_x, ty = (mt / p.tiles_x) % p.tiles_y, ti = mt / (p.tiles_x * p.tiles_y);
       const int x0 = tx << p.twl, y0 = ty << p.thl, n = ti * p.nb + nl;
@@ -252,23 +261,56 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const long long off = (long long)n * p.o_n + (long long)((y0 + yl) * p.o_sy + P.oa) * p.o_y +
                             (long long)((x0 + xl) * p.o_sx + P.ob) * p.o_x + nt * BN;
       const int acc = it & 1; const uint32_t accph = (it >> 1) & 1;
+      const bool use_add = valid && (p.flags & LSPS_EP_ADD), use_mask = valid && (p.flags & LSPS_EP_MASK);
+      const uint4* a4 = reinterpret_cast<const uint4*>(p.add + off);
+      const uint4* m4 = reinterpret_cast<const uint4*>(p.mask + off);
+      uint4* o4 = reinterpret_cast<uint4*>(p.out + off);
+      // software pipeline: the global loads (residual / mask) and the TMEM load of chunk c+1 are in flight while
+      // chunk c is converted and stored; TMEM is handed back to the MMA warp as soon as its last column is in registers
+      uint4 ga[4], gm[4];
+      if (use_add) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) ga[j] = __ldg(a4 + j);
+      }
+      if (use_mask) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) gm[j] = __ldg(m4 + j);
+      }
       mbar_wait(&tfull[acc], accph);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
+      uint32_t v[32];
+      tmem_ld32(taddr, v);
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += 32) {
-        uint32_t v[32];
-        tmem_ld32(taddr + c0, v);
+        float f[32];
+        uint4 ca[4], cm[4];
         tmem_ld_wait();
-        if (valid) {
-          float f[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { ca[j] = ga[j]; cm[j] = gm[j]; }
+        if (c0 + 32 < BN) {
+          tmem_ld32(taddr + c0 + 32, v);
+          if (use_add) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) ga[j] = __ldg(a4 + (c0 + 32) / 8 + j);
+          }
+          if (use_mask) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) gm[j] = __ldg(m4 + (c0 + 32) / 8 + j);
+          }
+        } else {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) { if (CG == 2) mbar_arrive_leader(&tempty[acc]); else mbar_arrive(&tempty[acc]); }
+        }
+        if (valid) {
           if (p.flags & LSPS_EP_BIAS) {
-            const float4* b4 = reinterpret_cast<const float4*>(p.bias + nt * BN + c0);
+            const float4* b4 = reinterpret_cast<const float4*>(sbias + nt * BN + c0);
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-              const float4 b = __ldg(b4 + j);
+              const float4 b = b4[j];
               f[4 * j] += b.x; f[4 * j + 1] += b.y; f[4 * j + 2] += b.z; f[4 * j + 3] += b.w;
             }
           }
@@ -277,11 +319,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             for (int j = 0; j < 32; ++j) f[j] = f[j] > 0.f ? f[j] : f[j] * p.slope;
           }
           if (p.flags & LSPS_EP_ADD) {
-            const uint4* a4 = reinterpret_cast<const uint4*>(p.add + off + c0);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              const uint4 m = __ldg(a4 + j);
-              const uint32_t w[4] = {m.x, m.y, m.z, m.w};
+              const uint32_t w[4] = {ca[j].x, ca[j].y, ca[j].z, ca[j].w};
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
                 f[8 * j + 2 * k] += bf16lo(w[k]);
@@ -290,11 +330,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             }
           }
           if (p.flags & LSPS_EP_MASK) {
-            const uint4* m4 = reinterpret_cast<const uint4*>(p.mask + off + c0);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              const uint4 m = __ldg(m4 + j);
-              const uint32_t w[4] = {m.x, m.y, m.z, m.w};
+              const uint32_t w[4] = {cm[j].x, cm[j].y, cm[j].z, cm[j].w};
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
                 if (!(bf16lo(w[k]) > 0.f)) f[8 * j + 2 * k] *= p.slope;
@@ -302,7 +340,6 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               }
             }
           }
-          uint4* o4 = reinterpret_cast<uint4*>(p.out + off + c0);
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             uint4 o;
@@ -310,13 +347,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             o.y = pack_bf16x2(f[8 * j + 2], f[8 * j + 3]);
             o.z = pack_bf16x2(f[8 * j + 4], f[8 * j + 5]);
             o.w = pack_bf16x2(f[8 * j + 6], f[8 * j + 7]);
-            o4[j] = o;
+            o4[c0 / 8 + j] = o;
           }
         }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) { if (CG == 2) mbar_arrive_leader(&tempty[acc]); else mbar_arrive(&tempty[acc]); }
     }
   }
   tc_fence_before();
@@ -331,8 +365,10 @@ struct WgradParams {
   int twl, thl, nb;  // K tile = 64 pixels
   int ntaps, co_tiles, ci_tiles, splits;   // co_tiles counts tiles of 128*CG output channels
   int cout, cin;
-  int dbg;
+  int dbg, pf;
   float* dw;
+  float* ws;            // split-K partials [splits][9][cout][cin] (plain stores) or nullptr (red.add into dw)
+  long long ws_stride;  // elements per split
   WTap taps[9];
 };
 constexpr int W_BOX_BYTES = 64 * 128;  // 64 pixels x 64 bf16
@@ -415,6 +451,15 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ CU
         if (CG == 2) tma_load_5d_cg2(s + (2 + j) * W_BOX_BYTES, &tmN, &full[stage], cbase, x0 + T.nx, T.np, y0 + T.ny, n0);
         else tma_load_5d(s + (2 + j) * W_BOX_BYTES, &tmN, &full[stage], cbase, x0 + T.nx, T.np, y0 + T.ny, n0);
       }
+      // both operands of wgrad are streamed from HBM exactly once per (tap, co tile) group; the centre-tap CTAs pull
+      // the boxes of a later K-step into L2 so that the demand loads of all 9 taps hit (prefetch distance p.pf steps)
+      if (p.pf > 0 && tap == 4 && pt + p.pf < pt1 && lane < nboxes) {
+        const int q = pt + p.pf;
+        const int qx = q % p.tiles_x, qy = (q / p.tiles_x) % p.tiles_y, qi = q / (p.tiles_x * p.tiles_y);
+        const int px0 = qx << p.twl, py0 = qy << p.thl, pn0 = qi * p.nb;
+        if (lane < nA) tma_prefetch_5d(&tmM, cot * 128 + lane * 64 + T.mc, px0 + T.mx, T.mp, py0 + T.my, pn0);
+        else tma_prefetch_5d(&tmN, cit * BN + (rank * Cfg::NB_BOXES + lane - nA) * 64 + T.nc, px0 + T.nx, T.np, py0 + T.ny, pn0);
+      }
       if (++stage == STAGES) { stage = 0; ph ^= 1; }
     }
   } else if (warp == 1) {
@@ -444,26 +489,49 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ CU
     const int co = cot * 128 + q * 32 + lane;
     mbar_wait(tfull, 0);
     tc_fence_after();
-    float* dst = p.dw + ((long long)tap * p.cout + co) * p.cin + cit * BN;
+    const long long eoff = ((long long)tap * p.cout + co) * p.cin + cit * BN;
+    float* dst = p.ws ? p.ws + (long long)split * p.ws_stride + eoff : p.dw + eoff;
     const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    uint32_t v[32];
+    tmem_ld32(taddr, v);
 #pragma unroll 1
     for (int c0 = 0; c0 < BN; c0 += 32) {
-      uint32_t v[32];
-      tmem_ld32(taddr + c0, v);
+      float f[32];
       tmem_ld_wait();
-      if (co < p.cout) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + c0 + 4 * j),
-                       "f"(__uint_as_float(v[4 * j])), "f"(__uint_as_float(v[4 * j + 1])),
-                       "f"(__uint_as_float(v[4 * j + 2])), "f"(__uint_as_float(v[4 * j + 3]))
-                       : "memory");
+      for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+      if (c0 + 32 < BN) tmem_ld32(taddr + c0 + 32, v);
+      if (co < p.cout) {
+        if (p.ws) {  // exclusive slice of the workspace: plain 16-byte stores (a reduce kernel folds the splits)
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<float4*>(dst + c0 + 4 * j) = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + c0 + 4 * j), "f"(f[4 * j]),
+                         "f"(f[4 * j + 1]), "f"(f[4 * j + 2]), "f"(f[4 * j + 3])
+                         : "memory");
+        }
       }
     }
   }
   tc_fence_before();
   if (CG == 2) cluster_sync_all(); else __syncthreads();
   if (warp == 1) { if (CG == 2) tmem_dealloc_cg2(tmem_base, Cfg::TMEM_COLS); else tmem_dealloc(tmem_base, Cfg::TMEM_COLS); }
+}
+
+// dw += sum over splits of the workspace partials
+__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float4* __restrict__ ws, float4* __restrict__ dw,
+                                                           long long n4, long long stride4, int splits) {
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n4; i += (long long)gridDim.x * 256) {
+    float4 a = dw[i];
+    for (int s = 0; s < splits; ++s) {
+      const float4 b = __ldg(ws + s * stride4 + i);
+      a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+    }
+    dw[i] = a;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ host side
@@ -504,6 +572,16 @@ enum Dir { FWD = 0, DGRAD = 1 };
 inline int lsps_force_cg() {
   static int v = -1;
   if (v < 0) { const char* e = getenv("LSPS_FORCE_CG"); v = e ? atoi(e) : 0; }
+  return v;
+}
+inline bool lsps_no_ws() {  // split-K workspace + reduce kernel instead of red.add: measured no faster (r01) -> opt-in
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("LSPS_WS"); v = (e && e[0] == '1') ? 0 : 1; }
+  return v == 1;
+}
+inline int lsps_pf() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("LSPS_PF"); v = e ? atoi(e) : 0; }
   return v;
 }
 inline int lsps_dbg() {
@@ -698,7 +776,7 @@ extern "C" int lsps_conv_wgrad(lsps_ctx* ctx, const lsps_conv_shape* s, const vo
   WgradParams p{};
   p.tiles_x = wg / g.tw; p.tiles_y = hg / g.th; p.tiles_i = (n + g.nb - 1) / g.nb;
   p.twl = g.twl; p.thl = g.thl; p.nb = g.nb;
-  p.ntaps = 9; p.cout = cout; p.cin = cin; p.dw = dw; p.dbg = lsps_dbg();
+  p.ntaps = 9; p.cout = cout; p.cin = cin; p.dw = dw; p.dbg = lsps_dbg(); p.pf = lsps_pf();
   const int bn = cin % 256 == 0 ? 256 : (cin % 128 == 0 ? 128 : 64);
   // CTA pairs: 256 output channels per pair, each CTA stages half of the x tile (needs >= 128 input channels)
   const int cg = (lsps_use_pairs() && cout % 256 == 0 && bn >= 128) ? 2 : 1;
@@ -725,17 +803,35 @@ extern "C" int lsps_conv_wgrad(lsps_ctx* ctx, const lsps_conv_shape* s, const vo
   if (splits < 1) splits = 1;
   if (splits > ptiles) splits = ptiles;
   p.splits = splits;
+  // split-K partials go to a workspace with plain stores and are folded by a small reduce kernel: per-SM fp32 red
+  // throughput (~1.3 cycles per element) made the 128x256 red.add epilogue cost ~25 us per CTA
+  p.ws = nullptr; p.ws_stride = (long long)9 * cout * cin;
+  if (splits > 1 && !lsps_no_ws()) {
+    const size_t need = (size_t)splits * p.ws_stride * sizeof(float);
+    if (ctx->ws_bytes < need) {
+      if (ctx->ws) cudaFree(ctx->ws);
+      ctx->ws = nullptr; ctx->ws_bytes = 0;
+      if (cudaMalloc(&ctx->ws, need) != cudaSuccess) return lsps_set_error(ctx, LSPS_E_CUDA, "wgrad workspace alloc of %zu bytes failed", need);
+      ctx->ws_bytes = need;
+    }
+    p.ws = static_cast<float*>(ctx->ws);
+  }
   CUtensorMap tmM, tmN;
   // M side: dy (cout channels) ; N side: x (cin channels)
   int rc = act_tmap(ctx, dy, n, ho, wo, cout, kind == LSPS_DECONV_S2, g, &tmM);
   if (rc) return rc;
   rc = act_tmap(ctx, x, n, h, w, cin, kind == LSPS_CONV_S2, g, &tmN);
   if (rc) return rc;
-  if (cg == 2) {
-    if (bn == 256) return launch_wgrad<256, 2>(ctx, tmM, tmN, p, st);
-    return launch_wgrad<128, 2>(ctx, tmM, tmN, p, st);
+  if (cg == 2) rc = bn == 256 ? launch_wgrad<256, 2>(ctx, tmM, tmN, p, st) : launch_wgrad<128, 2>(ctx, tmM, tmN, p, st);
+  else rc = bn == 256 ? launch_wgrad<256, 1>(ctx, tmM, tmN, p, st)
+                      : (bn == 128 ? launch_wgrad<128, 1>(ctx, tmM, tmN, p, st) : launch_wgrad<64, 1>(ctx, tmM, tmN, p, st));
+  if (rc) return rc;
+  if (p.ws) {
+    const long long n4 = p.ws_stride / 4;
+    long long grid = (n4 + 255) / 256;
+    if (grid > 4LL * ctx->num_sms) grid = 4LL * ctx->num_sms;
+    wgrad_reduce_kernel<<<(unsigned)grid, 256, 0, st>>>(reinterpret_cast<const float4*>(p.ws), reinterpret_cast<float4*>(dw), n4, n4, splits);
+    LSPS_CHECK_LAUNCH(ctx, "wgrad_reduce");
   }
-  if (bn == 256) return launch_wgrad<256, 1>(ctx, tmM, tmN, p, st);
-  if (bn == 128) return launch_wgrad<128, 1>(ctx, tmM, tmN, p, st);
-  return launch_wgrad<64, 1>(ctx, tmM, tmN, p, st);
+  return LSPS_OK;
 }
