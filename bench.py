@@ -134,6 +134,17 @@ def main():
     if args.impl == "reference":
         return run_reference(args)
 
+    # keep stdout clean for the ONE JSON line: NCCL / torch.distributed print banners ("NCCL version ...") to fd 1
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        print(json.dumps(obj), flush=True)
+        os.dup2(2, 1)
+
     import torch
     import torch.distributed as dist
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -190,7 +201,7 @@ def main():
     light = os.environ.get("LSPS_BENCH_LIGHT") == "1"     # profiler runs: timed loop only
     if light:
         if rank == 0:
-            print(json.dumps({"light": True, "ms_per_step": ms / K, "gpu_launches": launches, "value": value}))
+            emit({"light": True, "ms_per_step": ms / K, "gpu_launches": launches, "value": value})
         return
     for _ in range(2):
         step_e2e()
@@ -262,7 +273,7 @@ def main():
         "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
         "step_tflops": GFLOP_PER_PAIR * B / 1e3 / (ms / K / 1e3) * world,
     }
-    print(json.dumps(out))
+    emit(out)
     if world > 1:
         dist.destroy_process_group()
 

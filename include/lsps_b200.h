@@ -74,9 +74,10 @@ int lsps_head_bwd(lsps_ctx*, const void* x, const float* w, const float* out, co
 /* mode 0: y = lrelu(IN(h)) ; mode 1: y = res + IN(h).  h,y,res bf16 [n,hw,c]; stats f32 [n,c,2] = (mean, rstd) out */
 int lsps_instnorm_fwd(lsps_ctx*, const void* h, const void* res, void* y, float* stats, int n, int hw, int c, int mode,
                       float eps, float slope, lsps_stream);
-/* dh = IN_backward(g) with g = dy (mode 1) or dy*lrelu'(IN(h)) (mode 0) */
+/* dh = IN_backward(g) with g = dy (mode 1) or dy*lrelu'(IN(h)) (mode 0); db (may be NULL): db[c] += sum over (n, hw) of
+   dh -- the bias gradient of the conv that produced h, fused here instead of a separate colsum pass */
 int lsps_instnorm_bwd(lsps_ctx*, const void* dy, const void* h, const float* stats, void* dh, int n, int hw, int c,
-                      int mode, float slope, lsps_stream);
+                      int mode, float slope, float* db, lsps_stream);
 
 /* ---- GaussianNoiseLayer + KL term (common_net.py:36-40; lsps_trainer.py:55-58): z = x + noise, acc[0] += sum z^2 */
 int lsps_noise_kl_fwd(lsps_ctx*, const void* x, const float* noise, void* z, float* acc, long long n, lsps_stream);

@@ -360,7 +360,8 @@ __global__ void __launch_bounds__(512) instnorm_fwd_kernel(const bf16* __restric
 
 __global__ void __launch_bounds__(512) instnorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ h,
                                                           const float* __restrict__ stats, bf16* __restrict__ dh,
-                                                          int hw, int c, int mode, float slope) {
+                                                          int hw, int c, int mode, float slope,
+                                                          float* __restrict__ db) {
   __shared__ float red[64][64];
   __shared__ float s_a[64], s_b[64];
   const int n = blockIdx.y, cg = blockIdx.x;
@@ -386,9 +387,9 @@ __global__ void __launch_bounds__(512) instnorm_bwd_kernel(const bf16* __restric
   }
   in_reduce64(sg, red, s_a);
   in_reduce64(sgx, red, s_b);
-  float mg[8], mgx[8];
+  float mg[8], mgx[8], sdb[8];
 #pragma unroll
-  for (int k = 0; k < 8; ++k) { mg[k] = s_a[oct * 8 + k] / hw; mgx[k] = s_b[oct * 8 + k] / hw; }
+  for (int k = 0; k < 8; ++k) { mg[k] = s_a[oct * 8 + k] / hw; mgx[k] = s_b[oct * 8 + k] / hw; sdb[k] = 0.f; }
 #pragma unroll 8
   for (int p = pl; p < hw; p += 64) {
     float f[8], g[8];
@@ -400,7 +401,18 @@ __global__ void __launch_bounds__(512) instnorm_bwd_kernel(const bf16* __restric
       const float gg = (mode == 0 && !(xh > 0.f)) ? g[k] * slope : g[k];
       f[k] = rstd[k] * (gg - mg[k] - xh * mgx[k]);
     }
-    *reinterpret_cast<uint4*>(dh + base + (long long)p * c) = pack8(f);
+    const uint4 u = pack8(f);
+    *reinterpret_cast<uint4*>(dh + base + (long long)p * c) = u;
+    if (db) {  // bias gradient of the conv that produced h: column sum of the (bf16-rounded) dh -- analytically zero
+      float r[8];
+      unpack8(u, r);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) sdb[k] += r[k];
+    }
+  }
+  if (db) {
+    in_reduce64(sdb, red, s_a);
+    if (threadIdx.x < 64) atomicAdd(db + cg * 64 + threadIdx.x, s_a[threadIdx.x]);
   }
 }
 
@@ -714,6 +726,8 @@ int lsps_stem_fwd_tc(lsps_ctx* ctx, const float* img, const float* w, const floa
                      int stride, float slope, cudaStream_t st);
 int lsps_stem_wgrad_tc(lsps_ctx* ctx, const float* img, const void* dy, float* dw, float* db, int n, int h, int wd,
                        int stride, cudaStream_t st);
+int lsps_stem_dgrad_tc(lsps_ctx* ctx, const void* dy, const float* w, float* dimg, int n, int h, int wd, int stride,
+                       int accumulate, cudaStream_t st);
 static bool stem_use_tc(int wd, int stride) {
   static int simt = -1;
   if (simt < 0) { const char* e = getenv("LSPS_STEM_SIMT"); simt = (e && e[0] == '1') ? 1 : 0; }
@@ -760,6 +774,7 @@ extern "C" int lsps_stem_dgrad(lsps_ctx* ctx, const void* dy, const float* w, fl
   REQUIRE(ctx, dy && w && dimg, LSPS_E_ARG, "stem_dgrad: null");
   REQUIRE(ctx, (stride == 1 || stride == 2) && h % (ST * stride) == 0 && wd % (ST * stride) == 0 && n > 0, LSPS_E_SHAPE,
           "stem_dgrad: shape");
+  if (stem_use_tc(wd, stride)) return lsps_stem_dgrad_tc(ctx, dy, w, dimg, n, h, wd, stride, accumulate, ST_(st));
   dim3 grid(wd / ST, h / ST, n);
   const int de = stride == 1 ? ST + 6 : (ST + 6) / 2 + 1;
   const int smem = 49 * 64 * 4 + de * de * 128;
@@ -800,11 +815,11 @@ extern "C" int lsps_instnorm_fwd(lsps_ctx* ctx, const void* h, const void* res, 
   return LSPS_OK;
 }
 extern "C" int lsps_instnorm_bwd(lsps_ctx* ctx, const void* dy, const void* h, const float* stats, void* dh, int n,
-                                 int hw, int c, int mode, float slope, lsps_stream st) {
+                                 int hw, int c, int mode, float slope, float* db, lsps_stream st) {
   REQUIRE(ctx, dy && h && stats && dh, LSPS_E_ARG, "instnorm_bwd: null");
   REQUIRE(ctx, n > 0 && hw > 0 && c % 64 == 0, LSPS_E_SHAPE, "instnorm_bwd: c must be a multiple of 64");
   instnorm_bwd_kernel<<<dim3(c / 64, n), 512, 0, ST_(st)>>>(static_cast<const bf16*>(dy), static_cast<const bf16*>(h),
-                                                          stats, static_cast<bf16*>(dh), hw, c, mode, slope);
+                                                          stats, static_cast<bf16*>(dh), hw, c, mode, slope, db);
   LSPS_CHECK_LAUNCH(ctx, "instnorm_bwd");
   return LSPS_OK;
 }

@@ -245,6 +245,123 @@ __global__ void __launch_bounds__(128) stem_wgrad_tc_kernel(const float* __restr
   if (warp == 0) tmem_dealloc(tmem, 64);
 }
 
+// ------------------------------------------------------------------------------------------------ dgrad
+// dimg[y][x] = sum over taps (r,c), channels co of dy[(y+3-r)/S][(x+3-c)/S][co] * W[co][r][c]
+//   step 1 (tensor cores): G[px][tap] = dy[px][0:64] . W[0:64][tap] for every dy pixel that touches the 16x8 input tile
+//                          (one TMA box with halo, zero-filled outside the image)
+//   step 2 (gather)      : each thread owns one input pixel and adds the <= 49 G entries that map onto it.
+template <int S>
+__global__ void __launch_bounds__(128) stem_dgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDy,
+                                                           const float* __restrict__ w, float* __restrict__ dimg,
+                                                           int n, int h, int wd, int accumulate) {
+  constexpr int BW = S == 1 ? 22 : 11, BH = S == 1 ? 14 : 7;  // dy patch touching a 16 x 8 input tile
+  constexpr int ROWS = BW * BH, MT = (ROWS + 127) / 128;
+  constexpr int GP = 49;                                      // G row pitch (odd: conflict-free)
+  constexpr int TCOLS = MT == 1 ? 64 : 256;                   // TMEM columns: one 64-column accumulator per M tile
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* dyb = base;                                        // MT operand tiles of 128 rows
+  uint8_t* wt = base + MT * A_BYTES;                          // [64 tap rows][64 co] bf16, K-major, swizzled
+  float* G = reinterpret_cast<float*>(wt + 8192);
+  uint64_t* full = reinterpret_cast<uint64_t*>(G + MT * 128 * GP);
+  uint64_t* done = full + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
+
+  const int warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) { mbar_init(full, 1); mbar_init(done, 1); fence_barrier_init(); tma_prefetch_desc(&tmDy); }
+  if (warp == 0) { tmem_alloc(tmem_slot, TCOLS); tmem_relinquish(); }
+  if (threadIdx.x < 64) {
+    const int tap = threadIdx.x;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      uint32_t u[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int co = j * 8 + 2 * k;
+        u[k] = tap < 49 ? pack_bf16x2(w[co * 49 + tap], w[(co + 1) * 49 + tap]) : 0u;
+      }
+      *reinterpret_cast<uint4*>(wt + tap * 128 + ((j ^ (tap & 7)) << 4)) = make_uint4(u[0], u[1], u[2], u[3]);
+    }
+  }
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  constexpr uint32_t idesc = umma_idesc_bf16(128, 64, 0, 0);
+
+  const int ho = h / S, wo = wd / S;
+  const int tiles_x = wd / 16, tiles_y = h / 8;
+  const int total = tiles_x * tiles_y * n;
+  const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
+  auto issue_load = [&](int t) {
+    const int bx = t % tiles_x, by = (t / tiles_x) % tiles_y, im_i = t / (tiles_x * tiles_y);
+    const int oxb = S == 1 ? bx * 16 - 3 : bx * 8 - 1, oyb = S == 1 ? by * 8 - 3 : by * 4 - 1;
+    mbar_expect_tx(full, ROWS * 128);
+    tma_load_4d(dyb, &tmDy, full, 0, oxb, oyb, im_i);
+  };
+  if (threadIdx.x == 0 && (int)blockIdx.x < total) issue_load(blockIdx.x);
+  uint32_t phase = 0;
+  for (int t = blockIdx.x; t < total; t += gridDim.x) {
+    const int bx = t % tiles_x, by = (t / tiles_x) % tiles_y, im_i = t / (tiles_x * tiles_y);
+    if (threadIdx.x == 0) {
+      mbar_wait(full, phase);
+      tc_fence_after();
+      const uint32_t a0 = smem_u32(dyb), bw = smem_u32(wt);
+#pragma unroll
+      for (int m = 0; m < MT; ++m)
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_bf16(tmem + m * 64, umma_smem_desc(a0 + m * A_BYTES + k * 32, 0, 1024), umma_smem_desc(bw + k * 32, 0, 1024),
+                    idesc, k > 0 ? 1u : 0u);
+      umma_commit(done);
+    }
+    mbar_wait(done, phase);
+    tc_fence_after();
+    // the dy buffer is free again: fetch the next tile's patch while this one is scattered
+    if (threadIdx.x == 0 && t + (int)gridDim.x < total) issue_load(t + gridDim.x);
+    const uint32_t taddr = tmem + (static_cast<uint32_t>(warp * 32) << 16);
+#pragma unroll
+    for (int m = 0; m < MT; ++m) {
+      const int grow = m * 128 + threadIdx.x;
+#pragma unroll
+      for (int c0 = 0; c0 < 64; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(taddr + m * 64 + c0, v);
+        tmem_ld_wait();
+        if (grow < ROWS) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (c0 + j < 49) G[grow * GP + c0 + j] = __uint_as_float(v[j]);
+        }
+      }
+    }
+    tc_fence_before();
+    __syncthreads();
+    float acc = 0.f;
+#pragma unroll
+    for (int r = 0; r < 7; ++r) {
+      const int ny = ty + 3 - r;
+      if (S == 2 && (ny & 1)) continue;
+      const int prow = S == 1 ? ny + 3 : (ny >> 1) + 1;
+#pragma unroll
+      for (int c = 0; c < 7; ++c) {
+        const int nx = tx + 3 - c;
+        if (S == 2 && (nx & 1)) continue;
+        const int pcol = S == 1 ? nx + 3 : (nx >> 1) + 1;
+        acc += G[(prow * BW + pcol) * GP + r * 7 + c];
+      }
+    }
+    float* o = dimg + ((long long)im_i * h + by * 8 + ty) * wd + bx * 16 + tx;
+    *o = accumulate ? *o + acc : acc;
+    phase ^= 1;
+    __syncthreads();  // G is rewritten by the next tile
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, TCOLS);
+}
+
 template <typename K>
 int set_smem(lsps_ctx* ctx, K kernel, int bytes) {
   cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
@@ -293,5 +410,28 @@ int lsps_stem_wgrad_tc(lsps_ctx* ctx, const float* img, const void* dy, float* d
     stem_wgrad_tc_kernel<2><<<grid, 128, smem, st>>>(img, tm, dw, db, n, h, wd);
   }
   LSPS_CHECK_LAUNCH(ctx, "stem_wgrad_tc");
+  return LSPS_OK;
+}
+
+int lsps_stem_dgrad_tc(lsps_ctx* ctx, const void* dy, const float* w, float* dimg, int n, int h, int wd, int stride,
+                       int accumulate, cudaStream_t st) {
+  const int ho = h / stride, wo = wd / stride;
+  const int rows = stride == 1 ? 22 * 14 : 11 * 7, mt = (rows + 127) / 128;
+  const int smem = 1024 + mt * A_BYTES + 8192 + mt * 128 * 49 * 4 + 64;
+  const int total = (wd / 16) * (h / 8) * n;
+  const int grid = total < ctx->num_sms ? total : ctx->num_sms * (stride == 1 ? 1 : 2);
+  CUtensorMap tm;
+  uint32_t dims[4] = {64u, (uint32_t)wo, (uint32_t)ho, (uint32_t)n};
+  uint32_t box[4] = {64u, stride == 1 ? 22u : 11u, stride == 1 ? 14u : 7u, 1u};
+  int rc = lsps_get_tmap(ctx, dy, 4, dims, box, &tm);
+  if (rc) return rc;
+  if (stride == 1) {
+    if ((rc = set_smem(ctx, stem_dgrad_tc_kernel<1>, smem))) return rc;
+    stem_dgrad_tc_kernel<1><<<grid, 128, smem, st>>>(tm, w, dimg, n, h, wd, accumulate);
+  } else {
+    if ((rc = set_smem(ctx, stem_dgrad_tc_kernel<2>, smem))) return rc;
+    stem_dgrad_tc_kernel<2><<<grid, 128, smem, st>>>(tm, w, dimg, n, h, wd, accumulate);
+  }
+  LSPS_CHECK_LAUNCH(ctx, "stem_dgrad_tc");
   return LSPS_OK;
 }

@@ -61,11 +61,12 @@ class Ops:
                             dx.data_ptr(), _lib.ptr(mask), _lib.ptr(add), flags, SLOPE)
         return dx
 
-    def conv_wgrad(self, S, key, kind, x, dy):
+    def conv_wgrad(self, S, key, kind, x, dy, bias=True):
         n, h, w, cin = x.shape
         ci, co = self._io(S, key, kind)
         self.ctx.conv_wgrad(_shape(kind, n, h, w, ci, co), x.data_ptr(), dy.data_ptr(), S.G(key + ".weight").data_ptr())
-        self.ctx.colsum_bf16(dy.data_ptr(), dy.numel() // co, co, S.G(key + ".bias").data_ptr())
+        if bias:
+            self.ctx.colsum_bf16(dy.data_ptr(), dy.numel() // co, co, S.G(key + ".bias").data_ptr())
 
     # ---- InstanceNorm
     def in_fwd(self, h, mode, res=None, out=None):
@@ -76,10 +77,12 @@ class Ops:
                               SLOPE)
         return y, stats
 
-    def in_bwd(self, dy, h, stats, mode):
+    def in_bwd(self, dy, h, stats, mode, db=None):
+        """db: optional fp32 [c] accumulator for the bias gradient of the conv that produced h (fused column sum)."""
         n, hh, ww, c = h.shape
         dh = torch.empty_like(h)
-        self.ctx.instnorm_bwd(dy.data_ptr(), h.data_ptr(), stats.data_ptr(), dh.data_ptr(), n, hh * ww, c, mode, SLOPE)
+        self.ctx.instnorm_bwd(dy.data_ptr(), h.data_ptr(), stats.data_ptr(), dh.data_ptr(), n, hh * ww, c, mode, SLOPE,
+                              _lib.ptr(db))
         return dh
 
     # ---- LeakyINSResBlock (common_net.py:160-181)
@@ -94,13 +97,13 @@ class Ops:
 
     def res_bwd(self, S, saved, dout, wgrad=True, mask=None, out=None):
         key, x, h1, st1, a1, h2, st2 = saved
-        dh2 = self.in_bwd(dout, h2, st2, 1)
+        dh2 = self.in_bwd(dout, h2, st2, 1, db=S.G(key + ".model.3.bias") if wgrad else None)
         if wgrad:
-            self.conv_wgrad(S, key + ".model.3", CONV_S1, a1, dh2)
+            self.conv_wgrad(S, key + ".model.3", CONV_S1, a1, dh2, bias=False)
         da1 = self.conv_dgrad(S, key + ".model.3", CONV_S1, dh2, a1.shape)
-        dh1 = self.in_bwd(da1, h1, st1, 0)
+        dh1 = self.in_bwd(da1, h1, st1, 0, db=S.G(key + ".model.0.bias") if wgrad else None)
         if wgrad:
-            self.conv_wgrad(S, key + ".model.0", CONV_S1, x, dh1)
+            self.conv_wgrad(S, key + ".model.0", CONV_S1, x, dh1, bias=False)
         return self.conv_dgrad(S, key + ".model.0", CONV_S1, dh1, x.shape, mask=mask, add=dout, out=out)
 
     # ---- stems / head

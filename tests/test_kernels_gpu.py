@@ -105,10 +105,11 @@ def test_stem(ctx, stride, n):
     ctx.stem_wgrad(img.data_ptr(), dyb.data_ptr(), dw.data_ptr(), db.data_ptr(), n, 128, 128, stride)
     assert rel_l2(dw, w.grad.reshape(64, 49)) < 1e-4 and rel_l2(db, b.grad) < 1e-4
     dimg = torch.full((n, 128, 128), 0.5, device="cuda")
+    # tensor-core dgrad: bf16 weights (like every other conv operand), fp32 accumulation -> weight-rounding noise 2^-9
     ctx.stem_dgrad(dyb.data_ptr(), w.data_ptr(), dimg.data_ptr(), n, 128, 128, stride, 0)
-    assert rel_l2(dimg, img.grad[:, 0]) < 1e-4
+    assert rel_l2(dimg, img.grad[:, 0]) < BF16_L2
     ctx.stem_dgrad(dyb.data_ptr(), w.data_ptr(), dimg.data_ptr(), n, 128, 128, stride, 1)
-    assert rel_l2(dimg, 2 * img.grad[:, 0]) < 1e-4
+    assert rel_l2(dimg, 2 * img.grad[:, 0]) < BF16_L2
 
 
 def test_head(ctx):
@@ -151,8 +152,12 @@ def test_instnorm(ctx, mode):
     dy = torch.randn(n, c, hw, hw, device="cuda", generator=g).bfloat16().float()
     y.backward(dy)
     dh = torch.empty_like(hb)
-    ctx.instnorm_bwd(nhwc16(dy).data_ptr(), hb.data_ptr(), stats.data_ptr(), dh.data_ptr(), n, hw * hw, c, mode, SLOPE)
+    db = torch.zeros(c, device="cuda")
+    ctx.instnorm_bwd(nhwc16(dy).data_ptr(), hb.data_ptr(), stats.data_ptr(), dh.data_ptr(), n, hw * hw, c, mode, SLOPE,
+                     db.data_ptr())
     assert rel_l2(nchw32(dh), h.grad) < BF16_L2
+    assert torch.allclose(db, dh.float().sum((0, 1, 2)), atol=1e-3)      # fused bias gradient == column sum of dh
+    ctx.instnorm_bwd(nhwc16(dy).data_ptr(), hb.data_ptr(), stats.data_ptr(), dh.data_ptr(), n, hw * hw, c, mode, SLOPE, None)
 
 
 def test_losses_and_heads(ctx):
