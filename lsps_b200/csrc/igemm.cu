@@ -110,6 +110,7 @@ struct Phase { short tap0, ntaps, oa, ob; };  // output sub-pixel phase (oa, ob)
 struct IgemmParams {
   int tiles_x, tiles_y, tiles_i, tiles_n, nphases;
   int twl, thl, nb;   // M tile = 2^twl x 2^thl pixels x nb images = 128 rows
+  int txl, tyl;       // log2(tiles_x), log2(tiles_y)
   int nimg, kchunks;  // kchunks = K channels / 64
   long long o_n, o_y, o_x;  // output strides (elements)
   int o_sy, o_sx;           // output pixel = (y*o_sy + oa, x*o_sx + ob)
@@ -129,134 +130,52 @@ constexpr int A_STAGE_BYTES = 128 * 128;  // 128 rows x 64 bf16
 // CG = 1: one CTA per 128 x BN tile.  CG = 2: a CTA pair (cluster of 2, tcgen05 cta_group::2) per 256 x BN tile --
 // each CTA stages its own 128 rows of A and HALF of the weight tile, one MMA of M=256 reads both halves, so the
 // shared-memory fill + read traffic per MAC drops by a third and the pipeline gets 6 stages instead of 4.
-template <int BN, int CG>
+// KCH = 64-channel chunks per pipeline stage: every stage costs one barrier round trip and one tcgen05.commit (a drain
+// bubble in the tensor pipe), so the MMA-bound shapes stage 128 channels (8 MMAs) per handshake instead of 64 (4 MMAs).
+template <int BN, int CG, int KCH = 1>
 struct IgemmCfg {
-  static constexpr int B_STAGE_BYTES = (BN / CG) * 128;
-  static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+  static constexpr int B_CHUNK_BYTES = (BN / CG) * 128;
+  static constexpr int B_STAGE_BYTES = KCH * B_CHUNK_BYTES;
+  static constexpr int A_STAGE = KCH * A_STAGE_BYTES;
+  static constexpr int STAGE_BYTES = A_STAGE + B_STAGE_BYTES;
   static constexpr int STAGES = (196608 / STAGE_BYTES) > 8 ? 8 : (196608 / STAGE_BYTES);
   static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
   static constexpr int BIAS_BYTES = 2048 * 4;  // whole bias vector (Cout <= 2048) staged once per CTA
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256 + BIAS_BYTES;
+  static constexpr int KTAB_BYTES = 9 * 32 * 16;  // K-step table (<= 9 taps x 32 chunks)
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256 + BIAS_BYTES + KTAB_BYTES;
 };
 
-// warp 0: TMA producer | warp 1: TMEM owner + MMA issuer | warps 2-5: epilogue (TMEM -> regs -> global)
+// tile index -> (phase, n tile, m tile, pixel origin); the M grid dims are powers of two
+struct TileCoord { int pi, nt, mt, x0, y0, ti; };
+__device__ __forceinline__ TileCoord decode_tile(const IgemmParams& p, int t, int per_phase, int groups_m, int cg, int rank) {
+  TileCoord c;
+  int r = t;
+  c.pi = 0;
+  if (p.nphases > 1) { c.pi = t / per_phase; r = t - c.pi * per_phase; }
+  c.nt = 0;
+  int mg = r;
+  if (p.tiles_n > 1) { c.nt = r / groups_m; mg = r - c.nt * groups_m; }
+  c.mt = mg * cg + rank;
+  const int tx = c.mt & (p.tiles_x - 1), ty = (c.mt >> p.txl) & (p.tiles_y - 1);
+  c.ti = c.mt >> (p.txl + p.tyl);
+  c.x0 = tx << p.twl; c.y0 = ty << p.thl;
+  return c;
+}
+
+// Epilogue role (4 warps): TMEM -> registers -> (+bias, LeakyReLU, +residual gradient, *lrelu'(mask)) -> bf16 -> global.
 template <int BN, int CG>
-__global__ void __launch_bounds__(192, 1)
-conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                  const __grid_constant__ IgemmParams p) {
-  using Cfg = IgemmCfg<BN, CG>;
-  constexpr int STAGES = Cfg::STAGES;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sA = base;
-  uint8_t* sB = base + STAGES * A_STAGE_BYTES;
-  uint64_t* full = reinterpret_cast<uint64_t*>(base + STAGES * Cfg::STAGE_BYTES);
-  uint64_t* empty = full + STAGES;
-  uint64_t* tfull = empty + STAGES;
-  uint64_t* tempty = tfull + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
-  float* sbias = reinterpret_cast<float*>(base + STAGES * Cfg::STAGE_BYTES + 256);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int rank = CG == 2 ? (int)cluster_ctarank() : 0;  // position in the CTA pair
-  if (p.flags & LSPS_EP_BIAS) {
-    const int nc_total = p.tiles_n * BN;
-    for (int i = threadIdx.x; i < nc_total; i += blockDim.x) sbias[i] = p.bias[i];
-  }
-  const bool leader = rank == 0;
-  if (threadIdx.x == 0) {
-    for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4 * CG); }
-    fence_barrier_init();
-    tma_prefetch_desc(&tmA);
-    tma_prefetch_desc(&tmB);
-  }
-  if (warp == 1) {
-    if (CG == 2) { tmem_alloc_cg2(tmem_slot, Cfg::TMEM_COLS); tmem_relinquish_cg2(); }
-    else { tmem_alloc(tmem_slot, Cfg::TMEM_COLS); tmem_relinquish(); }
-  }
-  tc_fence_before();
-  if (CG == 2) cluster_sync_all(); else __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  // work items: (phase, n tile, group of CG consecutive m tiles); a phantom m tile (odd count) loads zeros, stores nothing
-  const int tiles_m = p.tiles_x * p.tiles_y * p.tiles_i;
-  const int groups_m = (tiles_m + CG - 1) / CG;
-  const int per_phase = groups_m * p.tiles_n;
-  const int total = per_phase * p.nphases;
-  const int worker = blockIdx.x / CG, nworkers = gridDim.x / CG;
-
-  if (warp == 0) {
-    if (lane == 0) {
-      int stage = 0; uint32_t ph = 0;
-      for (int t = worker; t < total; t += nworkers) {
-        const int pi = t / per_phase, r = t - pi * per_phase;
-        const int nt = r / groups_m, mt = (r - nt * groups_m) * CG + rank;
-        const int tx = mt % p.tiles_x, ty = (mt / p.tiles_x) % p.tiles_y, ti = mt / (p.tiles_x * p.tiles_y);
-        const int x0 = tx << p.twl, y0 = ty << p.thl, n0 = ti * p.nb;
-        const Phase P = p.ph[pi];
-        for (int tp = 0; tp < P.ntaps; ++tp) {
-          const Tap T = p.taps[P.tap0 + tp];
-          for (int kc = 0; kc < p.kchunks; ++kc) {
-            mbar_wait(&empty[stage], ph ^ 1);
-            if (p.dbg & 2) {
-              if (leader) mbar_arrive(&full[stage]);
-            } else if (CG == 2) {
-              if (leader) mbar_expect_tx(&full[stage], 2 * Cfg::STAGE_BYTES);  // both CTAs' boxes land on the leader's barrier
-              tma_load_5d_cg2(sA + stage * A_STAGE_BYTES, &tmA, &full[stage], kc * 64 + T.ac, x0 + T.ax, T.ap, y0 + T.ay, n0);
-              tma_load_2d_cg2(sB + stage * Cfg::B_STAGE_BYTES, &tmB, &full[stage], kc * 64, T.brow + nt * BN + rank * (BN / 2));
-            } else {
-              mbar_expect_tx(&full[stage], Cfg::STAGE_BYTES);
-              tma_load_5d(sA + stage * A_STAGE_BYTES, &tmA, &full[stage], kc * 64 + T.ac, x0 + T.ax, T.ap, y0 + T.ay, n0);
-              tma_load_2d(sB + stage * Cfg::B_STAGE_BYTES, &tmB, &full[stage], kc * 64, T.brow + nt * BN);
-            }
-            if (++stage == STAGES) { stage = 0; ph ^= 1; }
-          }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    if (lane == 0 && leader) {
-      constexpr uint32_t idesc = umma_idesc_bf16(128 * CG, BN, 0, 0);
-      int stage = 0; uint32_t ph = 0; int it = 0;
-      for (int t = worker; t < total; t += nworkers, ++it) {
-        const int pi = t / per_phase;
-        const int nk = p.ph[pi].ntaps * p.kchunks;
-        const int acc = it & 1; const uint32_t accph = (it >> 1) & 1;
-        mbar_wait(&tempty[acc], accph ^ 1);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * BN;
-        for (int ks = 0; ks < nk; ++ks) {
-          mbar_wait(&full[stage], ph);
-          tc_fence_after();
-          const uint32_t a_addr = smem_u32(sA + stage * A_STAGE_BYTES);
-          const uint32_t b_addr = smem_u32(sB + stage * Cfg::B_STAGE_BYTES);
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            if (p.dbg & 1) break;
-            const uint64_t ad = umma_smem_desc(a_addr + k * 32, 0, 1024), bd = umma_smem_desc(b_addr + k * 32, 0, 1024);
-            if (CG == 2) umma_bf16_cg2(d_tmem, ad, bd, idesc, (ks | k) != 0 ? 1u : 0u);
-            else umma_bf16(d_tmem, ad, bd, idesc, (ks | k) != 0 ? 1u : 0u);
-          }
-          if (CG == 2) umma_commit_cg2(&empty[stage]); else umma_commit(&empty[stage]);
-          if (++stage == STAGES) { stage = 0; ph ^= 1; }
-        }
-        if (CG == 2) umma_commit_cg2(&tfull[acc]); else umma_commit(&tfull[acc]);
-      }
-    }
-  } else {
+__device__ __forceinline__ void epilogue_role(const IgemmParams& p, const float* sbias, uint32_t tmem_base,
+                                              uint64_t* tfull, uint64_t* tempty, int warp, int lane, int rank,
+                                              int worker, int nworkers, int groups_m, int per_phase, int total) {
     const int q = warp & 3;  // TMEM lane quarter this warp may read
     const int row = q * 32 + lane;
     const int tw_mask = (1 << p.twl) - 1, th_mask = (1 << p.thl) - 1;
     const int xl = row & tw_mask, yl = (row >> p.twl) & th_mask, nl = row >> (p.twl + p.thl);
     int it = 0;
     for (int t = worker; t < total; t += nworkers, ++it) {
-      const int pi = t / per_phase, r = t - pi * per_phase;
-      const int nt = r / groups_m, mt = (r - nt * groups_m) * CG + rank;
-      const int tx = mt % p.tiles_x, ty = (mt / p.tiles_x) % p.tiles_y, ti = mt / (p.tiles_x * p.tiles_y);
-      const int x0 = tx << p.twl, y0 = ty << p.thl, n = ti * p.nb + nl;
-      const Phase P = p.ph[pi];
+      const TileCoord tc = decode_tile(p, t, per_phase, groups_m, CG, rank);
+      const int nt = tc.nt, x0 = tc.x0, y0 = tc.y0, n = tc.ti * p.nb + nl;
+      const Phase P = p.ph[tc.pi];
       const bool valid = n < p.nimg;
       const long long off = (long long)n * p.o_n + (long long)((y0 + yl) * p.o_sy + P.oa) * p.o_y +
                             (long long)((x0 + xl) * p.o_sx + P.ob) * p.o_x + nt * BN;
@@ -352,10 +271,269 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         }
       }
     }
+}
+
+// warp 0: TMA producer | warp 1: TMEM owner + MMA issuer | warps 2-5: epilogue (TMEM -> regs -> global)
+template <int BN, int CG, int KCH>
+__global__ void __launch_bounds__(192, 1)
+conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                  const __grid_constant__ IgemmParams p) {
+  using Cfg = IgemmCfg<BN, CG, KCH>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = base;
+  uint8_t* sB = base + STAGES * Cfg::A_STAGE;
+  uint64_t* full = reinterpret_cast<uint64_t*>(base + STAGES * Cfg::STAGE_BYTES);
+  uint64_t* empty = full + STAGES;
+  uint64_t* tfull = empty + STAGES;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  float* sbias = reinterpret_cast<float*>(base + STAGES * Cfg::STAGE_BYTES + 256);
+  int4* ktab = reinterpret_cast<int4*>(sbias + 2048);   // flattened K-steps: {A channel coord, x | y<<16, parity | kcol<<4, weight row}
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rank = CG == 2 ? (int)cluster_ctarank() : 0;  // position in the CTA pair
+  if (p.flags & LSPS_EP_BIAS) {
+    const int nc_total = p.tiles_n * BN;
+    for (int i = threadIdx.x; i < nc_total; i += blockDim.x) sbias[i] = p.bias[i];
+  }
+  // the producer is ONE thread whose per-stage latency bounds the whole pipeline: no divisions or parameter-space
+  // reads in its loop -- every (tap, 64-channel chunk) K-step is a precomputed 16-byte table entry
+  for (int i = threadIdx.x; i < 9 * p.kchunks; i += blockDim.x) {
+    const int tp = i / p.kchunks, kc = i - tp * p.kchunks;
+    const Tap T = p.taps[tp];
+    ktab[i] = make_int4(kc * 64 + T.ac, (T.ax & 0xFFFF) | (T.ay << 16), T.ap | ((kc * 64) << 4), T.brow);
+  }
+  const bool leader = rank == 0;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4 * CG); }
+    fence_barrier_init();
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1) {
+    if (CG == 2) { tmem_alloc_cg2(tmem_slot, Cfg::TMEM_COLS); tmem_relinquish_cg2(); }
+    else { tmem_alloc(tmem_slot, Cfg::TMEM_COLS); tmem_relinquish(); }
+  }
+  tc_fence_before();
+  if (CG == 2) cluster_sync_all(); else __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // work items: (phase, n tile, group of CG consecutive m tiles); a phantom m tile (odd count) loads zeros, stores nothing
+  const int tiles_m = p.tiles_x * p.tiles_y * p.tiles_i;
+  const int groups_m = (tiles_m + CG - 1) / CG;
+  const int per_phase = groups_m * p.tiles_n;
+  const int total = per_phase * p.nphases;
+  const int worker = blockIdx.x / CG, nworkers = gridDim.x / CG;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0; uint32_t ph = 0;
+      for (int t = worker; t < total; t += nworkers) {
+        const TileCoord tc = decode_tile(p, t, per_phase, groups_m, CG, rank);
+        const int nt = tc.nt, x0 = tc.x0, y0 = tc.y0, n0 = tc.ti * p.nb;
+        const Phase P = p.ph[tc.pi];
+        // K-steps (tap, 64-channel chunk) are flattened; a stage carries up to KCH consecutive ones
+        const int nks = P.ntaps * p.kchunks;
+        const int4* kt = ktab + P.tap0 * p.kchunks;
+        const int brow_off = nt * BN + rank * (BN / 2) * (CG - 1);
+        for (int i0 = 0; i0 < nks; i0 += KCH) {
+          const int cnt = nks - i0 < KCH ? nks - i0 : KCH;
+          mbar_wait(&empty[stage], ph ^ 1);
+          if (p.dbg & 2) {
+            if (leader) mbar_arrive(&full[stage]);
+          } else {
+            if (leader) mbar_expect_tx(&full[stage], CG * cnt * (A_STAGE_BYTES + Cfg::B_CHUNK_BYTES));
+#pragma unroll
+            for (int j = 0; j < KCH; ++j) {
+              if (j < cnt) {
+                const int4 e = kt[i0 + j];
+                const int ax = (short)(e.y & 0xFFFF), ay = e.y >> 16;
+                uint8_t* da = sA + stage * Cfg::A_STAGE + j * A_STAGE_BYTES;
+                uint8_t* db = sB + stage * Cfg::B_STAGE_BYTES + j * Cfg::B_CHUNK_BYTES;
+                const int ap = e.z & 15, kcol = e.z >> 4;
+                if (CG == 2) {
+                  tma_load_5d_cg2(da, &tmA, &full[stage], e.x, x0 + ax, ap, y0 + ay, n0);
+                  tma_load_2d_cg2(db, &tmB, &full[stage], kcol, e.w + brow_off);
+                } else {
+                  tma_load_5d(da, &tmA, &full[stage], e.x, x0 + ax, ap, y0 + ay, n0);
+                  tma_load_2d(db, &tmB, &full[stage], kcol, e.w + brow_off);
+                }
+              }
+            }
+          }
+          if (++stage == STAGES) { stage = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && leader) {
+      constexpr uint32_t idesc = umma_idesc_bf16(128 * CG, BN, 0, 0);
+      constexpr uint64_t dbase = umma_desc_base(0, 1024);
+      const uint32_t sA_u32 = smem_u32(sA), sB_u32 = smem_u32(sB);
+      int stage = 0; uint32_t ph = 0; int it = 0;
+      for (int t = worker; t < total; t += nworkers, ++it) {
+        const int pi = p.nphases > 1 ? t / per_phase : 0;
+        const int nks = p.ph[pi].ntaps * p.kchunks;
+        const int acc = it & 1; const uint32_t accph = (it >> 1) & 1;
+        mbar_wait(&tempty[acc], accph ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int i0 = 0; i0 < nks; i0 += KCH) {
+          const int cnt = nks - i0 < KCH ? nks - i0 : KCH;
+          mbar_wait(&full[stage], ph);
+          tc_fence_after();
+          const uint64_t a_base = dbase | ((sA_u32 + stage * Cfg::A_STAGE) >> 4);
+          const uint64_t b_base = dbase | ((sB_u32 + stage * Cfg::B_STAGE_BYTES) >> 4);
+#pragma unroll
+          for (int k = 0; k < 4 * KCH; ++k) {
+            if ((p.dbg & 1) || (k >> 2) >= cnt) break;
+            // +32 B per K=16 slice (2 in 16-byte units); next 64-channel chunk one operand tile further
+            const uint64_t ad = a_base + ((k >> 2) * (A_STAGE_BYTES >> 4) + (k & 3) * 2);
+            const uint64_t bd = b_base + ((k >> 2) * (Cfg::B_CHUNK_BYTES >> 4) + (k & 3) * 2);
+            if (CG == 2) umma_bf16_cg2(d_tmem, ad, bd, idesc, (i0 | k) != 0 ? 1u : 0u);
+            else umma_bf16(d_tmem, ad, bd, idesc, (i0 | k) != 0 ? 1u : 0u);
+          }
+          if (CG == 2) umma_commit_cg2(&empty[stage]); else umma_commit(&empty[stage]);
+          if (++stage == STAGES) { stage = 0; ph ^= 1; }
+        }
+        if (CG == 2) umma_commit_cg2(&tfull[acc]); else umma_commit(&tfull[acc]);
+      }
+    }
+  } else {
+    epilogue_role<BN, CG>(p, sbias, tmem_base, tfull, tempty, warp, lane, rank, worker, nworkers, groups_m, per_phase, total);
   }
   tc_fence_before();
   if (CG == 2) cluster_sync_all(); else __syncthreads();
   if (warp == 1) { if (CG == 2) tmem_dealloc_cg2(tmem_base, Cfg::TMEM_COLS); else tmem_dealloc(tmem_base, Cfg::TMEM_COLS); }
+}
+
+// ------------------------------------------------------------------------------------------------ 3x3 s1 "slab" kernel
+// The K1 shape (3x3 stride-1, >= 256 channels, forward and data gradient) as CTA pairs with TWO operand rings.
+// TMA cost is dominated by a fixed per-box overhead (measured: r01 probes), so instead of one 128-row A box per tap the
+// producer loads ONE slab of (th+2) image rows per (filter column s, 64-channel chunk): the three filter rows r are
+// the same slab shifted by whole image rows -- a multiple of 1024 bytes, i.e. only a different descriptor start
+// address, no second copy.  Boxes per 3 K-steps: 1 slab + 3 weight tiles instead of 6.
+constexpr int SLAB_BYTES = 24576;   // (th + 2) * tw * 128 <= 24 KB
+constexpr int SLAB_SLOTS = 3;
+constexpr int WS_BYTES = 128 * 128; // this CTA's half of a 256-row weight tile
+constexpr int WS_SLOTS = 6;
+constexpr int SLAB_SMEM = SLAB_SLOTS * SLAB_BYTES + WS_SLOTS * WS_BYTES + 1024 + 256 + 2048 * 4;
+
+__global__ void __launch_bounds__(192, 1)
+conv_s1_slab_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ CUtensorMap tmB,
+                    const __grid_constant__ IgemmParams p) {
+  constexpr int BN = 256, CG = 2;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sS = base;
+  uint8_t* sW = base + SLAB_SLOTS * SLAB_BYTES;
+  uint64_t* sfull = reinterpret_cast<uint64_t*>(sW + WS_SLOTS * WS_BYTES);
+  uint64_t* sempty = sfull + SLAB_SLOTS;
+  uint64_t* wfull = sempty + SLAB_SLOTS;
+  uint64_t* wempty = wfull + WS_SLOTS;
+  uint64_t* tfull = wempty + WS_SLOTS;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  float* sbias = reinterpret_cast<float*>(sW + WS_SLOTS * WS_BYTES + 256);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rank = (int)cluster_ctarank();
+  const bool leader = rank == 0;
+  if (p.flags & LSPS_EP_BIAS) {
+    for (int i = threadIdx.x; i < p.tiles_n * BN; i += blockDim.x) sbias[i] = p.bias[i];
+  }
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < SLAB_SLOTS; ++i) { mbar_init(&sfull[i], 1); mbar_init(&sempty[i], 1); }
+    for (int i = 0; i < WS_SLOTS; ++i) { mbar_init(&wfull[i], 1); mbar_init(&wempty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4 * CG); }
+    fence_barrier_init();
+    tma_prefetch_desc(&tmS);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1) { tmem_alloc_cg2(tmem_slot, 512); tmem_relinquish_cg2(); }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int tiles_m = p.tiles_x * p.tiles_y * p.tiles_i;
+  const int groups_m = (tiles_m + CG - 1) / CG;
+  const int per_phase = groups_m * p.tiles_n;
+  const int total = per_phase;                      // one phase
+  const int worker = blockIdx.x / CG, nworkers = gridDim.x / CG;
+  const int tw = 1 << p.twl, th = 1 << p.thl;
+  const uint32_t slab_bytes = (uint32_t)(th + 2) * tw * 128;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int ss = 0, ws = 0; uint32_t sph = 0, wph = 0;
+      for (int t = worker; t < total; t += nworkers) {
+        const int nt = t / groups_m, mt = (t - nt * groups_m) * CG + rank;
+        const int tx = mt % p.tiles_x, ty = (mt / p.tiles_x) % p.tiles_y, ti = mt / (p.tiles_x * p.tiles_y);
+        const int x0 = tx << p.twl, y0 = ty << p.thl, n0 = ti * p.nb;
+        for (int sc = 0; sc < 3; ++sc) {            // taps are ordered filter-column major: taps[sc*3 + r]
+          const int ax = p.taps[sc * 3].ax;
+          for (int kc = 0; kc < p.kchunks; ++kc) {
+            mbar_wait(&sempty[ss], sph ^ 1);
+            if (leader) mbar_expect_tx(&sfull[ss], 2 * slab_bytes);
+            tma_load_5d_cg2(sS + ss * SLAB_BYTES, &tmS, &sfull[ss], kc * 64, x0 + ax, 0, y0 - 1, n0);
+            if (++ss == SLAB_SLOTS) { ss = 0; sph ^= 1; }
+            for (int r = 0; r < 3; ++r) {
+              mbar_wait(&wempty[ws], wph ^ 1);
+              if (leader) mbar_expect_tx(&wfull[ws], 2 * WS_BYTES);
+              tma_load_2d_cg2(sW + ws * WS_BYTES, &tmB, &wfull[ws], kc * 64, p.taps[sc * 3 + r].brow + nt * BN + rank * (BN / 2));
+              if (++ws == WS_SLOTS) { ws = 0; wph ^= 1; }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && leader) {
+      constexpr uint32_t idesc = umma_idesc_bf16(256, BN, 0, 0);
+      int ss = 0, ws = 0; uint32_t sph = 0, wph = 0; int it = 0;
+      for (int t = worker; t < total; t += nworkers, ++it) {
+        const int acc = it & 1; const uint32_t accph = (it >> 1) & 1;
+        mbar_wait(&tempty[acc], accph ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        uint32_t first = 1;
+        for (int sc = 0; sc < 3; ++sc) {
+          for (int kc = 0; kc < p.kchunks; ++kc) {
+            mbar_wait(&sfull[ss], sph);
+            const uint32_t slab = smem_u32(sS + ss * SLAB_BYTES);
+            for (int r = 0; r < 3; ++r) {
+              mbar_wait(&wfull[ws], wph);
+              tc_fence_after();
+              // filter row r reads image rows y + ay: ay + 1 whole rows into the slab (tw * 128 B each, 1024-aligned)
+              const uint32_t a_addr = slab + (uint32_t)(p.taps[sc * 3 + r].ay + 1) * tw * 128;
+              const uint32_t b_addr = smem_u32(sW + ws * WS_BYTES);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                umma_bf16_cg2(d_tmem, umma_smem_desc(a_addr + k * 32, 0, 1024), umma_smem_desc(b_addr + k * 32, 0, 1024),
+                              idesc, first ? 0u : 1u);
+                first = 0;
+              }
+              umma_commit_cg2(&wempty[ws]);
+              if (++ws == WS_SLOTS) { ws = 0; wph ^= 1; }
+            }
+            umma_commit_cg2(&sempty[ss]);
+            if (++ss == SLAB_SLOTS) { ss = 0; sph ^= 1; }
+          }
+        }
+        umma_commit_cg2(&tfull[acc]);
+      }
+    }
+  } else {
+    epilogue_role<BN, CG>(p, sbias, tmem_base, tfull, tempty, warp, lane, rank, worker, nworkers, groups_m, per_phase, total);
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 1) tmem_dealloc_cg2(tmem_base, 512);
 }
 
 // ------------------------------------------------------------------------------------------------ wgrad
@@ -371,11 +549,15 @@ struct WgradParams {
   long long ws_stride;  // elements per split
   WTap taps[9];
 };
-constexpr int W_BOX_BYTES = 64 * 128;  // 64 pixels x 64 bf16
+// one TMA box = KPX pixels x 64 channels.  TMA cost is dominated by a fixed per-box overhead, so the CTA-pair kernel
+// (2 + 2 boxes per stage) uses 128-pixel boxes; the single-CTA kernel keeps 64 pixels to afford >= 4 stages.
+template <int BN, int CG> struct WBox { static constexpr int KPX = (CG == 2 || BN <= 128) ? 128 : 64; static constexpr int BYTES = KPX * 128; };
 
 template <int BN, int CG>
 struct WgradCfg {
   static constexpr int NB_BOXES = BN / 64 / CG;                    // x boxes staged by this CTA
+  static constexpr int KPX = WBox<BN, CG>::KPX;
+  static constexpr int W_BOX_BYTES = WBox<BN, CG>::BYTES;
   static constexpr int STAGE_BYTES = (2 + NB_BOXES) * W_BOX_BYTES;
   static constexpr int STAGES = (196608 / STAGE_BYTES) > 8 ? 8 : (196608 / STAGE_BYTES);
   static constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
@@ -388,6 +570,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ CU
              const __grid_constant__ WgradParams p) {
   using Cfg = WgradCfg<BN, CG>;
   constexpr int STAGES = Cfg::STAGES;
+  constexpr int W_BOX_BYTES = Cfg::W_BOX_BYTES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full = reinterpret_cast<uint64_t*>(base + STAGES * Cfg::STAGE_BYTES);
@@ -472,7 +655,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ CU
         const uint32_t a_addr = smem_u32(base + stage * Cfg::STAGE_BYTES);
         const uint32_t b_addr = a_addr + 2 * W_BOX_BYTES;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {  // 16 pixels per MMA = 16 rows of 128 B
+        for (int k = 0; k < Cfg::KPX / 16; ++k) {  // 16 pixels per MMA = 16 rows of 128 B
           if (p.dbg & 1) break;
           const uint64_t ad = umma_smem_desc(a_addr + k * 2048, W_BOX_BYTES, 1024);
           const uint64_t bd = umma_smem_desc(b_addr + k * 2048, W_BOX_BYTES, 1024);
@@ -579,6 +762,21 @@ inline bool lsps_no_ws() {  // split-K workspace + reduce kernel instead of red.
   if (v < 0) { const char* e = getenv("LSPS_WS"); v = (e && e[0] == '1') ? 0 : 1; }
   return v == 1;
 }
+inline bool lsps_no_slab() {  // slab kernel measured slower than the generic pair kernel (r01): opt-in via LSPS_SLAB=1
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("LSPS_SLAB"); v = (e && e[0] == '1') ? 0 : 1; }
+  return v == 1;
+}
+inline int lsps_kch_small() {  // K-steps per stage of the single-CTA BN<=128 kernels
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("LSPS_KCH_SMALL"); v = e ? atoi(e) : 1; }
+  return v;
+}
+inline bool lsps_no_kch2() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("LSPS_NO_KCH2"); v = (e && e[0] == '1') ? 1 : 0; }
+  return v == 1;
+}
 inline int lsps_pf() {
   static int v = -1;
   if (v < 0) { const char* e = getenv("LSPS_PF"); v = e ? atoi(e) : 0; }
@@ -606,19 +804,19 @@ cudaError_t launch_maybe_cluster(K kernel, int grid, int smem, int cg, cudaStrea
   return cudaLaunchKernelEx(&cfg, kernel, args...);
 }
 
-template <int BN, int CG>
+template <int BN, int CG, int KCH = 1>
 int launch_igemm(lsps_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tmB, const IgemmParams& p, cudaStream_t st) {
-  using Cfg = IgemmCfg<BN, CG>;
+  using Cfg = IgemmCfg<BN, CG, KCH>;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(conv_igemm_kernel<BN, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(conv_igemm_kernel<BN, CG, KCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return lsps_set_error(ctx, LSPS_E_CUDA, "igemm smem attr: %s", cudaGetErrorString(e));
     configured = true;
   }
   const int tiles_m = p.tiles_x * p.tiles_y * p.tiles_i;
   const int total = ((tiles_m + CG - 1) / CG) * p.tiles_n * p.nphases;
   const int workers = total < ctx->num_sms / CG ? total : ctx->num_sms / CG;
-  cudaError_t e = launch_maybe_cluster(conv_igemm_kernel<BN, CG>, workers * CG, Cfg::SMEM_BYTES, CG, st, tmA, tmB, p);
+  cudaError_t e = launch_maybe_cluster(conv_igemm_kernel<BN, CG, KCH>, workers * CG, Cfg::SMEM_BYTES, CG, st, tmA, tmB, p);
   if (e != cudaSuccess) return lsps_set_error(ctx, LSPS_E_CUDA, "conv_igemm launch: %s", cudaGetErrorString(e));
   LSPS_CHECK_LAUNCH(ctx, "conv_igemm");
   return LSPS_OK;
@@ -657,6 +855,7 @@ int run_igemm(lsps_ctx* ctx, const lsps_conv_shape* s, Dir dir, const void* in, 
   IgemmParams p{};
   p.tiles_x = wg / g.tw; p.tiles_y = hg / g.th; p.tiles_i = (n + g.nb - 1) / g.nb;
   p.twl = g.twl; p.thl = g.thl; p.nb = g.nb;
+  p.txl = ilog2(p.tiles_x); p.tyl = ilog2(p.tiles_y);
   p.nimg = n; p.kchunks = kc / 64;
   p.o_n = (long long)oh * ow * nc; p.o_y = (long long)ow * nc; p.o_x = nc;
   p.out = static_cast<__nv_bfloat16*>(out); p.bias = bias;
@@ -721,14 +920,39 @@ int run_igemm(lsps_ctx* ctx, const lsps_conv_shape* s, Dir dir, const void* in, 
   uint32_t wd[2] = {(uint32_t)kc, (uint32_t)(9 * nc)}, wb[2] = {64, (uint32_t)(bn / cg)};
   rc = lsps_get_tmap(ctx, wpk, 2, wd, wb, &tmB);
   if (rc) return rc;
+  if (cg == 2 && plain && bn == 256 && g.nb == 1 && g.tw % 8 == 0 && (g.th + 2) * g.tw * 128 <= SLAB_BYTES && !lsps_no_slab()) {
+    // slab kernel: taps reordered filter-column major so that taps[s*3 + r] share one slab (same x shift)
+    IgemmParams q = p;
+    for (int sc = 0; sc < 3; ++sc)
+      for (int r = 0; r < 3; ++r) q.taps[sc * 3 + r] = p.taps[r * 3 + sc];
+    CUtensorMap tmS;
+    uint32_t dims[5] = {(uint32_t)kc, (uint32_t)iw, 1u, (uint32_t)ih, (uint32_t)n};
+    uint32_t box[5] = {64u, (uint32_t)g.tw, 1u, (uint32_t)(g.th + 2), 1u};
+    rc = lsps_get_tmap(ctx, in, 5, dims, box, &tmS);
+    if (rc) return rc;
+    static bool configured = false;
+    if (!configured) {
+      cudaError_t e = cudaFuncSetAttribute(conv_s1_slab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SLAB_SMEM);
+      if (e != cudaSuccess) return lsps_set_error(ctx, LSPS_E_CUDA, "slab smem attr: %s", cudaGetErrorString(e));
+      configured = true;
+    }
+    const int total = ((tiles_m + 1) / 2) * q.tiles_n;
+    const int workers = total < ctx->num_sms / 2 ? total : ctx->num_sms / 2;
+    cudaError_t e = launch_maybe_cluster(conv_s1_slab_kernel, workers * 2, SLAB_SMEM, 2, st, tmS, tmB, q);
+    if (e != cudaSuccess) return lsps_set_error(ctx, LSPS_E_CUDA, "conv_s1_slab launch: %s", cudaGetErrorString(e));
+    LSPS_CHECK_LAUNCH(ctx, "conv_s1_slab");
+    return LSPS_OK;
+  }
+  if (cg == 2 && bn == 256 && !lsps_no_kch2()) return launch_igemm<256, 2, 2>(ctx, tmA, tmB, p, st);
   if (cg == 2) {
     if (bn == 256) return launch_igemm<256, 2>(ctx, tmA, tmB, p, st);
     if (bn == 128) return launch_igemm<128, 2>(ctx, tmA, tmB, p, st);
     return launch_igemm<64, 2>(ctx, tmA, tmB, p, st);
   }
   if (bn == 256) return launch_igemm<256, 1>(ctx, tmA, tmB, p, st);
-  if (bn == 128) return launch_igemm<128, 1>(ctx, tmA, tmB, p, st);
-  return launch_igemm<64, 1>(ctx, tmA, tmB, p, st);
+  const int kch = lsps_kch_small();
+  if (bn == 128) return kch == 2 ? launch_igemm<128, 1, 2>(ctx, tmA, tmB, p, st) : (kch == 3 ? launch_igemm<128, 1, 3>(ctx, tmA, tmB, p, st) : launch_igemm<128, 1>(ctx, tmA, tmB, p, st));
+  return kch == 2 ? launch_igemm<64, 1, 2>(ctx, tmA, tmB, p, st) : (kch == 3 ? launch_igemm<64, 1, 3>(ctx, tmA, tmB, p, st) : launch_igemm<64, 1>(ctx, tmA, tmB, p, st));
 }
 
 template <int BN, int CG>
@@ -772,14 +996,14 @@ extern "C" int lsps_conv_wgrad(lsps_ctx* ctx, const lsps_conv_shape* s, const vo
   const int wo = kind == LSPS_CONV_S1 ? w : (kind == LSPS_CONV_S2 ? w / 2 : 2 * w);
   // reduction grid: the coarser of the two spatial grids
   const int hg = kind == LSPS_CONV_S2 ? ho : h, wg = kind == LSPS_CONV_S2 ? wo : w;
-  const Geo g = geo_for(hg, wg, 64);
+  const int bn = cin % 256 == 0 ? 256 : (cin % 128 == 0 ? 128 : 64);
+  // CTA pairs: 256 output channels per pair, each CTA stages half of the x tile (needs >= 128 input channels)
+  const int cg = (lsps_use_pairs() && cout % 256 == 0 && bn >= 128) ? 2 : 1;
+  const Geo g = geo_for(hg, wg, (cg == 2 || bn <= 128) ? 128 : 64);
   WgradParams p{};
   p.tiles_x = wg / g.tw; p.tiles_y = hg / g.th; p.tiles_i = (n + g.nb - 1) / g.nb;
   p.twl = g.twl; p.thl = g.thl; p.nb = g.nb;
   p.ntaps = 9; p.cout = cout; p.cin = cin; p.dw = dw; p.dbg = lsps_dbg(); p.pf = lsps_pf();
-  const int bn = cin % 256 == 0 ? 256 : (cin % 128 == 0 ? 128 : 64);
-  // CTA pairs: 256 output channels per pair, each CTA stages half of the x tile (needs >= 128 input channels)
-  const int cg = (lsps_use_pairs() && cout % 256 == 0 && bn >= 128) ? 2 : 1;
   p.co_tiles = (cout + 128 * cg - 1) / (128 * cg);
   p.ci_tiles = cin / bn;
   for (int r = 0; r < 3; ++r)
