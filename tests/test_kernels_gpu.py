@@ -42,6 +42,9 @@ CONV_CASES = [  # kind, n, h, w, cin, cout
     (1, 2, 128, 128, 64, 128), (1, 3, 64, 64, 128, 256), (1, 5, 16, 16, 256, 512), (1, 9, 8, 8, 512, 1024),
     (1, 40, 4, 4, 1024, 2048), (1, 1, 4, 4, 1024, 2048),
     (2, 2, 32, 32, 256, 128), (2, 2, 64, 64, 128, 64), (2, 3, 8, 8, 64, 64),
+    # large enough for the CTA-pair (cta_group::2) conv kernels: >= 2*148 M tiles and >= 27 K-steps per tile
+    (0, 40, 32, 32, 256, 256),        # K1 shape, 320 tiles: pair kernel with 128-channel stages
+    (1, 297, 16, 16, 256, 512),       # dis trunk shape, 149 M tiles (odd): the pair's phantom tile path
 ]
 
 

@@ -207,3 +207,49 @@ def test_gradients_and_post_step_weights_match_oracle():
         assert cos > 0.9, ("adam update", k, cos)   # first Adam step ~ lr*sign(g): sign noise where g ~ 0
     for k in ("D.weight", "D.bias", "model_B.0.model.0.weight", "model_B.1.model.0.weight"):
         assert torch.equal(sd_t[k].cpu(), before[k]), "%s must not move in estimate0 (no gradient -> Adam skips it)" % k
+
+
+def test_eval_path_regress_decode_matches_oracle():
+    """Inference path of the drivers (depth_train.py:197-206): dis.regress_b -> vae.decode -> (N, J*3)."""
+    hp = _hp("nnyu")
+    oracle = O.OracleTrainer(hp, seed=0)
+    tr = _trainer(hp)
+    load_from_oracle(tr, oracle)
+    g = torch.Generator().manual_seed(5)
+    x = torch.rand(6, 1, 128, 128, generator=g) * 2 - 1
+    with torch.no_grad():
+        p_ref = oracle.dis.regress("B", x)
+        j_ref = oracle.vae.decode(p_ref)
+    tr.dis.eval()
+    p, _, _ = tr.dis.regress_b(x.cuda())
+    j = tr.vae.decode(p)
+    assert p.shape == (6, 20) and j.shape == (6, 108)
+    assert (p.cpu() - p_ref).abs().max().item() < 2e-3 * max(1.0, p_ref.abs().max().item())
+    assert (j.cpu() - j_ref).abs().max().item() < 2e-3 * max(1.0, j_ref.abs().max().item())
+    tr.dis.train()
+
+
+def test_snapshot_round_trip_uses_reference_keys_and_shapes(tmp_path):
+    """save()/resume() (lsps_trainer.py:278-319): file names, state_dict keys and OIHW / IOHW shapes of the reference."""
+    hp = _hp("nnyu")
+    oracle = O.OracleTrainer(hp, seed=0)
+    tr = _trainer(hp)
+    load_from_oracle(tr, oracle)
+    prefix = str(tmp_path / "pre")
+    tr.save(prefix, 41)
+    gen_sd = torch.load(prefix + "_gen_%08d.pkl" % 42)
+    dis_sd = torch.load(prefix + "_dis_%08d.pkl" % 42)
+    ref_gen, ref_dis = oracle.state_dict("gen"), oracle.state_dict("dis")
+    assert list(gen_sd.keys()) == list(ref_gen.keys()) and list(dis_sd.keys()) == list(ref_dis.keys())
+    for k in ref_gen:
+        assert gen_sd[k].shape == ref_gen[k].shape and torch.equal(gen_sd[k], ref_gen[k]), k
+    for k in ref_dis:
+        assert dis_sd[k].shape == ref_dis[k].shape and torch.equal(dis_sd[k], ref_dis[k]), k
+    tr2 = _trainer(hp)
+    assert tr2.resume(prefix) == 42
+    for k, v in tr2.dis_store.state_dict().items():
+        assert torch.equal(v.cpu(), ref_dis[k]), k
+    tr.save_vae(prefix, 9, 1.0)
+    tr2.load_vae(prefix, 1.0)
+    for k, v in tr2.vae_store.state_dict().items():
+        assert torch.equal(v.cpu(), oracle.state_dict("vae")[k]), k
