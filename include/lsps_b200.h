@@ -125,9 +125,11 @@ int lsps_vae_reparam_bwd(lsps_ctx*, const float* mu, const float* sd, const floa
                          float* dsd, float kl_scale, long long n, lsps_stream);
 
 /* ---- optimiser (torch.optim.Adam with L2 weight decay, lsps_trainer.py:26-34) on a flat fp32 segment.
-   g += wd*p ; m,v update ; p -= lr * mhat/(sqrt(vhat)+eps) ; optionally refresh the bf16 copy w16 (may be NULL). */
+   g += wd*p ; m,v update ; p -= lr * mhat/(sqrt(vhat)+eps) ; optionally refresh the bf16 copy w16 (may be NULL).
+   hyper (may be NULL): device pointer to {lr/(1-beta1^step), 1/sqrt(1-beta2^step)}; when given it overrides the values
+   derived from lr/step so that a captured CUDA graph can be replayed with advancing step counts. */
 int lsps_adam(lsps_ctx*, float* p, const float* g, float* m, float* v, void* w16, long long n, float lr, float beta1,
-              float beta2, float eps, float wd, int step, float grad_scale, lsps_stream);
+              float beta2, float eps, float wd, int step, float grad_scale, const float* hyper, lsps_stream);
 /* wt[tap][cin][cout] (bf16) = transpose of w[tap][cout][cin] (f32 master) : the dgrad operand */
 int lsps_pack_dgrad(lsps_ctx*, const float* w, void* wt, int taps, int cout, int cin, lsps_stream);
 int lsps_f32_to_bf16(lsps_ctx*, const float* x, void* y, long long n, lsps_stream);

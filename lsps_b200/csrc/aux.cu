@@ -680,7 +680,9 @@ __global__ void vae_reparam_bwd_kernel(const float* __restrict__ mu, const float
 __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g,
                                                   float* __restrict__ m, float* __restrict__ v, bf16* __restrict__ w16,
                                                   long long n, float step_size, float beta1, float beta2, float eps,
-                                                  float wd, float inv_sqrt_bc2, float grad_scale) {
+                                                  float wd, float inv_sqrt_bc2, float grad_scale,
+                                                  const float* __restrict__ hyper) {
+  if (hyper) { step_size = hyper[0]; inv_sqrt_bc2 = hyper[1]; }  // CUDA-graph replays: step-dependent factors from memory
   for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
     const float pv = p[i];
     const float gr = g[i] * grad_scale + wd * pv;
@@ -963,12 +965,13 @@ extern "C" int lsps_vae_reparam_bwd(lsps_ctx* ctx, const float* mu, const float*
 }
 
 extern "C" int lsps_adam(lsps_ctx* ctx, float* p, const float* g, float* m, float* v, void* w16, long long n, float lr,
-                         float beta1, float beta2, float eps, float wd, int step, float grad_scale, lsps_stream st) {
+                         float beta1, float beta2, float eps, float wd, int step, float grad_scale, const float* hyper,
+                         lsps_stream st) {
   REQUIRE(ctx, p && g && m && v && n > 0 && step > 0, LSPS_E_ARG, "adam: arg");
   const double bc1 = 1.0 - pow((double)beta1, step), bc2 = 1.0 - pow((double)beta2, step);
   adam_kernel<<<grid_for(n, 256, 8 * ctx->num_sms), 256, 0, ST_(st)>>>(p, g, m, v, static_cast<bf16*>(w16), n,
                                                                      (float)(lr / bc1), beta1, beta2, eps, wd,
-                                                                     (float)(1.0 / sqrt(bc2)), grad_scale);
+                                                                     (float)(1.0 / sqrt(bc2)), grad_scale, hyper);
   LSPS_CHECK_LAUNCH(ctx, "adam");
   return LSPS_OK;
 }

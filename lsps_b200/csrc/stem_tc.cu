@@ -362,10 +362,14 @@ __global__ void __launch_bounds__(128) stem_dgrad_tc_kernel(const __grid_constan
   if (warp == 0) tmem_dealloc(tmem, TCOLS);
 }
 
+// one cudaFuncSetAttribute per kernel instantiation (never inside a stream capture after the first call)
 template <typename K>
 int set_smem(lsps_ctx* ctx, K kernel, int bytes) {
+  static int configured = 0;   // per template instantiation = per kernel
+  if (configured >= bytes) return LSPS_OK;
   cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
   if (e != cudaSuccess) return lsps_set_error(ctx, LSPS_E_CUDA, "stem smem attr: %s", cudaGetErrorString(e));
+  configured = bytes;
   return LSPS_OK;
 }
 

@@ -156,12 +156,10 @@ class ParamStore:
     def zero_grad(self):
         self.gbuf.zero_()
 
-    def adam_step(self, active=None, grad_scale=1.0):
-        """torch.optim.Adam semantics incl. 'parameters without a gradient are skipped' (their step counter does not
-        advance).  `active`: None = all, else a predicate key -> bool.  Contiguous active runs with equal step
-        counts are fused into one launch over the flat buffer."""
+    def _segments(self, active):
+        """Maximal runs of consecutive active tensors with equal step counts -> [(first, last)] entry indices."""
         ents = list(self.entries.values())
-        i = 0
+        segs, i = [], 0
         while i < len(ents):
             e = ents[i]
             if active is not None and not active(e.key):
@@ -170,15 +168,49 @@ class ParamStore:
             j = i
             while j + 1 < len(ents) and ents[j + 1].step == e.step and (active is None or active(ents[j + 1].key)):
                 j += 1
-            lo, hi = e.off, ents[j].off + _round_up(ents[j].numel)
-            step = e.step + 1
+            segs.append((i, j))
+            i = j + 1
+        return segs
+
+    def _hyper(self, step):
+        b1, b2 = self.betas
+        return self.lr / (1.0 - b1 ** step), 1.0 / math.sqrt(1.0 - b2 ** step)
+
+    def adam_step(self, active=None, grad_scale=1.0, hyper=None):
+        """torch.optim.Adam semantics incl. 'parameters without a gradient are skipped' (their step counter does not
+        advance).  `active`: None = all, else a predicate key -> bool.  Contiguous active runs with equal step
+        counts are fused into one launch over the flat buffer.
+        hyper: optional (device float tensor [2*k], host list) pair -- CUDA-graph capture: the launches read their
+        step-dependent factors from hyper[2*i:2*i+2]; returns the segment list so that `advance()` can replay it."""
+        ents = list(self.entries.values())
+        segs = self._segments(active)
+        for si, (i, j) in enumerate(segs):
+            lo, hi = ents[i].off, ents[j].off + _round_up(ents[j].numel)
+            step = ents[i].step + 1
             for q in range(i, j + 1):
                 ents[q].step = step
-            n = hi - lo
+            hp = None
+            if hyper is not None:
+                hp = hyper[2 * si:].data_ptr()
             self.ctx.adam(self.w[lo:].data_ptr(), self.g[lo:].data_ptr(), self.m[lo:].data_ptr(),
-                          self.v[lo:].data_ptr(), self.w16[lo:].data_ptr(), n, float(self.lr), self.betas[0],
-                          self.betas[1], self.eps, float(self.wd), step, float(grad_scale))
-            i = j + 1
+                          self.v[lo:].data_ptr(), self.w16[lo:].data_ptr(), hi - lo, float(self.lr), self.betas[0],
+                          self.betas[1], self.eps, float(self.wd), step, float(grad_scale), hp)
+        return segs
+
+    def segments_consistent(self, segs):
+        ents = list(self.entries.values())
+        return all(ents[q].step == ents[i].step for i, j in segs for q in range(i, j + 1))
+
+    def advance(self, segs, hyper_host):
+        """Replay bookkeeping for a captured adam_step: bump the step counters of `segs` and write the factors the
+        captured launches will read into hyper_host (pinned float tensor)."""
+        ents = list(self.entries.values())
+        for si, (i, j) in enumerate(segs):
+            step = ents[i].step + 1
+            for q in range(i, j + 1):
+                ents[q].step = step
+            a, b = self._hyper(step)
+            hyper_host[2 * si], hyper_host[2 * si + 1] = a, b
 
     def opt_state(self):
         return {"m": self.m.clone(), "v": self.v.clone(), "steps": {k: e.step for k, e in self.entries.items()},

@@ -36,7 +36,7 @@ def _img(t, dev):
 
 
 class LSPSTrainerB200(object):
-    def __init__(self, hyperparameters, device=None, seed=0, noise="host"):
+    def __init__(self, hyperparameters, device=None, seed=0, noise="host", graphs=False):
         hp = hyperparameters
         if hp.get("train_map", False):
             raise NotImplementedError("train_map=True (Mapping net) is a SURVEY section 8f 'next' row")
@@ -46,6 +46,8 @@ class LSPSTrainerB200(object):
         self.gpu = self.device.index
         self.hp = hp
         self.noise_mode = noise  # "host": reference RNG stream (CPU torch.randn, same draw order); "device": Philox
+        self.graphs = graphs     # CUDA-graph replay of post_update / vae_update (device-noise mode only)
+        self._graphs = {}
         torch.cuda.set_device(self.device)
         self.ops = Ops(self.device)
         lr = hp["lr"]
@@ -109,22 +111,31 @@ class LSPSTrainerB200(object):
     # ------------------------------------------------------------------ vae_update (lsps_trainer.py:62-74)
     def vae_update(self, y, hyperparameters=None):
         hp = hyperparameters or self.hp
-        S, ctx = self.vae_store, self.ops.ctx
+        S = self.vae_store
         world, _ = _world()
         y = y.detach().to(device=self.device, dtype=torch.float32).contiguous()
         rows, dim = y.shape[0] * world, y.shape[1]
-        S.zero_grad()
-        sv = {}
-        dec, z, mu, sd = self.vae.forward(y, kl_acc=S.acc[0:], save=sv)
-        ddec = torch.empty_like(dec)
-        ctx.l1_f32(dec.data_ptr(), y.data_ptr(), ddec.data_ptr(), hp["ll_loss_vae"] / float(rows * dim), 0,
-                   S.acc[1:].data_ptr(), dec.numel())
-        self.vae.backward(sv, ddec, hp["kl_loss_vae"] / float(rows))
-        self._allreduce(S)
-        S.adam_step()
+
+        def body(t):
+            ctx = self.ops.ctx
+            S.zero_grad()
+            sv = {}
+            dec, z, mu, sd = self.vae.forward(t["y"], kl_acc=S.acc[0:], save=sv)
+            ddec = torch.empty_like(dec)
+            ctx.l1_f32(dec.data_ptr(), t["y"].data_ptr(), ddec.data_ptr(), hp["ll_loss_vae"] / float(rows * dim), 0,
+                       S.acc[1:].data_ptr(), dec.numel())
+            self.vae.backward(sv, ddec, hp["kl_loss_vae"] / float(rows))
+            return dict(dec=dec)
+
+        if self.graphs and self.noise_mode == "device":
+            st = self._graphed(("vae", y.shape[0], dim), dict(y=y), body, lambda hyper: S.adam_step(hyper=hyper), S)
+        else:
+            st = body(dict(y=y))
+            self._allreduce(S)
+            S.adam_step()
         acc = S.acc[:2].cpu().numpy().astype(np.float64)
         self.vae_total_loss = np.float32(hp["kl_loss_vae"] * acc[0] / rows + hp["ll_loss_vae"] * acc[1] / (rows * dim))
-        return dec
+        return st["dec"]
 
     # ------------------------------------------------------------------ dis_update (lsps_trainer.py:143-218)
     def dis_update(self, images_a, labels_a, images_b, labels_b, com_a=None, com_b=None, hyperparameters=None,
@@ -241,9 +252,30 @@ class LSPSTrainerB200(object):
     # ------------------------------------------------------------------ post_update (lsps_trainer.py:220-262)
     def post_update(self, images_a, labels_a, images_b, labels_b, com_a=None, com_b=None, mode=3, hyperparameters=None):
         hp = hyperparameters or self.hp
-        D, ctx, dis = self.dis_store, self.ops.ctx, self.dis
         world, rank = _world()
         ia, ib = _img(images_a, self.device), _img(images_b, self.device)
+        la = labels_a.detach().to(device=self.device, dtype=torch.float32).contiguous()
+        lb = labels_b.detach().to(device=self.device, dtype=torch.float32).contiguous()
+        # the reference uses the GLOBAL first 4 samples of each domain (lsps_trainer.py:238)
+        src_a, src_b = ia[0:4], ib[0:4]
+        if world > 1 and mode >= 2:
+            src_a, src_b = src_a.clone(), src_b.clone()
+            dist.broadcast(src_a, 0)
+            dist.broadcast(src_b, 0)
+        if self.graphs and self.noise_mode == "device":
+            st = self._graphed(("post", mode, ia.shape[0], la.shape[1]), dict(ia=ia, ib=ib, la=la, lb=lb, sa=src_a, sb=src_b),
+                               lambda t: self._post_body(t["ia"], t["la"], t["ib"], t["lb"], t["sa"], t["sb"], mode, hp),
+                               lambda hyper: self._post_tail(mode, hyper), self.dis_store)
+        else:
+            st = self._post_body(ia, la, ib, lb, src_a, src_b, mode, hp)
+            self._allreduce(self.dis_store)
+            self._post_tail(mode, None)
+        return self._post_finish(st, hp)
+
+    def _post_body(self, ia, la, ib, lb, src_a, src_b, mode, hp):
+        """zero_grad .. backward of post_update (everything before the gradient allreduce)."""
+        D, ctx, dis = self.dis_store, self.ops.ctx, self.dis
+        world, rank = _world()
         B = ia.shape[0]
         Bg = B * world
         D.zero_grad()
@@ -252,20 +284,15 @@ class LSPSTrainerB200(object):
         fa_extra = fb_extra = None
         nf, n4 = 0, 4
         if feat:
-            # the reference uses the GLOBAL first 4 samples of each domain (lsps_trainer.py:238); per-sample ops make
-            # it exact to give source image a_i to rank i % world and b_i to rank (4+i) % world
-            src_a, src_b = ia[0:4], ib[0:4]
+            # per-sample ops make it exact to give source image a_i to rank i % world and b_i to rank (4+i) % world
             n4 = src_a.shape[0]
-            if world > 1:
-                src_a, src_b = src_a.clone(), src_b.clone()
-                dist.broadcast(src_a, 0)
-                dist.broadcast(src_b, 0)
             noise = self._latent_noise(src_a.shape[0] + src_b.shape[0], shard=False)
             ka, kb = source_assignment(src_a.shape[0], src_b.shape[0], world, rank)
             if ka or kb:
-                xa = src_a[ka] if ka else None
-                xb = src_b[kb] if kb else None
-                nz = noise[ka + [src_a.shape[0] + i for i in kb]].contiguous()
+                xa = (src_a if len(ka) == src_a.shape[0] else src_a[ka]) if ka else None
+                xb = (src_b if len(kb) == src_b.shape[0] else src_b[kb]) if kb else None
+                idx = ka + [src_a.shape[0] + i for i in kb]
+                nz = noise if len(idx) == noise.shape[0] else noise[idx].contiguous()
                 oa, ob, _ = self.gen.forward(xa, xb, nz, self._scratch)     # (x_aa|x_ba), (x_ab|x_bb)
                 na, nb = len(ka), len(kb)
                 nf = na + nb
@@ -284,14 +311,14 @@ class LSPSTrainerB200(object):
         dF = torch.zeros(F.shape[0], per, dtype=torch.float32, device=self.device)
         pd = hp["dis"]["post_dim"]
         preds = []
-        for dom, on, row0, labels, slot in (("a", reg_a, nf, labels_a, 5), ("b", reg_b, n_a + nf, labels_b, 6)):
+        for dom, on, row0, labels, slot in (("a", reg_a, nf, la, 5), ("b", reg_b, n_a + nf, lb, 6)):
             if not on:
                 continue
             Fr = Ff[row0:row0 + B]
             p = self.ops.empty(B, pd, dtype=torch.float32)
             ctx.linear_fwd(Fr.data_ptr(), 1, D.W("Post.weight").data_ptr(), D.W("Post.bias").data_ptr(), p.data_ptr(),
                            B, pd, per, 0, SLOPE)
-            e = self.vae.encode(labels.detach().to(self.device))[0]
+            e = self.vae.encode(labels)[0]
             dp = torch.empty_like(p)
             ctx.mse(p.data_ptr(), e.data_ptr(), dp.data_ptr(), 2.0 * hp["reg_w"] / float(Bg * pd), D.acc[slot:].data_ptr(),
                     p.numel())
@@ -312,20 +339,72 @@ class LSPSTrainerB200(object):
         dFm = torch.empty_like(F)
         ctx.mask_to_bf16(dF.data_ptr(), F.data_ptr(), dFm.data_ptr(), SLOPE, F.numel())
         dis.features_bwd(sv, dFm, wgrad=True)
-        del sv
-        self._allreduce(D)
+        return dict(outs=outs, preds=preds, Bg=Bg, pd=pd, per=per, n4=n4, feat=feat)
+
+    def _post_tail(self, mode, hyper):
+        D = self.dis_store
+        reg_a, reg_b, feat = mode != 1, mode in (1, 4), mode >= 2
         skip = ["D."] + ([] if (reg_a or feat) else ["model_A."]) + ([] if (reg_b or feat) else ["model_B."])
-        D.adam_step(active=lambda k: not any(k.startswith(s) for s in skip))
+        segs = D.adam_step(active=lambda k: not any(k.startswith(s) for s in skip), hyper=hyper)
         D.refresh_dgrad_operands()
-        acc = D.acc[:8].cpu().numpy().astype(np.float64)
-        reg = (acc[5] + acc[6]) / (Bg * pd)
-        fm = acc[7] / (n4 * per) if feat else 0.0
+        return segs
+
+    def _post_finish(self, st, hp):
+        acc = self.dis_store.acc[:8].cpu().numpy().astype(np.float64)
+        reg = (acc[5] + acc[6]) / (st["Bg"] * st["pd"])
+        fm = acc[7] / (st["n4"] * st["per"]) if st["feat"] else 0.0
         self.dis_reg_loss = np.float32(reg)
         self.dis_total_loss = np.float32(hp["reg_w"] * reg + hp["feature_w_reg"] * fm)
-        self.last_pred_post = preds
+        self.last_pred_post = st["preds"]
         u = lambda t: t.unsqueeze(1)
-        x_aa, x_ba, x_ab, x_bb = outs
+        x_aa, x_ba, x_ab, x_bb = st["outs"]
         return (u(x_aa), u(x_ba), u(x_ab), u(x_bb), u(x_aa), u(x_bb), u(x_aa), u(x_bb))
+
+    # ------------------------------------------------------------------ CUDA graphs (launch-bound updates)
+    def _graphed(self, key, inputs, body, tail, store):
+        """Runs `body(inputs) -> state`, the gradient allreduce and `tail(hyper) -> adam segments` with the device work
+        of body and tail replayed from two captured CUDA graphs (estimate-mode steps are ~120 small launches: host
+        launch overhead, not the GPU, bounds them).  The first two calls per key run eagerly (they set kernel
+        attributes / fill caches), the third captures.  The NCCL allreduce stays outside the graphs; Adam's
+        step-dependent factors are read from a small device buffer refreshed before every replay."""
+        ent = self._graphs.get(key)
+        if ent is None:
+            ent = self._graphs[key] = dict(calls=0)
+        if ent["calls"] < 2:
+            ent["calls"] += 1
+            st = body(inputs)
+            self._allreduce(store)
+            tail(None)
+            return st
+        if "g1" not in ent:
+            ent["static"] = {k: v.clone() for k, v in inputs.items()}
+            ent["hyper"] = torch.zeros(32, dtype=torch.float32, device=self.device)
+            ent["hyper_host"] = torch.zeros(32, dtype=torch.float32).pin_memory()
+            torch.cuda.synchronize()
+            ent["g1"] = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(ent["g1"]):
+                ent["state"] = body(ent["static"])
+            steps = {k: e.step for k, e in store.entries.items()}
+            ent["g2"] = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(ent["g2"]):
+                ent["segs"] = tail(ent["hyper"])
+            for k, v in steps.items():           # capture executes nothing: undo its step bookkeeping
+                store.entries[k].step = v
+        if not store.segments_consistent(ent["segs"]):
+            # another update type stepped only part of a captured Adam segment: fall back to eager and re-capture later
+            self._graphs.pop(key)
+            st = body(inputs)
+            self._allreduce(store)
+            tail(None)
+            return st
+        for k, v in inputs.items():
+            ent["static"][k].copy_(v)
+        ent["g1"].replay()
+        self._allreduce(store)
+        store.advance(ent["segs"], ent["hyper_host"])
+        ent["hyper"].copy_(ent["hyper_host"], non_blocking=True)
+        ent["g2"].replay()
+        return ent["state"]
 
     # ------------------------------------------------------------------ outputs / snapshots
     def assemble_outputs(self, images_a, images_b, network_outputs):

@@ -282,8 +282,11 @@ def test_adam_matches_torch(ctx):
         gr = torch.randn(n, device="cuda", generator=g) * 0.01
         ref.grad = gr.clone()
         opt.step()
+        hyper = None
+        if step == 3:   # device-resident step factors (CUDA-graph replay path) must give the same update
+            hyper = torch.tensor([1e-4 / (1 - 0.5 ** step), 1.0 / (1 - 0.999 ** step) ** 0.5], device="cuda")
         ctx.adam(p.data_ptr(), gr.data_ptr(), m.data_ptr(), v.data_ptr(), w16.data_ptr(), n, 1e-4, 0.5, 0.999, 1e-8,
-                 1e-4, step, 1.0)
+                 1e-4, step if hyper is None else 1, 1.0, None if hyper is None else hyper.data_ptr())
         assert (p - ref.detach()).abs().max().item() < 2e-7
     assert torch.equal(w16, p.bfloat16())
 

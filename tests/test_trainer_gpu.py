@@ -253,3 +253,29 @@ def test_snapshot_round_trip_uses_reference_keys_and_shapes(tmp_path):
     tr2.load_vae(prefix, 1.0)
     for k, v in tr2.vae_store.state_dict().items():
         assert torch.equal(v.cpu(), oracle.state_dict("vae")[k]), k
+
+
+def test_cuda_graph_replay_equals_eager():
+    """graphs=True replays post_update / vae_update from captured CUDA graphs (Adam's step-dependent factors come
+    from device memory).  With the pose-VAE's sampling noise switched off the trajectory must equal the eager one."""
+    import lsps_b200
+    hp = _hp("nnyu")
+    oracle = O.OracleTrainer(hp, seed=0)
+    trs = [lsps_b200.LSPSTrainerB200(hp, device=0, noise="device", graphs=g) for g in (False, True)]
+    for tr in trs:
+        load_from_oracle(tr, oracle)
+        sd = tr.vae_store.state_dict()
+        sd["en_sigma.bias"] = torch.full_like(sd["en_sigma.bias"], -40.0)      # softplus -> ~0: no sampling noise
+        tr.vae_store.load_state_dict(sd)
+    g = torch.Generator().manual_seed(3)
+    hist = [[], []]
+    for s in range(7):
+        ia, ib, la, lb = (t.cuda() for t in O.synthetic_batch(8, 108, g, "uniform"))
+        for i, tr in enumerate(trs):
+            tr.post_update(ia, la, ib, lb, None, None, 0, hp)
+            hist[i].append(float(tr.dis_reg_loss))
+    assert "g1" in trs[1]._graphs[("post", 0, 8, 108)], "the graphed path never captured"
+    for a, b in zip(*hist):
+        assert abs(a - b) <= 5e-3 * abs(a) + 1e-7, hist       # fp32 atomics order is the only difference
+    wa, wb = trs[0].dis_store.state_dict()["Post.weight"], trs[1].dis_store.state_dict()["Post.weight"]
+    assert (wa - wb).abs().max().item() < 5e-5
