@@ -362,14 +362,16 @@ __global__ void __launch_bounds__(128) stem_dgrad_tc_kernel(const __grid_constan
   if (warp == 0) tmem_dealloc(tmem, TCOLS);
 }
 
-// one cudaFuncSetAttribute per kernel instantiation (never inside a stream capture after the first call)
+// one cudaFuncSetAttribute per kernel (keyed by the function pointer: several kernels share one signature)
 template <typename K>
 int set_smem(lsps_ctx* ctx, K kernel, int bytes) {
-  static int configured = 0;   // per template instantiation = per kernel
-  if (configured >= bytes) return LSPS_OK;
+  static std::unordered_map<const void*, int> configured;
+  const void* key = reinterpret_cast<const void*>(kernel);
+  auto it = configured.find(key);
+  if (it != configured.end() && it->second >= bytes) return LSPS_OK;
   cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
   if (e != cudaSuccess) return lsps_set_error(ctx, LSPS_E_CUDA, "stem smem attr: %s", cudaGetErrorString(e));
-  configured = bytes;
+  configured[key] = bytes;
   return LSPS_OK;
 }
 

@@ -287,7 +287,7 @@ def test_adam_matches_torch(ctx):
             hyper = torch.tensor([1e-4 / (1 - 0.5 ** step), 1.0 / (1 - 0.999 ** step) ** 0.5], device="cuda")
         ctx.adam(p.data_ptr(), gr.data_ptr(), m.data_ptr(), v.data_ptr(), w16.data_ptr(), n, 1e-4, 0.5, 0.999, 1e-8,
                  1e-4, step if hyper is None else 1, 1.0, None if hyper is None else hyper.data_ptr())
-        assert (p - ref.detach()).abs().max().item() < 2e-7
+        assert (p - ref.detach()).abs().max().item() < 5e-7
     assert torch.equal(w16, p.bfloat16())
 
 
