@@ -133,6 +133,11 @@ int lsps_adam(lsps_ctx*, float* p, const float* g, float* m, float* v, void* w16
 /* wt[tap][cin][cout] (bf16) = transpose of w[tap][cout][cin] (f32 master) : the dgrad operand */
 int lsps_pack_dgrad(lsps_ctx*, const float* w, void* wt, int taps, int cout, int cin, lsps_stream);
 int lsps_f32_to_bf16(lsps_ctx*, const float* x, void* y, long long n, lsps_stream);
+/* ---- evaluation sweep on device (src/depth_train.py:229-237; src/utils/handpose_evaluation.py:92-97,197-203):
+   per frame i: e_j = || (gt[i,j,:] - pred[i,j,:]) * (sx,sy,sz) ||  over joints j in joint_idx (NULL = first nj joints);
+   err_mean[i] = mean_j e_j ; err_max[i] = max_j e_j.  pred/gt f32 [n, j3] normalised joints, (sx,sy,sz) = cube/2 in mm. */
+int lsps_joint_errors(lsps_ctx*, const float* pred, const float* gt, const int* joint_idx, int nj, int j3, float sx,
+                      float sy, float sz, float* err_mean, float* err_max, int n, lsps_stream);
 int lsps_bf16_to_f32(lsps_ctx*, const void* x, float* y, long long n, lsps_stream);
 
 #ifdef __cplusplus

@@ -52,6 +52,7 @@ _SIGS = {
     "lsps_adam": [_vp, _vp, _vp, _vp, _vp, _ll, _f, _f, _f, _f, _f, _i, _f, _vp],
     "lsps_pack_dgrad": [_vp, _vp, _i, _i, _i],
     "lsps_f32_to_bf16": [_vp, _vp, _ll],
+    "lsps_joint_errors": [_vp, _vp, _vp, _i, _i, _f, _f, _f, _vp, _vp, _i],
     "lsps_bf16_to_f32": [_vp, _vp, _ll],
 }
 EXPORTS = sorted(list(_SIGS) + ["lsps_ctx_create", "lsps_ctx_destroy", "lsps_last_error", "lsps_abi_version",

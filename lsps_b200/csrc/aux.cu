@@ -416,6 +416,103 @@ __global__ void __launch_bounds__(512) instnorm_bwd_kernel(const bf16* __restric
   }
 }
 
+// ----- register-resident variants for hw == 1024 (the 32x32 latent of every LeakyINSResBlock) --------------------------
+// One CTA (512 threads) per (image, 32-channel group): the whole 64 KB slab of each input lives in the register file
+// (8 x 16 B per thread and tensor), so HBM is touched exactly once per element -- read the inputs, write the output --
+// and all 8 loads of a thread are in flight together.  Statistics stay two-pass (mean, then centred sum of squares),
+// but the second pass runs over registers.  (Forward only: the backward needs two slabs twice and spills; it keeps the
+// three-pass kernel above.)
+constexpr int INR_PPT = 8;  // pixels per thread: 1024 pixels / 128 pixel lanes
+
+// sum over the 128 pixel lanes of v8 (8 channels of this thread's octet) -> out[32] (all threads see it after return)
+__device__ __forceinline__ void inr_reduce(float* v8, float (*red)[32], float* out) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, oct = threadIdx.x & 3;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    float x = v8[k];
+    x += __shfl_xor_sync(0xffffffffu, x, 4);
+    x += __shfl_xor_sync(0xffffffffu, x, 8);
+    x += __shfl_xor_sync(0xffffffffu, x, 16);
+    v8[k] = x;
+  }
+  __syncthreads();
+  if (lane < 4) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) red[warp][oct * 8 + k] = v8[k];
+  }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < 16; ++w) s += red[w][threadIdx.x];
+    out[threadIdx.x] = s;
+  }
+  __syncthreads();
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(512) instnorm_fwd_reg_kernel(const bf16* __restrict__ h, const bf16* __restrict__ res,
+                                                              bf16* __restrict__ y, float* __restrict__ stats, int c,
+                                                              float eps, float slope) {
+  __shared__ float red[16][32];
+  __shared__ float s_a[32], s_b[32];
+  constexpr int hw = 128 * INR_PPT;
+  const int n = blockIdx.y, cg = blockIdx.x;
+  const int oct = threadIdx.x & 3, pl = threadIdx.x >> 2;
+  const long long base = (long long)n * hw * c + cg * 32 + oct * 8;
+  uint4 xv[INR_PPT], rv[MODE == 1 ? INR_PPT : 1];
+#pragma unroll
+  for (int i = 0; i < INR_PPT; ++i) xv[i] = __ldg(reinterpret_cast<const uint4*>(h + base + (long long)(pl + 128 * i) * c));
+  if (MODE == 1) {
+#pragma unroll
+    for (int i = 0; i < INR_PPT; ++i) rv[i] = __ldg(reinterpret_cast<const uint4*>(res + base + (long long)(pl + 128 * i) * c));
+  }
+  float a[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) a[k] = 0.f;
+#pragma unroll
+  for (int i = 0; i < INR_PPT; ++i) {
+    float f[8];
+    unpack8(xv[i], f);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) a[k] += f[k];
+  }
+  inr_reduce(a, red, s_a);
+  float mean[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { mean[k] = s_a[oct * 8 + k] * (1.f / hw); a[k] = 0.f; }
+#pragma unroll
+  for (int i = 0; i < INR_PPT; ++i) {
+    float f[8];
+    unpack8(xv[i], f);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { const float d = f[k] - mean[k]; a[k] += d * d; }
+  }
+  inr_reduce(a, red, s_b);
+  float rstd[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) rstd[k] = rsqrtf(s_b[oct * 8 + k] * (1.f / hw) + eps);
+  if (pl == 0) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      float* st = stats + ((long long)n * c + cg * 32 + oct * 8 + k) * 2;
+      st[0] = mean[k]; st[1] = rstd[k];
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < INR_PPT; ++i) {
+    float f[8], r[8];
+    unpack8(xv[i], f);
+    if (MODE == 1) unpack8(rv[i], r);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float v = (f[k] - mean[k]) * rstd[k];
+      f[k] = MODE == 1 ? r[k] + v : (v > 0.f ? v : v * slope);
+    }
+    *reinterpret_cast<uint4*>(y + base + (long long)(pl + 128 * i) * c) = pack8(f);
+  }
+}
+
 // =============================================================================================== elementwise / losses
 __global__ void __launch_bounds__(256) noise_kl_kernel(const bf16* __restrict__ x, const float* __restrict__ noise,
                                                       bf16* __restrict__ z, float* __restrict__ acc, long long n8) {
@@ -712,6 +809,26 @@ __global__ void pack_dgrad_kernel(const float* __restrict__ w, bf16* __restrict_
   }
 }
 
+// per-frame mean / max joint error in mm (depth_train.py:229-237 + handpose_evaluation.py:92-97,197-203)
+__global__ void joint_errors_kernel(const float* __restrict__ pred, const float* __restrict__ gt,
+                                    const int* __restrict__ jidx, int nj, int j3, float sx, float sy, float sz,
+                                    float* __restrict__ emean, float* __restrict__ emax, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float* p = pred + (long long)i * j3;
+  const float* g = gt + (long long)i * j3;
+  float s = 0.f, m = 0.f;
+  for (int q = 0; q < nj; ++q) {
+    const int j = jidx ? jidx[q] : q;
+    const float dx = (g[3 * j] - p[3 * j]) * sx, dy = (g[3 * j + 1] - p[3 * j + 1]) * sy, dz = (g[3 * j + 2] - p[3 * j + 2]) * sz;
+    const float e = sqrtf(dx * dx + dy * dy + dz * dz);
+    s += e;
+    m = fmaxf(m, e);
+  }
+  emean[i] = s / nj;
+  emax[i] = m;
+}
+
 __global__ void f32_to_bf16_kernel(const float* __restrict__ x, bf16* __restrict__ y, long long n) {
   for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256)
     y[i] = __float2bfloat16(x[i]);
@@ -735,6 +852,12 @@ static bool stem_use_tc(int wd, int stride) {
   if (simt < 0) { const char* e = getenv("LSPS_STEM_SIMT"); simt = (e && e[0] == '1') ? 1 : 0; }
   const int wo = wd / stride;
   return !simt && (wo == 64 || wo == 128);
+}
+
+static bool in_no_reg() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("LSPS_IN_NO_REG"); v = (e && e[0] == '1') ? 1 : 0; }
+  return v == 1;
 }
 
 #define ST_(s) static_cast<cudaStream_t>(s)
@@ -811,6 +934,12 @@ extern "C" int lsps_instnorm_fwd(lsps_ctx* ctx, const void* h, const void* res, 
                                  int c, int mode, float eps, float slope, lsps_stream st) {
   REQUIRE(ctx, h && y && stats && (mode == 0 || res), LSPS_E_ARG, "instnorm_fwd: null");
   REQUIRE(ctx, n > 0 && hw > 0 && c % 64 == 0, LSPS_E_SHAPE, "instnorm_fwd: c must be a multiple of 64");
+  if (hw == 128 * INR_PPT && !in_no_reg()) {
+    if (mode == 0) instnorm_fwd_reg_kernel<0><<<dim3(c / 32, n), 512, 0, ST_(st)>>>(static_cast<const bf16*>(h), nullptr, static_cast<bf16*>(y), stats, c, eps, slope);
+    else instnorm_fwd_reg_kernel<1><<<dim3(c / 32, n), 512, 0, ST_(st)>>>(static_cast<const bf16*>(h), static_cast<const bf16*>(res), static_cast<bf16*>(y), stats, c, eps, slope);
+    LSPS_CHECK_LAUNCH(ctx, "instnorm_fwd_reg");
+    return LSPS_OK;
+  }
   instnorm_fwd_kernel<<<dim3(c / 64, n), 512, 0, ST_(st)>>>(static_cast<const bf16*>(h), static_cast<const bf16*>(res),
                                                           static_cast<bf16*>(y), stats, hw, c, mode, eps, slope);
   LSPS_CHECK_LAUNCH(ctx, "instnorm_fwd");
@@ -991,5 +1120,13 @@ extern "C" int lsps_bf16_to_f32(lsps_ctx* ctx, const void* x, float* y, long lon
   REQUIRE(ctx, x && y && n > 0, LSPS_E_ARG, "bf16_to_f32: arg");
   bf16_to_f32_kernel<<<grid_for(n, 256, 8 * ctx->num_sms), 256, 0, ST_(st)>>>(static_cast<const bf16*>(x), y, n);
   LSPS_CHECK_LAUNCH(ctx, "bf16_to_f32");
+  return LSPS_OK;
+}
+
+extern "C" int lsps_joint_errors(lsps_ctx* ctx, const float* pred, const float* gt, const int* joint_idx, int nj, int j3,
+                                 float sx, float sy, float sz, float* err_mean, float* err_max, int n, lsps_stream st) {
+  REQUIRE(ctx, pred && gt && err_mean && err_max && n > 0 && nj > 0 && j3 >= 3 * nj, LSPS_E_ARG, "joint_errors: arg");
+  joint_errors_kernel<<<(n + 127) / 128, 128, 0, ST_(st)>>>(pred, gt, joint_idx, nj, j3, sx, sy, sz, err_mean, err_max, n);
+  LSPS_CHECK_LAUNCH(ctx, "joint_errors");
   return LSPS_OK;
 }

@@ -446,3 +446,23 @@ def synthetic_batch(batch, label_dim, generator, kind="uniform"):
     la = torch.randn(batch, label_dim, generator=generator) * 0.3
     lb = torch.randn(batch, label_dim, generator=generator) * 0.3
     return ia, ib, la, lb
+
+
+# ----------------------------------------------------------------------------------------
+# evaluation metrics (src/depth_train.py:229-237; src/utils/handpose_evaluation.py:92-97,197-203)
+# ----------------------------------------------------------------------------------------
+NYU_RESTRICTED_JOINTS = (0, 3, 6, 9, 12, 15, 18, 21, 24, 25, 27, 30, 31, 32)
+
+
+def evaluation_metrics(gt, pred, cube0, com=None, restricted=None, dist=40.0):
+    """numpy restatement: gt/pred (n, J*3) normalised joints -> (mean error mm, % frames with max joint error <= dist)."""
+    import numpy as np
+    gt = np.asarray(gt, np.float64).reshape(gt.shape[0], -1, 3)
+    pred = np.asarray(pred, np.float64).reshape(pred.shape[0], -1, 3)
+    if restricted is not None:
+        gt, pred = gt[:, list(restricted)], pred[:, list(restricted)]
+    scale = np.asarray(cube0, np.float64).reshape(3) / 2.0
+    com = np.zeros((gt.shape[0], 1, 3)) if com is None else np.asarray(com, np.float64).reshape(-1, 1, 3)
+    g3, p3 = gt * scale + com, pred * scale + com
+    e = np.sqrt(np.square(g3 - p3).sum(axis=2))
+    return float(np.nanmean(np.nanmean(e, axis=1))), float(100.0 * (np.nanmax(e, axis=1) <= dist).sum() / len(e))

@@ -280,3 +280,36 @@ def test_cuda_graph_replay_equals_eager():
     wa, wb = trs[0].dis_store.state_dict()["Post.weight"], trs[1].dis_store.state_dict()["Post.weight"]
     # Adam's sign-like early steps turn atomics-order noise on near-zero gradients into +-lr flips of single weights
     assert (wa - wb).abs().mean().item() < 5e-6 and (wa - wb).abs().max().item() < 7 * 2e-4
+
+
+def test_device_evaluation_sweep_matches_oracle():
+    """regress -> decode -> mm errors on the device vs the numpy restatement of the reference."""
+    import lsps_b200
+    hp = _hp("nnyu")
+    oracle = O.OracleTrainer(hp, seed=0)
+    tr = _trainer(hp)
+    load_from_oracle(tr, oracle)
+    g = torch.Generator().manual_seed(11)
+    ev = lsps_b200.PoseEvaluator(tr, domain="b", restricted_joints=lsps_b200.NYU_RESTRICTED_JOINTS)
+    gts, preds = [], []
+    cube = torch.tensor([300.0, 300.0, 300.0])
+    for _ in range(3):
+        x = torch.rand(5, 1, 128, 128, generator=g) * 2 - 1
+        y = torch.randn(5, 108, generator=g) * 0.3
+        ev.add_batch(x.cuda(), y.cuda(), cube)
+        with torch.no_grad():
+            preds.append(oracle.vae.decode(oracle.dis.regress("B", x)).numpy())
+        gts.append(y.numpy())
+    mean_err, within = ev.summary(40.0)
+    ref_mean, ref_within = O.evaluation_metrics(np.concatenate(gts), np.concatenate(preds), cube.numpy(),
+                                                restricted=O.NYU_RESTRICTED_JOINTS)
+    assert abs(mean_err - ref_mean) <= 2e-3 * ref_mean, (mean_err, ref_mean)
+    assert abs(within - ref_within) <= 100.0 / 15 + 1e-6, (within, ref_within)     # at most one borderline frame
+    # the kernel alone, on identical inputs: fp32 vs float64 numpy
+    P, G = torch.randn(64, 108, generator=g), torch.randn(64, 108, generator=g)
+    Pd, Gd = P.cuda(), G.cuda()
+    em, ex = torch.empty(64, device="cuda"), torch.empty(64, device="cuda")
+    tr.ops.ctx.joint_errors(Pd.data_ptr(), Gd.data_ptr(), None, 36, 108, 150.0, 125.0, 175.0, em.data_ptr(), ex.data_ptr(), 64)
+    d = (G - P).numpy().reshape(64, 36, 3).astype(np.float64) * np.array([150.0, 125.0, 175.0])
+    e = np.sqrt(np.square(d).sum(2))
+    assert np.allclose(em.cpu().numpy(), e.mean(1), rtol=1e-5) and np.allclose(ex.cpu().numpy(), e.max(1), rtol=1e-5)
