@@ -40,8 +40,6 @@ struct lsps_ctx {
   std::string err;
   void* encode_fn = nullptr;  // cuTensorMapEncodeTiled
   std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> tmaps;
-  void* ws = nullptr;  // split-K workspace of the wgrad kernel (grown on demand, freed with the ctx)
-  size_t ws_bytes = 0;
 };
 
 int lsps_set_error(lsps_ctx* ctx, int code, const char* fmt, ...);

@@ -59,10 +59,7 @@ extern "C" int lsps_ctx_create(lsps_ctx** out, int device) {
   *out = ctx;
   return LSPS_OK;
 }
-extern "C" void lsps_ctx_destroy(lsps_ctx* ctx) {
-  if (ctx && ctx->ws) cudaFree(ctx->ws);
-  delete ctx;
-}
+extern "C" void lsps_ctx_destroy(lsps_ctx* ctx) { delete ctx; }
 extern "C" const char* lsps_last_error(lsps_ctx* ctx) { return ctx ? ctx->err.c_str() : "null ctx"; }
 extern "C" long long lsps_launch_count(lsps_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
@@ -411,131 +408,6 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   if (warp == 1) { if (CG == 2) tmem_dealloc_cg2(tmem_base, Cfg::TMEM_COLS); else tmem_dealloc(tmem_base, Cfg::TMEM_COLS); }
 }
 
-// ------------------------------------------------------------------------------------------------ 3x3 s1 "slab" kernel
-// The K1 shape (3x3 stride-1, >= 256 channels, forward and data gradient) as CTA pairs with TWO operand rings.
-// TMA cost is dominated by a fixed per-box overhead (measured: r01 probes), so instead of one 128-row A box per tap the
-// producer loads ONE slab of (th+2) image rows per (filter column s, 64-channel chunk): the three filter rows r are
-// the same slab shifted by whole image rows -- a multiple of 1024 bytes, i.e. only a different descriptor start
-// address, no second copy.  Boxes per 3 K-steps: 1 slab + 3 weight tiles instead of 6.
-constexpr int SLAB_BYTES = 24576;   // (th + 2) * tw * 128 <= 24 KB
-constexpr int SLAB_SLOTS = 3;
-constexpr int WS_BYTES = 128 * 128; // this CTA's half of a 256-row weight tile
-constexpr int WS_SLOTS = 6;
-constexpr int SLAB_SMEM = SLAB_SLOTS * SLAB_BYTES + WS_SLOTS * WS_BYTES + 1024 + 256 + 2048 * 4;
-
-__global__ void __launch_bounds__(192, 1)
-conv_s1_slab_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ CUtensorMap tmB,
-                    const __grid_constant__ IgemmParams p) {
-  constexpr int BN = 256, CG = 2;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sS = base;
-  uint8_t* sW = base + SLAB_SLOTS * SLAB_BYTES;
-  uint64_t* sfull = reinterpret_cast<uint64_t*>(sW + WS_SLOTS * WS_BYTES);
-  uint64_t* sempty = sfull + SLAB_SLOTS;
-  uint64_t* wfull = sempty + SLAB_SLOTS;
-  uint64_t* wempty = wfull + WS_SLOTS;
-  uint64_t* tfull = wempty + WS_SLOTS;
-  uint64_t* tempty = tfull + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
-  float* sbias = reinterpret_cast<float*>(sW + WS_SLOTS * WS_BYTES + 256);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int rank = (int)cluster_ctarank();
-  const bool leader = rank == 0;
-  if (p.flags & LSPS_EP_BIAS) {
-    for (int i = threadIdx.x; i < p.tiles_n * BN; i += blockDim.x) sbias[i] = p.bias[i];
-  }
-  if (threadIdx.x == 0) {
-    for (int i = 0; i < SLAB_SLOTS; ++i) { mbar_init(&sfull[i], 1); mbar_init(&sempty[i], 1); }
-    for (int i = 0; i < WS_SLOTS; ++i) { mbar_init(&wfull[i], 1); mbar_init(&wempty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4 * CG); }
-    fence_barrier_init();
-    tma_prefetch_desc(&tmS);
-    tma_prefetch_desc(&tmB);
-  }
-  if (warp == 1) { tmem_alloc_cg2(tmem_slot, 512); tmem_relinquish_cg2(); }
-  tc_fence_before();
-  cluster_sync_all();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  const int tiles_m = p.tiles_x * p.tiles_y * p.tiles_i;
-  const int groups_m = (tiles_m + CG - 1) / CG;
-  const int per_phase = groups_m * p.tiles_n;
-  const int total = per_phase;                      // one phase
-  const int worker = blockIdx.x / CG, nworkers = gridDim.x / CG;
-  const int tw = 1 << p.twl, th = 1 << p.thl;
-  const uint32_t slab_bytes = (uint32_t)(th + 2) * tw * 128;
-
-  if (warp == 0) {
-    if (lane == 0) {
-      int ss = 0, ws = 0; uint32_t sph = 0, wph = 0;
-      for (int t = worker; t < total; t += nworkers) {
-        const int nt = t / groups_m, mt = (t - nt * groups_m) * CG + rank;
-        const int tx = mt % p.tiles_x, ty = (mt / p.tiles_x) % p.tiles_y, ti = mt / (p.tiles_x * p.tiles_y);
-        const int x0 = tx << p.twl, y0 = ty << p.thl, n0 = ti * p.nb;
-        for (int sc = 0; sc < 3; ++sc) {            // taps are ordered filter-column major: taps[sc*3 + r]
-          const int ax = p.taps[sc * 3].ax;
-          for (int kc = 0; kc < p.kchunks; ++kc) {
-            mbar_wait(&sempty[ss], sph ^ 1);
-            if (leader) mbar_expect_tx(&sfull[ss], 2 * slab_bytes);
-            tma_load_5d_cg2(sS + ss * SLAB_BYTES, &tmS, &sfull[ss], kc * 64, x0 + ax, 0, y0 - 1, n0);
-            if (++ss == SLAB_SLOTS) { ss = 0; sph ^= 1; }
-            for (int r = 0; r < 3; ++r) {
-              mbar_wait(&wempty[ws], wph ^ 1);
-              if (leader) mbar_expect_tx(&wfull[ws], 2 * WS_BYTES);
-              tma_load_2d_cg2(sW + ws * WS_BYTES, &tmB, &wfull[ws], kc * 64, p.taps[sc * 3 + r].brow + nt * BN + rank * (BN / 2));
-              if (++ws == WS_SLOTS) { ws = 0; wph ^= 1; }
-            }
-          }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    if (lane == 0 && leader) {
-      constexpr uint32_t idesc = umma_idesc_bf16(256, BN, 0, 0);
-      int ss = 0, ws = 0; uint32_t sph = 0, wph = 0; int it = 0;
-      for (int t = worker; t < total; t += nworkers, ++it) {
-        const int acc = it & 1; const uint32_t accph = (it >> 1) & 1;
-        mbar_wait(&tempty[acc], accph ^ 1);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * BN;
-        uint32_t first = 1;
-        for (int sc = 0; sc < 3; ++sc) {
-          for (int kc = 0; kc < p.kchunks; ++kc) {
-            mbar_wait(&sfull[ss], sph);
-            const uint32_t slab = smem_u32(sS + ss * SLAB_BYTES);
-            for (int r = 0; r < 3; ++r) {
-              mbar_wait(&wfull[ws], wph);
-              tc_fence_after();
-              // filter row r reads image rows y + ay: ay + 1 whole rows into the slab (tw * 128 B each, 1024-aligned)
-              const uint32_t a_addr = slab + (uint32_t)(p.taps[sc * 3 + r].ay + 1) * tw * 128;
-              const uint32_t b_addr = smem_u32(sW + ws * WS_BYTES);
-#pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                umma_bf16_cg2(d_tmem, umma_smem_desc(a_addr + k * 32, 0, 1024), umma_smem_desc(b_addr + k * 32, 0, 1024),
-                              idesc, first ? 0u : 1u);
-                first = 0;
-              }
-              umma_commit_cg2(&wempty[ws]);
-              if (++ws == WS_SLOTS) { ws = 0; wph ^= 1; }
-            }
-            umma_commit_cg2(&sempty[ss]);
-            if (++ss == SLAB_SLOTS) { ss = 0; sph ^= 1; }
-          }
-        }
-        umma_commit_cg2(&tfull[acc]);
-      }
-    }
-  } else {
-    epilogue_role<BN, CG>(p, sbias, tmem_base, tfull, tempty, warp, lane, rank, worker, nworkers, groups_m, per_phase, total);
-  }
-  tc_fence_before();
-  cluster_sync_all();
-  if (warp == 1) tmem_dealloc_cg2(tmem_base, 512);
-}
-
 // ------------------------------------------------------------------------------------------------ wgrad
 struct WTap { short mc, mx, mp, my, nc, nx, np, ny; };  // tap offsets in the dy (M side) / x (N side) maps
 struct WgradParams {
@@ -543,10 +415,8 @@ struct WgradParams {
   int twl, thl, nb;  // K tile = 64 pixels
   int ntaps, co_tiles, ci_tiles, splits;   // co_tiles counts tiles of 128*CG output channels
   int cout, cin;
-  int dbg, pf;
+  int dbg;
   float* dw;
-  float* ws;            // split-K partials [splits][9][cout][cin] (plain stores) or nullptr (red.add into dw)
-  long long ws_stride;  // elements per split
   WTap taps[9];
 };
 // one TMA box = KPX pixels x 64 channels.  TMA cost is dominated by a fixed per-box overhead, so the CTA-pair kernel
@@ -634,15 +504,6 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ CU
         if (CG == 2) tma_load_5d_cg2(s + (2 + j) * W_BOX_BYTES, &tmN, &full[stage], cbase, x0 + T.nx, T.np, y0 + T.ny, n0);
         else tma_load_5d(s + (2 + j) * W_BOX_BYTES, &tmN, &full[stage], cbase, x0 + T.nx, T.np, y0 + T.ny, n0);
       }
-      // both operands of wgrad are streamed from HBM exactly once per (tap, co tile) group; the centre-tap CTAs pull
-      // the boxes of a later K-step into L2 so that the demand loads of all 9 taps hit (prefetch distance p.pf steps)
-      if (p.pf > 0 && tap == 4 && pt + p.pf < pt1 && lane < nboxes) {
-        const int q = pt + p.pf;
-        const int qx = q % p.tiles_x, qy = (q / p.tiles_x) % p.tiles_y, qi = q / (p.tiles_x * p.tiles_y);
-        const int px0 = qx << p.twl, py0 = qy << p.thl, pn0 = qi * p.nb;
-        if (lane < nA) tma_prefetch_5d(&tmM, cot * 128 + lane * 64 + T.mc, px0 + T.mx, T.mp, py0 + T.my, pn0);
-        else tma_prefetch_5d(&tmN, cit * BN + (rank * Cfg::NB_BOXES + lane - nA) * 64 + T.nc, px0 + T.nx, T.np, py0 + T.ny, pn0);
-      }
       if (++stage == STAGES) { stage = 0; ph ^= 1; }
     }
   } else if (warp == 1) {
@@ -672,8 +533,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ CU
     const int co = cot * 128 + q * 32 + lane;
     mbar_wait(tfull, 0);
     tc_fence_after();
-    const long long eoff = ((long long)tap * p.cout + co) * p.cin + cit * BN;
-    float* dst = p.ws ? p.ws + (long long)split * p.ws_stride + eoff : p.dw + eoff;
+    float* dst = p.dw + ((long long)tap * p.cout + co) * p.cin + cit * BN;
     const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     uint32_t v[32];
     tmem_ld32(taddr, v);
@@ -685,36 +545,17 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ CU
       for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
       if (c0 + 32 < BN) tmem_ld32(taddr + c0 + 32, v);
       if (co < p.cout) {
-        if (p.ws) {  // exclusive slice of the workspace: plain 16-byte stores (a reduce kernel folds the splits)
 #pragma unroll
-          for (int j = 0; j < 8; ++j)
-            *reinterpret_cast<float4*>(dst + c0 + 4 * j) = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
-        } else {
-#pragma unroll
-          for (int j = 0; j < 8; ++j)
-            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + c0 + 4 * j), "f"(f[4 * j]),
-                         "f"(f[4 * j + 1]), "f"(f[4 * j + 2]), "f"(f[4 * j + 3])
-                         : "memory");
-        }
+        for (int j = 0; j < 8; ++j)
+          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + c0 + 4 * j), "f"(f[4 * j]),
+                       "f"(f[4 * j + 1]), "f"(f[4 * j + 2]), "f"(f[4 * j + 3])
+                       : "memory");
       }
     }
   }
   tc_fence_before();
   if (CG == 2) cluster_sync_all(); else __syncthreads();
   if (warp == 1) { if (CG == 2) tmem_dealloc_cg2(tmem_base, Cfg::TMEM_COLS); else tmem_dealloc(tmem_base, Cfg::TMEM_COLS); }
-}
-
-// dw += sum over splits of the workspace partials
-__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float4* __restrict__ ws, float4* __restrict__ dw,
-                                                           long long n4, long long stride4, int splits) {
-  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n4; i += (long long)gridDim.x * 256) {
-    float4 a = dw[i];
-    for (int s = 0; s < splits; ++s) {
-      const float4 b = __ldg(ws + s * stride4 + i);
-      a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
-    }
-    dw[i] = a;
-  }
 }
 
 // ------------------------------------------------------------------------------------------------ host side
@@ -757,17 +598,7 @@ inline int lsps_force_cg() {
   if (v < 0) { const char* e = getenv("LSPS_FORCE_CG"); v = e ? atoi(e) : 0; }
   return v;
 }
-inline bool lsps_no_ws() {  // split-K workspace + reduce kernel instead of red.add: measured no faster (r01) -> opt-in
-  static int v = -1;
-  if (v < 0) { const char* e = getenv("LSPS_WS"); v = (e && e[0] == '1') ? 0 : 1; }
-  return v == 1;
-}
-inline bool lsps_no_slab() {  // slab kernel measured slower than the generic pair kernel (r01): opt-in via LSPS_SLAB=1
-  static int v = -1;
-  if (v < 0) { const char* e = getenv("LSPS_SLAB"); v = (e && e[0] == '1') ? 0 : 1; }
-  return v == 1;
-}
-inline int lsps_kch_small() {  // K-steps per stage of the single-CTA BN<=128 kernels
+inline int lsps_kch_small() {  // K-steps per stage of the single-CTA BN<=128 kernels (measured: 1 is best, r01 probes)
   static int v = -1;
   if (v < 0) { const char* e = getenv("LSPS_KCH_SMALL"); v = e ? atoi(e) : 1; }
   return v;
@@ -776,11 +607,6 @@ inline bool lsps_no_kch2() {
   static int v = -1;
   if (v < 0) { const char* e = getenv("LSPS_NO_KCH2"); v = (e && e[0] == '1') ? 1 : 0; }
   return v == 1;
-}
-inline int lsps_pf() {
-  static int v = -1;
-  if (v < 0) { const char* e = getenv("LSPS_PF"); v = e ? atoi(e) : 0; }
-  return v;
 }
 inline int lsps_dbg() {
   static int v = -1;
@@ -920,29 +746,6 @@ int run_igemm(lsps_ctx* ctx, const lsps_conv_shape* s, Dir dir, const void* in, 
   uint32_t wd[2] = {(uint32_t)kc, (uint32_t)(9 * nc)}, wb[2] = {64, (uint32_t)(bn / cg)};
   rc = lsps_get_tmap(ctx, wpk, 2, wd, wb, &tmB);
   if (rc) return rc;
-  if (cg == 2 && plain && bn == 256 && g.nb == 1 && g.tw % 8 == 0 && (g.th + 2) * g.tw * 128 <= SLAB_BYTES && !lsps_no_slab()) {
-    // slab kernel: taps reordered filter-column major so that taps[s*3 + r] share one slab (same x shift)
-    IgemmParams q = p;
-    for (int sc = 0; sc < 3; ++sc)
-      for (int r = 0; r < 3; ++r) q.taps[sc * 3 + r] = p.taps[r * 3 + sc];
-    CUtensorMap tmS;
-    uint32_t dims[5] = {(uint32_t)kc, (uint32_t)iw, 1u, (uint32_t)ih, (uint32_t)n};
-    uint32_t box[5] = {64u, (uint32_t)g.tw, 1u, (uint32_t)(g.th + 2), 1u};
-    rc = lsps_get_tmap(ctx, in, 5, dims, box, &tmS);
-    if (rc) return rc;
-    static bool configured = false;
-    if (!configured) {
-      cudaError_t e = cudaFuncSetAttribute(conv_s1_slab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SLAB_SMEM);
-      if (e != cudaSuccess) return lsps_set_error(ctx, LSPS_E_CUDA, "slab smem attr: %s", cudaGetErrorString(e));
-      configured = true;
-    }
-    const int total = ((tiles_m + 1) / 2) * q.tiles_n;
-    const int workers = total < ctx->num_sms / 2 ? total : ctx->num_sms / 2;
-    cudaError_t e = launch_maybe_cluster(conv_s1_slab_kernel, workers * 2, SLAB_SMEM, 2, st, tmS, tmB, q);
-    if (e != cudaSuccess) return lsps_set_error(ctx, LSPS_E_CUDA, "conv_s1_slab launch: %s", cudaGetErrorString(e));
-    LSPS_CHECK_LAUNCH(ctx, "conv_s1_slab");
-    return LSPS_OK;
-  }
   if (cg == 2 && bn == 256 && !lsps_no_kch2()) return launch_igemm<256, 2, 2>(ctx, tmA, tmB, p, st);
   if (cg == 2) {
     if (bn == 256) return launch_igemm<256, 2>(ctx, tmA, tmB, p, st);
@@ -1003,7 +806,7 @@ extern "C" int lsps_conv_wgrad(lsps_ctx* ctx, const lsps_conv_shape* s, const vo
   WgradParams p{};
   p.tiles_x = wg / g.tw; p.tiles_y = hg / g.th; p.tiles_i = (n + g.nb - 1) / g.nb;
   p.twl = g.twl; p.thl = g.thl; p.nb = g.nb;
-  p.ntaps = 9; p.cout = cout; p.cin = cin; p.dw = dw; p.dbg = lsps_dbg(); p.pf = lsps_pf();
+  p.ntaps = 9; p.cout = cout; p.cin = cin; p.dw = dw; p.dbg = lsps_dbg();
   p.co_tiles = (cout + 128 * cg - 1) / (128 * cg);
   p.ci_tiles = cin / bn;
   for (int r = 0; r < 3; ++r)
@@ -1027,19 +830,6 @@ extern "C" int lsps_conv_wgrad(lsps_ctx* ctx, const lsps_conv_shape* s, const vo
   if (splits < 1) splits = 1;
   if (splits > ptiles) splits = ptiles;
   p.splits = splits;
-  // split-K partials go to a workspace with plain stores and are folded by a small reduce kernel: per-SM fp32 red
-  // throughput (~1.3 cycles per element) made the 128x256 red.add epilogue cost ~25 us per CTA
-  p.ws = nullptr; p.ws_stride = (long long)9 * cout * cin;
-  if (splits > 1 && !lsps_no_ws()) {
-    const size_t need = (size_t)splits * p.ws_stride * sizeof(float);
-    if (ctx->ws_bytes < need) {
-      if (ctx->ws) cudaFree(ctx->ws);
-      ctx->ws = nullptr; ctx->ws_bytes = 0;
-      if (cudaMalloc(&ctx->ws, need) != cudaSuccess) return lsps_set_error(ctx, LSPS_E_CUDA, "wgrad workspace alloc of %zu bytes failed", need);
-      ctx->ws_bytes = need;
-    }
-    p.ws = static_cast<float*>(ctx->ws);
-  }
   CUtensorMap tmM, tmN;
   // M side: dy (cout channels) ; N side: x (cin channels)
   int rc = act_tmap(ctx, dy, n, ho, wo, cout, kind == LSPS_DECONV_S2, g, &tmM);
@@ -1049,13 +839,5 @@ extern "C" int lsps_conv_wgrad(lsps_ctx* ctx, const lsps_conv_shape* s, const vo
   if (cg == 2) rc = bn == 256 ? launch_wgrad<256, 2>(ctx, tmM, tmN, p, st) : launch_wgrad<128, 2>(ctx, tmM, tmN, p, st);
   else rc = bn == 256 ? launch_wgrad<256, 1>(ctx, tmM, tmN, p, st)
                       : (bn == 128 ? launch_wgrad<128, 1>(ctx, tmM, tmN, p, st) : launch_wgrad<64, 1>(ctx, tmM, tmN, p, st));
-  if (rc) return rc;
-  if (p.ws) {
-    const long long n4 = p.ws_stride / 4;
-    long long grid = (n4 + 255) / 256;
-    if (grid > 4LL * ctx->num_sms) grid = 4LL * ctx->num_sms;
-    wgrad_reduce_kernel<<<(unsigned)grid, 256, 0, st>>>(reinterpret_cast<const float4*>(p.ws), reinterpret_cast<float4*>(dw), n4, n4, splits);
-    LSPS_CHECK_LAUNCH(ctx, "wgrad_reduce");
-  }
-  return LSPS_OK;
+  return rc;
 }

@@ -84,13 +84,6 @@ __device__ __forceinline__ void tma_load_5d(void* dst, const void* tmap, uint64_
       : "memory");
 }
 
-// L2 prefetch of a box (no shared memory, no barrier): hides the DRAM latency of streamed operands
-__device__ __forceinline__ void tma_prefetch_5d(const void* tmap, int c0, int c1, int c2, int c3, int c4) {
-  asm volatile("cp.async.bulk.prefetch.tensor.5d.L2.global.tile [%0, {%1, %2, %3, %4, %5}];" ::"l"(tmap), "r"(c0),
-               "r"(c1), "r"(c2), "r"(c3), "r"(c4)
-               : "memory");
-}
-
 // ------------------------------------------------------------------ tcgen05 / TMEM
 __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)),
