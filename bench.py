@@ -230,8 +230,12 @@ def main():
                 return out
             return f
         _engine.Ops.conv_fwd, _engine.Ops.conv_dgrad = wrap(orig_f, True), wrap(orig_d, False)
+    # per-launch durations are only meaningful without the concurrent side-stream wgrad kernels: this one extra step
+    # runs them inline (the timed region above uses the side stream)
+    tr.ops.use_side = False
     step_dev()
     torch.cuda.synchronize()
+    tr.ops.use_side = os.environ.get("LSPS_NO_SIDE", "0") != "1"
     _engine.Ops.conv_fwd, _engine.Ops.conv_dgrad = orig_f, orig_d
     if rank == 0:
         pk = _peaks()
@@ -244,7 +248,8 @@ def main():
                 "profiles/r01_ncu_k1_wgrad_v4.md (algorithmic: 64 MB in + 64 MB out + 1.2 MB weights; part of the "
                 "output is still in L2 at kernel end)",
                 "launches": len(ev), "avg_launch_ms": tot_ms / max(1, len(ev)),
-                "share_of_step": tot_ms / (ms / K), "peak_source": pk["src"] + ", sustained bf16"}
+                "share_of_step": tot_ms / (ms / K), "peak_source": pk["src"] + ", sustained bf16",
+                "note": "launch durations from one extra step with the wgrad side stream disabled (no concurrent kernels)"}
 
     if world > 1:
         dist.barrier()

@@ -9,6 +9,7 @@ Layouts: images fp32 [n,128,128]; activations bf16 NHWC; InstanceNorm statistics
 gradients fp32.  Network structure follows lsps_nets.py:86-160 (SharedDis) and :164-272 (SharedResGen).
 """
 import ctypes as C
+import os
 
 import torch
 
@@ -29,6 +30,29 @@ class Ops:
     def __init__(self, device):
         self.device = torch.device(device)
         self.ctx = _lib.context(self.device.index)
+        # weight-gradient kernels run on a side stream: they only feed the optimiser, so the tensor-bound wgrad GEMMs
+        # overlap the HBM-bound InstanceNorm-backward / small kernels of the data-gradient chain (join_side() before Adam)
+        self.side = torch.cuda.Stream(device=self.device)
+        self.use_side = os.environ.get("LSPS_NO_SIDE", "0") != "1"
+        self._side_refs = []
+
+    def _on_side(self, fn, *keep):
+        if not self.use_side or torch.cuda.is_current_stream_capturing():
+            fn()
+            return
+        ev = torch.cuda.Event()
+        ev.record()                      # everything the kernel reads has been enqueued on the main stream
+        self.side.wait_event(ev)
+        with torch.cuda.stream(self.side):
+            fn()
+        self._side_refs.append(keep)     # keep the operands alive (and their memory unrecycled) until the join
+
+    def join_side(self):
+        if self._side_refs:
+            ev = torch.cuda.Event()
+            ev.record(self.side)
+            torch.cuda.current_stream().wait_event(ev)
+            self._side_refs = []
 
     def empty(self, *shape, dtype=torch.bfloat16):
         return torch.empty(shape, dtype=dtype, device=self.device)
@@ -64,9 +88,12 @@ class Ops:
     def conv_wgrad(self, S, key, kind, x, dy, bias=True):
         n, h, w, cin = x.shape
         ci, co = self._io(S, key, kind)
-        self.ctx.conv_wgrad(_shape(kind, n, h, w, ci, co), x.data_ptr(), dy.data_ptr(), S.G(key + ".weight").data_ptr())
-        if bias:
-            self.ctx.colsum_bf16(dy.data_ptr(), dy.numel() // co, co, S.G(key + ".bias").data_ptr())
+
+        def launch():
+            self.ctx.conv_wgrad(_shape(kind, n, h, w, ci, co), x.data_ptr(), dy.data_ptr(), S.G(key + ".weight").data_ptr())
+            if bias:
+                self.ctx.colsum_bf16(dy.data_ptr(), dy.numel() // co, co, S.G(key + ".bias").data_ptr())
+        self._on_side(launch, x, dy)
 
     # ---- InstanceNorm
     def in_fwd(self, h, mode, res=None, out=None):
@@ -116,8 +143,8 @@ class Ops:
 
     def stem_wgrad(self, S, key, img, dy, stride):
         n, h, w = img.shape
-        self.ctx.stem_wgrad(img.data_ptr(), dy.data_ptr(), S.G(key + ".weight").data_ptr(),
-                            S.G(key + ".bias").data_ptr(), n, h, w, stride)
+        self._on_side(lambda: self.ctx.stem_wgrad(img.data_ptr(), dy.data_ptr(), S.G(key + ".weight").data_ptr(),
+                                                  S.G(key + ".bias").data_ptr(), n, h, w, stride), img, dy)
 
     def stem_dgrad(self, S, key, dy, dimg, stride, accumulate):
         n, h, w = dimg.shape

@@ -178,6 +178,7 @@ class LSPSTrainerB200(object):
         dFm = torch.empty_like(F)
         ctx.mask_to_bf16(dF.data_ptr(), F.data_ptr(), dFm.data_ptr(), SLOPE, F.numel())
         dis.features_bwd(sv, dFm, wgrad=True)
+        self.ops.join_side()
         del sv
         self._allreduce(D)
         D.adam_step(active=lambda k: not k.startswith("Post."))
@@ -233,6 +234,7 @@ class LSPSTrainerB200(object):
         ctx.l1_f32(x_bb.data_ptr(), ib.data_ptr(), dob[B:].data_ptr(), hp["ll_direct_link_w"] / npx, 0, G.acc[6:].data_ptr(), x_bb.numel())
         # kl_direct * (enc + enc) with enc = mean over the 2B latents
         gen.backward(s1, doa, dob, 2.0 * hp["kl_direct_link_w"] / float(2 * Bg * _LATENT))
+        self.ops.join_side()
         del s1
         self._allreduce(G)
         G.adam_step()
@@ -339,6 +341,7 @@ class LSPSTrainerB200(object):
         dFm = torch.empty_like(F)
         ctx.mask_to_bf16(dF.data_ptr(), F.data_ptr(), dFm.data_ptr(), SLOPE, F.numel())
         dis.features_bwd(sv, dFm, wgrad=True)
+        self.ops.join_side()
         return dict(outs=outs, preds=preds, Bg=Bg, pd=pd, per=per, n4=n4, feat=feat)
 
     def _post_tail(self, mode, hyper):
