@@ -657,6 +657,7 @@ int run_igemm(lsps_ctx* ctx, const lsps_conv_shape* s, Dir dir, const void* in, 
   if (kind < 0 || kind > 2 || n <= 0 || !is_pow2(h) || !is_pow2(w) || cin % 64 || cout % 64 || cin <= 0 || cout <= 0)
     return lsps_set_error(ctx, LSPS_E_SHAPE, "conv shape kind %d n %d h %d w %d cin %d cout %d", kind, n, h, w, cin, cout);
   if (kind != LSPS_CONV_S1 && (h < 2 || w < 2)) return lsps_set_error(ctx, LSPS_E_SHAPE, "stride-2 op needs h,w >= 2");
+  if (cin > 2048 || cout > 2048) return lsps_set_error(ctx, LSPS_E_SHAPE, "channels > 2048 (bias / K-step tables are sized for 2048)");
   if ((flags & LSPS_EP_BIAS) && !bias) return lsps_set_error(ctx, LSPS_E_ARG, "bias flag without bias");
   if ((flags & LSPS_EP_MASK) && !mask) return lsps_set_error(ctx, LSPS_E_ARG, "mask flag without mask");
   if ((flags & LSPS_EP_ADD) && !add) return lsps_set_error(ctx, LSPS_E_ARG, "add flag without add");
