@@ -27,8 +27,9 @@ typedef void* lsps_stream; /* cudaStream_t */
 
 enum { LSPS_OK = 0, LSPS_E_ARG = -1, LSPS_E_SHAPE = -2, LSPS_E_ARCH = -3, LSPS_E_CUDA = -4 };
 
-/* conv kinds: 3x3 stride-1 pad-1 Conv2d | 3x3 stride-2 pad-1 Conv2d | 3x3 stride-2 pad-1 output_padding-1 ConvTranspose2d */
-enum { LSPS_CONV_S1 = 0, LSPS_CONV_S2 = 1, LSPS_DECONV_S2 = 2 };
+/* conv kinds: 3x3 stride-1 pad-1 Conv2d | 3x3 stride-2 pad-1 Conv2d | 3x3 stride-2 pad-1 output_padding-1 ConvTranspose2d
+   | 4x4 stride-2 pad-1 ConvTranspose2d (Mapping net, lsps_nets.py:17-23; 16 taps, tap = r*4+s) */
+enum { LSPS_CONV_S1 = 0, LSPS_CONV_S2 = 1, LSPS_DECONV_S2 = 2, LSPS_DECONV4_S2 = 3 };
 /* epilogue flags of the implicit-GEMM kernels, applied in this order: +bias, LeakyReLU, +add, *lrelu'(mask) */
 enum { LSPS_EP_BIAS = 1, LSPS_EP_LRELU = 2, LSPS_EP_MASK = 4, LSPS_EP_ADD = 8 };
 

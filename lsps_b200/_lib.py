@@ -11,7 +11,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "liblsps_b200.so")
 
-CONV_S1, CONV_S2, DECONV_S2 = 0, 1, 2
+CONV_S1, CONV_S2, DECONV_S2, DECONV4_S2 = 0, 1, 2, 3
 EP_BIAS, EP_LRELU, EP_MASK, EP_ADD = 1, 2, 4, 8
 ACT_NONE, ACT_LRELU, ACT_SOFTPLUS = 0, 1, 2
 

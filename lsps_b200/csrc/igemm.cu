@@ -109,6 +109,7 @@ struct IgemmParams {
   int twl, thl, nb;   // M tile = 2^twl x 2^thl pixels x nb images = 128 rows
   int txl, tyl;       // log2(tiles_x), log2(tiles_y)
   int nimg, kchunks;  // kchunks = K channels / 64
+  int ntaps_all;      // filter taps in the table (9, or 16 for the 4x4 transposed conv)
   long long o_n, o_y, o_x;  // output strides (elements)
   int o_sy, o_sx;           // output pixel = (y*o_sy + oa, x*o_sx + ob)
   __nv_bfloat16* out;
@@ -119,7 +120,7 @@ struct IgemmParams {
   int flags;
   int dbg;  // profiling experiments only: 1 = skip MMA issue, 2 = skip TMA issue (results are garbage)
   Phase ph[4];
-  Tap taps[9];
+  Tap taps[16];
 };
 
 constexpr int A_STAGE_BYTES = 128 * 128;  // 128 rows x 64 bf16
@@ -138,7 +139,7 @@ struct IgemmCfg {
   static constexpr int STAGES = (196608 / STAGE_BYTES) > 8 ? 8 : (196608 / STAGE_BYTES);
   static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
   static constexpr int BIAS_BYTES = 2048 * 4;  // whole bias vector (Cout <= 2048) staged once per CTA
-  static constexpr int KTAB_BYTES = 9 * 32 * 16;  // K-step table (<= 9 taps x 32 chunks)
+  static constexpr int KTAB_BYTES = 16 * 32 * 16;  // K-step table (<= 16 taps x 32 chunks)
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256 + BIAS_BYTES + KTAB_BYTES;
 };
 
@@ -297,7 +298,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   }
   // the producer is ONE thread whose per-stage latency bounds the whole pipeline: no divisions or parameter-space
   // reads in its loop -- every (tap, 64-channel chunk) K-step is a precomputed 16-byte table entry
-  for (int i = threadIdx.x; i < 9 * p.kchunks; i += blockDim.x) {
+  for (int i = threadIdx.x; i < p.ntaps_all * p.kchunks; i += blockDim.x) {
     const int tp = i / p.kchunks, kc = i - tp * p.kchunks;
     const Tap T = p.taps[tp];
     ktab[i] = make_int4(kc * 64 + T.ac, (T.ax & 0xFFFF) | (T.ay << 16), T.ap | ((kc * 64) << 4), T.brow);
@@ -417,7 +418,7 @@ struct WgradParams {
   int cout, cin;
   int dbg;
   float* dw;
-  WTap taps[9];
+  WTap taps[16];
 };
 // one TMA box = KPX pixels x 64 channels.  TMA cost is dominated by a fixed per-box overhead, so the CTA-pair kernel
 // (2 + 2 boxes per stage) uses 128-pixel boxes; the single-CTA kernel keeps 64 pixels to afford >= 4 stages.
@@ -590,6 +591,15 @@ inline int t2_axis(int a, int* rs, int* ds) {
   if (a == 0) { rs[0] = 1; ds[0] = 0; return 1; }
   rs[0] = 0; ds[0] = 1; rs[1] = 2; ds[1] = 0; return 2;
 }
+// 4x4 stride-2 pad-1 transposed conv (output index 2*i - 1 + r).  Gather form along one axis: row 2*o - 1 + r of the
+// fine tensor = pair o + d, parity par
+inline void s4_axis(int r, int* d, int* par) { *d = r == 0 ? -1 : (r == 3 ? 1 : 0); *par = (r == 0 || r == 2) ? 1 : 0; }
+// scatter form: output parity a gets taps (r, coarse offset d): a=0 -> (1,0),(3,-1) ; a=1 -> (2,0),(0,+1)
+inline int t4_axis(int a, int* rs, int* ds) {
+  if (a == 0) { rs[0] = 1; ds[0] = 0; rs[1] = 3; ds[1] = -1; }
+  else { rs[0] = 2; ds[0] = 0; rs[1] = 0; ds[1] = 1; }
+  return 2;
+}
 
 enum Dir { FWD = 0, DGRAD = 1 };
 
@@ -654,7 +664,7 @@ int run_igemm(lsps_ctx* ctx, const lsps_conv_shape* s, Dir dir, const void* in, 
               void* out, const void* mask, const void* add, int flags, float slope, cudaStream_t st) {
   if (!ctx || !s || !in || !wpk || !out) return lsps_set_error(ctx, LSPS_E_ARG, "null argument");
   const int kind = s->kind, n = s->n, h = s->h, w = s->w, cin = s->cin, cout = s->cout;
-  if (kind < 0 || kind > 2 || n <= 0 || !is_pow2(h) || !is_pow2(w) || cin % 64 || cout % 64 || cin <= 0 || cout <= 0)
+  if (kind < 0 || kind > 3 || n <= 0 || !is_pow2(h) || !is_pow2(w) || cin % 64 || cout % 64 || cin <= 0 || cout <= 0)
     return lsps_set_error(ctx, LSPS_E_SHAPE, "conv shape kind %d n %d h %d w %d cin %d cout %d", kind, n, h, w, cin, cout);
   if (kind != LSPS_CONV_S1 && (h < 2 || w < 2)) return lsps_set_error(ctx, LSPS_E_SHAPE, "stride-2 op needs h,w >= 2");
   if (cin > 2048 || cout > 2048) return lsps_set_error(ctx, LSPS_E_SHAPE, "channels > 2048 (bias / K-step tables are sized for 2048)");
@@ -665,6 +675,8 @@ int run_igemm(lsps_ctx* ctx, const lsps_conv_shape* s, Dir dir, const void* in, 
   // forward-op output dims
   const int ho = kind == LSPS_CONV_S1 ? h : (kind == LSPS_CONV_S2 ? h / 2 : 2 * h);
   const int wo = kind == LSPS_CONV_S1 ? w : (kind == LSPS_CONV_S2 ? w / 2 : 2 * w);
+  const bool k4 = kind == LSPS_DECONV4_S2;
+  const int ks = k4 ? 4 : 3;
   // GEMM dims: K channels (of `in`), N channels (of `out`)
   const int kc = dir == FWD ? cin : cout, nc = dir == FWD ? cout : cin;
   // `in` / `out` tensor dims
@@ -675,7 +687,7 @@ int run_igemm(lsps_ctx* ctx, const lsps_conv_shape* s, Dir dir, const void* in, 
   //   down   : out grid = in grid / 2, pair view on `in`                 (S2 fwd, DECONV dgrad)
   //   up     : out grid = 2 * in grid, 4 phases, strided store           (DECONV fwd, S2 dgrad)
   const bool plain = kind == LSPS_CONV_S1;
-  const bool down = (kind == LSPS_CONV_S2 && dir == FWD) || (kind == LSPS_DECONV_S2 && dir == DGRAD);
+  const bool down = (kind == LSPS_CONV_S2 && dir == FWD) || ((kind == LSPS_DECONV_S2 || k4) && dir == DGRAD);
   const int hg = down ? ih / 2 : ih, wg = down ? iw / 2 : iw;  // GEMM pixel grid
   const Geo g = geo_for(hg, wg, 128);
 
@@ -683,7 +695,7 @@ int run_igemm(lsps_ctx* ctx, const lsps_conv_shape* s, Dir dir, const void* in, 
   p.tiles_x = wg / g.tw; p.tiles_y = hg / g.th; p.tiles_i = (n + g.nb - 1) / g.nb;
   p.twl = g.twl; p.thl = g.thl; p.nb = g.nb;
   p.txl = ilog2(p.tiles_x); p.tyl = ilog2(p.tiles_y);
-  p.nimg = n; p.kchunks = kc / 64;
+  p.nimg = n; p.kchunks = kc / 64; p.ntaps_all = ks * ks;
   p.o_n = (long long)oh * ow * nc; p.o_y = (long long)ow * nc; p.o_x = nc;
   p.out = static_cast<__nv_bfloat16*>(out); p.bias = bias;
   p.mask = static_cast<const __nv_bfloat16*>(mask); p.add = static_cast<const __nv_bfloat16*>(add);
@@ -703,15 +715,15 @@ int run_igemm(lsps_ctx* ctx, const lsps_conv_shape* s, Dir dir, const void* in, 
       }
   } else if (down) {
     p.nphases = 1; p.o_sy = p.o_sx = 1;
-    p.ph[0] = Phase{0, 9, 0, 0};
-    for (int r = 0; r < 3; ++r)
-      for (int c = 0; c < 3; ++c) {
+    p.ph[0] = Phase{0, (short)(ks * ks), 0, 0};
+    for (int r = 0; r < ks; ++r)
+      for (int c = 0; c < ks; ++c) {
         Tap& T = p.taps[nt++];
         int dy, py, dx, px;
-        s2_axis(r, &dy, &py);
-        s2_axis(c, &dx, &px);
+        if (k4) { s4_axis(r, &dy, &py); s4_axis(c, &dx, &px); }
+        else { s2_axis(r, &dy, &py); s2_axis(c, &dx, &px); }
         T.ay = dy; T.ap = py; T.ax = dx; T.ac = px * kc;
-        T.brow = (r * 3 + c) * nc;
+        T.brow = (r * ks + c) * nc;
       }
   } else {  // up: heaviest phase first
     p.nphases = 4; p.o_sy = p.o_sx = 2;
@@ -719,13 +731,13 @@ int run_igemm(lsps_ctx* ctx, const lsps_conv_shape* s, Dir dir, const void* in, 
     for (int i = 0; i < 4; ++i) {
       const int a = order[i][0], b = order[i][1];
       int rs[2], dys[2], cs[2], dxs[2];
-      const int nr = t2_axis(a, rs, dys), ncs = t2_axis(b, cs, dxs);
+      const int nr = k4 ? t4_axis(a, rs, dys) : t2_axis(a, rs, dys), ncs = k4 ? t4_axis(b, cs, dxs) : t2_axis(b, cs, dxs);
       p.ph[i] = Phase{(short)nt, (short)(nr * ncs), (short)a, (short)b};
       for (int ri = 0; ri < nr; ++ri)
         for (int ci = 0; ci < ncs; ++ci) {
           Tap& T = p.taps[nt++];
           T.ac = 0; T.ap = 0; T.ay = dys[ri]; T.ax = dxs[ci];
-          T.brow = (rs[ri] * 3 + cs[ci]) * nc;
+          T.brow = (rs[ri] * ks + cs[ci]) * nc;
         }
     }
   }
@@ -744,7 +756,7 @@ int run_igemm(lsps_ctx* ctx, const lsps_conv_shape* s, Dir dir, const void* in, 
   CUtensorMap tmA, tmB;
   int rc = act_tmap(ctx, in, n, ih, iw, kc, down, g, &tmA);
   if (rc) return rc;
-  uint32_t wd[2] = {(uint32_t)kc, (uint32_t)(9 * nc)}, wb[2] = {64, (uint32_t)(bn / cg)};
+  uint32_t wd[2] = {(uint32_t)kc, (uint32_t)(ks * ks * nc)}, wb[2] = {64, (uint32_t)(bn / cg)};
   rc = lsps_get_tmap(ctx, wpk, 2, wd, wb, &tmB);
   if (rc) return rc;
   if (cg == 2 && bn == 256 && !lsps_no_kch2()) return launch_igemm<256, 2, 2>(ctx, tmA, tmB, p, st);
@@ -794,7 +806,7 @@ extern "C" int lsps_conv_wgrad(lsps_ctx* ctx, const lsps_conv_shape* s, const vo
   cudaStream_t st = static_cast<cudaStream_t>(st_);
   if (!ctx || !s || !x || !dy || !dw) return lsps_set_error(ctx, LSPS_E_ARG, "null argument");
   const int kind = s->kind, n = s->n, h = s->h, w = s->w, cin = s->cin, cout = s->cout;
-  if (kind < 0 || kind > 2 || n <= 0 || !is_pow2(h) || !is_pow2(w) || cin % 64 || cout % 64 || cin <= 0 || cout <= 0)
+  if (kind < 0 || kind > 3 || n <= 0 || !is_pow2(h) || !is_pow2(w) || cin % 64 || cout % 64 || cin <= 0 || cout <= 0)
     return lsps_set_error(ctx, LSPS_E_SHAPE, "wgrad shape kind %d n %d h %d w %d cin %d cout %d", kind, n, h, w, cin, cout);
   const int ho = kind == LSPS_CONV_S1 ? h : (kind == LSPS_CONV_S2 ? h / 2 : 2 * h);
   const int wo = kind == LSPS_CONV_S1 ? w : (kind == LSPS_CONV_S2 ? w / 2 : 2 * w);
@@ -807,14 +819,19 @@ extern "C" int lsps_conv_wgrad(lsps_ctx* ctx, const lsps_conv_shape* s, const vo
   WgradParams p{};
   p.tiles_x = wg / g.tw; p.tiles_y = hg / g.th; p.tiles_i = (n + g.nb - 1) / g.nb;
   p.twl = g.twl; p.thl = g.thl; p.nb = g.nb;
-  p.ntaps = 9; p.cout = cout; p.cin = cin; p.dw = dw; p.dbg = lsps_dbg();
+  const bool k4 = kind == LSPS_DECONV4_S2;
+  const int ks = k4 ? 4 : 3;
+  p.ntaps = ks * ks; p.cout = cout; p.cin = cin; p.dw = dw; p.dbg = lsps_dbg();
   p.co_tiles = (cout + 128 * cg - 1) / (128 * cg);
   p.ci_tiles = cin / bn;
-  for (int r = 0; r < 3; ++r)
-    for (int c = 0; c < 3; ++c) {
-      WTap& T = p.taps[r * 3 + c];
+  for (int r = 0; r < ks; ++r)
+    for (int c = 0; c < ks; ++c) {
+      WTap& T = p.taps[r * ks + c];
       T = WTap{0, 0, 0, 0, 0, 0, 0, 0};
-      if (kind == LSPS_CONV_S1) { T.ny = r - 1; T.nx = c - 1; }
+      if (k4) {  // dy pair view at parity ((r+1)&1, (c+1)&1); x shifted by +1 (tap 0), 0 (taps 1, 2), -1 (tap 3)
+        T.mp = (r + 1) & 1; T.mc = ((c + 1) & 1) * cout;
+        T.ny = r == 0 ? 1 : (r == 3 ? -1 : 0); T.nx = c == 0 ? 1 : (c == 3 ? -1 : 0);
+      } else if (kind == LSPS_CONV_S1) { T.ny = r - 1; T.nx = c - 1; }
       else if (kind == LSPS_CONV_S2) {
         int dy_, py, dx_, px;
         s2_axis(r, &dy_, &py); s2_axis(c, &dx_, &px);
@@ -833,7 +850,7 @@ extern "C" int lsps_conv_wgrad(lsps_ctx* ctx, const lsps_conv_shape* s, const vo
   p.splits = splits;
   CUtensorMap tmM, tmN;
   // M side: dy (cout channels) ; N side: x (cin channels)
-  int rc = act_tmap(ctx, dy, n, ho, wo, cout, kind == LSPS_DECONV_S2, g, &tmM);
+  int rc = act_tmap(ctx, dy, n, ho, wo, cout, kind == LSPS_DECONV_S2 || k4, g, &tmM);
   if (rc) return rc;
   rc = act_tmap(ctx, x, n, h, w, cin, kind == LSPS_CONV_S2, g, &tmN);
   if (rc) return rc;

@@ -119,6 +119,16 @@ def vae_spec(p):
     return spec
 
 
+def map_spec(p):
+    """Mapping parameter table: lsps_nets.py:8-25 (ConvTranspose2d weights are (Cin, Cout, 4, 4))."""
+    ch, d, spec = p["output_ch"], p["input_dim"], OrderedDict()
+    for key, ci, co in (("model.0.model.0", d, 4 * ch), ("model.1.model.0", 4 * ch, 4 * ch),
+                        ("model.2.model.0", 4 * ch, 2 * ch), ("model.3", 2 * ch, ch)):
+        spec[key + ".weight"] = ((ci, co, 4, 4), "conv", co * 16)
+        spec[key + ".bias"] = ((co,), "bias", co * 16)
+    return spec
+
+
 def init_params(spec, seed):
     """Deterministic init with the reference's *laws* (not its RNG stream):
     Conv*/ConvTranspose* weights ~ N(0, 0.02) (init.py:8-12); biases and Linear weights
@@ -201,6 +211,11 @@ class Gen:
             idx += 1
         x = F.conv_transpose2d(x, self.P["%s.%d.weight" % (d, idx)], self.P["%s.%d.bias" % (d, idx)])
         return torch.tanh(x)
+
+    def decode(self, z):
+        """lsps_nets.py:239-243: both decoders on an externally supplied latent (no noise layer)."""
+        out = self._dec_shared(z)
+        return self._decode_back("A", out), self._decode_back("B", out)
 
     def forward(self, xa, xb):
         out = torch.cat((self._encode_front("A", xa), self._encode_front("B", xb)), 0)
@@ -285,6 +300,21 @@ class PoseVAE:
         return self.decode(z), z, mu, sd
 
 
+class Mapping:
+    """Functional Mapping net (lsps_nets.py:8-31): pose latent (n, 20) -> (n, 256, 32, 32)."""
+
+    def __init__(self, hp_map, params):
+        self.p, self.P = hp_map, params
+
+    def forward(self, x):
+        P = self.P
+        x = x.unsqueeze(2).unsqueeze(3)
+        x = _lrelu(F.conv_transpose2d(x, P["model.0.model.0.weight"], P["model.0.model.0.bias"], stride=1, padding=0))
+        x = _lrelu(F.conv_transpose2d(x, P["model.1.model.0.weight"], P["model.1.model.0.bias"], stride=2, padding=1))
+        x = _lrelu(F.conv_transpose2d(x, P["model.2.model.0.weight"], P["model.2.model.0.bias"], stride=2, padding=1))
+        return F.conv_transpose2d(x, P["model.3.weight"], P["model.3.bias"], stride=2, padding=1)
+
+
 # ----------------------------------------------------------------------------------------
 # trainer
 # ----------------------------------------------------------------------------------------
@@ -295,7 +325,9 @@ def _bce_logits_as_reference(logits, target_value):
 
 
 class OracleTrainer:
-    """CPU restatement of LSPSTrainer (train_map=False paths)."""
+    """CPU restatement of LSPSTrainer.  The Mapping net exists only when `hp["train_map"]` is set (the reference always
+    builds it and hands its parameters to gen_opt, lsps_trainer.py:24-28, but Adam skips parameters without a gradient,
+    so with train_map False it never changes)."""
 
     def __init__(self, hp, seed=0, params=None):
         self.hp = hp
@@ -303,15 +335,18 @@ class OracleTrainer:
             params = {"gen": init_params(gen_spec(hp["gen"]), seed + 1),
                       "dis": init_params(dis_spec(hp["dis"]), seed + 2),
                       "vae": init_params(vae_spec(hp["vae"]), seed + 3)}
+            if hp.get("train_map"):
+                params["map"] = init_params(map_spec(hp["map"]), seed + 4)
         self.params = {net: OrderedDict((k, v.clone().requires_grad_(True)) for k, v in d.items())
                        for net, d in params.items()}
         self.gen = Gen(hp["gen"], self.params["gen"])
         self.dis = Dis(hp["dis"], self.params["dis"])
         self.vae = PoseVAE(hp["vae"], self.params["vae"])
+        self.map = Mapping(hp["map"], self.params["map"]) if "map" in self.params else None
         lr = hp["lr"]
         adam = torch.optim.Adam
         self.dis_opt = adam(list(self.params["dis"].values()), lr=lr, betas=(0.5, 0.999), weight_decay=1e-4)
-        self.gen_opt = adam(list(self.params["gen"].values()), lr=lr, betas=(0.5, 0.999), weight_decay=1e-4)
+        self.gen_opt = adam(list(self.params["gen"].values()) + list(self.params.get("map", {}).values()), lr=lr, betas=(0.5, 0.999), weight_decay=1e-4)
         self.vae_opt = adam(list(self.params["vae"].values()), lr=lr * 10.0, betas=(0.5, 0.999), weight_decay=1e-3)
         msl = torch.optim.lr_scheduler.MultiStepLR
         self.dis_sch = msl(self.dis_opt, milestones=[200, 300, 400, 450], gamma=0.5)
@@ -322,8 +357,18 @@ class OracleTrainer:
         return OrderedDict((k, v.detach().clone()) for k, v in self.params[net].items())
 
     def _zero(self, net):
-        for v in self.params[net].values():
+        for v in self.params.get(net, {}).values():
             v.grad = None
+
+    def _map_decode(self, la, lb):
+        """lsps_trainer.py:86-93 / :148-155: pose labels -> vae.encode -> Mapping -> both decoders; domain A keeps the
+        first half of decode_A, domain B the second half of decode_B.  Also returns nothing else; the mapped latent is
+        recomputed by the caller when it needs it."""
+        z = self.map.forward(self.vae.encode(torch.cat((la, lb), 0))[0])
+        self._z_pose2depth = z
+        dec_a, dec_b = self.gen.decode(z)
+        n = dec_a.size(0) // 2
+        return dec_a[:n], dec_b[n:]
 
     @staticmethod
     def _kl(mu, sd=None):
@@ -345,10 +390,12 @@ class OracleTrainer:
     # --- lsps_trainer.py:143-218 (feat_mat branch, train_map False)
     def dis_update(self, ia, la, ib, lb, com_a=None, com_b=None, hp=None, feat_mat=True):
         hp = hp or self.hp
-        assert not hp["train_map"]
         self._zero("dis")
         x_aa, x_ba, x_ab, x_bb, _ = self.gen.forward(ia, ib)
-        if feat_mat:
+        if hp["train_map"]:          # :147-158
+            dec_a, dec_b = self._map_decode(la, lb)
+            da, db, ndiv = torch.cat((ia, x_ba, x_aa, dec_a), 0), torch.cat((ib, x_ab, x_bb, dec_b), 0), 4
+        elif feat_mat:
             da, db, ndiv = torch.cat((ia, x_ba, x_aa), 0), torch.cat((ib, x_ab, x_bb), 0), 3
         else:
             da, db, ndiv = torch.cat((ia, x_ba), 0), torch.cat((ib, x_ab), 0), 2
@@ -360,6 +407,8 @@ class OracleTrainer:
         la_, lb_ = torch.split(ra, ra.size(0) // ndiv, 0), torch.split(rb, rb.size(0) // ndiv, 0)
         ad = (_bce_logits_as_reference(la_[0], 1.0) + _bce_logits_as_reference(la_[1], 0.0) +
               _bce_logits_as_reference(lb_[0], 1.0) + _bce_logits_as_reference(lb_[1], 0.0))
+        if hp["train_map"]:          # :201-204
+            ad = ad + _bce_logits_as_reference(la_[3], 0.0) + _bce_logits_as_reference(lb_[3], 0.0)
         with torch.no_grad():   # helpers.py:20-32
             self.dis_true_acc = 0.5 * ((torch.sigmoid(la_[0]) >= 0.5).float().mean().item() +
                                        (torch.sigmoid(lb_[0]) >= 0.5).float().mean().item())
@@ -368,6 +417,8 @@ class OracleTrainer:
         loss = hp["gan_w"] * ad + hp["feature_w"] * feat
         loss.backward()
         self._zero("gen")            # the reference clears these in gen_update before use (:77)
+        self._zero("map")            # ... and these at :85 ; vae grads are cleared by vae.zero_grad() (:63)
+        self._zero("vae")
         self.dis_opt.step()
         self.dis_ad_loss = ad.item()
         self.dis_feat_loss = float(feat.detach()) if torch.is_tensor(feat) else float(feat)
@@ -376,26 +427,38 @@ class OracleTrainer:
     # --- lsps_trainer.py:76-141 (train_map False)
     def gen_update(self, ia, la, ib, lb, hp=None):
         hp = hp or self.hp
-        assert not hp["train_map"]
         self._zero("gen")
         x_aa, x_ba, x_ab, x_bb, shared = self.gen.forward(ia, ib)
         x_bab, shared_bab = self.gen.forward_a2b(x_ba)
         x_aba, shared_aba = self.gen.forward_b2a(x_ab)
-        oa, ob, _, _ = self.dis.forward(x_ba, x_ab)
+        map_z, map_ll = 0.0, 0.0
+        if hp["train_map"]:          # :84-99
+            self._zero("map")
+            dec_a, dec_b = self._map_decode(la, lb)
+            da, db = torch.cat((x_ba, dec_a), 0), torch.cat((x_ab, dec_b), 0)
+            map_z = ((shared - self._z_pose2depth) ** 2).mean()
+            map_ll = F.l1_loss(dec_a, ia) + F.l1_loss(dec_b, ib)
+        else:
+            da, db, dec_a, dec_b = x_ba, x_ab, x_ba, x_ab
+        oa, ob, _, _ = self.dis.forward(da, db)
         ad = _bce_logits_as_reference(oa, 1.0) + _bce_logits_as_reference(ob, 1.0)
         enc, enc_bab, enc_aba = self._kl(shared), self._kl(shared_bab), self._kl(shared_aba)
         ll_a, ll_b = F.l1_loss(x_aa, ia), F.l1_loss(x_bb, ib)
         ll_aba, ll_bab = F.l1_loss(x_aba, ia), F.l1_loss(x_bab, ib)
         total = (hp["gan_w"] * ad + hp["ll_direct_link_w"] * (ll_a + ll_b) +
                  hp["ll_cycle_link_w"] * (ll_aba + ll_bab) + hp["kl_direct_link_w"] * (enc + enc) +
-                 hp["kl_cycle_link_w"] * (enc_bab + enc_aba))
+                 hp["kl_cycle_link_w"] * (enc_bab + enc_aba) +
+                 hp["ll_map_z_w"] * map_z + hp["ll_map_w"] * map_ll)
         total.backward()
+        self._zero("vae")            # vae.encode sits inside the graph (:88); vae_opt never sees these gradients
         self.gen_opt.step()
         self.gen_enc_loss, self.gen_enc_loss2 = enc.item(), (enc_aba + enc_bab).item()
         self.gen_ad_loss = ad.item()
         self.gen_ll_loss, self.gen_ll_loss2 = (ll_a + ll_b).item(), (ll_bab + ll_aba).item()
+        if hp["train_map"]:
+            self.gen_map_loss, self.gen_map_loss2 = map_z.item(), map_ll.item()
         self.gen_total_loss = total.item()
-        return tuple(t.detach() for t in (x_aa, x_ba, x_ab, x_bb, x_aba, x_bab, x_ba, x_ab))
+        return tuple(t.detach() for t in (x_aa, x_ba, x_ab, x_bb, x_aba, x_bab, dec_a, dec_b))
 
     # --- lsps_trainer.py:220-262
     def post_update(self, ia, la, ib, lb, com_a=None, com_b=None, mode=3, hp=None):

@@ -23,7 +23,7 @@ import ref_loader                # noqa: E402
 OUT = os.path.join(HERE, "..", "tests", "golden")
 LOSS_KEYS = ("dis_loss", "dis_ad_loss", "dis_feat_loss", "dis_true_acc", "dis_fake_acc", "gen_total_loss",
              "gen_ad_loss", "gen_ll_loss", "gen_ll_loss2", "gen_enc_loss", "gen_enc_loss2",
-             "dis_reg_loss", "dis_total_loss", "vae_total_loss")
+             "dis_reg_loss", "dis_total_loss", "vae_total_loss", "gen_map_loss", "gen_map_loss2")
 
 
 def _ref_trainer(trainers, hp, oracle):
@@ -33,6 +33,8 @@ def _ref_trainer(trainers, hp, oracle):
     tr.gen.load_state_dict(oracle.state_dict("gen"))
     tr.dis.load_state_dict(oracle.state_dict("dis"))
     tr.vae.load_state_dict(oracle.state_dict("vae"))
+    if "map" in oracle.params:
+        tr.map.load_state_dict(oracle.state_dict("map"))
     return tr
 
 
@@ -76,6 +78,8 @@ def run_case(trainers, name, hp, schedule, batch, kind="uniform", steps=2, seed=
                     outs = tr.gen_update(ia, la, ib, lb, hp)
                     for i, nm in enumerate(("x_aa", "x_ba", "x_ab", "x_bb", "x_aba", "x_bab")):
                         rec["s%d_%s" % (s, nm)] = _sample(outs[i])
+                    if hp["train_map"]:
+                        rec["s%d_decode_A" % s], rec["s%d_decode_B" % s] = _sample(outs[6]), _sample(outs[7])
                 elif upd.startswith("post"):
                     outs = tr.post_update(ia, la, ib, lb, com, com, int(upd[4:]), hp)
                     rec["s%d_post_x_ba" % s] = _sample(outs[1])
@@ -84,7 +88,11 @@ def run_case(trainers, name, hp, schedule, batch, kind="uniform", steps=2, seed=
         sd = (lambda n: getattr(tr, n).state_dict()) if who == "ref" else tr.state_dict
         for net, keys in (("dis", ("model_S.3.model.0.weight", "model_A.0.model.0.weight", "D.weight", "Post.weight")),
                           ("gen", ("encode_A.0.model.0.weight", "enc_shared.0.model.0.weight", "decode_B.5.weight")),
-                          ("vae", ("en_fc1.weight", "de_fc2.bias"))):
+                          ("vae", ("en_fc1.weight", "de_fc2.bias")),
+                          ("map", ("model.0.model.0.weight", "model.1.model.0.weight", "model.2.model.0.bias",
+                                   "model.3.weight") if hp["train_map"] else ())):
+            if not keys:
+                continue
             d = sd(net)
             for k in keys:
                 rec["w_%s_%s" % (net, k)] = _sample(d[k])
@@ -104,7 +112,14 @@ def run_case(trainers, name, hp, schedule, batch, kind="uniform", steps=2, seed=
     print("%-28s ok  (oracle vs reference worst rel %.2e, %d arrays)" % (name, worst, len(results["ref"])))
 
 
-def main():
+def main(only=None):
+    global run_case
+    if only:
+        _run = run_case
+
+        def run_case(trainers, name, *a, **k):   # noqa: regenerate just the named fixtures
+            if name in only:
+                _run(trainers, name, *a, **k)
     os.makedirs(OUT, exist_ok=True)
     trainers = ref_loader.load_reference()
     torch.set_num_threads(os.cpu_count())
@@ -121,7 +136,11 @@ def main():
     run_case(trainers, "estimate4_nnyu_b5", nnyu, ["post4"], batch=5, steps=1)
     # config 4: ICVL shapes (48-d pose vector; conv nets identical)
     run_case(trainers, "estimate3_nicvl_b4", nicvl, ["post3"], batch=4, steps=1)
+    # the train_map=True branches (Mapping net, ndiv=4 discriminator batch, map losses)
+    nnyu_map = dict(nnyu, train_map=True)
+    run_case(trainers, "pretrain_map_nnyu_b1", nnyu_map, ["dis", "gen"], batch=1, steps=2)
+    run_case(trainers, "pretrain_map_nnyu_b2_hand", nnyu_map, ["dis", "gen"], batch=2, steps=1, kind="hand")
 
 
 if __name__ == "__main__":
-    main()
+    main(only=set(sys.argv[1:]))

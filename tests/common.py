@@ -6,7 +6,7 @@ import lsps_oracle as O
 
 LOSS_KEYS = ("dis_loss", "dis_ad_loss", "dis_feat_loss", "dis_true_acc", "dis_fake_acc", "gen_total_loss",
              "gen_ad_loss", "gen_ll_loss", "gen_ll_loss2", "gen_enc_loss", "gen_enc_loss2",
-             "dis_reg_loss", "dis_total_loss", "vae_total_loss")
+             "dis_reg_loss", "dis_total_loss", "vae_total_loss", "gen_map_loss", "gen_map_loss2")
 
 
 def sample(t):
@@ -41,6 +41,8 @@ def run_schedule(tr, hp, schedule, batch, steps, kind="uniform", device=None, on
                 outs = tr.gen_update(ia, la, ib, lb, hp)
                 for i, nm in enumerate(("x_aa", "x_ba", "x_ab", "x_bb", "x_aba", "x_bab")):
                     rec["s%d_%s" % (s, nm)] = sample(outs[i])
+                if hp["train_map"]:
+                    rec["s%d_decode_A" % s], rec["s%d_decode_B" % s] = sample(outs[6]), sample(outs[7])
             elif upd.startswith("post"):
                 outs = tr.post_update(ia, la, ib, lb, com, com, int(upd[4:]), hp)
                 rec["s%d_post_x_ba" % s] = sample(outs[1])
@@ -54,6 +56,8 @@ def load_from_oracle(tr, oracle):
     tr.gen_store.load_state_dict(oracle.state_dict("gen"))
     tr.dis_store.load_state_dict(oracle.state_dict("dis"))
     tr.vae_store.load_state_dict(oracle.state_dict("vae"))
+    if "map" in oracle.params:
+        tr.map_store.load_state_dict(oracle.state_dict("map"))
 
 
 GOLDEN_CASES = {
@@ -66,4 +70,20 @@ GOLDEN_CASES = {
     "estimate0_nnyu_b4": ("nnyu", ["post0"], 4, 2, "uniform"),
     "estimate4_nnyu_b5": ("nnyu", ["post4"], 5, 1, "uniform"),
     "estimate3_nicvl_b4": ("nicvl", ["post3"], 4, 1, "uniform"),
+    # train_map=True branches (Mapping net): config name "<yaml>:map"
+    "pretrain_map_nnyu_b1": ("nnyu:map", ["dis", "gen"], 1, 2, "uniform"),
+    "pretrain_map_nnyu_b2_hand": ("nnyu:map", ["dis", "gen"], 2, 1, "hand"),
 }
+
+
+def load_hp(name):
+    """Hyper-parameters of exps/<yaml>.yaml; a ":map" suffix switches the train_map branches on."""
+    import os
+    import yaml
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    base, _, opt = name.partition(":")
+    with open(os.path.join(root, "exps", base + ".yaml")) as fh:
+        hp = yaml.safe_load(fh)["train"]["hyperparameters"]
+    if opt == "map":
+        hp["train_map"] = True
+    return hp

@@ -14,8 +14,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def _hp(name):
-    with open(os.path.join(ROOT, "exps", name + ".yaml")) as fh:
-        return yaml.safe_load(fh)["train"]["hyperparameters"]
+    from common import load_hp
+    return load_hp(name)
 
 
 @pytest.mark.parametrize("case", sorted(GOLDEN_CASES))

@@ -28,8 +28,8 @@ def _trainer(hp):
 
 
 def _hp(name):
-    import lsps_b200
-    return lsps_b200.load_hyperparameters(name)
+    from common import load_hp
+    return load_hp(name)
 
 
 @pytest.mark.parametrize("case", sorted(GOLDEN_CASES))
