@@ -85,6 +85,10 @@ int lsps_noise_kl_fwd(lsps_ctx*, const void* x, const float* noise, void* z, flo
 /* out = a + alpha * b  (bf16 tensors; a may be NULL) */
 int lsps_axpy_bf16(lsps_ctx*, const void* a, const void* b, float alpha, void* out, long long n, lsps_stream);
 
+/* Mapping latent-matching term (lsps_trainer.py:52-53,97 `_compute_l2_loss(shared, z_pose2depth)`), bf16 tensors:
+   acc += sum (a-b)^2 ; g = scale*(a-b) */
+int lsps_l2_bf16(lsps_ctx*, const void* a, const void* b, void* g, float scale, float* acc, long long n, lsps_stream);
+
 /* ---- losses.  All `acc` arguments are single float accumulators (sum, not mean) in device memory. */
 /* L1 (nn.L1Loss, lsps_trainer.py:42,118-121): acc += sum|x-t| ; dx (+)= scale*sign(x-t) */
 int lsps_l1_f32(lsps_ctx*, const float* x, const float* t, float* dx, float scale, int accumulate, float* acc,

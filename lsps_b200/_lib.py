@@ -37,6 +37,7 @@ _SIGS = {
     "lsps_instnorm_bwd": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _vp],
     "lsps_noise_kl_fwd": [_vp, _vp, _vp, _vp, _ll],
     "lsps_axpy_bf16": [_vp, _vp, _f, _vp, _ll],
+    "lsps_l2_bf16": [_vp, _vp, _vp, _f, _vp, _ll],
     "lsps_l1_f32": [_vp, _vp, _vp, _f, _i, _vp, _ll],
     "lsps_l1_feat": [_vp, _vp, _vp, _vp, _f, _vp, _ll],
     "lsps_dhead_fwd": [_vp, _vp, _vp, _vp, _ll, _i],

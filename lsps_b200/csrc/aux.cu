@@ -544,6 +544,28 @@ __global__ void __launch_bounds__(256) axpy_bf16_kernel(const bf16* __restrict__
   }
 }
 
+// latent matching term of the Mapping net (lsps_trainer.py:52-53,97): acc += sum (a-b)^2 ; g = scale*(a-b)
+__global__ void __launch_bounds__(256) l2_bf16_kernel(const bf16* __restrict__ a, const bf16* __restrict__ b,
+                                                     bf16* __restrict__ g, float scale, float* __restrict__ acc,
+                                                     long long n8) {
+  __shared__ float sm[8];
+  float s = 0.f;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n8; i += (long long)gridDim.x * 256) {
+    float f[8], h[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(a) + i), f);
+    unpack8(__ldg(reinterpret_cast<const uint4*>(b) + i), h);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float d = f[k] - h[k];
+      s += d * d;
+      f[k] = scale * d;
+    }
+    reinterpret_cast<uint4*>(g)[i] = pack8(f);
+  }
+  const float t = block_sum(s, sm);
+  if (threadIdx.x == 0) atomicAdd(acc, t);
+}
+
 __global__ void __launch_bounds__(256) l1_f32_kernel(const float* __restrict__ x, const float* __restrict__ t,
                                                     float* __restrict__ dx, float scale, int accumulate,
                                                     float* __restrict__ acc, long long n) {
@@ -971,6 +993,15 @@ extern "C" int lsps_axpy_bf16(lsps_ctx* ctx, const void* a, const void* b, float
   axpy_bf16_kernel<<<grid_for(n / 8, 256, 8 * ctx->num_sms), 256, 0, ST_(st)>>>(
       static_cast<const bf16*>(a), static_cast<const bf16*>(b), alpha, static_cast<bf16*>(out), n / 8);
   LSPS_CHECK_LAUNCH(ctx, "axpy");
+  return LSPS_OK;
+}
+extern "C" int lsps_l2_bf16(lsps_ctx* ctx, const void* a, const void* b, void* g, float scale, float* acc, long long n,
+                            lsps_stream st) {
+  REQUIRE(ctx, a && b && g && acc, LSPS_E_ARG, "l2_bf16: null");
+  REQUIRE(ctx, n > 0 && n % 8 == 0, LSPS_E_SHAPE, "l2_bf16: n % 8");
+  l2_bf16_kernel<<<grid_for(n / 8, 256, 8 * ctx->num_sms), 256, 0, ST_(st)>>>(
+      static_cast<const bf16*>(a), static_cast<const bf16*>(b), static_cast<bf16*>(g), scale, acc, n / 8);
+  LSPS_CHECK_LAUNCH(ctx, "l2_bf16");
   return LSPS_OK;
 }
 extern "C" int lsps_l1_f32(lsps_ctx* ctx, const float* x, const float* t, float* dx, float scale, int accumulate,

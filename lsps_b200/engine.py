@@ -14,7 +14,7 @@ import os
 import torch
 
 from . import _lib
-from ._lib import CONV_S1, CONV_S2, DECONV_S2, EP_BIAS, EP_LRELU, EP_MASK, EP_ADD, ConvShape
+from ._lib import CONV_S1, CONV_S2, DECONV_S2, DECONV4_S2, EP_BIAS, EP_LRELU, EP_MASK, EP_ADD, ConvShape
 
 SLOPE = 0.01   # nn.LeakyReLU() default (common_net.py:169,251)
 IN_EPS = 1e-5  # nn.InstanceNorm2d default
@@ -64,7 +64,7 @@ class Ops:
     @staticmethod
     def _io(S, key, kind):
         sh = S.entries[key + ".weight"].shape
-        return (sh[1], sh[0]) if kind != DECONV_S2 else (sh[0], sh[1])  # (cin, cout)
+        return (sh[1], sh[0]) if kind not in (DECONV_S2, DECONV4_S2) else (sh[0], sh[1])  # (cin, cout)
 
     def conv_fwd(self, S, key, kind, x, lrelu, out=None):
         n, h, w, cin = x.shape
@@ -209,7 +209,7 @@ class Generator:
             save.append(dict(eb=eb, db=db, z=z))
         return y, z
 
-    def shared_bwd(self, sv, dy, kl_alpha):
+    def shared_bwd(self, sv, dy, kl_alpha, dz_extra=None):
         """kl_alpha = d(loss)/d(sum z^2): the KL term contributes 2*kl_alpha*z to dz."""
         o, S = self.ops, self.S
         for blk in reversed(sv["db"]):
@@ -217,6 +217,8 @@ class Generator:
         z = sv["z"]
         dz = torch.empty_like(z)
         o.ctx.axpy_bf16(dy.data_ptr(), z.data_ptr(), 2.0 * kl_alpha, dz.data_ptr(), z.numel())
+        if dz_extra is not None:
+            o.ctx.axpy_bf16(dz.data_ptr(), dz_extra.data_ptr(), 1.0, dz.data_ptr(), z.numel())
         for blk in reversed(sv["eb"]):
             dz = o.res_bwd(S, blk, dz)
         return dz
@@ -279,19 +281,47 @@ class Generator:
             save.update(enc=se, shared=ss[0], dec=sd, na=na, nb=nb)
         return oa, ob, z
 
-    def backward(self, save, doa, dob, kl_alpha):
-        """doa/dob: fp32 gradients w.r.t. the [na+nb,128,128] outputs of decode_A / decode_B."""
+    def backward(self, save, doa, dob, kl_alpha, dz_extra=None):
+        """doa/dob: fp32 gradients w.r.t. the [na+nb,128,128] outputs of decode_A / decode_B; dz_extra: optional bf16
+        gradient added at the noised shared latent (the Mapping net's latent-matching term)."""
         na, nb = save["na"], save["nb"]
         dy = self.dec_bwd(save["dec"][0], doa)
         dy2 = self.dec_bwd(save["dec"][1], dob)
         self.ops.ctx.axpy_bf16(dy.data_ptr(), dy2.data_ptr(), 1.0, dy.data_ptr(), dy.numel())
-        dh = self.shared_bwd(save["shared"], dy, kl_alpha)
+        dh = self.shared_bwd(save["shared"], dy, kl_alpha, dz_extra)
         i = 0
         if na:
             self.enc_bwd(save["enc"][i], dh[:na])
             i += 1
         if nb:
             self.enc_bwd(save["enc"][i], dh[na:])
+
+    # -- decode of an external latent (lsps_nets.py:239-243, used by the train_map branches): dec_shared on all 2n
+    #    latents, decode_A on the first half and decode_B on the second -- the halves the reference keeps
+    #    (lsps_trainer.py:92-93); the discarded halves carry no gradient and all layers are per-sample
+    def decode_fwd(self, z, save=None):
+        o, S = self.ops, self.S
+        n = z.shape[0] // 2
+        db = [] if save is not None else None
+        y = z
+        for i in range(self.p["n_gen_shared_blk"]):
+            y = o.res_fwd(S, "dec_shared.%d" % i, y, db)
+        sd = [] if save is not None else None
+        dec_a = self.dec_fwd("A", y[:n], sd)
+        dec_b = self.dec_fwd("B", y[n:], sd)
+        if save is not None:
+            save.update(db=db, dec=sd, n=n)
+        return dec_a, dec_b
+
+    def decode_bwd(self, save, d_a, d_b):
+        """Returns the gradient w.r.t. the latent handed to decode_fwd."""
+        o, S, n = self.ops, self.S, save["n"]
+        dy = o.empty(2 * n, 32, 32, 4 * self.p["ch"])
+        self.dec_bwd(save["dec"][0], d_a, out=dy[:n])
+        self.dec_bwd(save["dec"][1], d_b, out=dy[n:])
+        for blk in reversed(save["db"]):
+            dy = o.res_bwd(S, blk, dy)
+        return dy
 
     # -- cycle passes (lsps_nets.py:260-272), batched: first half a2b (encode_A -> decode_B), second half b2a
     def forward_cycle(self, x_ba, x_ab, noise, kl_acc_bab, kl_acc_aba, save=None):
@@ -336,6 +366,63 @@ class Generator:
         dh = self.shared_bwd(save["shared"], dy, kl_alpha)
         self.enc_bwd(save["enc"][0], dh[:n], dimg=dimg_ba)
         self.enc_bwd(save["enc"][1], dh[n:], dimg=dimg_ab)
+
+
+class Mapping:
+    """Mapping net (lsps_nets.py:8-31): pose latent (m, 20) -> shared latent (m, 32, 32, 256).  Layer 0 is a transposed
+    4x4 conv on a 1x1 input, i.e. a dense layer 20 -> 16*4ch (small dense kernels); layers 1-3 are 4x4 stride-2
+    transposed convs on the tcgen05 implicit-GEMM path (16 taps, 4 sub-pixel phases x 2x2 taps each)."""
+    KEYS = ("model.0.model.0", "model.1.model.0", "model.2.model.0", "model.3")
+
+    def __init__(self, ops, store, hp):
+        self.ops, self.S, self.p = ops, store, hp
+        assert hp["output_ch"] % 64 == 0
+
+    def forward(self, e, save=None):
+        o, S, (k0, k1, k2, k3) = self.ops, self.S, self.KEYS
+        e = e.contiguous().float()
+        m, d = e.shape
+        c0 = 4 * self.p["output_ch"]
+        bias16 = S.W(k0 + ".bias").repeat(16)                 # bias per (r, s, co) output column of the dense form
+        y0f = o.empty(m, 16 * c0, dtype=torch.float32)
+        o.ctx.linear_fwd(e.data_ptr(), 0, S.W(k0 + ".weight").data_ptr(), bias16.data_ptr(), y0f.data_ptr(), m, 16 * c0,
+                         d, _lib.ACT_LRELU, SLOPE)
+        y0 = o.empty(m, 4, 4, c0)
+        o.ctx.f32_to_bf16(y0f.data_ptr(), y0.data_ptr(), y0.numel())
+        y1 = o.conv_fwd(S, k1, DECONV4_S2, y0, True)
+        y2 = o.conv_fwd(S, k2, DECONV4_S2, y1, True)
+        z = o.conv_fwd(S, k3, DECONV4_S2, y2, False)
+        if save is not None:
+            save.update(e=e, y0=y0, y1=y1, y2=y2)
+        return z
+
+    def backward(self, sv, dz):
+        """dz: bf16 gradient w.r.t. the output latent.  The gradient w.r.t. the pose latent is not formed: it would only
+        reach the poseVAE encoder, which no optimiser steps from the GAN updates (lsps_trainer.py:26-31)."""
+        o, S, (k0, k1, k2, k3) = self.ops, self.S, self.KEYS
+        e, y0, y1, y2 = sv["e"], sv["y0"], sv["y1"], sv["y2"]
+        o.conv_wgrad(S, k3, DECONV4_S2, y2, dz)
+        d2 = o.conv_dgrad(S, k3, DECONV4_S2, dz, y2.shape, mask=y2)
+        o.conv_wgrad(S, k2, DECONV4_S2, y1, d2)
+        d1 = o.conv_dgrad(S, k2, DECONV4_S2, d2, y1.shape, mask=y1)
+        o.conv_wgrad(S, k1, DECONV4_S2, y0, d1)
+        d0 = o.conv_dgrad(S, k1, DECONV4_S2, d1, y0.shape, mask=y0)
+        m, c0 = y0.shape[0], y0.shape[3]
+        o.ctx.colsum_bf16(d0.data_ptr(), m * 16, c0, S.G(k0 + ".bias").data_ptr())
+        d0f = o.empty(m, 16 * c0, dtype=torch.float32)
+        o.ctx.bf16_to_f32(d0.data_ptr(), d0f.data_ptr(), d0.numel())
+        o.ctx.linear_bwd(e.data_ptr(), 0, S.W(k0 + ".weight").data_ptr(), d0f.data_ptr(), None, 0,
+                         S.G(k0 + ".weight").data_ptr(), None, m, 16 * c0, e.shape[1])
+
+    def __call__(self, e):
+        """Reference-style call: returns (m, 256, 32, 32) fp32."""
+        return self.forward(e).permute(0, 3, 1, 2).float()
+
+    def state_dict(self):
+        return self.S.state_dict()
+
+    def load_state_dict(self, sd, strict=True):
+        self.S.load_state_dict(sd, strict)
 
 
 class Discriminator:

@@ -27,6 +27,8 @@ def to_kernel_layout(kind, t):
         return t.permute(2, 3, 0, 1).reshape(9, t.shape[0], t.shape[1])
     if kind == "deconv3":    # IOHW (ci,co,3,3) -> [tap][co][ci]
         return t.permute(2, 3, 1, 0).reshape(9, t.shape[1], t.shape[0])
+    if kind in ("deconv4", "map0"):   # IOHW (ci,co,4,4) -> [tap][co][ci]; map0 (1x1 input) reads it as FC [16*co][ci]
+        return t.permute(2, 3, 1, 0).reshape(16, t.shape[1], t.shape[0])
     if kind == "post":       # (20,c,2,2) -> [20][pos*c + ch]
         return t.permute(0, 2, 3, 1).reshape(t.shape[0], -1)
     return t.reshape(-1)     # stem (64,1,7,7)->[64][49]; head (64,1,1,1)->[64]; D (1,c,1,1)->[c]; linear; bias
@@ -39,6 +41,9 @@ def from_kernel_layout(kind, flat, shape):
     if kind == "deconv3":
         ci, co = shape[0], shape[1]
         return flat.reshape(3, 3, co, ci).permute(3, 2, 0, 1).contiguous()
+    if kind in ("deconv4", "map0"):
+        ci, co = shape[0], shape[1]
+        return flat.reshape(4, 4, co, ci).permute(3, 2, 0, 1).contiguous()
     if kind == "post":
         o, c = shape[0], shape[1]
         return flat.reshape(o, 2, 2, c).permute(0, 3, 1, 2).contiguous()
@@ -56,7 +61,8 @@ class Entry:
 
 
 class ParamStore:
-    """entries: list of (key, shape, kind, law, fan_in).  kind in conv3|deconv3|stem|head|dhead|post|linear|bias."""
+    """entries: list of (key, shape, kind, law, fan_in).
+    kind in conv3|deconv3|deconv4|map0|stem|head|dhead|post|linear|bias."""
 
     def __init__(self, entries, device, lr, weight_decay, betas=(0.5, 0.999), eps=1e-8):
         self.device = torch.device(device)
@@ -66,7 +72,7 @@ class ParamStore:
             ent = Entry(*e)
             ent.off = off
             off += _round_up(ent.numel)
-            if ent.kind in ("conv3", "deconv3"):
+            if ent.kind in ("conv3", "deconv3", "deconv4"):
                 ent.dg_off = dg
                 dg += _round_up(ent.numel)
             self.entries[ent.key] = ent
@@ -150,7 +156,7 @@ class ParamStore:
                 co, ci = e.shape[0], e.shape[1]
             else:
                 ci, co = e.shape[0], e.shape[1]
-            self.ctx.pack_dgrad(self.W(k).data_ptr(), self.W16T(k).data_ptr(), 9, co, ci)
+            self.ctx.pack_dgrad(self.W(k).data_ptr(), self.W16T(k).data_ptr(), 16 if e.kind == "deconv4" else 9, co, ci)
 
     # --- optimiser
     def zero_grad(self):
@@ -333,4 +339,16 @@ def vae_entries(p):
                              ("de_fc1.model.0", (h, z), "linear"), ("de_fc2", (d, h), "linear")):
         out.append((key + ".weight", (o, i), "linear", law, i))
         out.append((key + ".bias", (o,), "bias", "small" if law == "small" else "bias", i))
+    return out
+
+
+def map_entries(p):
+    """Mapping (lsps_nets.py:8-25): ConvTranspose2d(20 -> 4ch, k4 s1 p0) on the 1x1 pose latent, then three
+    ConvTranspose2d(k4 s2 p1) up to (ch, 32, 32); LeakyReLU after the first three.  `output_dim` is informational in the
+    reference too (only stored in an attribute): the four layers always produce 32x32."""
+    ch, d, out = p["output_ch"], p["input_dim"], []
+    for key, ci, co, kind in (("model.0.model.0", d, 4 * ch, "map0"), ("model.1.model.0", 4 * ch, 4 * ch, "deconv4"),
+                              ("model.2.model.0", 4 * ch, 2 * ch, "deconv4"), ("model.3", 2 * ch, ch, "deconv4")):
+        out.append((key + ".weight", (ci, co, 4, 4), kind, "conv", co * 16))
+        out.append((key + ".bias", (co,), "bias", "bias", co * 16))
     return out

@@ -15,9 +15,9 @@ import torch
 import torch.distributed as dist
 
 from . import _lib
-from .engine import Ops, Generator, Discriminator, PoseVAE, SLOPE
+from .engine import Ops, Generator, Discriminator, PoseVAE, Mapping, SLOPE
 from .sharding import shard_rows, source_assignment
-from .params import ParamStore, MultiStepLR, Optimizer, gen_entries, dis_entries, vae_entries
+from .params import ParamStore, MultiStepLR, Optimizer, gen_entries, dis_entries, vae_entries, map_entries
 
 _LATENT = 256 * 32 * 32
 _NPIX = 128 * 128
@@ -35,11 +35,25 @@ def _img(t, dev):
     return t.reshape(t.shape[0], t.shape[-2], t.shape[-1]).to(device=dev, dtype=torch.float32).contiguous()
 
 
+class _JointSchedule:
+    """gen_sch when the Mapping store exists: steps both MultiStepLRs (one optimiser in the reference)."""
+
+    def __init__(self, *schedules):
+        self.schedules = schedules
+
+    def step(self):
+        for s in self.schedules:
+            s.step()
+
+    def get_lr(self):
+        return self.schedules[0].get_lr()
+
+    get_last_lr = get_lr
+
+
 class LSPSTrainerB200(object):
     def __init__(self, hyperparameters, device=None, seed=0, noise="host", graphs=False):
         hp = hyperparameters
-        if hp.get("train_map", False):
-            raise NotImplementedError("train_map=True (Mapping net) is a SURVEY section 8f 'next' row")
         if device is None:
             device = torch.cuda.current_device() if torch.cuda.is_available() else 0
         self.device = torch.device("cuda", device if isinstance(device, int) else torch.device(device).index)
@@ -62,11 +76,21 @@ class LSPSTrainerB200(object):
         self.dis = Discriminator(self.ops, self.dis_store, hp["dis"])
         self.vae = PoseVAE(self.ops, self.vae_store, hp["vae"], self._vae_noise)
         self.gen.state_dict, self.gen.load_state_dict = self.gen_store.state_dict, self.gen_store.load_state_dict
-        self.map = None
+        # The reference always builds Mapping and hands its parameters to gen_opt (lsps_trainer.py:24-28); without
+        # train_map they never receive a gradient, so Adam never touches them -- the 27.6 M-parameter store (and its
+        # moments) is only allocated when the train_map branches are on.  Same lr / weight decay as the generator.
+        self.map_store = self.map = None
+        if hp.get("train_map", False):
+            self.map_store = ParamStore(map_entries(hp["map"]), self.device, lr, 1e-4)
+            self.map_store.init_(seed + 4)
+            self.map = Mapping(self.ops, self.map_store, hp["map"])
+        self._vae_noise_groups = 1
         self.dis_opt, self.gen_opt, self.vae_opt = Optimizer(self.dis_store), Optimizer(self.gen_store), Optimizer(self.vae_store)
         # lsps_trainer.py:32-34
         self.dis_sch = MultiStepLR(self.dis_store, [200, 300, 400, 450], 0.5)
         self.gen_sch = MultiStepLR(self.gen_store, [200, 300, 400, 450], 0.5)
+        if self.map_store is not None:      # map parameters sit in gen_opt: one schedule drives both stores
+            self.gen_sch = _JointSchedule(self.gen_sch, MultiStepLR(self.map_store, [200, 300, 400, 450], 0.5))
         self.vae_sch = MultiStepLR(self.vae_store, [125, 175], 0.1)
         self._scratch = torch.zeros(8, dtype=torch.float32, device=self.device)
         self.last_outputs = None
@@ -97,7 +121,7 @@ class LSPSTrainerB200(object):
             if world == 1:
                 return torch.normal(torch.zeros(shape), std=0.05).to(self.device)
             t = torch.normal(torch.zeros((shape[0] * world,) + tuple(shape[1:])), std=0.05)
-            return shard_rows(t, 1, world, rank).to(self.device)
+            return shard_rows(t, self._vae_noise_groups, world, rank).to(self.device)
         return torch.randn(shape, device=self.device) * 0.05
 
     def _allreduce(self, store):
@@ -107,6 +131,22 @@ class LSPSTrainerB200(object):
 
     def _p(self, t):
         return t.data_ptr()
+
+    def _map_decode(self, labels_a, labels_b, hp, save_map=None, save_dec=None):
+        """lsps_trainer.py:86-93 / :148-155: cat(labels) -> vae.encode -> Mapping -> gen.decode; decode_A keeps the
+        domain-a half, decode_B the domain-b half.  Returns (z_pose2depth, decode_A, decode_B)."""
+        if self.map is None:
+            raise RuntimeError("train_map=True needs a trainer constructed with hyperparameters['train_map'] = True")
+        la = labels_a.detach().to(device=self.device, dtype=torch.float32)
+        lb = labels_b.detach().to(device=self.device, dtype=torch.float32)
+        self._vae_noise_groups = 2          # rows are (a-block | b-block): shard the host draw per block
+        try:
+            e = self.vae.encode(torch.cat((la, lb), 0))[0]
+        finally:
+            self._vae_noise_groups = 1
+        z = self.map.forward(e, save_map)
+        dec_a, dec_b = self.gen.decode_fwd(z, save_dec)
+        return z, dec_a, dec_b
 
     # ------------------------------------------------------------------ vae_update (lsps_trainer.py:62-74)
     def vae_update(self, y, hyperparameters=None):
@@ -150,7 +190,11 @@ class LSPSTrainerB200(object):
         noise = self._latent_noise(2 * B, groups=2)
         oa, ob, _ = self.gen.forward(ia, ib, noise, self._scratch)           # no activations kept: gen gets no grads
         x_aa, x_ba, x_ab, x_bb = oa[:B], oa[B:], ob[:B], ob[B:]
-        if feat_mat:
+        train_map = bool(hp.get("train_map", False))
+        if train_map:                                                        # :147-158, no activations kept either
+            _, dec_a, dec_b = self._map_decode(labels_a, labels_b, hp)
+            imgs_a, imgs_b, ndiv = torch.cat((ia, x_ba, x_aa, dec_a), 0), torch.cat((ib, x_ab, x_bb, dec_b), 0), 4
+        elif feat_mat:
             imgs_a, imgs_b, ndiv = torch.cat((ia, x_ba, x_aa), 0), torch.cat((ib, x_ab, x_bb), 0), 3
         else:
             imgs_a, imgs_b, ndiv = torch.cat((ia, x_ba), 0), torch.cat((ib, x_ab), 0), 2
@@ -164,6 +208,9 @@ class LSPSTrainerB200(object):
         for off in (0, ndiv * r):                                            # domain a, domain b
             ctx.bce_logits(lg[off:].data_ptr(), 1.0, scale, dlg[off:].data_ptr(), D.acc[0:].data_ptr(), r)
             ctx.bce_logits(lg[off + r:].data_ptr(), 0.0, scale, dlg[off + r:].data_ptr(), D.acc[2:].data_ptr(), r)
+            if train_map:                                                    # ad_fake_dec (:201-204): 4th group vs zeros
+                ctx.bce_logits(lg[off + 3 * r:].data_ptr(), 0.0, scale, dlg[off + 3 * r:].data_ptr(),
+                               D.acc[8:].data_ptr(), r)
         dF = torch.zeros(F.numel(), dtype=torch.float32, device=self.device)
         ctx.dhead_bwd(F.data_ptr(), D.W("D.weight").data_ptr(), dlg.data_ptr(), dF.data_ptr(),
                       D.G("D.weight").data_ptr(), D.G("D.bias").data_ptr(), lg.numel(), cf)
@@ -171,8 +218,8 @@ class LSPSTrainerB200(object):
             fs = B * 4 * cf
             Ff = F.reshape(-1)
             fscale = hp["feature_w"] / float(Bg * 4 * cf)
-            # mean|F_b(x_ab) - F_a(x_aa)| + mean|F_a(x_ba) - F_b(x_bb)|   groups: a=(ia,x_ba,x_aa) b=(ib,x_ab,x_bb)
-            for ga, gb in ((4, 2), (1, 5)):
+            # mean|F_b(x_ab) - F_a(x_aa)| + mean|F_a(x_ba) - F_b(x_bb)|   groups: a=(ia,x_ba,x_aa[,dec]) b=(ib,x_ab,x_bb[,dec])
+            for ga, gb in ((ndiv + 1, 2), (1, ndiv + 2)):
                 ctx.l1_feat(Ff[ga * fs:].data_ptr(), Ff[gb * fs:].data_ptr(), dF[ga * fs:].data_ptr(),
                             dF[gb * fs:].data_ptr(), fscale, D.acc[4:].data_ptr(), fs)
         dFm = torch.empty_like(F)
@@ -183,8 +230,8 @@ class LSPSTrainerB200(object):
         self._allreduce(D)
         D.adam_step(active=lambda k: not k.startswith("Post."))
         D.refresh_dgrad_operands()
-        acc = D.acc[:8].cpu().numpy().astype(np.float64)
-        ad = (acc[0] + acc[2]) / (4 * Bg)
+        acc = D.acc[:16].cpu().numpy().astype(np.float64)
+        ad = (acc[0] + acc[2] + acc[8]) / (4 * Bg)
         feat = acc[4] / (Bg * 4 * cf) if feat_mat else 0.0
         self.dis_ad_loss, self.dis_feat_loss = np.float32(ad), np.float32(feat)
         self.dis_loss = np.float32(hp["gan_w"] * ad + hp["feature_w"] * feat)
@@ -199,22 +246,32 @@ class LSPSTrainerB200(object):
         ia, ib = _img(images_a, self.device), _img(images_b, self.device)
         B = ia.shape[0]
         Bg = B * world
+        train_map = bool(hp.get("train_map", False))
+        M = self.map_store
         G.zero_grad()
+        if train_map and M is not None:
+            M.zero_grad()
         n2 = self._latent_noise(2 * B, groups=2)  # host RNG draw order of the reference: gen(), forward_a2b, forward_b2a
         n3 = self._latent_noise(B)
         n4 = self._latent_noise(B)
         s1 = {}
-        oa, ob, _ = gen.forward(ia, ib, n2, G.acc[2:], s1)
+        oa, ob, shared = gen.forward(ia, ib, n2, G.acc[2:], s1)
         x_aa, x_ba, x_ab, x_bb = oa[:B], oa[B:], ob[:B], ob[B:]
         s2 = {}
         x_bab, x_aba = gen.forward_cycle(x_ba, x_ab, torch.cat((n3, n4), 0), G.acc[3:], G.acc[4:], s2)
         del n2, n3, n4
+        dec_a, dec_b, nd = x_ba, x_ab, 1
+        if train_map:                        # :84-99 (the vae.encode draw comes after the three latent draws, as there)
+            sm, sdm = {}, {}
+            z_map, dec_a, dec_b = self._map_decode(labels_a, labels_b, hp, sm, sdm)
+            nd = 2
         # adversarial term through the discriminator (data gradient only)
         sd = {}
-        F = dis.features(x_ba, x_ab, sd)
+        F = dis.features(torch.cat((x_ba, dec_a), 0) if train_map else x_ba,
+                         torch.cat((x_ab, dec_b), 0) if train_map else x_ab, sd)
         lg = dis.logits(F)
         dlg = torch.empty_like(lg)
-        ctx.bce_logits(lg.data_ptr(), 1.0, hp["gan_w"] / float(4 * Bg), dlg.data_ptr(), G.acc[0:].data_ptr(), lg.numel())
+        ctx.bce_logits(lg.data_ptr(), 1.0, hp["gan_w"] / float(4 * nd * Bg), dlg.data_ptr(), G.acc[0:].data_ptr(), lg.numel())
         dF = torch.zeros(F.numel(), dtype=torch.float32, device=self.device)
         ctx.dhead_bwd(F.data_ptr(), D.W("D.weight").data_ptr(), dlg.data_ptr(), dF.data_ptr(), None, None, lg.numel(),
                       F.shape[-1])
@@ -222,9 +279,29 @@ class LSPSTrainerB200(object):
         ctx.mask_to_bf16(dF.data_ptr(), F.data_ptr(), dFm.data_ptr(), SLOPE, F.numel())
         doa = torch.empty_like(oa)           # d/d(x_aa | x_ba)
         dob = torch.empty_like(ob)           # d/d(x_ab | x_bb)
-        dis.features_bwd(sd, dFm, wgrad=False, dimg_a=doa[B:], dimg_b=dob[:B])
+        if train_map:
+            dia, dib = torch.empty(2 * B, 128, 128, device=self.device), torch.empty(2 * B, 128, 128, device=self.device)
+            dis.features_bwd(sd, dFm, wgrad=False, dimg_a=dia, dimg_b=dib)
+            doa[B:].copy_(dia[:B])
+            dob[:B].copy_(dib[:B])
+            d_dec_a, d_dec_b = dia[B:], dib[B:]
+        else:
+            dis.features_bwd(sd, dFm, wgrad=False, dimg_a=doa[B:], dimg_b=dob[:B])
         del sd
         npx = float(Bg * _NPIX)
+        g_z = None
+        if train_map:
+            # matching losses (:97-99): ll_map_w * (L1(decode_A, images_a) + L1(decode_B, images_b)) on top of the
+            # adversarial gradient; ll_map_z_w * mean((shared - z_pose2depth)^2) pulls both latents together
+            ctx.l1_f32(dec_a.data_ptr(), ia.data_ptr(), d_dec_a.data_ptr(), hp["ll_map_w"] / npx, 1, G.acc[10:].data_ptr(), dec_a.numel())
+            ctx.l1_f32(dec_b.data_ptr(), ib.data_ptr(), d_dec_b.data_ptr(), hp["ll_map_w"] / npx, 1, G.acc[11:].data_ptr(), dec_b.numel())
+            g_z = torch.empty_like(shared)
+            ctx.l2_bf16(shared.data_ptr(), z_map.data_ptr(), g_z.data_ptr(), 2.0 * hp["ll_map_z_w"] / float(2 * Bg * _LATENT),
+                        G.acc[12:].data_ptr(), shared.numel())
+            dzm = gen.decode_bwd(sdm, d_dec_a.contiguous(), d_dec_b.contiguous())
+            ctx.axpy_bf16(dzm.data_ptr(), g_z.data_ptr(), -1.0, dzm.data_ptr(), dzm.numel())
+            self.map.backward(sm, dzm)
+            del sdm, sm
         d_bab, d_aba = torch.empty_like(x_bab), torch.empty_like(x_aba)
         ctx.l1_f32(x_bab.data_ptr(), ib.data_ptr(), d_bab.data_ptr(), hp["ll_cycle_link_w"] / npx, 0, G.acc[8:].data_ptr(), x_bab.numel())
         ctx.l1_f32(x_aba.data_ptr(), ia.data_ptr(), d_aba.data_ptr(), hp["ll_cycle_link_w"] / npx, 0, G.acc[7:].data_ptr(), x_aba.numel())
@@ -233,23 +310,32 @@ class LSPSTrainerB200(object):
         ctx.l1_f32(x_aa.data_ptr(), ia.data_ptr(), doa[:B].data_ptr(), hp["ll_direct_link_w"] / npx, 0, G.acc[5:].data_ptr(), x_aa.numel())
         ctx.l1_f32(x_bb.data_ptr(), ib.data_ptr(), dob[B:].data_ptr(), hp["ll_direct_link_w"] / npx, 0, G.acc[6:].data_ptr(), x_bb.numel())
         # kl_direct * (enc + enc) with enc = mean over the 2B latents
-        gen.backward(s1, doa, dob, 2.0 * hp["kl_direct_link_w"] / float(2 * Bg * _LATENT))
+        gen.backward(s1, doa, dob, 2.0 * hp["kl_direct_link_w"] / float(2 * Bg * _LATENT), dz_extra=g_z)
         self.ops.join_side()
         del s1
         self._allreduce(G)
         G.adam_step()
         G.refresh_dgrad_operands()
+        if train_map:                        # gen_opt holds gen + map parameters (lsps_trainer.py:27)
+            self._allreduce(M)
+            M.adam_step()
+            M.refresh_dgrad_operands()
         acc = G.acc[:16].cpu().numpy().astype(np.float64)
-        ad = acc[0] / (4 * Bg)
+        ad = acc[0] / (4 * nd * Bg)
         enc, enc2 = acc[2] / (2 * Bg * _LATENT), (acc[3] + acc[4]) / (Bg * _LATENT)
         ll, ll2 = (acc[5] + acc[6]) / npx, (acc[7] + acc[8]) / npx
         self.gen_enc_loss, self.gen_enc_loss2 = np.float32(enc), np.float32(enc2)
         self.gen_ad_loss = np.float32(ad)
         self.gen_ll_loss, self.gen_ll_loss2 = np.float32(ll), np.float32(ll2)
-        self.gen_total_loss = np.float32(hp["gan_w"] * ad + hp["ll_direct_link_w"] * ll + hp["ll_cycle_link_w"] * ll2 +
-                                         hp["kl_direct_link_w"] * 2.0 * enc + hp["kl_cycle_link_w"] * enc2)
+        total = (hp["gan_w"] * ad + hp["ll_direct_link_w"] * ll + hp["ll_cycle_link_w"] * ll2 +
+                 hp["kl_direct_link_w"] * 2.0 * enc + hp["kl_cycle_link_w"] * enc2)
+        if train_map:
+            mz, ml = acc[12] / (2 * Bg * _LATENT), (acc[10] + acc[11]) / npx
+            self.gen_map_loss, self.gen_map_loss2 = np.float32(mz), np.float32(ml)
+            total += hp["ll_map_z_w"] * mz + hp["ll_map_w"] * ml
+        self.gen_total_loss = np.float32(total)
         u = lambda t: t.unsqueeze(1)
-        return (u(x_aa), u(x_ba), u(x_ab), u(x_bb), u(x_aba), u(x_bab), u(x_ba), u(x_ab))
+        return (u(x_aa), u(x_ba), u(x_ab), u(x_bb), u(x_aba), u(x_bab), u(dec_a), u(dec_b))
 
     # ------------------------------------------------------------------ post_update (lsps_trainer.py:220-262)
     def post_update(self, images_a, labels_a, images_b, labels_b, com_a=None, com_b=None, mode=3, hyperparameters=None):
@@ -421,8 +507,11 @@ class LSPSTrainerB200(object):
         """lsps_trainer.py:307-319: <prefix>_gen_%08d.pkl / _dis_ ; state_dict keys and shapes of the reference."""
         torch.save({k: v.cpu() for k, v in self.gen_store.state_dict().items()}, "%s_gen_%08d.pkl" % (snapshot_prefix, iterations + 1))
         torch.save({k: v.cpu() for k, v in self.dis_store.state_dict().items()}, "%s_dis_%08d.pkl" % (snapshot_prefix, iterations + 1))
-        torch.save({"gen": self._cpu(self.gen_store.opt_state()), "dis": self._cpu(self.dis_store.opt_state())},
-                   "%s_opt_%08d.pkl" % (snapshot_prefix, iterations + 1))
+        opt = {"gen": self._cpu(self.gen_store.opt_state()), "dis": self._cpu(self.dis_store.opt_state())}
+        if self.map_store is not None:   # the reference has this line commented out (:319) yet resume() looks for it (:299)
+            torch.save({k: v.cpu() for k, v in self.map_store.state_dict().items()}, "%s_map_%08d.pkl" % (snapshot_prefix, iterations + 1))
+            opt["map"] = self._cpu(self.map_store.opt_state())
+        torch.save(opt, "%s_opt_%08d.pkl" % (snapshot_prefix, iterations + 1))
 
     @staticmethod
     def _cpu(st):
@@ -433,7 +522,9 @@ class LSPSTrainerB200(object):
         import glob
         dirname, base = os.path.dirname(snapshot_prefix), os.path.basename(snapshot_prefix)
         iterations = 0
-        for net, store in (("gen", self.gen_store), ("dis", self.dis_store)):
+        for net, store in (("gen", self.gen_store), ("dis", self.dis_store), ("map", self.map_store)):
+            if store is None:
+                continue
             pref = base + ("_est" if (est and net == "dis") else "")
             files = sorted(glob.glob(os.path.join(dirname, "%s_%s_*.pkl" % (pref, net))))
             if not files:
@@ -444,7 +535,9 @@ class LSPSTrainerB200(object):
             if load_opt:
                 fo = f.replace("_%s_" % net, "_opt_")
                 if os.path.exists(fo):
-                    st = torch.load(fo, map_location="cpu")[net]
+                    st = torch.load(fo, map_location="cpu").get(net)
+                    if st is None:
+                        continue
                     store.load_opt_state({k: (v.to(self.device) if torch.is_tensor(v) else v) for k, v in st.items()})
         return iterations
 

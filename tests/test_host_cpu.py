@@ -15,11 +15,11 @@ def _hp(name):
 
 
 def test_parameter_tables_match_reference_state_dict_keys():
-    from lsps_b200.params import gen_entries, dis_entries, vae_entries
+    from lsps_b200.params import gen_entries, dis_entries, vae_entries, map_entries
     for cfg in ("nnyu", "nicvl"):
         hp = _hp(cfg)
         for mine, spec in ((gen_entries(hp["gen"]), O.gen_spec(hp["gen"])), (dis_entries(hp["dis"]), O.dis_spec(hp["dis"])),
-                           (vae_entries(hp["vae"]), O.vae_spec(hp["vae"]))):
+                           (vae_entries(hp["vae"]), O.vae_spec(hp["vae"])), (map_entries(hp["map"]), O.map_spec(hp["map"]))):
             assert [e[0] for e in mine] == list(spec.keys())
             for e in mine:
                 assert tuple(e[1]) == tuple(spec[e[0]][0]), e[0]
@@ -29,7 +29,7 @@ def test_parameter_tables_match_reference_state_dict_keys():
 def test_kernel_layout_round_trip_and_semantics():
     from lsps_b200.params import to_kernel_layout, from_kernel_layout
     g = torch.Generator().manual_seed(0)
-    for kind, shape in (("conv3", (8, 4, 3, 3)), ("deconv3", (4, 8, 3, 3)), ("post", (20, 16, 2, 2)), ("stem", (64, 1, 7, 7)),
+    for kind, shape in (("conv3", (8, 4, 3, 3)), ("deconv3", (4, 8, 3, 3)), ("deconv4", (4, 8, 4, 4)), ("map0", (5, 8, 4, 4)), ("post", (20, 16, 2, 2)), ("stem", (64, 1, 7, 7)),
                         ("head", (64, 1, 1, 1)), ("dhead", (1, 32, 1, 1)), ("linear", (5, 7)), ("bias", (9,))):
         t = torch.randn(shape, generator=g)
         k = to_kernel_layout(kind, t)
@@ -40,6 +40,13 @@ def test_kernel_layout_round_trip_and_semantics():
     wt = torch.randn(4, 8, 3, 3, generator=g)     # ConvTranspose2d IOHW
     k = to_kernel_layout("deconv3", wt)
     assert k.shape == (9, 8, 4) and torch.equal(k[2 * 3 + 0], wt[:, :, 2, 0].t())
+    w4 = torch.randn(4, 8, 4, 4, generator=g)     # Mapping: ConvTranspose2d k4, IOHW -> [tap = r*4+s][co][ci]
+    k = to_kernel_layout("deconv4", w4)
+    assert k.shape == (16, 8, 4) and torch.equal(k[3 * 4 + 1], w4[:, :, 3, 1].t())
+    # ... and layer 0 (k4 s1 p0 on a 1x1 input) read as a dense layer [16*co][ci] producing NHWC (4, 4, co)
+    e = torch.randn(3, 4, generator=g)
+    ref = torch.nn.functional.conv_transpose2d(e[:, :, None, None], w4).permute(0, 2, 3, 1).reshape(3, -1)
+    assert torch.allclose(ref, e @ to_kernel_layout("map0", w4).reshape(16 * 8, 4).t(), atol=1e-5)
     p = torch.randn(20, 16, 2, 2, generator=g)    # Post conv == FC over (pos, channel)
     k = to_kernel_layout("post", p)
     f = torch.randn(3, 16, 2, 2, generator=g)

@@ -45,6 +45,9 @@ CONV_CASES = [  # kind, n, h, w, cin, cout
     # large enough for the CTA-pair (cta_group::2) conv kernels: >= 2*148 M tiles and >= 27 K-steps per tile
     (0, 40, 32, 32, 256, 256),        # K1 shape, 320 tiles: pair kernel with 128-channel stages
     (1, 297, 16, 16, 256, 512),       # dis trunk shape, 149 M tiles (odd): the pair's phantom tile path
+    # kind 3 = 4x4 stride-2 pad-1 ConvTranspose2d (Mapping net layers 1-3, lsps_nets.py:19-23) + odd / larger batches
+    (3, 2, 4, 4, 1024, 1024), (3, 2, 8, 8, 1024, 512), (3, 2, 16, 16, 512, 256), (3, 5, 4, 4, 128, 64),
+    (3, 150, 16, 16, 512, 256),     # >= 296 tiles: CTA-pair kernels with 16 taps / 4 phases
 ]
 
 
@@ -53,7 +56,12 @@ def test_conv_fwd_dgrad_wgrad(ctx, kind, n, h, w, cin, cout):
     from lsps_b200._lib import ConvShape
     g = gen(kind * 100 + n)
     x = torch.randn(n, cin, h, w, device="cuda", generator=g).bfloat16().float().requires_grad_(True)
-    if kind == 2:
+    taps = 16 if kind == 3 else 9
+    if kind == 3:
+        wt = (torch.randn(cin, cout, 4, 4, device="cuda", generator=g) * 0.05).bfloat16().float().requires_grad_(True)
+        pack = lambda t: t.permute(2, 3, 1, 0).reshape(16, cout, cin)
+        y = F.conv_transpose2d(x, wt, None, stride=2, padding=1)
+    elif kind == 2:
         wt = (torch.randn(cin, cout, 3, 3, device="cuda", generator=g) * 0.05).bfloat16().float().requires_grad_(True)
         pack = lambda t: t.permute(2, 3, 1, 0).reshape(9, cout, cin)
         y = F.conv_transpose2d(x, wt, None, stride=2, padding=1, output_padding=1)
@@ -79,7 +87,7 @@ def test_conv_fwd_dgrad_wgrad(ctx, kind, n, h, w, cin, cout):
     ctx.conv_dgrad(sh, dyb.data_ptr(), wd.data_ptr(), dxb.data_ptr(), mask.data_ptr(), add.data_ptr(), 12, SLOPE)
     ref = (x.grad + nchw32(add)) * torch.where(nchw32(mask) > 0, 1.0, SLOPE)
     assert rel_l2(nchw32(dxb), ref) < BF16_L2
-    dw = torch.zeros(9, cout, cin, device="cuda")
+    dw = torch.zeros(taps, cout, cin, device="cuda")
     ctx.conv_wgrad(sh, xb.data_ptr(), dyb.data_ptr(), dw.data_ptr())
     assert rel_l2(dw, pack(wt.grad)) < 1e-4
     ctx.conv_wgrad(sh, xb.data_ptr(), dyb.data_ptr(), dw.data_ptr())       # accumulates
@@ -87,6 +95,18 @@ def test_conv_fwd_dgrad_wgrad(ctx, kind, n, h, w, cin, cout):
     db = torch.zeros(cout, device="cuda")
     ctx.colsum_bf16(dyb.data_ptr(), dyb.numel() // cout, cout, db.data_ptr())
     assert rel_l2(db, dy.sum((0, 2, 3))) < 1e-4
+
+
+def test_l2_bf16(ctx):
+    g = gen(5)
+    a = torch.randn(3, 32, 32, 256, device="cuda", generator=g).bfloat16()
+    b = torch.randn(3, 32, 32, 256, device="cuda", generator=g).bfloat16()
+    gr = torch.empty_like(a)
+    acc = torch.zeros(2, device="cuda")
+    ctx.l2_bf16(a.data_ptr(), b.data_ptr(), gr.data_ptr(), 0.25, acc.data_ptr(), a.numel())
+    d = a.float() - b.float()
+    assert abs(acc[0].item() - (d * d).sum().item()) <= 1e-5 * (d * d).sum().item()
+    assert rel_l2(gr, 0.25 * d) < BF16_L2 and acc[1].item() == 0.0
 
 
 @pytest.mark.parametrize("stride,n", [(1, 3), (2, 5)])

@@ -209,6 +209,45 @@ def test_gradients_and_post_step_weights_match_oracle():
         assert torch.equal(sd_t[k].cpu(), before[k]), "%s must not move in estimate0 (no gradient -> Adam skips it)" % k
 
 
+def test_train_map_gradients_and_losses_match_oracle():
+    """gen_update with train_map=True (lsps_trainer.py:84-99): Mapping + generator gradients, the two map losses and
+    the returned decode_A / decode_B against the oracle on the same weights and host RNG stream."""
+    from lsps_b200.params import from_kernel_layout
+    hp = _hp("nnyu:map")
+    oracle = O.OracleTrainer(hp, seed=0)
+    tr = _trainer(hp)
+    load_from_oracle(tr, oracle)
+    before = oracle.state_dict("map")
+    g = torch.Generator().manual_seed(1234)
+    ia, ib, la, lb = O.synthetic_batch(2, 108, g, "hand")
+    torch.manual_seed(7)
+    ref_out = oracle.gen_update(ia, la, ib, lb, hp)
+    torch.manual_seed(7)
+    out = tr.gen_update(ia.cuda(), la.cuda(), ib.cuda(), lb.cuda(), hp)
+    for k, tol in (("gen_map_loss", 5e-3), ("gen_map_loss2", 5e-3), ("gen_ll_loss", 5e-3), ("gen_total_loss", 5e-3),
+                   ("gen_ad_loss", 3e-2)):
+        a, b = float(getattr(oracle, k)), float(getattr(tr, k))
+        assert abs(a - b) <= tol * abs(a) + 1e-6, (k, a, b)
+    for i in (6, 7):
+        assert out[i].shape == ref_out[i].shape
+        assert (out[i].cpu() - ref_out[i]).abs().max().item() < IMG_ATOL, i
+    for net, store, keys in (("map", tr.map_store, list(oracle.params["map"])),
+                             ("gen", tr.gen_store, ["dec_shared.0.model.0.weight", "decode_A.4.model.0.weight",
+                                                    "decode_B.5.weight", "enc_shared.0.model.3.weight",
+                                                    "encode_A.1.model.0.weight"])):
+        for k in keys:
+            e = store.entries[k]
+            mine = from_kernel_layout(e.kind, store.G(k), e.shape).cpu()
+            ref = oracle.params[net][k].grad
+            err = ((mine - ref).norm() / ref.norm()).item()
+            assert err < 2e-1, ("gradient", net, k, err)      # LeakyReLU mask flips under bf16, see the estimate0 test
+    sd = tr.map_store.state_dict()
+    for k, w0 in before.items():
+        a, b = oracle.state_dict("map")[k], sd[k].cpu()
+        cos = torch.nn.functional.cosine_similarity((a - w0).reshape(1, -1), (b - w0).reshape(1, -1)).item()
+        assert cos > 0.9, ("adam update", k, cos)
+
+
 def test_eval_path_regress_decode_matches_oracle():
     """Inference path of the drivers (depth_train.py:197-206): dis.regress_b -> vae.decode -> (N, J*3)."""
     hp = _hp("nnyu")
