@@ -27,6 +27,49 @@ def run(tr, hp, ia, ib, la, lb):
     return {k: float(getattr(tr, k)) for k in KEYS}
 
 
+MAP_KEYS = ("dis_loss", "dis_ad_loss", "gen_total_loss", "gen_ad_loss", "gen_ll_loss", "gen_map_loss", "gen_map_loss2")
+
+
+def check_train_map(world, rank, local):
+    """Same equivalence for the train_map=True branches: dis_update + gen_update with the Mapping net (its own flat
+    gradient buffer and allreduce; the vae.encode noise is drawn for the (labels_a | labels_b) concatenation)."""
+    hp = dict(lsps_b200.load_hyperparameters("nnyu"), train_map=True)
+    per = 2
+    g = torch.Generator().manual_seed(4321)
+    ia, ib, la, lb = lsps_b200.synthetic_batch(per * world, 108, g, "hand")
+    sh = lambda t: shard_rows(t, 1, world, rank).cuda()
+
+    def run_map(tr, a, b, x, y):
+        torch.manual_seed(43)
+        tr.dis_update(a, x, b, y, None, None, hp)
+        tr.gen_update(a, x, b, y, hp)
+        return {k: float(getattr(tr, k)) for k in MAP_KEYS}
+    tr = lsps_b200.LSPSTrainerB200(hp, device=local, seed=0, noise="host")
+    got = run_map(tr, sh(ia), sh(ib), sh(la), sh(lb))
+    w_dp = {k: v.clone() for k, v in tr.map_store.state_dict().items()}
+    dist.barrier()
+    ok = True
+    if rank == 0:
+        import lsps_b200.trainer as T
+        saved = T._world
+        T._world = lambda: (1, 0)
+        tr1 = lsps_b200.LSPSTrainerB200(hp, device=local, seed=0, noise="host")
+        ref = run_map(tr1, ia.cuda(), ib.cuda(), la.cuda(), lb.cuda())
+        for k in MAP_KEYS:
+            rel = abs(got[k] - ref[k]) / (abs(ref[k]) + 1e-12)
+            print("train_map %-16s dp %.6f  single %.6f  rel %.2e" % (k, got[k], ref[k], rel))
+            ok &= rel < 2e-3
+        w1 = tr1.map_store.state_dict()
+        w0 = lsps_b200.LSPSTrainerB200(hp, device=local, seed=0, noise="host").map_store.state_dict()
+        for k in ("model.0.model.0.weight", "model.1.model.0.weight", "model.3.weight", "model.3.bias"):
+            cos = torch.nn.functional.cosine_similarity((w_dp[k] - w0[k]).reshape(1, -1),
+                                                        (w1[k] - w0[k]).reshape(1, -1)).item()
+            print("train_map weight update %-24s cosine(dp, single) %.6f" % (k, cos))
+            ok &= cos > 0.98
+        T._world = saved
+    return ok
+
+
 def main():
     world, rank, local = int(os.environ["WORLD_SIZE"]), int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
@@ -46,9 +89,11 @@ def main():
     if rank == 0:
         # single-process reference on the global batch: temporarily hide the process group from the trainer
         import lsps_b200.trainer as T
+        saved = T._world
         T._world = lambda: (1, 0)
         tr1 = lsps_b200.LSPSTrainerB200(hp, device=local, seed=0, noise="host")
         ref = run(tr1, hp, ia.cuda(), ib.cuda(), la.cuda(), lb.cuda())
+        T._world = saved
         for k in KEYS:
             if k == "vae_total_loss":
                 continue   # vae noise rows are drawn for the (la|lb) concatenation: different row order under DP
@@ -62,6 +107,9 @@ def main():
                                                         (w1[k] - w0[k]).reshape(1, -1)).item()
             print("weight update %-28s cosine(dp, single) %.6f" % (k, cos))
             ok &= cos > 0.98
+    del tr
+    ok = check_train_map(world, rank, local) and ok
+    if rank == 0:
         print("DP_CHECK", "OK" if ok else "FAIL")
     dist.barrier()
     dist.destroy_process_group()
