@@ -226,7 +226,8 @@ def main():
                 out = orig(self, S, key, kind, x, *a, **kw)
                 if k1:
                     e1.record()
-                    ev.append((e0, e1, shp[0]))
+                    masked = (not is_fwd) and (kw.get("mask") is not None or kw.get("add") is not None)
+                    ev.append((e0, e1, shp[0], ("fwd" if is_fwd else ("dgrad+ep" if masked else "dgrad")) + "_n%d" % shp[0]))
                 return out
             return f
         _engine.Ops.conv_fwd, _engine.Ops.conv_dgrad = wrap(orig_f, True), wrap(orig_d, False)
@@ -239,8 +240,16 @@ def main():
     _engine.Ops.conv_fwd, _engine.Ops.conv_dgrad = orig_f, orig_d
     if rank == 0:
         pk = _peaks()
-        tot_ms = sum(a.elapsed_time(b_) for a, b_, _ in ev)
-        tot_flop = sum(2.0 * n * 1024 * 256 * 2304 for _, _, n in ev)
+        tot_ms = sum(a.elapsed_time(b_) for a, b_, _, _ in ev)
+        tot_flop = sum(2.0 * n * 1024 * 256 * 2304 for _, _, n, _ in ev)
+        classes = {}
+        for a, b_, n, cls in ev:
+            c = classes.setdefault(cls, {"launches": 0, "ms": 0.0, "flop": 0.0})
+            c["launches"] += 1
+            c["ms"] += a.elapsed_time(b_)
+            c["flop"] += 2.0 * n * 1024 * 256 * 2304
+        classes = {k: {"launches": c["launches"], "avg_ms": round(c["ms"] / c["launches"], 4),
+                       "tflops": round(c["flop"] / (c["ms"] * 1e-3) / 1e12, 1)} for k, c in sorted(classes.items())}
         ach = tot_flop / (tot_ms * 1e-3) / 1e12
         roof = {"bound": "tensor", "kernel": "conv_igemm_kernel<256> (3x3 s1 256->256 @32x32, fwd+dgrad)",
                 "achieved": ach, "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": ach / pk["tf_sustained"],
@@ -249,7 +258,8 @@ def main():
                 "output is still in L2 at kernel end)",
                 "launches": len(ev), "avg_launch_ms": tot_ms / max(1, len(ev)),
                 "share_of_step": tot_ms / (ms / K), "peak_source": pk["src"] + ", sustained bf16",
-                "note": "launch durations from one extra step with the wgrad side stream disabled (no concurrent kernels)"}
+                "note": "launch durations from one extra step with the wgrad side stream disabled (no concurrent kernels)",
+                "by_class": classes}
 
     if world > 1:
         dist.barrier()

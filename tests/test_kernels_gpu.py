@@ -157,10 +157,11 @@ def test_head(ctx):
     assert rel_l2(dw, w.grad.reshape(-1)) < 1e-4 and rel_l2(db, b.grad) < 1e-4
 
 
+# (3, 256, 32): the LeakyINSResBlock latent -> register-resident forward; the other shapes -> generic three-pass kernels
+@pytest.mark.parametrize("n,c,hw", [(3, 256, 32), (2, 128, 16), (2, 64, 32)])
 @pytest.mark.parametrize("mode", [0, 1])
-def test_instnorm(ctx, mode):
+def test_instnorm(ctx, mode, n, c, hw):
     g = gen(4 + mode)
-    n, c, hw = 3, 256, 32
     h = (torch.randn(n, c, hw, hw, device="cuda", generator=g) * 2 + 0.3).bfloat16().float().requires_grad_(True)
     res = torch.randn(n, c, hw, hw, device="cuda", generator=g).bfloat16().float()
     v = F.instance_norm(h, eps=1e-5)
