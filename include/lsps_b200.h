@@ -50,6 +50,14 @@ int lsps_conv_fwd(lsps_ctx*, const lsps_conv_shape*, const void* x, const void* 
 /* dx = (conv_backward_data(dy, w) + add) * lrelu'(mask) ; mask/add: bf16 tensors shaped like dx (flags ADD / MASK) */
 int lsps_conv_dgrad(lsps_ctx*, const lsps_conv_shape*, const void* dy, const void* w_dgrad, void* dx,
                     const void* mask, const void* add, int flags, float slope, lsps_stream);
+/* Two weight sets in ONE launch: images [0, n_split) use (w, bias), images [n_split, n) use (w2, bias2).  The reference
+   runs encode_A / encode_B (and decode_B / decode_A in the cycle pass) as separate nn.Sequential calls on half batches
+   (lsps_nets.py:245-272); on the concatenated batch the GEMM fills whole waves of CTA pairs.  w2 must lie in the same
+   allocation as w, a whole number of GEMM-K rows (cin resp. cout elements) away (either direction). */
+int lsps_conv_fwd_grouped(lsps_ctx*, const lsps_conv_shape*, const void* x, const void* w_fwd, const float* bias,
+                          const void* w_fwd2, const float* bias2, int n_split, void* y, int flags, float slope, lsps_stream);
+int lsps_conv_dgrad_grouped(lsps_ctx*, const lsps_conv_shape*, const void* dy, const void* w_dgrad, const void* w_dgrad2,
+                            int n_split, void* dx, const void* mask, const void* add, int flags, float slope, lsps_stream);
 /* dw[tap][cout][cin] += conv_backward_weight(x, dy)   (fp32, accumulating; split-K over pixels with red.add) */
 int lsps_conv_wgrad(lsps_ctx*, const lsps_conv_shape*, const void* x, const void* dy, float* dw, lsps_stream);
 /* db[c] += sum over rows of dy[rows][c]   (bias gradients; dy bf16) */
@@ -79,6 +87,10 @@ int lsps_instnorm_fwd(lsps_ctx*, const void* h, const void* res, void* y, float*
    dh -- the bias gradient of the conv that produced h, fused here instead of a separate colsum pass */
 int lsps_instnorm_bwd(lsps_ctx*, const void* dy, const void* h, const float* stats, void* dh, int n, int hw, int c,
                       int mode, float slope, float* db, lsps_stream);
+
+/* same, for a batch whose images [n_split, n) went through a second conv: their bias gradient goes to db2 */
+int lsps_instnorm_bwd_grouped(lsps_ctx*, const void* dy, const void* h, const float* stats, void* dh, int n, int hw, int c,
+                              int mode, float slope, float* db, float* db2, int n_split, lsps_stream);
 
 /* ---- GaussianNoiseLayer + KL term (common_net.py:36-40; lsps_trainer.py:55-58): z = x + noise, acc[0] += sum z^2 */
 int lsps_noise_kl_fwd(lsps_ctx*, const void* x, const float* noise, void* z, float* acc, long long n, lsps_stream);

@@ -26,6 +26,8 @@ _SH = C.POINTER(ConvShape)
 _SIGS = {
     "lsps_conv_fwd": [_SH, _vp, _vp, _vp, _vp, _i, _f],
     "lsps_conv_dgrad": [_SH, _vp, _vp, _vp, _vp, _vp, _i, _f],
+    "lsps_conv_fwd_grouped": [_SH, _vp, _vp, _vp, _vp, _vp, _i, _vp, _i, _f],
+    "lsps_conv_dgrad_grouped": [_SH, _vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _f],
     "lsps_conv_wgrad": [_SH, _vp, _vp, _vp],
     "lsps_colsum_bf16": [_vp, _ll, _i, _vp],
     "lsps_stem_fwd": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _f],
@@ -35,6 +37,7 @@ _SIGS = {
     "lsps_head_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _ll, _f],
     "lsps_instnorm_fwd": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _f],
     "lsps_instnorm_bwd": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _vp],
+    "lsps_instnorm_bwd_grouped": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _vp, _vp, _i],
     "lsps_noise_kl_fwd": [_vp, _vp, _vp, _vp, _ll],
     "lsps_axpy_bf16": [_vp, _vp, _f, _vp, _ll],
     "lsps_l2_bf16": [_vp, _vp, _vp, _f, _vp, _ll],

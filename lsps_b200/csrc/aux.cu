@@ -361,10 +361,12 @@ __global__ void __launch_bounds__(512) instnorm_fwd_kernel(const bf16* __restric
 __global__ void __launch_bounds__(512) instnorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ h,
                                                           const float* __restrict__ stats, bf16* __restrict__ dh,
                                                           int hw, int c, int mode, float slope,
-                                                          float* __restrict__ db) {
+                                                          float* __restrict__ db_, float* __restrict__ db2,
+                                                          int nsplit) {
   __shared__ float red[64][64];
   __shared__ float s_a[64], s_b[64];
   const int n = blockIdx.y, cg = blockIdx.x;
+  float* db = (nsplit && n >= nsplit) ? db2 : db_;   // images >= nsplit belong to the second conv (grouped res blocks)
   const int oct = threadIdx.x & 7, pl = threadIdx.x >> 3;
   const long long base = (long long)n * hw * c + cg * 64 + oct * 8;
   float mean[8], rstd[8], sg[8], sgx[8];
@@ -972,8 +974,20 @@ extern "C" int lsps_instnorm_bwd(lsps_ctx* ctx, const void* dy, const void* h, c
   REQUIRE(ctx, dy && h && stats && dh, LSPS_E_ARG, "instnorm_bwd: null");
   REQUIRE(ctx, n > 0 && hw > 0 && c % 64 == 0, LSPS_E_SHAPE, "instnorm_bwd: c must be a multiple of 64");
   instnorm_bwd_kernel<<<dim3(c / 64, n), 512, 0, ST_(st)>>>(static_cast<const bf16*>(dy), static_cast<const bf16*>(h),
-                                                          stats, static_cast<bf16*>(dh), hw, c, mode, slope, db);
+                                                          stats, static_cast<bf16*>(dh), hw, c, mode, slope, db,
+                                                          nullptr, 0);
   LSPS_CHECK_LAUNCH(ctx, "instnorm_bwd");
+  return LSPS_OK;
+}
+extern "C" int lsps_instnorm_bwd_grouped(lsps_ctx* ctx, const void* dy, const void* h, const float* stats, void* dh,
+                                         int n, int hw, int c, int mode, float slope, float* db, float* db2, int n_split,
+                                         lsps_stream st) {
+  REQUIRE(ctx, dy && h && stats && dh && db && db2, LSPS_E_ARG, "instnorm_bwd_grouped: null");
+  REQUIRE(ctx, n > 0 && hw > 0 && c % 64 == 0 && n_split > 0 && n_split < n, LSPS_E_SHAPE, "instnorm_bwd_grouped: shape");
+  instnorm_bwd_kernel<<<dim3(c / 64, n), 512, 0, ST_(st)>>>(static_cast<const bf16*>(dy), static_cast<const bf16*>(h),
+                                                          stats, static_cast<bf16*>(dh), hw, c, mode, slope, db, db2,
+                                                          n_split);
+  LSPS_CHECK_LAUNCH(ctx, "instnorm_bwd_grouped");
   return LSPS_OK;
 }
 

@@ -110,6 +110,10 @@ struct IgemmParams {
   int txl, tyl;       // log2(tiles_x), log2(tiles_y)
   int nimg, kchunks;  // kchunks = K channels / 64
   int ntaps_all;      // filter taps in the table (9, or 16 for the 4x4 transposed conv)
+  // two weight sets in one launch (encoder A | encoder B res blocks on the concatenated batch): images >= nsplit use
+  // the rows brow1.. of the weight tensor map and the second bias vector; nsplit = 0 -> one set, brow0 = brow1 = 0
+  int nsplit, brow0, brow1;
+  const float* bias2;
   long long o_n, o_y, o_x;  // output strides (elements)
   int o_sy, o_sx;           // output pixel = (y*o_sy + oa, x*o_sx + ob)
   __nv_bfloat16* out;
@@ -175,6 +179,7 @@ __device__ __forceinline__ void epilogue_role(const IgemmParams& p, const float*
       const int nt = tc.nt, x0 = tc.x0, y0 = tc.y0, n = tc.ti * p.nb + nl;
       const Phase P = p.ph[tc.pi];
       const bool valid = n < p.nimg;
+      const int boff = (p.nsplit && n >= p.nsplit) ? p.tiles_n * BN : 0;   // second bias vector
       const long long off = (long long)n * p.o_n + (long long)((y0 + yl) * p.o_sy + P.oa) * p.o_y +
                             (long long)((x0 + xl) * p.o_sx + P.ob) * p.o_x + nt * BN;
       const int acc = it & 1; const uint32_t accph = (it >> 1) & 1;
@@ -224,7 +229,7 @@ __device__ __forceinline__ void epilogue_role(const IgemmParams& p, const float*
         }
         if (valid) {
           if (p.flags & LSPS_EP_BIAS) {
-            const float4* b4 = reinterpret_cast<const float4*>(sbias + nt * BN + c0);
+            const float4* b4 = reinterpret_cast<const float4*>(sbias + boff + nt * BN + c0);
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               const float4 b = b4[j];
@@ -295,6 +300,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   if (p.flags & LSPS_EP_BIAS) {
     const int nc_total = p.tiles_n * BN;
     for (int i = threadIdx.x; i < nc_total; i += blockDim.x) sbias[i] = p.bias[i];
+    if (p.nsplit)
+      for (int i = threadIdx.x; i < nc_total; i += blockDim.x) sbias[nc_total + i] = p.bias2[i];
   }
   // the producer is ONE thread whose per-stage latency bounds the whole pipeline: no divisions or parameter-space
   // reads in its loop -- every (tap, 64-channel chunk) K-step is a precomputed 16-byte table entry
@@ -337,7 +344,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         // K-steps (tap, 64-channel chunk) are flattened; a stage carries up to KCH consecutive ones
         const int nks = P.ntaps * p.kchunks;
         const int4* kt = ktab + P.tap0 * p.kchunks;
-        const int brow_off = nt * BN + rank * (BN / 2) * (CG - 1);
+        const int brow_off = nt * BN + rank * (BN / 2) * (CG - 1) + ((p.nsplit && n0 >= p.nsplit) ? p.brow1 : p.brow0);
         for (int i0 = 0; i0 < nks; i0 += KCH) {
           const int cnt = nks - i0 < KCH ? nks - i0 : KCH;
           mbar_wait(&empty[stage], ph ^ 1);
@@ -661,7 +668,8 @@ int launch_igemm(lsps_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tmB, 
 // Builds the plan for forward / data-gradient of any of the three conv kinds and launches it.
 //   in : the tensor the GEMM reads (x for FWD, dy for DGRAD); out: what it writes (y / dx)
 int run_igemm(lsps_ctx* ctx, const lsps_conv_shape* s, Dir dir, const void* in, const void* wpk, const float* bias,
-              void* out, const void* mask, const void* add, int flags, float slope, cudaStream_t st) {
+              void* out, const void* mask, const void* add, int flags, float slope, cudaStream_t st,
+              const void* wpk2 = nullptr, const float* bias2 = nullptr, int nsplit = 0) {
   if (!ctx || !s || !in || !wpk || !out) return lsps_set_error(ctx, LSPS_E_ARG, "null argument");
   const int kind = s->kind, n = s->n, h = s->h, w = s->w, cin = s->cin, cout = s->cout;
   if (kind < 0 || kind > 3 || n <= 0 || !is_pow2(h) || !is_pow2(w) || cin % 64 || cout % 64 || cin <= 0 || cout <= 0)
@@ -744,6 +752,23 @@ int run_igemm(lsps_ctx* ctx, const lsps_conv_shape* s, Dir dir, const void* in, 
 
   const int bn = nc % 256 == 0 ? 256 : (nc % 128 == 0 ? 128 : 64);
   p.tiles_n = nc / bn;
+  // grouped launch: one tensor map over both weight sets (they live in one flat buffer)
+  const char* wbase = static_cast<const char*>(wpk);
+  long long wrows = (long long)ks * ks * nc;
+  if (nsplit > 0) {
+    const long long delta = static_cast<const char*>(wpk2) - static_cast<const char*>(wpk);   // bytes
+    const long long row_bytes = 2LL * kc;
+    if (!wpk2 || nsplit >= n || nsplit % g.nb || delta == 0 || delta % row_bytes || 2 * nc > 2048 ||
+        ((flags & LSPS_EP_BIAS) && !bias2))
+      return lsps_set_error(ctx, LSPS_E_ARG, "grouped conv: n_split %d / weight distance %lld not usable", nsplit, delta);
+    const long long drows = (delta < 0 ? -delta : delta) / row_bytes;
+    if (drows + wrows > 0x7fffffffLL) return lsps_set_error(ctx, LSPS_E_ARG, "grouped conv: weight sets too far apart");
+    p.nsplit = nsplit; p.bias2 = bias2;
+    p.brow0 = delta < 0 ? (int)drows : 0;
+    p.brow1 = delta < 0 ? 0 : (int)drows;
+    if (delta < 0) wbase = static_cast<const char*>(wpk2);
+    wrows += drows;
+  }
   // CTA pairs (cta_group::2) whenever there are at least two M tiles to pair up
   const int tiles_m = p.tiles_x * p.tiles_y * p.tiles_i;
   //   ... and the tile is MMA-bound (>= 27 K-steps) and there are enough tiles to keep every SM busy in pairs;
@@ -756,8 +781,8 @@ int run_igemm(lsps_ctx* ctx, const lsps_conv_shape* s, Dir dir, const void* in, 
   CUtensorMap tmA, tmB;
   int rc = act_tmap(ctx, in, n, ih, iw, kc, down, g, &tmA);
   if (rc) return rc;
-  uint32_t wd[2] = {(uint32_t)kc, (uint32_t)(ks * ks * nc)}, wb[2] = {64, (uint32_t)(bn / cg)};
-  rc = lsps_get_tmap(ctx, wpk, 2, wd, wb, &tmB);
+  uint32_t wd[2] = {(uint32_t)kc, (uint32_t)wrows}, wb[2] = {64, (uint32_t)(bn / cg)};
+  rc = lsps_get_tmap(ctx, wbase, 2, wd, wb, &tmB);
   if (rc) return rc;
   if (cg == 2 && bn == 256 && !lsps_no_kch2()) return launch_igemm<256, 2, 2>(ctx, tmA, tmB, p, st);
   if (cg == 2) {
@@ -799,6 +824,22 @@ extern "C" int lsps_conv_dgrad(lsps_ctx* ctx, const lsps_conv_shape* s, const vo
                                const void* mask, const void* add, int flags, float slope, lsps_stream st) {
   return run_igemm(ctx, s, DGRAD, dy, w_dgrad, nullptr, dx, mask, add, flags & (LSPS_EP_MASK | LSPS_EP_ADD), slope,
                    static_cast<cudaStream_t>(st));
+}
+
+extern "C" int lsps_conv_fwd_grouped(lsps_ctx* ctx, const lsps_conv_shape* s, const void* x, const void* w_fwd,
+                                     const float* bias, const void* w_fwd2, const float* bias2, int n_split, void* y,
+                                     int flags, float slope, lsps_stream st) {
+  if (n_split <= 0 || !w_fwd2) return lsps_set_error(ctx, LSPS_E_ARG, "conv_fwd_grouped: n_split / second weight set");
+  return run_igemm(ctx, s, FWD, x, w_fwd, bias, y, nullptr, nullptr, flags & (LSPS_EP_BIAS | LSPS_EP_LRELU), slope,
+                   static_cast<cudaStream_t>(st), w_fwd2, bias2, n_split);
+}
+
+extern "C" int lsps_conv_dgrad_grouped(lsps_ctx* ctx, const lsps_conv_shape* s, const void* dy, const void* w_dgrad,
+                                       const void* w_dgrad2, int n_split, void* dx, const void* mask, const void* add,
+                                       int flags, float slope, lsps_stream st) {
+  if (n_split <= 0 || !w_dgrad2) return lsps_set_error(ctx, LSPS_E_ARG, "conv_dgrad_grouped: n_split / second weight set");
+  return run_igemm(ctx, s, DGRAD, dy, w_dgrad, nullptr, dx, mask, add, flags & (LSPS_EP_MASK | LSPS_EP_ADD), slope,
+                   static_cast<cudaStream_t>(st), w_dgrad2, nullptr, n_split);
 }
 
 extern "C" int lsps_conv_wgrad(lsps_ctx* ctx, const lsps_conv_shape* s, const void* x, const void* dy, float* dw,

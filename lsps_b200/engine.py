@@ -66,26 +66,48 @@ class Ops:
         sh = S.entries[key + ".weight"].shape
         return (sh[1], sh[0]) if kind not in (DECONV_S2, DECONV4_S2) else (sh[0], sh[1])  # (cin, cout)
 
+    # `key` may be a pair (key_a, key_b, split): images [0, split) go through conv key_a, the rest through key_b --
+    # ONE grouped launch for forward / data gradient (full waves of CTA pairs instead of two half-size launches)
     def conv_fwd(self, S, key, kind, x, lrelu, out=None):
         n, h, w, cin = x.shape
-        ci, co = self._io(S, key, kind)
+        k0 = key[0] if isinstance(key, tuple) else key
+        ci, co = self._io(S, k0, kind)
         assert ci == cin, (key, ci, cin)
         ho, wo = (h, w) if kind == CONV_S1 else ((h // 2, w // 2) if kind == CONV_S2 else (2 * h, 2 * w))
         y = out if out is not None else self.empty(n, ho, wo, co)
-        self.ctx.conv_fwd(_shape(kind, n, h, w, ci, co), x.data_ptr(), S.W16(key + ".weight").data_ptr(),
-                          S.W(key + ".bias").data_ptr(), y.data_ptr(), EP_BIAS | (EP_LRELU if lrelu else 0), SLOPE)
+        flags = EP_BIAS | (EP_LRELU if lrelu else 0)
+        if isinstance(key, tuple):
+            ka, kb, split = key
+            self.ctx.conv_fwd_grouped(_shape(kind, n, h, w, ci, co), x.data_ptr(), S.W16(ka + ".weight").data_ptr(),
+                                      S.W(ka + ".bias").data_ptr(), S.W16(kb + ".weight").data_ptr(),
+                                      S.W(kb + ".bias").data_ptr(), split, y.data_ptr(), flags, SLOPE)
+        else:
+            self.ctx.conv_fwd(_shape(kind, n, h, w, ci, co), x.data_ptr(), S.W16(key + ".weight").data_ptr(),
+                              S.W(key + ".bias").data_ptr(), y.data_ptr(), flags, SLOPE)
         return y
 
     def conv_dgrad(self, S, key, kind, dy, x_shape, mask=None, add=None, out=None):
         n, h, w, cin = x_shape
-        ci, co = self._io(S, key, kind)
+        k0 = key[0] if isinstance(key, tuple) else key
+        ci, co = self._io(S, k0, kind)
         dx = out if out is not None else self.empty(n, h, w, ci)
         flags = (EP_MASK if mask is not None else 0) | (EP_ADD if add is not None else 0)
-        self.ctx.conv_dgrad(_shape(kind, n, h, w, ci, co), dy.data_ptr(), S.W16T(key + ".weight").data_ptr(),
-                            dx.data_ptr(), _lib.ptr(mask), _lib.ptr(add), flags, SLOPE)
+        if isinstance(key, tuple):
+            ka, kb, split = key
+            self.ctx.conv_dgrad_grouped(_shape(kind, n, h, w, ci, co), dy.data_ptr(), S.W16T(ka + ".weight").data_ptr(),
+                                        S.W16T(kb + ".weight").data_ptr(), split, dx.data_ptr(), _lib.ptr(mask),
+                                        _lib.ptr(add), flags, SLOPE)
+        else:
+            self.ctx.conv_dgrad(_shape(kind, n, h, w, ci, co), dy.data_ptr(), S.W16T(key + ".weight").data_ptr(),
+                                dx.data_ptr(), _lib.ptr(mask), _lib.ptr(add), flags, SLOPE)
         return dx
 
     def conv_wgrad(self, S, key, kind, x, dy, bias=True):
+        if isinstance(key, tuple):       # weight gradients stay per conv: one launch per half
+            ka, kb, split = key
+            self.conv_wgrad(S, ka, kind, x[:split], dy[:split], bias)
+            self.conv_wgrad(S, kb, kind, x[split:], dy[split:], bias)
+            return
         n, h, w, cin = x.shape
         ci, co = self._io(S, key, kind)
 
@@ -104,19 +126,31 @@ class Ops:
                               SLOPE)
         return y, stats
 
-    def in_bwd(self, dy, h, stats, mode, db=None):
-        """db: optional fp32 [c] accumulator for the bias gradient of the conv that produced h (fused column sum)."""
+    def in_bwd(self, dy, h, stats, mode, db=None, db2=None, split=0):
+        """db: optional fp32 [c] accumulator for the bias gradient of the conv that produced h (fused column sum);
+        db2/split: images [split, n) came from a second conv (grouped res block) and accumulate into db2."""
         n, hh, ww, c = h.shape
         dh = torch.empty_like(h)
-        self.ctx.instnorm_bwd(dy.data_ptr(), h.data_ptr(), stats.data_ptr(), dh.data_ptr(), n, hh * ww, c, mode, SLOPE,
-                              _lib.ptr(db))
+        if db2 is not None:
+            self.ctx.instnorm_bwd_grouped(dy.data_ptr(), h.data_ptr(), stats.data_ptr(), dh.data_ptr(), n, hh * ww, c,
+                                          mode, SLOPE, db.data_ptr(), db2.data_ptr(), split)
+        else:
+            self.ctx.instnorm_bwd(dy.data_ptr(), h.data_ptr(), stats.data_ptr(), dh.data_ptr(), n, hh * ww, c, mode,
+                                  SLOPE, _lib.ptr(db))
         return dh
 
     # ---- LeakyINSResBlock (common_net.py:160-181)
+    @staticmethod
+    def _sub(key, suffix):
+        """conv key of a res block; a (block_a, block_b, split) pair maps to the pair of conv keys."""
+        if isinstance(key, tuple):
+            return (key[0] + suffix, key[1] + suffix, key[2])
+        return key + suffix
+
     def res_fwd(self, S, key, x, save, out=None):
-        h1 = self.conv_fwd(S, key + ".model.0", CONV_S1, x, False)
+        h1 = self.conv_fwd(S, self._sub(key, ".model.0"), CONV_S1, x, False)
         a1, st1 = self.in_fwd(h1, 0)
-        h2 = self.conv_fwd(S, key + ".model.3", CONV_S1, a1, False)
+        h2 = self.conv_fwd(S, self._sub(key, ".model.3"), CONV_S1, a1, False)
         y, st2 = self.in_fwd(h2, 1, res=x, out=out)
         if save is not None:
             save.append((key, x, h1, st1, a1, h2, st2))
@@ -124,14 +158,22 @@ class Ops:
 
     def res_bwd(self, S, saved, dout, wgrad=True, mask=None, out=None):
         key, x, h1, st1, a1, h2, st2 = saved
-        dh2 = self.in_bwd(dout, h2, st2, 1, db=S.G(key + ".model.3.bias") if wgrad else None)
+        k0, k3 = self._sub(key, ".model.0"), self._sub(key, ".model.3")
+
+        def dbs(k):
+            if not wgrad:
+                return {}
+            if isinstance(k, tuple):
+                return dict(db=S.G(k[0] + ".bias"), db2=S.G(k[1] + ".bias"), split=k[2])
+            return dict(db=S.G(k + ".bias"))
+        dh2 = self.in_bwd(dout, h2, st2, 1, **dbs(k3))
         if wgrad:
-            self.conv_wgrad(S, key + ".model.3", CONV_S1, a1, dh2, bias=False)
-        da1 = self.conv_dgrad(S, key + ".model.3", CONV_S1, dh2, a1.shape)
-        dh1 = self.in_bwd(da1, h1, st1, 0, db=S.G(key + ".model.0.bias") if wgrad else None)
+            self.conv_wgrad(S, k3, CONV_S1, a1, dh2, bias=False)
+        da1 = self.conv_dgrad(S, k3, CONV_S1, dh2, a1.shape)
+        dh1 = self.in_bwd(da1, h1, st1, 0, **dbs(k0))
         if wgrad:
-            self.conv_wgrad(S, key + ".model.0", CONV_S1, x, dh1, bias=False)
-        return self.conv_dgrad(S, key + ".model.0", CONV_S1, dh1, x.shape, mask=mask, add=dout, out=out)
+            self.conv_wgrad(S, k0, CONV_S1, x, dh1, bias=False)
+        return self.conv_dgrad(S, k0, CONV_S1, dh1, x.shape, mask=mask, add=dout, out=out)
 
     # ---- stems / head
     def stem_fwd(self, S, key, img, stride, out=None):
@@ -160,6 +202,9 @@ class Generator:
         assert hp["n_enc_front_blk"] == 3 and hp["n_gen_front_blk"] == 3 and hp["ch"] == 64, \
             "kernel set covers the reference configs (exps/nnyu.yaml, nicvl.yaml): 3 front blocks, ch=64"
         self.training = True  # the reference drivers never call gen.eval()
+        # encoder-A/B (and cycle decoder-B/A) res blocks as grouped launches on the concatenated batch: any split on an
+        # image boundary works, the two weight sets only have to sit in one flat buffer (params.ALIGN)
+        self.grouped = os.environ.get("LSPS_NO_GROUP", "0") != "1"
 
     # -- encoder: 7x7 s1 stem, two 3x3 s2 convs, n_enc_res_blk res blocks
     def enc_fwd(self, dom, img, save, out=None):
@@ -189,6 +234,79 @@ class Generator:
         o.stem_wgrad(S, e + ".0.model.0", sv["img"], d0, 1)
         if dimg is not None:
             o.stem_dgrad(S, e + ".0.model.0", d0, dimg, 1, accumulate=True)
+
+    # -- both encoders on (xa | xb) with the res blocks of A and B grouped into single launches.  Same arithmetic as
+    #    enc_fwd("A") + enc_fwd("B"): only the launch shape changes (one 2B-image GEMM instead of two B-image ones)
+    def enc_pair_fwd(self, xa, xb, save, out):
+        o, S = self.ops, self.S
+        na = xa.shape[0]
+        nres = self.p["n_enc_res_blk"]
+        f2 = o.empty(na + xb.shape[0], 32, 32, 4 * self.p["ch"]) if nres else out
+        fr = []
+        for dom, img, dst in (("A", xa, f2[:na]), ("B", xb, f2[na:])):
+            e = "encode_%s" % dom
+            f0 = o.stem_fwd(S, e + ".0.model.0", img, 1)
+            f1 = o.conv_fwd(S, e + ".1.model.0", CONV_S2, f0, True)
+            o.conv_fwd(S, e + ".2.model.0", CONV_S2, f1, True, out=dst)
+            fr.append(dict(dom=dom, img=img, f0=f0, f1=f1))
+        blocks = [] if save is not None else None
+        x = f2
+        for i in range(nres):
+            key = ("encode_A.%d" % (3 + i), "encode_B.%d" % (3 + i), na)
+            x = o.res_fwd(S, key, x, blocks, out=out if i == nres - 1 else None)
+        if save is not None:
+            save.append(dict(pair=True, fronts=fr, f2=f2, blocks=blocks, na=na))
+        return x
+
+    def enc_pair_bwd(self, sv, dx, dimg_a=None, dimg_b=None):
+        o, S, na = self.ops, self.S, sv["na"]
+        blocks = sv["blocks"]
+        for i in range(len(blocks) - 1, -1, -1):
+            dx = o.res_bwd(S, blocks[i], dx, mask=sv["f2"] if i == 0 else None)
+        for fr, d2, dimg in ((sv["fronts"][0], dx[:na], dimg_a), (sv["fronts"][1], dx[na:], dimg_b)):
+            e = "encode_%s" % fr["dom"]
+            o.conv_wgrad(S, e + ".2.model.0", CONV_S2, fr["f1"], d2)
+            d1 = o.conv_dgrad(S, e + ".2.model.0", CONV_S2, d2, fr["f1"].shape, mask=fr["f1"])
+            o.conv_wgrad(S, e + ".1.model.0", CONV_S2, fr["f0"], d1)
+            d0 = o.conv_dgrad(S, e + ".1.model.0", CONV_S2, d1, fr["f0"].shape, mask=fr["f0"])
+            o.stem_wgrad(S, e + ".0.model.0", fr["img"], d0, 1)
+            if dimg is not None:
+                o.stem_dgrad(S, e + ".0.model.0", d0, dimg, 1, accumulate=True)
+
+    # -- two decoders on the halves of x (doms = ("B", "A") in the cycle pass, ("A", "B") for gen.decode): grouped res
+    #    blocks, then each domain's transposed convs + head on its half
+    def dec_pair_fwd(self, doms, x, save):
+        o, S = self.ops, self.S
+        n = x.shape[0] // 2
+        blocks = [] if save is not None else None
+        nres = self.p["n_gen_res_blk"]
+        for i in range(nres):
+            x = o.res_fwd(S, ("decode_%s.%d" % (doms[0], i), "decode_%s.%d" % (doms[1], i), n), x, blocks)
+        outs, tails = [], []
+        for dom, xh in ((doms[0], x[:n]), (doms[1], x[n:])):
+            d = "decode_%s" % dom
+            g1 = o.conv_fwd(S, "%s.%d.model.0" % (d, nres), DECONV_S2, xh, True)
+            g2 = o.conv_fwd(S, "%s.%d.model.0" % (d, nres + 1), DECONV_S2, g1, True)
+            img = o.empty(n, g2.shape[1], g2.shape[2], dtype=torch.float32)
+            hk = "%s.%d" % (d, nres + 2)
+            o.ctx.head_fwd(g2.data_ptr(), S.W(hk + ".weight").data_ptr(), S.W(hk + ".bias").data_ptr(), img.data_ptr(),
+                           img.numel())
+            outs.append(img)
+            tails.append(dict(dom=dom, blocks=[], x3=xh, g1=g1, g2=g2, out=img))
+        if save is not None:
+            save.append(dict(pair=True, tails=tails, blocks=blocks, n=n))
+        return outs
+
+    def dec_pair_bwd(self, sv, douts, out=None):
+        """douts: gradients w.r.t. the two image halves.  Returns the gradient w.r.t. the [2n] input of dec_pair_fwd."""
+        o, S, n = self.ops, self.S, sv["n"]
+        nb = len(sv["blocks"])
+        dx = (out if (out is not None and nb == 0) else o.empty(2 * n, 32, 32, 4 * self.p["ch"]))
+        self.dec_bwd(sv["tails"][0], douts[0], out=dx[:n])     # tails carry no res blocks: head + transposed convs only
+        self.dec_bwd(sv["tails"][1], douts[1], out=dx[n:])
+        for i in range(nb - 1, -1, -1):
+            dx = o.res_bwd(S, sv["blocks"][i], dx, out=out if i == 0 else None)
+        return dx
 
     # -- shared latent: res blocks + GaussianNoiseLayer (+ KL sum of the noised latent) ; then dec_shared
     def shared_fwd(self, x, noise, kl_acc, save):
@@ -268,10 +386,13 @@ class Generator:
         nb = xb.shape[0] if xb is not None else 0
         h = o.empty(na + nb, 32, 32, 4 * self.p["ch"])
         se = [] if save is not None else None
-        if na:
-            self.enc_fwd("A", xa, se, out=h[:na])
-        if nb:
-            self.enc_fwd("B", xb, se, out=h[na:])
+        if na and nb and self.grouped:
+            self.enc_pair_fwd(xa, xb, se, h)
+        else:
+            if na:
+                self.enc_fwd("A", xa, se, out=h[:na])
+            if nb:
+                self.enc_fwd("B", xb, se, out=h[na:])
         ss = [] if save is not None else None
         y, z = self.shared_fwd(h, noise, kl_acc, ss)
         sd = [] if save is not None else None
@@ -289,6 +410,9 @@ class Generator:
         dy2 = self.dec_bwd(save["dec"][1], dob)
         self.ops.ctx.axpy_bf16(dy.data_ptr(), dy2.data_ptr(), 1.0, dy.data_ptr(), dy.numel())
         dh = self.shared_bwd(save["shared"], dy, kl_alpha, dz_extra)
+        if save["enc"] and save["enc"][0].get("pair"):
+            self.enc_pair_bwd(save["enc"][0], dh)
+            return
         i = 0
         if na:
             self.enc_bwd(save["enc"][i], dh[:na])
@@ -307,8 +431,11 @@ class Generator:
         for i in range(self.p["n_gen_shared_blk"]):
             y = o.res_fwd(S, "dec_shared.%d" % i, y, db)
         sd = [] if save is not None else None
-        dec_a = self.dec_fwd("A", y[:n], sd)
-        dec_b = self.dec_fwd("B", y[n:], sd)
+        if self.grouped:
+            dec_a, dec_b = self.dec_pair_fwd(("A", "B"), y, sd)
+        else:
+            dec_a = self.dec_fwd("A", y[:n], sd)
+            dec_b = self.dec_fwd("B", y[n:], sd)
         if save is not None:
             save.update(db=db, dec=sd, n=n)
         return dec_a, dec_b
@@ -316,9 +443,12 @@ class Generator:
     def decode_bwd(self, save, d_a, d_b):
         """Returns the gradient w.r.t. the latent handed to decode_fwd."""
         o, S, n = self.ops, self.S, save["n"]
-        dy = o.empty(2 * n, 32, 32, 4 * self.p["ch"])
-        self.dec_bwd(save["dec"][0], d_a, out=dy[:n])
-        self.dec_bwd(save["dec"][1], d_b, out=dy[n:])
+        if save["dec"][0].get("pair"):
+            dy = self.dec_pair_bwd(save["dec"][0], (d_a, d_b))
+        else:
+            dy = o.empty(2 * n, 32, 32, 4 * self.p["ch"])
+            self.dec_bwd(save["dec"][0], d_a, out=dy[:n])
+            self.dec_bwd(save["dec"][1], d_b, out=dy[n:])
         for blk in reversed(save["db"]):
             dy = o.res_bwd(S, blk, dy)
         return dy
@@ -329,14 +459,20 @@ class Generator:
         n = x_ba.shape[0]
         h = o.empty(2 * n, 32, 32, 4 * self.p["ch"])
         se = [] if save is not None else None
-        self.enc_fwd("A", x_ba, se, out=h[:n])
-        self.enc_fwd("B", x_ab, se, out=h[n:])
+        if self.grouped:
+            self.enc_pair_fwd(x_ba, x_ab, se, h)
+        else:
+            self.enc_fwd("A", x_ba, se, out=h[:n])
+            self.enc_fwd("B", x_ab, se, out=h[n:])
         ss = [] if save is not None else None
         # two KL sums (bab / aba halves): run the noise kernel per half via shared_fwd's single call on a split
         y, z = self._shared_fwd_split(h, noise, kl_acc_bab, kl_acc_aba, n, ss)
         sd = [] if save is not None else None
-        x_bab = self.dec_fwd("B", y[:n], sd)
-        x_aba = self.dec_fwd("A", y[n:], sd)
+        if self.grouped:
+            x_bab, x_aba = self.dec_pair_fwd(("B", "A"), y, sd)
+        else:
+            x_bab = self.dec_fwd("B", y[:n], sd)
+            x_aba = self.dec_fwd("A", y[n:], sd)
         if save is not None:
             save.update(enc=se, shared=ss[0], dec=sd, n=n)
         return x_bab, x_aba
@@ -360,12 +496,18 @@ class Generator:
 
     def backward_cycle(self, save, d_bab, d_aba, kl_alpha, dimg_ba, dimg_ab):
         n = save["n"]
-        dy = self.ops.empty(2 * n, 32, 32, 4 * self.p["ch"])
-        self.dec_bwd(save["dec"][0], d_bab, out=dy[:n])
-        self.dec_bwd(save["dec"][1], d_aba, out=dy[n:])
+        if save["dec"][0].get("pair"):
+            dy = self.dec_pair_bwd(save["dec"][0], (d_bab, d_aba))
+        else:
+            dy = self.ops.empty(2 * n, 32, 32, 4 * self.p["ch"])
+            self.dec_bwd(save["dec"][0], d_bab, out=dy[:n])
+            self.dec_bwd(save["dec"][1], d_aba, out=dy[n:])
         dh = self.shared_bwd(save["shared"], dy, kl_alpha)
-        self.enc_bwd(save["enc"][0], dh[:n], dimg=dimg_ba)
-        self.enc_bwd(save["enc"][1], dh[n:], dimg=dimg_ab)
+        if save["enc"][0].get("pair"):
+            self.enc_pair_bwd(save["enc"][0], dh, dimg_a=dimg_ba, dimg_b=dimg_ab)
+        else:
+            self.enc_bwd(save["enc"][0], dh[:n], dimg=dimg_ba)
+            self.enc_bwd(save["enc"][1], dh[n:], dimg=dimg_ab)
 
 
 class Mapping:

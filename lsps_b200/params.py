@@ -13,7 +13,8 @@ import torch
 
 from . import _lib
 
-ALIGN = 64  # elements; keeps every tensor 16-byte aligned in fp32 and bf16 buffers
+ALIGN = 256  # elements: 16-byte alignment in every buffer, and any two conv weights are a whole number of 256-channel
+             # GEMM-K rows apart, which lets ONE weight tensor map span two convs (grouped launches, engine.py)
 ACC_SLOTS = 64  # float accumulators (loss sums) appended to the gradient buffer so they ride the same allreduce
 
 

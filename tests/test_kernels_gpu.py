@@ -97,6 +97,59 @@ def test_conv_fwd_dgrad_wgrad(ctx, kind, n, h, w, cin, cout):
     assert rel_l2(db, dy.sum((0, 2, 3))) < 1e-4
 
 
+@pytest.mark.parametrize("n,split,order", [(6, 3, 0), (5, 2, 1), (80, 40, 0)])
+def test_conv_grouped_two_weight_sets(ctx, n, split, order):
+    """lsps_conv_{fwd,dgrad}_grouped: images [0, split) through conv A, the rest through conv B, in one launch
+    (n=80: the CTA-pair kernel); the second set may sit before or after the first in the flat weight buffer."""
+    from lsps_b200._lib import ConvShape
+    g = gen(50 + n)
+    c = 256
+    x = torch.randn(n, c, 32, 32, device="cuda", generator=g).bfloat16().float()
+    dy = torch.randn(n, c, 32, 32, device="cuda", generator=g).bfloat16().float()
+    ws = [(torch.randn(c, c, 3, 3, device="cuda", generator=g) * 0.05).bfloat16().float() for _ in range(2)]
+    bs = [torch.randn(c, device="cuda", generator=g) for _ in range(2)]
+    pack = lambda t: t.permute(2, 3, 0, 1).reshape(9, c, c)
+    per = 9 * c * c
+    gap = 5 * 256                                   # some other tensor in between (multiple of the 256-element rows)
+    flat_f = torch.zeros(2 * per + gap, device="cuda", dtype=torch.bfloat16)
+    flat_d = torch.zeros(2 * per + gap, device="cuda", dtype=torch.bfloat16)
+    offs = (0, per + gap) if order == 0 else (per + gap, 0)
+    for i in range(2):
+        flat_f[offs[i]:offs[i] + per] = pack(ws[i]).reshape(-1).bfloat16()
+        flat_d[offs[i]:offs[i] + per] = pack(ws[i]).transpose(1, 2).reshape(-1).bfloat16()
+    sh = C.byref(ConvShape(0, n, 32, 32, c, c))
+    xb, dyb = nhwc16(x), nhwc16(dy)
+    yb = torch.empty_like(xb)
+    ctx.conv_fwd_grouped(sh, xb.data_ptr(), flat_f[offs[0]:].data_ptr(), bs[0].data_ptr(), flat_f[offs[1]:].data_ptr(),
+                         bs[1].data_ptr(), split, yb.data_ptr(), 1, SLOPE)
+    ref = torch.cat((F.conv2d(x[:split], ws[0], bs[0], padding=1), F.conv2d(x[split:], ws[1], bs[1], padding=1)), 0)
+    assert rel_l2(nchw32(yb), ref) < BF16_L2
+    assert rel_l2(nchw32(yb)[split:], ref[split:]) < BF16_L2 and rel_l2(nchw32(yb)[:split], ref[:split]) < BF16_L2
+    dxb = torch.empty_like(xb)
+    ctx.conv_dgrad_grouped(sh, dyb.data_ptr(), flat_d[offs[0]:].data_ptr(), flat_d[offs[1]:].data_ptr(), split,
+                           dxb.data_ptr(), None, None, 0, SLOPE)
+    refd = torch.cat((F.conv_transpose2d(dy[:split], ws[0], padding=1), F.conv_transpose2d(dy[split:], ws[1], padding=1)), 0)
+    assert rel_l2(nchw32(dxb)[:split], refd[:split]) < BF16_L2 and rel_l2(nchw32(dxb)[split:], refd[split:]) < BF16_L2
+
+
+def test_instnorm_bwd_grouped_bias_gradients(ctx):
+    g = gen(61)
+    n, c, hw, split = 5, 256, 1024, 2
+    h = torch.randn(n, hw, c, device="cuda", generator=g).bfloat16()
+    dy = torch.randn(n, hw, c, device="cuda", generator=g).bfloat16()
+    y, stats = torch.empty_like(h), torch.empty(n, c, 2, device="cuda")
+    ctx.instnorm_fwd(h.data_ptr(), None, y.data_ptr(), stats.data_ptr(), n, hw, c, 0, 1e-5, SLOPE)
+    dh, dh2 = torch.empty_like(h), torch.empty_like(h)
+    db = torch.zeros(c, device="cuda")
+    ctx.instnorm_bwd(dy.data_ptr(), h.data_ptr(), stats.data_ptr(), dh.data_ptr(), n, hw, c, 0, SLOPE, db.data_ptr())
+    da, dbb = torch.zeros(c, device="cuda"), torch.zeros(c, device="cuda")
+    ctx.instnorm_bwd_grouped(dy.data_ptr(), h.data_ptr(), stats.data_ptr(), dh2.data_ptr(), n, hw, c, 0, SLOPE,
+                             da.data_ptr(), dbb.data_ptr(), split)
+    assert torch.equal(dh, dh2)
+    assert torch.allclose(da, dh[:split].float().sum((0, 1)), atol=1e-3)
+    assert torch.allclose(dbb, dh[split:].float().sum((0, 1)), atol=1e-3)
+
+
 def test_l2_bf16(ctx):
     g = gen(5)
     a = torch.randn(3, 32, 32, 256, device="cuda", generator=g).bfloat16()
