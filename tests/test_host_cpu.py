@@ -114,3 +114,36 @@ def test_synthetic_dataset_item_contract():
     assert img.shape == (1, 128, 128) and img.dtype == torch.float32 and label.shape == (48,)
     assert float(img.max()) == 1.0 and float(img.min()) >= -1.0 and com.shape == (3,) and M.shape == (3, 3)
     assert torch.equal(ds[1][0], img)
+
+
+def test_conv_weights_are_whole_gemm_rows_apart():
+    """Grouped launches (engine.py) put ONE weight tensor map over two convs of the flat buffer: encoder-A/B and
+    decoder-A/B res-block weights must be a multiple of 256 elements (one K row of the 256-channel GEMM) apart.
+    Checked on the entry tables alone (no device needed): offsets are cumulative sizes rounded up to params.ALIGN."""
+    from lsps_b200.params import gen_entries, ALIGN, _round_up
+    import math
+    assert ALIGN % 256 == 0
+    hp = _hp("nnyu")
+    off, offs = 0, {}
+    for key, shape, kind, law, fan in gen_entries(hp["gen"]):
+        offs[key] = off
+        off += _round_up(int(math.prod(shape)))
+    for i in range(3, 3 + hp["gen"]["n_enc_res_blk"]):
+        for conv in ("model.0", "model.3"):
+            d = offs["encode_B.%d.%s.weight" % (i, conv)] - offs["encode_A.%d.%s.weight" % (i, conv)]
+            assert d > 0 and d % 256 == 0
+    for i in range(hp["gen"]["n_gen_res_blk"]):
+        d = offs["decode_B.%d.model.0.weight" % i] - offs["decode_A.%d.model.0.weight" % i]
+        assert d % 256 == 0
+
+
+def test_joint_schedule_steps_both_stores():
+    from lsps_b200.params import MultiStepLR
+    from lsps_b200.trainer import _JointSchedule
+
+    class S(object):
+        lr = base_lr = 1e-4
+    a, b = S(), S()
+    sch = _JointSchedule(MultiStepLR(a, [2], 0.5), MultiStepLR(b, [2], 0.5))
+    sch.step(); sch.step()
+    assert a.lr == b.lr == 5e-5 and sch.get_lr() == [5e-5]
