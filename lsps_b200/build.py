@@ -41,7 +41,7 @@ def build(force=False, verbose=False):
             sys.stderr.write(out)
         if p.returncode:
             raise RuntimeError("nvcc failed: %s" % " ".join(cmd))
-    cmd = [NVCC, "-shared", "-o", LIB] + objs
+    cmd = [NVCC, "-shared", "-Wno-deprecated-gpu-targets", "-o", LIB] + objs
     subprocess.check_call(cmd)
     return LIB
 
