@@ -32,6 +32,10 @@ CPU_SAMPLE_BATCH = int(os.environ.get("LSPS_BENCH_CPU_BATCH", "2"))
 GFLOP_PER_PAIR = 390.7
 
 
+WORKLOAD = "depth_train.py --mode pretrain, exps/nnyu.yaml, 128x128 synthetic depth, batch %d per domain per GPU " \
+           "(dis_update + gen_update)"
+
+
 def _peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -117,7 +121,9 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
         "warmup": warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "pretrain nnyu 128x128, CPU sample batch %d/domain" % CPU_SAMPLE_BATCH},
+        # the workload is the B200 arm's; each CPU step is a bounded sample of it (see cpu_baseline.sample)
+        "config": {"workload": WORKLOAD % BATCH, "sample_batch_per_domain": CPU_SAMPLE_BATCH,
+                   "noise": "host RNG (the reference's own draws)"},
         "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -282,8 +288,7 @@ def main():
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
         "data": "synthetic",
-        "config": {"workload": "depth_train.py --mode pretrain, exps/nnyu.yaml, 128x128 synthetic depth, batch %d per "
-                               "domain per GPU (dis_update + gen_update)" % B,
+        "config": {"workload": WORKLOAD % B,
                    "global_batch_per_domain": B * world, "parallelism": "dp%d" % world,
                    "noise": "device Philox (host-RNG parity mode is not the timed mode)",
                    "l2": "working set >> 126 MB L2 (activations of one step are several GB); no explicit flush",
