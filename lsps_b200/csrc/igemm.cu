@@ -615,11 +615,6 @@ inline int lsps_force_cg() {
   if (v < 0) { const char* e = getenv("LSPS_FORCE_CG"); v = e ? atoi(e) : 0; }
   return v;
 }
-inline int lsps_kch_small() {  // K-steps per stage of the single-CTA BN<=128 kernels (measured: 1 is best, r01 probes)
-  static int v = -1;
-  if (v < 0) { const char* e = getenv("LSPS_KCH_SMALL"); v = e ? atoi(e) : 1; }
-  return v;
-}
 inline bool lsps_no_kch2() {
   static int v = -1;
   if (v < 0) { const char* e = getenv("LSPS_NO_KCH2"); v = (e && e[0] == '1') ? 1 : 0; }
@@ -791,9 +786,9 @@ int run_igemm(lsps_ctx* ctx, const lsps_conv_shape* s, Dir dir, const void* in, 
     return launch_igemm<64, 2>(ctx, tmA, tmB, p, st);
   }
   if (bn == 256) return launch_igemm<256, 1>(ctx, tmA, tmB, p, st);
-  const int kch = lsps_kch_small();
-  if (bn == 128) return kch == 2 ? launch_igemm<128, 1, 2>(ctx, tmA, tmB, p, st) : (kch == 3 ? launch_igemm<128, 1, 3>(ctx, tmA, tmB, p, st) : launch_igemm<128, 1>(ctx, tmA, tmB, p, st));
-  return kch == 2 ? launch_igemm<64, 1, 2>(ctx, tmA, tmB, p, st) : (kch == 3 ? launch_igemm<64, 1, 3>(ctx, tmA, tmB, p, st) : launch_igemm<64, 1>(ctx, tmA, tmB, p, st));
+  // single-CTA BN <= 128 kernels stage one 64-channel chunk per pipeline stage (2 and 3 chunks measured slower, r01 probes)
+  if (bn == 128) return launch_igemm<128, 1>(ctx, tmA, tmB, p, st);
+  return launch_igemm<64, 1>(ctx, tmA, tmB, p, st);
 }
 
 template <int BN, int CG>
