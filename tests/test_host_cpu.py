@@ -147,3 +147,29 @@ def test_joint_schedule_steps_both_stores():
     sch = _JointSchedule(MultiStepLR(a, [2], 0.5), MultiStepLR(b, [2], 0.5))
     sch.step(); sch.step()
     assert a.lr == b.lr == 5e-5 and sch.get_lr() == [5e-5]
+
+
+def test_train_map_noise_sharding_matches_the_global_draw():
+    """train_map: vae.encode runs on cat(labels_a, labels_b) (lsps_trainer.py:86-88); under data parallelism rank r holds
+    cat(labels_a[r-th shard], labels_b[r-th shard]) and must use the rows of the reference's (2B, z) host draw that
+    belong to exactly those samples: shard_rows(noise, groups=2).  Checked with the oracle's poseVAE arithmetic."""
+    from lsps_b200.sharding import shard_rows
+    hp = _hp("nnyu")
+    vae = O.PoseVAE(hp["vae"], O.init_params(O.vae_spec(hp["vae"]), 3))
+    g = torch.Generator().manual_seed(5)
+    B, world = 6, 3
+    la, lb = torch.randn(B, 108, generator=g), torch.randn(B, 108, generator=g)
+    torch.manual_seed(11)
+    z_ref = vae.encode(torch.cat((la, lb), 0))[0]                 # single process: one (2B, 20) draw
+    torch.manual_seed(11)
+    noise = torch.normal(torch.zeros(2 * B, 20), std=0.05)        # the same global draw, made on every rank
+    for rank in range(world):
+        la_r, lb_r = shard_rows(la, 1, world, rank), shard_rows(lb, 1, world, rank)
+        y = torch.cat((la_r, lb_r), 0)
+        P = vae.P
+        h = torch.nn.functional.leaky_relu(torch.nn.functional.linear(y, P["en_fc1.weight"], P["en_fc1.bias"]), 0.01)
+        mu = torch.nn.functional.linear(h, P["en_mu.weight"], P["en_mu.bias"])
+        sd = torch.nn.functional.softplus(torch.nn.functional.linear(h, P["en_sigma.weight"], P["en_sigma.bias"]))
+        z = mu + sd * shard_rows(noise, 2, world, rank)
+        want = torch.cat((shard_rows(z_ref[:B], 1, world, rank), shard_rows(z_ref[B:], 1, world, rank)), 0)
+        assert torch.allclose(z, want, atol=1e-6)
