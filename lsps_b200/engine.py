@@ -261,6 +261,8 @@ class Generator:
     def enc_pair_bwd(self, sv, dx, dimg_a=None, dimg_b=None):
         o, S, na = self.ops, self.S, sv["na"]
         blocks = sv["blocks"]
+        if not blocks:
+            raise NotImplementedError("n_enc_res_blk == 0")   # the LeakyReLU mask of f2 is applied by the first block's dgrad
         for i in range(len(blocks) - 1, -1, -1):
             dx = o.res_bwd(S, blocks[i], dx, mask=sv["f2"] if i == 0 else None)
         for fr, d2, dimg in ((sv["fronts"][0], dx[:na], dimg_a), (sv["fronts"][1], dx[na:], dimg_b)):
