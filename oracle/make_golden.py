@@ -134,6 +134,7 @@ def main(only=None):
     run_case(trainers, "estimate3_nnyu_b8", nnyu, ["post3"], batch=8, steps=3)
     run_case(trainers, "estimate0_nnyu_b4", nnyu, ["post0"], batch=4, steps=2)
     run_case(trainers, "estimate4_nnyu_b5", nnyu, ["post4"], batch=5, steps=1)
+    run_case(trainers, "estimate1_nnyu_b4", nnyu, ["post1"], batch=4, steps=2)
     # config 4: ICVL shapes (48-d pose vector; conv nets identical)
     run_case(trainers, "estimate3_nicvl_b4", nicvl, ["post3"], batch=4, steps=1)
     # the train_map=True branches (Mapping net, ndiv=4 discriminator batch, map losses)

@@ -69,6 +69,7 @@ GOLDEN_CASES = {
     "estimate3_nnyu_b8": ("nnyu", ["post3"], 8, 3, "uniform"),
     "estimate0_nnyu_b4": ("nnyu", ["post0"], 4, 2, "uniform"),
     "estimate4_nnyu_b5": ("nnyu", ["post4"], 5, 1, "uniform"),
+    "estimate1_nnyu_b4": ("nnyu", ["post1"], 4, 2, "uniform"),
     "estimate3_nicvl_b4": ("nicvl", ["post3"], 4, 1, "uniform"),
     # train_map=True branches (Mapping net): config name "<yaml>:map"
     "pretrain_map_nnyu_b1": ("nnyu:map", ["dis", "gen"], 1, 2, "uniform"),
