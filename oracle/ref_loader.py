@@ -60,6 +60,34 @@ def load_reference(cpu_shim=True):
     return trainers
 
 
+def load_reference_augment():
+    """The reference's input pipeline pieces for the section-8f n3 row: (normalize, augmentCrop, HandDetector,
+    DepthImporter).  Extra shims on top of load_reference(): `utils/handdetector.py` has ONE python-2 print statement
+    (:214, a warning) which is rewritten as a call, `xrange` is aliased to `range`, and `pylab` is stubbed like
+    matplotlib.  No arithmetic is edited."""
+    import builtins
+    import re
+    load_reference()
+    src = os.path.join(_scratch, "src")
+    hd = os.path.join(src, "utils", "handdetector.py")
+    with open(hd) as fh:
+        text = fh.read()
+    text = re.sub(r'^(\s*)print "([^"]*)"\s*$', r'\1print("\2")', text, flags=re.M)
+    with open(hd, "w") as fh:
+        fh.write(text)
+    builtins.xrange = range
+    for m in ("pylab", "progressbar"):
+        if m not in sys.modules:
+            sys.modules[m] = types.ModuleType(m)
+    if "cPickle" not in sys.modules:                           # python-2 module name (data/importers.py:34)
+        import pickle
+        sys.modules["cPickle"] = pickle
+    from data.dataset_hand2 import normalize, augmentCrop      # noqa
+    from utils.handdetector import HandDetector                # noqa
+    from data.importers import DepthImporter                   # noqa
+    return normalize, augmentCrop, HandDetector, DepthImporter
+
+
 def load_hyperparameters(name="nnyu"):
     import yaml
 
