@@ -46,7 +46,7 @@ def test_oracle_reproduces_reference(case, golden_dir):
 
 
 def test_oracle_header_says_test_infrastructure():
-    for f in ("lsps_oracle.py", "ref_loader.py", "make_golden.py"):
+    for f in ("lsps_oracle.py", "ref_loader.py", "make_golden.py", "augment_oracle.py", "make_augment_golden.py"):
         with open(os.path.join(ROOT, "oracle", f)) as fh:
             assert "TEST INFRASTRUCTURE ONLY" in fh.read(400)
 
