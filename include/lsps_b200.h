@@ -157,6 +157,14 @@ int lsps_joint_errors(lsps_ctx*, const float* pred, const float* gt, const int* 
                       float sy, float sz, float* err_mean, float* err_max, int n, lsps_stream);
 int lsps_bf16_to_f32(lsps_ctx*, const void* x, float* y, long long n, lsps_stream);
 
+/* ---- input pipeline (data/dataset_hand2.py:34-119 augmentCrop, utils/handdetector.py:682-808, cv2
+   nearest-neighbour warps): img/out = n normalised 128x128 fp32 crops (distinct buffers), params = n device-resident
+   `lsps_aug_sample` records (lsps_b200/csrc/augment_core.h; sizeof via lsps_aug_sample_bytes) computed on the host from
+   the reference's random draws, premax = n floats of scratch.  Per pixel: de-normalise, warp (perspective: com / scale
+   moves; affine: in-plane rotation), z-threshold, clamp to the new cube, normalise. */
+int lsps_augment_crops(lsps_ctx*, const float* img, const void* params, float* premax, float* out, int n, lsps_stream);
+int lsps_aug_sample_bytes(void);
+
 #ifdef __cplusplus
 }
 #endif

@@ -10,9 +10,10 @@ from .engine import Generator as SharedResGenB200, Discriminator as SharedDisB20
 from .data import SyntheticHandDataset, synthetic_batch
 from .config import NetConfig, load_hyperparameters
 from .evaluation import PoseEvaluator, NYU_RESTRICTED_JOINTS
+from .augment import CropAugmenter
 
 LSPSTrainer = LSPSTrainerB200  # the reference's own name selects the B200 trainer as well
 
-__all__ = ["LSPSTrainerB200", "LSPSTrainer", "SharedResGenB200", "SharedDisB200", "poseVAEB200",
+__all__ = ["CropAugmenter", "LSPSTrainerB200", "LSPSTrainer", "SharedResGenB200", "SharedDisB200", "poseVAEB200",
            "SyntheticHandDataset", "synthetic_batch", "NetConfig", "load_hyperparameters", "PoseEvaluator",
            "NYU_RESTRICTED_JOINTS"]

@@ -58,9 +58,10 @@ _SIGS = {
     "lsps_f32_to_bf16": [_vp, _vp, _ll],
     "lsps_joint_errors": [_vp, _vp, _vp, _i, _i, _f, _f, _f, _vp, _vp, _i],
     "lsps_bf16_to_f32": [_vp, _vp, _ll],
+    "lsps_augment_crops": [_vp, _vp, _vp, _vp, _i],
 }
 EXPORTS = sorted(list(_SIGS) + ["lsps_ctx_create", "lsps_ctx_destroy", "lsps_last_error", "lsps_abi_version",
-                                "lsps_launch_count"])
+                                "lsps_launch_count", "lsps_aug_sample_bytes"])
 
 
 class LspsError(RuntimeError):
@@ -82,6 +83,8 @@ def _load():
     lib.lsps_ctx_destroy.argtypes = [_vp]
     lib.lsps_launch_count.restype = _ll
     lib.lsps_launch_count.argtypes = [_vp]
+    lib.lsps_aug_sample_bytes.restype = _i
+    lib.lsps_aug_sample_bytes.argtypes = []
     for name, sig in _SIGS.items():
         fn = getattr(lib, name)
         fn.argtypes = [_vp] + sig + [_vp]
