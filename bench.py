@@ -2,7 +2,7 @@
 """bench.py -- train-step depth-images/sec of the LSPS pretrain step (dis_update + gen_update) on B200.
 
   python bench.py --gpus N --steps K --warmup W          (N>1: launched by torch.distributed.run, one rank per GPU)
-  python bench.py --impl reference ...                   (the reference's CPU path = the oracle port, host cores)
+  python bench.py --impl reference ...                   (the reference's own CPU path: oracle/_ref, else the oracle port)
 
 Workload (BASELINE.json configs[1]): depth_train.py --mode pretrain, exps/nnyu.yaml, synthetic 128x128 depth
 crops, batch 64 per domain per GPU (weak scaling: the per-GPU batch is fixed as N grows).  One step = one
@@ -11,7 +11,8 @@ dis_update + one gen_update (src/depth_train.py:158-161) = 2*64 depth images per
 Prints ONE JSON line.  `value`: inputs already resident in HBM.  `e2e`: same calls with pinned HOST inputs, the
 host->device copies and the per-update device->host loss read inside the timed region.  `roofline`: the dominant
 kernel (3x3 s1 256->256 implicit GEMM on tcgen05, the K1 shape of SURVEY.md 2.2) timed per launch with CUDA events
-in an extra instrumented step.  `cpu_baseline`: the oracle port timed on this box's host cores on a bounded sample.
+in an extra instrumented step.  `cpu_baseline`: the unmodified reference (oracle/_ref; else the oracle port) timed on this box's host cores on a
+bounded sample.
 """
 import argparse
 import json
@@ -86,37 +87,61 @@ class ClockSampler(threading.Thread):
 
 
 def cpu_reference_rate(steps, warmup, batch):
-    """The reference's own CPU path of this workload (oracle port of LSPSTrainer) on all host cores."""
+    """The reference's own CPU path of this workload on all host cores: the UNMODIFIED reference LSPSTrainer from the
+    staged copy oracle/_ref (kind "reference") when it travelled to this box, else the oracle port (kind "port")."""
     import torch
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import lsps_oracle as O
-    import yaml
-    with open(os.path.join(ROOT, "exps", "nnyu.yaml")) as fh:
-        hp = yaml.safe_load(fh)["train"]["hyperparameters"]
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    tr = O.OracleTrainer(hp, seed=0)
+    kind = "port"
+    try:
+        import ref_loader
+        if ref_loader.reference_available() or ref_loader.staged_available():
+            trainers = ref_loader.load_reference(cpu_shim="force")
+            hp = ref_loader.load_hyperparameters("nnyu")
+            torch.manual_seed(0)
+            tr = trainers.LSPSTrainer(hp)
+            tr.gpu = 0
+            kind = "reference"
+    except Exception as e:  # noqa
+        sys.stderr.write("bench: staged reference not usable (%r); timing the oracle port\n" % (e,))
+        kind = "port"
+    if kind == "port":
+        import lsps_oracle as O
+        import yaml
+        with open(os.path.join(ROOT, "exps", "nnyu.yaml")) as fh:
+            hp = yaml.safe_load(fh)["train"]["hyperparameters"]
+        tr = O.OracleTrainer(hp, seed=0)
+    # synthetic crops of the same kind as the B200 arm's (background +1, hand pixels in [-1,1])
     g = torch.Generator().manual_seed(1234)
-    ia, ib, la, lb = O.synthetic_batch(batch, 108, g, "hand")
+    ia = (torch.randn(batch, 1, 128, 128, generator=g) * 0.35).clamp(-1, 1)
+    ib = (torch.randn(batch, 1, 128, 128, generator=g) * 0.35).clamp(-1, 1)
+    yy, xx = torch.meshgrid(torch.arange(128.0), torch.arange(128.0), indexing="ij")
+    bg = (((yy - 63.5) / 40.0) ** 2 + ((xx - 63.5) / 40.0) ** 2 > 1.0)
+    ia[:, 0][:, bg] = 1.0
+    ib[:, 0][:, bg] = 1.0
+    la, lb = torch.randn(batch, 108, generator=g) * 0.3, torch.randn(batch, 108, generator=g) * 0.3
+    com = torch.zeros(batch, 3)
     times = []
     for s in range(warmup + steps):
         t0 = time.perf_counter()
-        tr.dis_update(ia, la, ib, lb, None, None, hp)
+        tr.dis_update(ia, la, ib, lb, com, com, hp)
         tr.gen_update(ia, la, ib, lb, hp)
         if s >= warmup:
             times.append(time.perf_counter() - t0)
     sec = sum(times) / len(times)
-    return 2 * batch / sec, sec, cores
+    return 2 * batch / sec, sec, cores, kind
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps, warmup = max(1, min(args.steps, 3)), max(1, min(args.warmup, 1))
-    rate, sec, cores = cpu_reference_rate(steps, warmup, CPU_SAMPLE_BATCH)
-    sample = "pretrain step (dis_update+gen_update) at batch %d per domain, %d timed steps, oracle port of " \
-             "LSPSTrainer on torch CPU fp32" % (CPU_SAMPLE_BATCH, steps)
+    steps, warmup = max(1, min(args.steps, 5)), max(1, min(args.warmup, 1))
+    rate, sec, cores, kind = cpu_reference_rate(steps, warmup, CPU_SAMPLE_BATCH)
+    sample = "pretrain step (dis_update+gen_update) at batch %d per domain, %d timed steps, %s on torch CPU fp32" % (
+        CPU_SAMPLE_BATCH, steps, "the unmodified reference LSPSTrainer (oracle/_ref)" if kind == "reference"
+        else "oracle port of LSPSTrainer")
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
         "warmup": warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -124,7 +149,7 @@ def run_reference(args):
         # the workload is the B200 arm's; each CPU step is a bounded sample of it (see cpu_baseline.sample)
         "config": {"workload": WORKLOAD % BATCH, "sample_batch_per_domain": CPU_SAMPLE_BATCH,
                    "noise": "host RNG (the reference's own draws)"},
-        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
@@ -280,10 +305,11 @@ def main():
         return
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        rate, sec, cores = cpu_reference_rate(2, 1, CPU_SAMPLE_BATCH)
-        cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": "pretrain step at batch %d per domain, 1 warm-up + 2 timed steps (%.1f s/step), oracle port "
-                         "of the reference LSPSTrainer on torch CPU fp32" % (CPU_SAMPLE_BATCH, sec)}
+        rate, sec, cores, kind = cpu_reference_rate(4, 1, CPU_SAMPLE_BATCH)
+        cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": kind,
+               "sample": "pretrain step at batch %d per domain, 1 warm-up + 4 timed steps (%.1f s/step), %s on torch "
+                         "CPU fp32" % (CPU_SAMPLE_BATCH, sec, "the unmodified reference LSPSTrainer (oracle/_ref)"
+                                       if kind == "reference" else "oracle port of the reference LSPSTrainer")}
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",

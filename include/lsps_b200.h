@@ -31,10 +31,33 @@ enum { LSPS_OK = 0, LSPS_E_ARG = -1, LSPS_E_SHAPE = -2, LSPS_E_ARCH = -3, LSPS_E
    | 4x4 stride-2 pad-1 ConvTranspose2d (Mapping net, lsps_nets.py:17-23; 16 taps, tap = r*4+s) */
 enum { LSPS_CONV_S1 = 0, LSPS_CONV_S2 = 1, LSPS_DECONV_S2 = 2, LSPS_DECONV4_S2 = 3 };
 /* epilogue flags of the implicit-GEMM kernels, applied in this order: +bias, LeakyReLU, +add, *lrelu'(mask) */
-enum { LSPS_EP_BIAS = 1, LSPS_EP_LRELU = 2, LSPS_EP_MASK = 4, LSPS_EP_ADD = 8 };
+enum { LSPS_EP_BIAS = 1, LSPS_EP_LRELU = 2, LSPS_EP_MASK = 4, LSPS_EP_ADD = 8,
+       /* forward: accumulate per-(image, channel) sum / sum of squares of the fp32 result (after bias) -- the statistics of
+          the InstanceNorm2d / BatchNorm2d that follows the conv (common_net.py:168,171,187,190) -- into ext->sums */
+       LSPS_EP_STATS = 16,
+       /* data gradient landing on lrelu(IN(h)): stores g = acc * lrelu'(xhat) and accumulates per-(image, channel)
+          sum g, sum g*xhat into ext->bsums (front half of InstanceNorm backward, finished by lsps_norm_bwd_apply) */
+       LSPS_EP_INBWD = 32 };
 
 /* n images; h,w = INPUT spatial size of the FORWARD op; cin/cout of the forward op (multiples of 64). */
 typedef struct { int kind, n, h, w, cin, cout; } lsps_conv_shape;
+
+/* Optional extras of lsps_conv_{fwd,dgrad}_ex; zero-initialise, set what is used.
+     grouped launch : images [0, n_split) use (w, bias), images [n_split, n) use (w2, bias2)   (see lsps_conv_fwd_grouped)
+     LSPS_EP_STATS  : sums  f32 [n][2][cout]  (zeroed by the call, then red.add'ed by the kernel)
+     LSPS_EP_INBWD  : in_h bf16 [n,h,w,cin] = the conv output that was normalised, in_stats f32 [n][2][cin] = its (mean, rstd)
+                      rows, bsums f32 [n][2][cin] (zeroed by the call)
+     split          : "bf16x3" operands for layers whose bf16 rounding shows in the losses (the discriminator stack,
+                      lsps_nets.py:102-126): activations are stored as [n,h,w,2c] = (bf16 hi | bf16 lo) channel halves with
+                      hi + lo carrying 16 mantissa bits, weights as two tensors (w = hi, w_lo = lo, same layout); the GEMM
+                      accumulates hi*hi + hi*lo + lo*hi in fp32 and writes its result in the same split form.  mask (if
+                      any) is a split tensor too (its hi half carries the sign). */
+typedef struct {
+  const void* w2; const float* bias2; int n_split;
+  float* sums;
+  const void* in_h; const float* in_stats; float* bsums;
+  const void* w_lo; int split;
+} lsps_conv_ext;
 
 int lsps_ctx_create(lsps_ctx** out, int device);
 void lsps_ctx_destroy(lsps_ctx* ctx);
@@ -58,6 +81,10 @@ int lsps_conv_fwd_grouped(lsps_ctx*, const lsps_conv_shape*, const void* x, cons
                           const void* w_fwd2, const float* bias2, int n_split, void* y, int flags, float slope, lsps_stream);
 int lsps_conv_dgrad_grouped(lsps_ctx*, const lsps_conv_shape*, const void* dy, const void* w_dgrad, const void* w_dgrad2,
                             int n_split, void* dx, const void* mask, const void* add, int flags, float slope, lsps_stream);
+int lsps_conv_fwd_ex(lsps_ctx*, const lsps_conv_shape*, const void* x, const void* w_fwd, const float* bias, void* y,
+                     int flags, float slope, const lsps_conv_ext* ext, lsps_stream);
+int lsps_conv_dgrad_ex(lsps_ctx*, const lsps_conv_shape*, const void* dy, const void* w_dgrad, void* dx, const void* mask,
+                       const void* add, int flags, float slope, const lsps_conv_ext* ext, lsps_stream);
 /* dw[tap][cout][cin] += conv_backward_weight(x, dy)   (fp32, accumulating; split-K over pixels with red.add) */
 int lsps_conv_wgrad(lsps_ctx*, const lsps_conv_shape*, const void* x, const void* dy, float* dw, lsps_stream);
 /* db[c] += sum over rows of dy[rows][c]   (bias gradients; dy bf16) */

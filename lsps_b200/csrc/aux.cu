@@ -515,6 +515,161 @@ __global__ void __launch_bounds__(512) instnorm_fwd_reg_kernel(const bf16* __res
   }
 }
 
+// ----- statistics-from-the-conv-epilogue path (round 2) --------------------------------------------------------------
+// The conv that produces h already accumulated per-(image, channel) sum / sum of squares of its fp32 result
+// (LSPS_EP_STATS, igemm.cu), so the norm itself is ONE streaming pass: no reductions, no block-wide syncs, 8 independent
+// 16-byte loads in flight per thread.  `sums` rows are [img][2][c]; BatchNorm passes img_stride = 0 and a batch-reduced
+// row.  The blocks of pixel-block 0 write (mean, rstd) to stats_out[img][2][c] for the backward pass.
+//   MODE 0: y = lrelu(xhat)   MODE 1: y = res + xhat   MODE 2: y = xhat
+template <int MODE>
+__global__ void __launch_bounds__(256) norm_apply_fwd_kernel(const bf16* __restrict__ h, const bf16* __restrict__ res,
+                                                            bf16* __restrict__ y, const float* __restrict__ sums,
+                                                            float* __restrict__ stats_out, int hw, int c, int ppb,
+                                                            long long img_stride, float inv_count, float eps,
+                                                            float slope) {
+  const int octs = c >> 3, lanes = 256 / octs;
+  const int oct = threadIdx.x % octs, pl = threadIdx.x / octs;
+  const int n = blockIdx.y, p0 = blockIdx.x * ppb;
+  const float* sr = sums + n * img_stride + oct * 8;
+  float mean[8], rstd[8];
+  {
+    const float4 a0 = __ldg(reinterpret_cast<const float4*>(sr)), a1 = __ldg(reinterpret_cast<const float4*>(sr) + 1);
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(sr + c)), b1 = __ldg(reinterpret_cast<const float4*>(sr + c) + 1);
+    const float s1[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+    const float s2[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      mean[k] = s1[k] * inv_count;
+      const float var = fmaxf(s2[k] * inv_count - mean[k] * mean[k], 0.f);
+      rstd[k] = rsqrtf(var + eps);
+    }
+  }
+  if (stats_out && blockIdx.x == 0 && pl == 0) {
+    float* so = stats_out + (long long)n * 2 * c + oct * 8;
+    reinterpret_cast<float4*>(so)[0] = make_float4(mean[0], mean[1], mean[2], mean[3]);
+    reinterpret_cast<float4*>(so)[1] = make_float4(mean[4], mean[5], mean[6], mean[7]);
+    reinterpret_cast<float4*>(so + c)[0] = make_float4(rstd[0], rstd[1], rstd[2], rstd[3]);
+    reinterpret_cast<float4*>(so + c)[1] = make_float4(rstd[4], rstd[5], rstd[6], rstd[7]);
+  }
+  const long long base = (long long)n * hw * c + oct * 8;
+  const int pend = min(p0 + ppb, hw);
+#pragma unroll 4
+  for (int p = p0 + pl; p < pend; p += lanes) {
+    float f[8], r[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(h + base + (long long)p * c)), f);
+    if (MODE == 1) unpack8(__ldg(reinterpret_cast<const uint4*>(res + base + (long long)p * c)), r);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float v = (f[k] - mean[k]) * rstd[k];
+      f[k] = MODE == 1 ? r[k] + v : (MODE == 0 ? (v > 0.f ? v : v * slope) : v);
+    }
+    *reinterpret_cast<uint4*>(y + base + (long long)p * c) = pack8(f);
+  }
+}
+
+// Backward statistics when the producer of the gradient could not take them (gradient arriving at `res + IN(h)`):
+// bsums[img][2][c] += (sum g, sum g*xhat) over this block's pixels; g = dy (MODE 1) or dy * lrelu'(xhat) (MODE 0).
+template <int MODE>
+__global__ void __launch_bounds__(256) norm_bwd_stats_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ h,
+                                                            const float* __restrict__ stats, float* __restrict__ bsums,
+                                                            int hw, int c, int ppb, long long stat_stride,
+                                                            long long bsum_stride, float slope) {
+  extern __shared__ float nred[];   // [lanes][c] x 2
+  const int octs = c >> 3, lanes = 256 / octs;
+  const int oct = threadIdx.x % octs, pl = threadIdx.x / octs;
+  const int n = blockIdx.y, p0 = blockIdx.x * ppb;
+  const float* st = stats + n * stat_stride + oct * 8;
+  float mean[8], rstd[8], sg[8], sgx[8];
+  {
+    const float4 a0 = __ldg(reinterpret_cast<const float4*>(st)), a1 = __ldg(reinterpret_cast<const float4*>(st) + 1);
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(st + c)), b1 = __ldg(reinterpret_cast<const float4*>(st + c) + 1);
+    mean[0] = a0.x; mean[1] = a0.y; mean[2] = a0.z; mean[3] = a0.w; mean[4] = a1.x; mean[5] = a1.y; mean[6] = a1.z; mean[7] = a1.w;
+    rstd[0] = b0.x; rstd[1] = b0.y; rstd[2] = b0.z; rstd[3] = b0.w; rstd[4] = b1.x; rstd[5] = b1.y; rstd[6] = b1.z; rstd[7] = b1.w;
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { sg[k] = 0.f; sgx[k] = 0.f; }
+  const long long base = (long long)n * hw * c + oct * 8;
+  const int pend = min(p0 + ppb, hw);
+#pragma unroll 4
+  for (int p = p0 + pl; p < pend; p += lanes) {
+    float f[8], g[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(h + base + (long long)p * c)), f);
+    unpack8(__ldg(reinterpret_cast<const uint4*>(dy + base + (long long)p * c)), g);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float xh = (f[k] - mean[k]) * rstd[k];
+      const float gg = (MODE == 0 && !(xh > 0.f)) ? g[k] * slope : g[k];
+      sg[k] += gg; sgx[k] += gg * xh;
+    }
+  }
+  float* r1 = nred;
+  float* r2 = nred + lanes * c;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { r1[pl * c + oct * 8 + k] = sg[k]; r2[pl * c + oct * 8 + k] = sgx[k]; }
+  __syncthreads();
+  for (int ch = threadIdx.x; ch < c; ch += 256) {
+    float a = 0.f, b = 0.f;
+    for (int l = 0; l < lanes; ++l) { a += r1[l * c + ch]; b += r2[l * c + ch]; }
+    atomicAdd(bsums + n * bsum_stride + ch, a);
+    atomicAdd(bsums + n * bsum_stride + c + ch, b);
+  }
+}
+
+// dh = rstd * (g - mean(g) - xhat * mean(g*xhat)), the means from bsums (taken by the dgrad epilogue, LSPS_EP_INBWD, or
+// by norm_bwd_stats_kernel).  GMODE 0: `g` is the raw gradient w.r.t. lrelu(xhat) (mask applied here); 1: g is used as is
+// (already masked by the dgrad epilogue, or the gradient w.r.t. res + xhat).
+template <int GMODE>
+__global__ void __launch_bounds__(256) norm_bwd_apply_kernel(const bf16* __restrict__ g_, const bf16* __restrict__ h,
+                                                            const float* __restrict__ stats,
+                                                            const float* __restrict__ bsums, bf16* __restrict__ dh,
+                                                            int hw, int c, int ppb, long long stat_stride,
+                                                            long long bsum_stride, float inv_count, float slope) {
+  const int octs = c >> 3, lanes = 256 / octs;
+  const int oct = threadIdx.x % octs, pl = threadIdx.x / octs;
+  const int n = blockIdx.y, p0 = blockIdx.x * ppb;
+  const float* st = stats + n * stat_stride + oct * 8;
+  const float* bs = bsums + n * bsum_stride + oct * 8;
+  float mean[8], rstd[8], mg[8], mgx[8];
+  {
+    const float4 a0 = __ldg(reinterpret_cast<const float4*>(st)), a1 = __ldg(reinterpret_cast<const float4*>(st) + 1);
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(st + c)), b1 = __ldg(reinterpret_cast<const float4*>(st + c) + 1);
+    const float4 c0 = __ldg(reinterpret_cast<const float4*>(bs)), c1 = __ldg(reinterpret_cast<const float4*>(bs) + 1);
+    const float4 d0 = __ldg(reinterpret_cast<const float4*>(bs + c)), d1 = __ldg(reinterpret_cast<const float4*>(bs + c) + 1);
+    mean[0] = a0.x; mean[1] = a0.y; mean[2] = a0.z; mean[3] = a0.w; mean[4] = a1.x; mean[5] = a1.y; mean[6] = a1.z; mean[7] = a1.w;
+    rstd[0] = b0.x; rstd[1] = b0.y; rstd[2] = b0.z; rstd[3] = b0.w; rstd[4] = b1.x; rstd[5] = b1.y; rstd[6] = b1.z; rstd[7] = b1.w;
+    mg[0] = c0.x; mg[1] = c0.y; mg[2] = c0.z; mg[3] = c0.w; mg[4] = c1.x; mg[5] = c1.y; mg[6] = c1.z; mg[7] = c1.w;
+    mgx[0] = d0.x; mgx[1] = d0.y; mgx[2] = d0.z; mgx[3] = d0.w; mgx[4] = d1.x; mgx[5] = d1.y; mgx[6] = d1.z; mgx[7] = d1.w;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { mg[k] *= inv_count; mgx[k] *= inv_count; }
+  }
+  const long long base = (long long)n * hw * c + oct * 8;
+  const int pend = min(p0 + ppb, hw);
+#pragma unroll 4
+  for (int p = p0 + pl; p < pend; p += lanes) {
+    float f[8], g[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(h + base + (long long)p * c)), f);
+    unpack8(__ldg(reinterpret_cast<const uint4*>(g_ + base + (long long)p * c)), g);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float xh = (f[k] - mean[k]) * rstd[k];
+      const float gg = (GMODE == 0 && !(xh > 0.f)) ? g[k] * slope : g[k];
+      f[k] = rstd[k] * (gg - mg[k] - xh * mgx[k]);
+    }
+    *reinterpret_cast<uint4*>(dh + base + (long long)p * c) = pack8(f);
+  }
+}
+
+// BatchNorm: per-channel batch statistics = the per-image rows of `sums` added up (tiny: n x 2c floats).
+// out[0][c] = sum over images of sums[img][0][c], out[1][c] likewise
+__global__ void __launch_bounds__(256) norm_reduce_images_kernel(const float* __restrict__ sums, float* __restrict__ out,
+                                                                int n, int c2) {
+  const int j = blockIdx.x * 256 + threadIdx.x;
+  if (j >= c2) return;
+  float s = 0.f;
+  for (int i = 0; i < n; ++i) s += sums[(long long)i * c2 + j];
+  out[j] = s;
+}
+
 // =============================================================================================== elementwise / losses
 __global__ void __launch_bounds__(256) noise_kl_kernel(const bf16* __restrict__ x, const float* __restrict__ noise,
                                                       bf16* __restrict__ z, float* __restrict__ acc, long long n8) {

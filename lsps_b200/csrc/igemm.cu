@@ -123,6 +123,18 @@ struct IgemmParams {
   float slope;
   int flags;
   int dbg;  // profiling experiments only: 1 = skip MMA issue, 2 = skip TMA issue (results are garbage)
+  // LSPS_EP_STATS: per-(image, channel) sum / sum of squares of the fp32 result (after bias), accumulated with red.add
+  //   into sums[nimg][2][nc_total] -- the InstanceNorm / BatchNorm statistics of the NEXT layer, taken while the values
+  //   are still in registers (one streaming apply pass is all that is left of the norm).
+  float* sums;
+  // LSPS_EP_INBWD (data gradient that lands on lrelu(IN(h))): `mask` points at h, in_stats[nimg][2][nc_total] holds its
+  //   (mean, rstd); the epilogue stores g = acc * lrelu'(xhat) and accumulates sum g, sum g*xhat into bsums[nimg][2][nc]
+  const float* in_stats;
+  float* bsums;
+  int nc_total;     // output channels of the GEMM (row pitch of sums / in_stats / bsums, lo-half offset of split outputs)
+  // split-bf16 ("bf16x3") operands: A tensor channels are [hi | lo] (lo half a_lo channels in), the weights come as two
+  // tensors (tmB hi, tmBlo lo); K-steps per (tap, chunk): hi*hi, hi*lo, lo*hi; the output is written as [hi | lo] too
+  int split, a_lo, kch_eff;
   Phase ph[4];
   Tap taps[16];
 };
@@ -143,7 +155,7 @@ struct IgemmCfg {
   static constexpr int STAGES = (196608 / STAGE_BYTES) > 8 ? 8 : (196608 / STAGE_BYTES);
   static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
   static constexpr int BIAS_BYTES = 2048 * 4;  // whole bias vector (Cout <= 2048) staged once per CTA
-  static constexpr int KTAB_BYTES = 16 * 32 * 16;  // K-step table (<= 16 taps x 32 chunks)
+  static constexpr int KTAB_BYTES = 1024 * 16;     // K-step table (<= 16 taps x 32 chunks, or 9 taps x 3 x 32 split)
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256 + BIAS_BYTES + KTAB_BYTES;
 };
 
@@ -164,7 +176,27 @@ __device__ __forceinline__ TileCoord decode_tile(const IgemmParams& p, int t, in
   return c;
 }
 
-// Epilogue role (4 warps): TMEM -> registers -> (+bias, LeakyReLU, +residual gradient, *lrelu'(mask)) -> bf16 -> global.
+// Sum over the 32 lanes of v[j] for every j, the total for index j landing in lane j: a butterfly that halves the number
+// of live values each step (16 + 8 + 4 + 2 + 1 = 31 shuffles instead of 32 x 5).
+__device__ __forceinline__ float lane_transpose_sum(float (&v)[32], int lane) {
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const bool up = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < off; ++i) {
+      const float send = up ? v[i] : v[i + off];
+      const float keep = up ? v[i + off] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  return v[0];
+}
+__device__ __forceinline__ void red_add_f32(float* addr, float v) {
+  asm volatile("red.global.add.f32 [%0], %1;" ::"l"(addr), "f"(v) : "memory");
+}
+
+// Epilogue role (4 warps): TMEM -> registers -> (+bias, statistics, LeakyReLU, +residual gradient, *lrelu'(mask) or the
+// InstanceNorm-backward front half) -> bf16 (or split hi|lo) -> global.
 template <int BN, int CG>
 __device__ __forceinline__ void epilogue_role(const IgemmParams& p, const float* sbias, uint32_t tmem_base,
                                               uint64_t* tfull, uint64_t* tempty, int warp, int lane, int rank,
@@ -173,6 +205,7 @@ __device__ __forceinline__ void epilogue_role(const IgemmParams& p, const float*
     const int row = q * 32 + lane;
     const int tw_mask = (1 << p.twl) - 1, th_mask = (1 << p.thl) - 1;
     const int xl = row & tw_mask, yl = (row >> p.twl) & th_mask, nl = row >> (p.twl + p.thl);
+    const bool inbwd = (p.flags & LSPS_EP_INBWD) != 0;
     int it = 0;
     for (int t = worker; t < total; t += nworkers, ++it) {
       const TileCoord tc = decode_tile(p, t, per_phase, groups_m, CG, rank);
@@ -183,10 +216,12 @@ __device__ __forceinline__ void epilogue_role(const IgemmParams& p, const float*
       const long long off = (long long)n * p.o_n + (long long)((y0 + yl) * p.o_sy + P.oa) * p.o_y +
                             (long long)((x0 + xl) * p.o_sx + P.ob) * p.o_x + nt * BN;
       const int acc = it & 1; const uint32_t accph = (it >> 1) & 1;
-      const bool use_add = valid && (p.flags & LSPS_EP_ADD), use_mask = valid && (p.flags & LSPS_EP_MASK);
+      const bool use_add = valid && (p.flags & LSPS_EP_ADD), use_mask = valid && ((p.flags & LSPS_EP_MASK) || inbwd);
       const uint4* a4 = reinterpret_cast<const uint4*>(p.add + off);
       const uint4* m4 = reinterpret_cast<const uint4*>(p.mask + off);
       uint4* o4 = reinterpret_cast<uint4*>(p.out + off);
+      // per-(image, channel) rows of the statistics buffers (every row of a warp lies in ONE image: host-checked)
+      const long long srow = ((long long)(valid ? n : 0) * 2) * p.nc_total + nt * BN;
       // software pipeline: the global loads (residual / mask) and the TMEM load of chunk c+1 are in flight while
       // chunk c is converted and stored; TMEM is handed back to the MMA warp as soon as its last column is in registers
       uint4 ga[4], gm[4];
@@ -227,49 +262,110 @@ __device__ __forceinline__ void epilogue_role(const IgemmParams& p, const float*
           __syncwarp();
           if (lane == 0) { if (CG == 2) mbar_arrive_leader(&tempty[acc]); else mbar_arrive(&tempty[acc]); }
         }
-        if (valid) {
-          if (p.flags & LSPS_EP_BIAS) {
-            const float4* b4 = reinterpret_cast<const float4*>(sbias + boff + nt * BN + c0);
+        if (p.flags & LSPS_EP_BIAS) {
+          const float4* b4 = reinterpret_cast<const float4*>(sbias + boff + nt * BN + c0);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float4 b = b4[j];
-              f[4 * j] += b.x; f[4 * j + 1] += b.y; f[4 * j + 2] += b.z; f[4 * j + 3] += b.w;
-            }
+          for (int j = 0; j < 8; ++j) {
+            const float4 b = b4[j];
+            f[4 * j] += b.x; f[4 * j + 1] += b.y; f[4 * j + 2] += b.z; f[4 * j + 3] += b.w;
           }
-          if (p.flags & LSPS_EP_LRELU) {
+        }
+        if (p.flags & LSPS_EP_STATS) {   // warp-uniform branch; invalid (phantom) rows contribute zeros
+          float s[32];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] = f[j] > 0.f ? f[j] : f[j] * p.slope;
+          for (int j = 0; j < 32; ++j) s[j] = valid ? f[j] : 0.f;
+          const float s1 = lane_transpose_sum(s, lane);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) s[j] = valid ? f[j] * f[j] : 0.f;
+          const float s2 = lane_transpose_sum(s, lane);
+          if (valid) {
+            red_add_f32(p.sums + srow + c0 + lane, s1);
+            red_add_f32(p.sums + srow + p.nc_total + c0 + lane, s2);
           }
-          if (p.flags & LSPS_EP_ADD) {
+        }
+        if (p.flags & LSPS_EP_LRELU) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const uint32_t w[4] = {ca[j].x, ca[j].y, ca[j].z, ca[j].w};
-#pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                f[8 * j + 2 * k] += bf16lo(w[k]);
-                f[8 * j + 2 * k + 1] += bf16hi(w[k]);
-              }
-            }
-          }
-          if (p.flags & LSPS_EP_MASK) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const uint32_t w[4] = {cm[j].x, cm[j].y, cm[j].z, cm[j].w};
-#pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                if (!(bf16lo(w[k]) > 0.f)) f[8 * j + 2 * k] *= p.slope;
-                if (!(bf16hi(w[k]) > 0.f)) f[8 * j + 2 * k + 1] *= p.slope;
-              }
-            }
-          }
+          for (int j = 0; j < 32; ++j) f[j] = f[j] > 0.f ? f[j] : f[j] * p.slope;
+        }
+        if (p.flags & LSPS_EP_ADD) {
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            uint4 o;
-            o.x = pack_bf16x2(f[8 * j], f[8 * j + 1]);
-            o.y = pack_bf16x2(f[8 * j + 2], f[8 * j + 3]);
-            o.z = pack_bf16x2(f[8 * j + 4], f[8 * j + 5]);
-            o.w = pack_bf16x2(f[8 * j + 6], f[8 * j + 7]);
-            o4[c0 / 8 + j] = o;
+            const uint32_t w[4] = {ca[j].x, ca[j].y, ca[j].z, ca[j].w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              f[8 * j + 2 * k] += bf16lo(w[k]);
+              f[8 * j + 2 * k + 1] += bf16hi(w[k]);
+            }
+          }
+        }
+        if (p.flags & LSPS_EP_MASK) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint32_t w[4] = {cm[j].x, cm[j].y, cm[j].z, cm[j].w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              if (!(bf16lo(w[k]) > 0.f)) f[8 * j + 2 * k] *= p.slope;
+              if (!(bf16hi(w[k]) > 0.f)) f[8 * j + 2 * k + 1] *= p.slope;
+            }
+          }
+        }
+        if (inbwd) {
+          // f = dL/d lrelu(IN(h)); h in cm.  g = f * lrelu'(xhat); per-(image, channel) sums of g and g*xhat
+          const float4* mu4 = reinterpret_cast<const float4*>(p.in_stats + srow + c0);
+          const float4* rs4 = reinterpret_cast<const float4*>(p.in_stats + srow + p.nc_total + c0);
+          float gx[32];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint32_t w[4] = {cm[j].x, cm[j].y, cm[j].z, cm[j].w};
+            const float4 m0 = __ldg(mu4 + 2 * j), m1 = __ldg(mu4 + 2 * j + 1);
+            const float4 r0 = __ldg(rs4 + 2 * j), r1 = __ldg(rs4 + 2 * j + 1);
+            const float mu[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+            const float rs[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              const float hv = (k & 1) ? bf16hi(w[k >> 1]) : bf16lo(w[k >> 1]);
+              const float xh = (hv - mu[k]) * rs[k];
+              float g = xh > 0.f ? f[8 * j + k] : f[8 * j + k] * p.slope;
+              g = valid ? g : 0.f;
+              f[8 * j + k] = g;
+              gx[8 * j + k] = g * xh;
+            }
+          }
+          const float s2 = lane_transpose_sum(gx, lane);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) gx[j] = f[j];
+          const float s1 = lane_transpose_sum(gx, lane);
+          if (valid) {
+            red_add_f32(p.bsums + srow + c0 + lane, s1);
+            red_add_f32(p.bsums + srow + p.nc_total + c0 + lane, s2);
+          }
+        }
+        if (valid) {
+          if (p.split) {
+            // 16 mantissa bits: hi = bf16(f), lo = bf16(f - hi); the lo half sits nc_total channels further
+            uint4* o4l = reinterpret_cast<uint4*>(p.out + off + p.nc_total);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint32_t hi[4], lo[4];
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const float a = f[8 * j + 2 * k], b = f[8 * j + 2 * k + 1];
+                hi[k] = pack_bf16x2(a, b);
+                lo[k] = pack_bf16x2(a - bf16lo(hi[k]), b - bf16hi(hi[k]));
+              }
+              o4[c0 / 8 + j] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+              o4l[c0 / 8 + j] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint4 o;
+              o.x = pack_bf16x2(f[8 * j], f[8 * j + 1]);
+              o.y = pack_bf16x2(f[8 * j + 2], f[8 * j + 3]);
+              o.z = pack_bf16x2(f[8 * j + 4], f[8 * j + 5]);
+              o.w = pack_bf16x2(f[8 * j + 6], f[8 * j + 7]);
+              o4[c0 / 8 + j] = o;
+            }
           }
         }
       }
@@ -280,7 +376,7 @@ __device__ __forceinline__ void epilogue_role(const IgemmParams& p, const float*
 template <int BN, int CG, int KCH>
 __global__ void __launch_bounds__(192, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                  const __grid_constant__ IgemmParams p) {
+                  const __grid_constant__ CUtensorMap tmBlo, const __grid_constant__ IgemmParams p) {
   using Cfg = IgemmCfg<BN, CG, KCH>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -305,10 +401,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   }
   // the producer is ONE thread whose per-stage latency bounds the whole pipeline: no divisions or parameter-space
   // reads in its loop -- every (tap, 64-channel chunk) K-step is a precomputed 16-byte table entry
-  for (int i = threadIdx.x; i < p.ntaps_all * p.kchunks; i += blockDim.x) {
-    const int tp = i / p.kchunks, kc = i - tp * p.kchunks;
+  // split-bf16: three K-steps per (tap, chunk) -- A hi x B hi, A hi x B lo (bit 3 of .z), A lo (a_lo channels in) x B hi
+  for (int i = threadIdx.x; i < p.ntaps_all * p.kch_eff; i += blockDim.x) {
+    const int tp = i / p.kch_eff, r = i - tp * p.kch_eff;
+    const int kc = p.split ? r / 3 : r, v = p.split ? r - kc * 3 : 0;
     const Tap T = p.taps[tp];
-    ktab[i] = make_int4(kc * 64 + T.ac, (T.ax & 0xFFFF) | (T.ay << 16), T.ap | ((kc * 64) << 4), T.brow);
+    ktab[i] = make_int4(kc * 64 + T.ac + (v == 2 ? p.a_lo : 0), (T.ax & 0xFFFF) | (T.ay << 16),
+                        T.ap | (v == 1 ? 8 : 0) | ((kc * 64) << 4), T.brow);
   }
   const bool leader = rank == 0;
   if (threadIdx.x == 0) {
@@ -317,6 +416,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     fence_barrier_init();
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    if (p.split) tma_prefetch_desc(&tmBlo);
   }
   if (warp == 1) {
     if (CG == 2) { tmem_alloc_cg2(tmem_slot, Cfg::TMEM_COLS); tmem_relinquish_cg2(); }
@@ -342,8 +442,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const int nt = tc.nt, x0 = tc.x0, y0 = tc.y0, n0 = tc.ti * p.nb;
         const Phase P = p.ph[tc.pi];
         // K-steps (tap, 64-channel chunk) are flattened; a stage carries up to KCH consecutive ones
-        const int nks = P.ntaps * p.kchunks;
-        const int4* kt = ktab + P.tap0 * p.kchunks;
+        const int nks = P.ntaps * p.kch_eff;
+        const int4* kt = ktab + P.tap0 * p.kch_eff;
         const int brow_off = nt * BN + rank * (BN / 2) * (CG - 1) + ((p.nsplit && n0 >= p.nsplit) ? p.brow1 : p.brow0);
         for (int i0 = 0; i0 < nks; i0 += KCH) {
           const int cnt = nks - i0 < KCH ? nks - i0 : KCH;
@@ -359,13 +459,14 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 const int ax = (short)(e.y & 0xFFFF), ay = e.y >> 16;
                 uint8_t* da = sA + stage * Cfg::A_STAGE + j * A_STAGE_BYTES;
                 uint8_t* db = sB + stage * Cfg::B_STAGE_BYTES + j * Cfg::B_CHUNK_BYTES;
-                const int ap = e.z & 15, kcol = e.z >> 4;
+                const int ap = e.z & 7, kcol = e.z >> 4;
+                const CUtensorMap* tb = (e.z & 8) ? &tmBlo : &tmB;
                 if (CG == 2) {
                   tma_load_5d_cg2(da, &tmA, &full[stage], e.x, x0 + ax, ap, y0 + ay, n0);
-                  tma_load_2d_cg2(db, &tmB, &full[stage], kcol, e.w + brow_off);
+                  tma_load_2d_cg2(db, tb, &full[stage], kcol, e.w + brow_off);
                 } else {
                   tma_load_5d(da, &tmA, &full[stage], e.x, x0 + ax, ap, y0 + ay, n0);
-                  tma_load_2d(db, &tmB, &full[stage], kcol, e.w + brow_off);
+                  tma_load_2d(db, tb, &full[stage], kcol, e.w + brow_off);
                 }
               }
             }
@@ -382,7 +483,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       int stage = 0; uint32_t ph = 0; int it = 0;
       for (int t = worker; t < total; t += nworkers, ++it) {
         const int pi = p.nphases > 1 ? t / per_phase : 0;
-        const int nks = p.ph[pi].ntaps * p.kchunks;
+        const int nks = p.ph[pi].ntaps * p.kch_eff;
         const int acc = it & 1; const uint32_t accph = (it >> 1) & 1;
         mbar_wait(&tempty[acc], accph ^ 1);
         tc_fence_after();
@@ -643,7 +744,8 @@ cudaError_t launch_maybe_cluster(K kernel, int grid, int smem, int cg, cudaStrea
 }
 
 template <int BN, int CG, int KCH = 1>
-int launch_igemm(lsps_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tmB, const IgemmParams& p, cudaStream_t st) {
+int launch_igemm(lsps_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmBlo, const IgemmParams& p,
+                 cudaStream_t st) {
   using Cfg = IgemmCfg<BN, CG, KCH>;
   static bool configured = false;
   if (!configured) {
@@ -654,7 +756,7 @@ int launch_igemm(lsps_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tmB, 
   const int tiles_m = p.tiles_x * p.tiles_y * p.tiles_i;
   const int total = ((tiles_m + CG - 1) / CG) * p.tiles_n * p.nphases;
   const int workers = total < ctx->num_sms / CG ? total : ctx->num_sms / CG;
-  cudaError_t e = launch_maybe_cluster(conv_igemm_kernel<BN, CG, KCH>, workers * CG, Cfg::SMEM_BYTES, CG, st, tmA, tmB, p);
+  cudaError_t e = launch_maybe_cluster(conv_igemm_kernel<BN, CG, KCH>, workers * CG, Cfg::SMEM_BYTES, CG, st, tmA, tmB, tmBlo, p);
   if (e != cudaSuccess) return lsps_set_error(ctx, LSPS_E_CUDA, "conv_igemm launch: %s", cudaGetErrorString(e));
   LSPS_CHECK_LAUNCH(ctx, "conv_igemm");
   return LSPS_OK;
@@ -664,8 +766,20 @@ int launch_igemm(lsps_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tmB, 
 //   in : the tensor the GEMM reads (x for FWD, dy for DGRAD); out: what it writes (y / dx)
 int run_igemm(lsps_ctx* ctx, const lsps_conv_shape* s, Dir dir, const void* in, const void* wpk, const float* bias,
               void* out, const void* mask, const void* add, int flags, float slope, cudaStream_t st,
-              const void* wpk2 = nullptr, const float* bias2 = nullptr, int nsplit = 0) {
+              const lsps_conv_ext* ext) {
   if (!ctx || !s || !in || !wpk || !out) return lsps_set_error(ctx, LSPS_E_ARG, "null argument");
+  static const lsps_conv_ext no_ext{};
+  if (!ext) ext = &no_ext;
+  const void* wpk2 = ext->w2;
+  const float* bias2 = ext->bias2;
+  const int nsplit = ext->n_split;
+  const bool split = ext->split != 0;
+  if (split && (!ext->w_lo || nsplit > 0 || (flags & (LSPS_EP_ADD | LSPS_EP_STATS | LSPS_EP_INBWD))))
+    return lsps_set_error(ctx, LSPS_E_ARG, "split-bf16 conv: needs w_lo; not combinable with grouped / add / stats");
+  if ((flags & LSPS_EP_STATS) && !ext->sums) return lsps_set_error(ctx, LSPS_E_ARG, "stats flag without sums");
+  if ((flags & LSPS_EP_INBWD) && (!ext->in_h || !ext->in_stats || !ext->bsums || (flags & LSPS_EP_MASK)))
+    return lsps_set_error(ctx, LSPS_E_ARG, "inbwd flag needs in_h, in_stats, bsums and excludes mask");
+  if (flags & LSPS_EP_INBWD) mask = ext->in_h;
   const int kind = s->kind, n = s->n, h = s->h, w = s->w, cin = s->cin, cout = s->cout;
   if (kind < 0 || kind > 3 || n <= 0 || !is_pow2(h) || !is_pow2(w) || cin % 64 || cout % 64 || cin <= 0 || cout <= 0)
     return lsps_set_error(ctx, LSPS_E_SHAPE, "conv shape kind %d n %d h %d w %d cin %d cout %d", kind, n, h, w, cin, cout);
@@ -699,7 +813,13 @@ int run_igemm(lsps_ctx* ctx, const lsps_conv_shape* s, Dir dir, const void* in, 
   p.twl = g.twl; p.thl = g.thl; p.nb = g.nb;
   p.txl = ilog2(p.tiles_x); p.tyl = ilog2(p.tiles_y);
   p.nimg = n; p.kchunks = kc / 64; p.ntaps_all = ks * ks;
-  p.o_n = (long long)oh * ow * nc; p.o_y = (long long)ow * nc; p.o_x = nc;
+  p.split = split ? 1 : 0; p.a_lo = kc; p.kch_eff = split ? 3 * p.kchunks : p.kchunks; p.nc_total = nc;
+  if (p.ntaps_all * p.kch_eff > 1024) return lsps_set_error(ctx, LSPS_E_SHAPE, "K-step table overflow (%d steps)", p.ntaps_all * p.kch_eff);
+  p.sums = ext->sums; p.in_stats = ext->in_stats; p.bsums = ext->bsums;
+  const int kct = split ? 2 * kc : kc, nct = split ? 2 * nc : nc;     // channels of the `in` / `out` TENSORS
+  if ((flags & (LSPS_EP_STATS | LSPS_EP_INBWD)) && hg * wg < 32)
+    return lsps_set_error(ctx, LSPS_E_SHAPE, "fused statistics need >= 32 GEMM pixels per image");
+  p.o_n = (long long)oh * ow * nct; p.o_y = (long long)ow * nct; p.o_x = nct;
   p.out = static_cast<__nv_bfloat16*>(out); p.bias = bias;
   p.mask = static_cast<const __nv_bfloat16*>(mask); p.add = static_cast<const __nv_bfloat16*>(add);
   p.slope = slope; p.flags = flags; p.dbg = lsps_dbg();
@@ -725,7 +845,7 @@ int run_igemm(lsps_ctx* ctx, const lsps_conv_shape* s, Dir dir, const void* in, 
         int dy, py, dx, px;
         if (k4) { s4_axis(r, &dy, &py); s4_axis(c, &dx, &px); }
         else { s2_axis(r, &dy, &py); s2_axis(c, &dx, &px); }
-        T.ay = dy; T.ap = py; T.ax = dx; T.ac = px * kc;
+        T.ay = dy; T.ap = py; T.ax = dx; T.ac = px * kct;
         T.brow = (r * ks + c) * nc;
       }
   } else {  // up: heaviest phase first
@@ -769,26 +889,34 @@ int run_igemm(lsps_ctx* ctx, const lsps_conv_shape* s, Dir dir, const void* in, 
   //   ... and the tile is MMA-bound (>= 27 K-steps) and there are enough tiles to keep every SM busy in pairs;
   //   short-K layers are issue-/latency-bound per tile and run faster as 148 independent CTAs (measured, r01 probes)
   int nk_min = 1 << 30;
-  for (int i = 0; i < p.nphases; ++i) nk_min = p.ph[i].ntaps * p.kchunks < nk_min ? p.ph[i].ntaps * p.kchunks : nk_min;
+  for (int i = 0; i < p.nphases; ++i) nk_min = p.ph[i].ntaps * p.kch_eff < nk_min ? p.ph[i].ntaps * p.kch_eff : nk_min;
   const int force = lsps_force_cg();
   int cg = (lsps_use_pairs() && tiles_m >= 2 && nk_min >= 27 && (long long)tiles_m * p.tiles_n >= 2 * ctx->num_sms) ? 2 : 1;
   if (force && tiles_m >= 2) cg = force;
-  CUtensorMap tmA, tmB;
-  int rc = act_tmap(ctx, in, n, ih, iw, kc, down, g, &tmA);
+  CUtensorMap tmA, tmB, tmBlo;
+  int rc = act_tmap(ctx, in, n, ih, iw, kct, down, g, &tmA);
   if (rc) return rc;
   uint32_t wd[2] = {(uint32_t)kc, (uint32_t)wrows}, wb[2] = {64, (uint32_t)(bn / cg)};
   rc = lsps_get_tmap(ctx, wbase, 2, wd, wb, &tmB);
   if (rc) return rc;
-  if (cg == 2 && bn == 256 && !lsps_no_kch2()) return launch_igemm<256, 2, 2>(ctx, tmA, tmB, p, st);
+  tmBlo = tmB;
+  if (split && (rc = lsps_get_tmap(ctx, ext->w_lo, 2, wd, wb, &tmBlo))) return rc;
+  // the statistics accumulators are zeroed here, on the same stream, ahead of the kernel that red.adds into them
+  const size_t sbytes = (size_t)n * 2 * nc * sizeof(float);
+  if ((flags & LSPS_EP_STATS) && cudaMemsetAsync(ext->sums, 0, sbytes, st) != cudaSuccess)
+    return lsps_set_error(ctx, LSPS_E_CUDA, "memset sums");
+  if ((flags & LSPS_EP_INBWD) && cudaMemsetAsync(ext->bsums, 0, sbytes, st) != cudaSuccess)
+    return lsps_set_error(ctx, LSPS_E_CUDA, "memset bsums");
+  if (cg == 2 && bn == 256 && !lsps_no_kch2()) return launch_igemm<256, 2, 2>(ctx, tmA, tmB, tmBlo, p, st);
   if (cg == 2) {
-    if (bn == 256) return launch_igemm<256, 2>(ctx, tmA, tmB, p, st);
-    if (bn == 128) return launch_igemm<128, 2>(ctx, tmA, tmB, p, st);
-    return launch_igemm<64, 2>(ctx, tmA, tmB, p, st);
+    if (bn == 256) return launch_igemm<256, 2>(ctx, tmA, tmB, tmBlo, p, st);
+    if (bn == 128) return launch_igemm<128, 2>(ctx, tmA, tmB, tmBlo, p, st);
+    return launch_igemm<64, 2>(ctx, tmA, tmB, tmBlo, p, st);
   }
-  if (bn == 256) return launch_igemm<256, 1>(ctx, tmA, tmB, p, st);
+  if (bn == 256) return launch_igemm<256, 1>(ctx, tmA, tmB, tmBlo, p, st);
   // single-CTA BN <= 128 kernels stage one 64-channel chunk per pipeline stage (2 and 3 chunks measured slower, r01 probes)
-  if (bn == 128) return launch_igemm<128, 1>(ctx, tmA, tmB, p, st);
-  return launch_igemm<64, 1>(ctx, tmA, tmB, p, st);
+  if (bn == 128) return launch_igemm<128, 1>(ctx, tmA, tmB, tmBlo, p, st);
+  return launch_igemm<64, 1>(ctx, tmA, tmB, tmBlo, p, st);
 }
 
 template <int BN, int CG>
@@ -809,32 +937,53 @@ int launch_wgrad(lsps_ctx* ctx, const CUtensorMap& tmM, const CUtensorMap& tmN, 
 
 }  // namespace
 
+constexpr int FWD_FLAGS = LSPS_EP_BIAS | LSPS_EP_LRELU | LSPS_EP_STATS;
+constexpr int DGRAD_FLAGS = LSPS_EP_MASK | LSPS_EP_ADD | LSPS_EP_INBWD;
+
 extern "C" int lsps_conv_fwd(lsps_ctx* ctx, const lsps_conv_shape* s, const void* x, const void* w_fwd,
                              const float* bias, void* y, int flags, float slope, lsps_stream st) {
   return run_igemm(ctx, s, FWD, x, w_fwd, bias, y, nullptr, nullptr, flags & (LSPS_EP_BIAS | LSPS_EP_LRELU), slope,
-                   static_cast<cudaStream_t>(st));
+                   static_cast<cudaStream_t>(st), nullptr);
 }
 
 extern "C" int lsps_conv_dgrad(lsps_ctx* ctx, const lsps_conv_shape* s, const void* dy, const void* w_dgrad, void* dx,
                                const void* mask, const void* add, int flags, float slope, lsps_stream st) {
   return run_igemm(ctx, s, DGRAD, dy, w_dgrad, nullptr, dx, mask, add, flags & (LSPS_EP_MASK | LSPS_EP_ADD), slope,
-                   static_cast<cudaStream_t>(st));
+                   static_cast<cudaStream_t>(st), nullptr);
+}
+
+extern "C" int lsps_conv_fwd_ex(lsps_ctx* ctx, const lsps_conv_shape* s, const void* x, const void* w_fwd,
+                                const float* bias, void* y, int flags, float slope, const lsps_conv_ext* ext,
+                                lsps_stream st) {
+  return run_igemm(ctx, s, FWD, x, w_fwd, bias, y, nullptr, nullptr, flags & FWD_FLAGS, slope,
+                   static_cast<cudaStream_t>(st), ext);
+}
+
+extern "C" int lsps_conv_dgrad_ex(lsps_ctx* ctx, const lsps_conv_shape* s, const void* dy, const void* w_dgrad, void* dx,
+                                  const void* mask, const void* add, int flags, float slope, const lsps_conv_ext* ext,
+                                  lsps_stream st) {
+  return run_igemm(ctx, s, DGRAD, dy, w_dgrad, nullptr, dx, mask, add, flags & DGRAD_FLAGS, slope,
+                   static_cast<cudaStream_t>(st), ext);
 }
 
 extern "C" int lsps_conv_fwd_grouped(lsps_ctx* ctx, const lsps_conv_shape* s, const void* x, const void* w_fwd,
                                      const float* bias, const void* w_fwd2, const float* bias2, int n_split, void* y,
                                      int flags, float slope, lsps_stream st) {
   if (n_split <= 0 || !w_fwd2) return lsps_set_error(ctx, LSPS_E_ARG, "conv_fwd_grouped: n_split / second weight set");
+  lsps_conv_ext ext{};
+  ext.w2 = w_fwd2; ext.bias2 = bias2; ext.n_split = n_split;
   return run_igemm(ctx, s, FWD, x, w_fwd, bias, y, nullptr, nullptr, flags & (LSPS_EP_BIAS | LSPS_EP_LRELU), slope,
-                   static_cast<cudaStream_t>(st), w_fwd2, bias2, n_split);
+                   static_cast<cudaStream_t>(st), &ext);
 }
 
 extern "C" int lsps_conv_dgrad_grouped(lsps_ctx* ctx, const lsps_conv_shape* s, const void* dy, const void* w_dgrad,
                                        const void* w_dgrad2, int n_split, void* dx, const void* mask, const void* add,
                                        int flags, float slope, lsps_stream st) {
   if (n_split <= 0 || !w_dgrad2) return lsps_set_error(ctx, LSPS_E_ARG, "conv_dgrad_grouped: n_split / second weight set");
+  lsps_conv_ext ext{};
+  ext.w2 = w_dgrad2; ext.n_split = n_split;
   return run_igemm(ctx, s, DGRAD, dy, w_dgrad, nullptr, dx, mask, add, flags & (LSPS_EP_MASK | LSPS_EP_ADD), slope,
-                   static_cast<cudaStream_t>(st), w_dgrad2, nullptr, n_split);
+                   static_cast<cudaStream_t>(st), &ext);
 }
 
 extern "C" int lsps_conv_wgrad(lsps_ctx* ctx, const lsps_conv_shape* s, const void* x, const void* dy, float* dw,

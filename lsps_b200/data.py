@@ -38,6 +38,10 @@ class SyntheticHandDataset(torch.utils.data.Dataset):
     def __len__(self):
         return self.n
 
+    def set_nmax(self, frac):
+        """dataset_hand2.py:202,368: keep the first `frac` of the labelled real samples."""
+        self.n = max(1, int(self.n * frac))
+
     def __getitem__(self, i):
         g = torch.Generator().manual_seed(self.seed * 1000003 + i)
         ia, _, la, _ = synthetic_batch(1, self.label_dim, g, kind="hand")

@@ -168,7 +168,7 @@ class LSPSTrainerB200(object):
             return dict(dec=dec)
 
         if self.graphs and self.noise_mode == "device":
-            st = self._graphed(("vae", y.shape[0], dim), dict(y=y), body, lambda hyper: S.adam_step(hyper=hyper), S)
+            st = self._graphed(("vae", y.shape[0], dim, self._hp_key(hp)), dict(y=y), body, lambda hyper: S.adam_step(hyper=hyper), S)
         else:
             st = body(dict(y=y))
             self._allreduce(S)
@@ -351,7 +351,7 @@ class LSPSTrainerB200(object):
             dist.broadcast(src_a, 0)
             dist.broadcast(src_b, 0)
         if self.graphs and self.noise_mode == "device":
-            st = self._graphed(("post", mode, ia.shape[0], la.shape[1]), dict(ia=ia, ib=ib, la=la, lb=lb, sa=src_a, sb=src_b),
+            st = self._graphed(("post", mode, ia.shape[0], la.shape[1], self._hp_key(hp)), dict(ia=ia, ib=ib, la=la, lb=lb, sa=src_a, sb=src_b),
                                lambda t: self._post_body(t["ia"], t["la"], t["ib"], t["lb"], t["sa"], t["sb"], mode, hp),
                                lambda hyper: self._post_tail(mode, hyper), self.dis_store)
         else:
@@ -450,6 +450,11 @@ class LSPSTrainerB200(object):
         return (u(x_aa), u(x_ba), u(x_ab), u(x_bb), u(x_aa), u(x_bb), u(x_aa), u(x_bb))
 
     # ------------------------------------------------------------------ CUDA graphs (launch-bound updates)
+    @staticmethod
+    def _hp_key(hp):
+        """loss weights are baked into a captured graph: they are part of its key"""
+        return tuple(sorted((k, float(v)) for k, v in hp.items() if isinstance(v, (int, float)) and not isinstance(v, bool)))
+
     def _graphed(self, key, inputs, body, tail, store):
         """Runs `body(inputs) -> state`, the gradient allreduce and `tail(hyper) -> adam segments` with the device work
         of body and tail replayed from two captured CUDA graphs (estimate-mode steps are ~120 small launches: host
@@ -493,15 +498,17 @@ class LSPSTrainerB200(object):
         store.advance(ent["segs"], ent["hyper_host"])
         ent["hyper"].copy_(ent["hyper_host"], non_blocking=True)
         ent["g2"].replay()
-        return ent["state"]
+        # the captured state lives in graph-owned memory that the next replay overwrites: hand out copies
+        cl = lambda v: v.clone() if torch.is_tensor(v) else (type(v)(cl(x) for x in v) if isinstance(v, (tuple, list)) else v)
+        return {k: cl(v) for k, v in ent["state"].items()}
 
     # ------------------------------------------------------------------ outputs / snapshots
     def assemble_outputs(self, images_a, images_b, network_outputs):
         """lsps_trainer.py:264-276: first sample of each tensor concatenated along width -> (1,1,128,1280)."""
         f = lambda t: t[0:1].detach().to(self.device).reshape(1, 1, t.shape[-2], t.shape[-1]).float()
         o = network_outputs
-        return torch.cat((f(images_a), f(o[0]), f(o[2]), f(o[4]), f(o[6]), f(images_b), f(o[3]), f(o[1]), f(o[5]),
-                          f(o[7])), 3)
+        return torch.cat((f(images_a), f(o[0]), f(o[2]), f(o[4]), f(o[6]), f(o[7]), f(images_b), f(o[3]), f(o[1]),
+                          f(o[5])), 3)
 
     def save(self, snapshot_prefix, iterations):
         """lsps_trainer.py:307-319: <prefix>_gen_%08d.pkl / _dis_ ; state_dict keys and shapes of the reference."""
@@ -517,28 +524,46 @@ class LSPSTrainerB200(object):
     def _cpu(st):
         return {k: (v.cpu() if torch.is_tensor(v) else v) for k, v in st.items()}
 
+    @staticmethod
+    def _model_list(dirname, key, idx=-1):
+        """helpers.py:9-18 `get_model_list`: files of `dirname` whose name contains `key` and "pkl", sorted."""
+        if not os.path.isdir(dirname):
+            return None
+        files = sorted(os.path.join(dirname, f) for f in os.listdir(dirname)
+                       if os.path.isfile(os.path.join(dirname, f)) and key in f and "pkl" in f)
+        if not files:
+            return None
+        try:
+            return files[idx]
+        except IndexError:
+            return None
+
     def resume(self, snapshot_prefix, idx=-1, load_opt=False, est=False):
-        """lsps_trainer.py:278-305: newest (or idx-th) snapshot; iteration parsed from the file name."""
-        import glob
-        dirname, base = os.path.dirname(snapshot_prefix), os.path.basename(snapshot_prefix)
-        iterations = 0
-        for net, store in (("gen", self.gen_store), ("dis", self.dis_store), ("map", self.map_store)):
-            if store is None:
-                continue
-            pref = base + ("_est" if (est and net == "dis") else "")
-            files = sorted(glob.glob(os.path.join(dirname, "%s_%s_*.pkl" % (pref, net))))
-            if not files:
-                continue
-            f = files[idx]
-            store.load_state_dict(torch.load(f, map_location="cpu"), strict=False)
-            iterations = int(f[-12:-4])
-            if load_opt:
-                fo = f.replace("_%s_" % net, "_opt_")
-                if os.path.exists(fo):
-                    st = torch.load(fo, map_location="cpu").get(net)
-                    if st is None:
-                        continue
-                    store.load_opt_state({k: (v.to(self.device) if torch.is_tensor(v) else v) for k, v in st.items()})
+        """lsps_trainer.py:278-305: gen and dis of the newest (or idx-th) snapshot in the prefix's directory -- with
+        `est` both come from the `*_est_*` files; the iteration count is parsed from the GENERATOR file name; the
+        Mapping snapshot is optional.  Optimiser state (which the reference's save() leaves commented out) is read
+        from this trainer's own `*_opt_*` file when `load_opt` is set."""
+        dirname = os.path.dirname(snapshot_prefix)
+        f = self._model_list(dirname, "est_gen" if est else "gen", idx)
+        if f is None:
+            return 0
+        self.gen_store.load_state_dict(torch.load(f, map_location="cpu"), strict=False)
+        iterations = int(f[-12:-4])
+        fd = self._model_list(dirname, "est_dis" if est else "dis", idx)
+        if fd is not None:
+            self.dis_store.load_state_dict(torch.load(fd, map_location="cpu"), strict=False)
+        if load_opt:
+            fo = f.replace("_gen_", "_opt_")
+            if os.path.exists(fo):
+                st = torch.load(fo, map_location="cpu")
+                for net, store in (("gen", self.gen_store), ("dis", self.dis_store), ("map", self.map_store)):
+                    if store is not None and st.get(net) is not None:
+                        store.load_opt_state({k: (v.to(self.device) if torch.is_tensor(v) else v)
+                                              for k, v in st[net].items()})
+        if self.map_store is not None:
+            fm = self._model_list(dirname, "map", idx)
+            if fm is not None:
+                self.map_store.load_state_dict(torch.load(fm, map_location="cpu"), strict=False)
         return iterations
 
     def save_vae(self, snapshot_prefix, iterations, frac):
@@ -546,8 +571,7 @@ class LSPSTrainerB200(object):
                    "%s_vae_%.2f_%08d.pkl" % (snapshot_prefix, frac, iterations + 1))
 
     def load_vae(self, snapshot_prefix, frac):
-        import glob
-        files = sorted(glob.glob("%s_vae_%.2f_*.pkl" % (snapshot_prefix, frac)))
-        if not files:
-            raise IOError("no pose-VAE snapshot for %s" % snapshot_prefix)
-        self.vae_store.load_state_dict(torch.load(files[-1], map_location="cpu"))
+        f = self._model_list(os.path.dirname(snapshot_prefix), "vae_%.2f" % frac)
+        if f is None:
+            raise IOError("no pose-VAE snapshot vae_%.2f next to %s" % (frac, snapshot_prefix))
+        self.vae_store.load_state_dict(torch.load(f, map_location="cpu"))

@@ -17,24 +17,44 @@ import tempfile
 import types
 
 REFERENCE_ROOT = os.environ.get("LSPS_REFERENCE_ROOT", "/root/reference")
+# tab-expanded copy staged by oracle/build_ref.py (git-ignored; travels to the GPU box, where /root/reference is absent)
+STAGED_ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
 
 
 def reference_available():
     return os.path.isdir(os.path.join(REFERENCE_ROOT, "src", "trainers"))
 
 
+def staged_available():
+    return os.path.isdir(os.path.join(STAGED_ROOT, "src", "trainers"))
+
+
 _scratch = None
 
 
 def load_reference(cpu_shim=True):
-    """Returns the imported `trainers` package of the reference."""
+    """Returns the imported `trainers` package of the reference.  cpu_shim: True = make `.cuda()` a no-op when no GPU is
+    present; "force" = always (the CPU arm of bench.py on a GPU box); False = never (tools/library_line.py on the GPU)."""
     global _scratch
     import torch
 
     if "trainers" in sys.modules and getattr(sys.modules["trainers"], "_lsps_ref", False):
         return sys.modules["trainers"]
     if not reference_available():
-        raise RuntimeError("reference sources not mounted at %s" % REFERENCE_ROOT)
+        if not staged_available():
+            raise RuntimeError("reference sources neither mounted at %s nor staged at %s" % (REFERENCE_ROOT, STAGED_ROOT))
+        # the staged copy is already tab-expanded: import it in place
+        _scratch = STAGED_ROOT
+        sys.path.insert(0, os.path.join(STAGED_ROOT, "src"))
+        for m in ("matplotlib", "matplotlib.pyplot"):
+            if m not in sys.modules:
+                sys.modules[m] = types.ModuleType(m)
+        if cpu_shim == "force" or (cpu_shim and not torch.cuda.is_available()):
+            torch.Tensor.cuda = lambda self, *a, **k: self
+            torch.nn.Module.cuda = lambda self, *a, **k: self
+        import trainers  # noqa: the reference package
+        trainers._lsps_ref = True
+        return trainers
     _scratch = tempfile.mkdtemp(prefix="lsps_ref_")
     dst = os.path.join(_scratch, "src")
     shutil.copytree(os.path.join(REFERENCE_ROOT, "src"), dst,
@@ -51,7 +71,7 @@ def load_reference(cpu_shim=True):
     for m in ("matplotlib", "matplotlib.pyplot"):
         if m not in sys.modules:
             sys.modules[m] = types.ModuleType(m)
-    if cpu_shim and not torch.cuda.is_available():
+    if cpu_shim == "force" or (cpu_shim and not torch.cuda.is_available()):
         torch.Tensor.cuda = lambda self, *a, **k: self
         torch.nn.Module.cuda = lambda self, *a, **k: self
     import trainers  # noqa: the reference package
@@ -91,5 +111,6 @@ def load_reference_augment():
 def load_hyperparameters(name="nnyu"):
     import yaml
 
-    with open(os.path.join(REFERENCE_ROOT, "exps", name + ".yaml")) as fh:
+    root = REFERENCE_ROOT if reference_available() else STAGED_ROOT
+    with open(os.path.join(root, "exps", name + ".yaml")) as fh:
         return yaml.safe_load(fh)["train"]["hyperparameters"]

@@ -28,6 +28,7 @@ parser.add_option('--config', type=str, help="net configuration")
 parser.add_option('--mode', type=str, help="pretrain/estimate", default="pretrain")
 parser.add_option('--log', type=str, help="log path", default="../logs")
 parser.add_option('--batch', type=int, help="(new) per-GPU batch override for pretrain; reference hard-codes 1", default=0)
+parser.add_option('--snapshot_prefix', type=str, help="(new) overrides the YAML snapshot_prefix", default="")
 parser.add_option('--iters', type=int, help="(new) stop after this many iterations", default=0)
 parser.add_option('--noise', type=str, help="(new) host = reference RNG stream, device = Philox", default="device")
 
@@ -36,6 +37,8 @@ def main(argv):
     (opts, args) = parser.parse_args(argv)
     config = NetConfig(opts.config)
     hp = config.hyperparameters
+    if opts.snapshot_prefix:
+        config.snapshot_prefix = opts.snapshot_prefix
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", str(opts.gpu)))
     torch.cuda.set_device(local)
@@ -70,6 +73,13 @@ def main(argv):
     except Exception:  # noqa  (reference: bare except + print, depth_train.py:118-124)
         if rank == 0:
             print('Failed to load the parameters of vae')
+    if estimate:
+        # depth_train.py:126-130 -- the estimate phases start from the pretrained generator / discriminator
+        # (`--idx` selects the snapshot, default -1 = newest; 0 = start from scratch); mode 5 resumes a *_est run
+        if opts.idx != 0:
+            trainer.resume(config.snapshot_prefix, idx=opts.idx, est=(mode_idx == 5))
+        if 0. < opts.frac < 1. and hasattr(dataset_b, 'set_nmax'):
+            dataset_b.set_nmax(opts.frac)
     start_time = time.time()
     while iterations < max_iterations:
         for (images_a, labels_a, com_a, _, _, _), (images_b, labels_b, com_b, _, _, _) in zip(loader_a, loader_b):
@@ -98,6 +108,10 @@ def main(argv):
             iterations += 1
             if iterations >= max_iterations:
                 break
+    if opts.iters and rank == 0 and opts.iters % config.snapshot_save_iterations != 0:
+        # (new) short runs (--iters) leave a snapshot so that the next phase can chain onto them
+        os.makedirs(os.path.dirname(config.snapshot_prefix) or ".", exist_ok=True)
+        trainer.save(config.snapshot_prefix + ('_est' if estimate else ''), iterations - 1)
     if world > 1:
         dist.destroy_process_group()
     return trainer
