@@ -35,8 +35,9 @@ enum { LSPS_EP_BIAS = 1, LSPS_EP_LRELU = 2, LSPS_EP_MASK = 4, LSPS_EP_ADD = 8,
        /* forward: accumulate per-(image, channel) sum / sum of squares of the fp32 result (after bias) -- the statistics of
           the InstanceNorm2d / BatchNorm2d that follows the conv (common_net.py:168,171,187,190) -- into ext->sums */
        LSPS_EP_STATS = 16,
-       /* data gradient landing on lrelu(IN(h)): stores g = acc * lrelu'(xhat) and accumulates per-(image, channel)
-          sum g, sum g*xhat into ext->bsums (front half of InstanceNorm backward, finished by lsps_norm_bwd_apply) */
+       /* data gradient landing on a = lrelu(IN(h)): stores g = acc * lrelu'(xhat) and accumulates per-(image, channel)
+          sum g, sum g*xhat into ext->bsums (front half of InstanceNorm backward, finished by lsps_norm_bwd_apply);
+          xhat is recovered from the stored activation: xhat = a > 0 ? a : a / slope */
        LSPS_EP_INBWD = 32 };
 
 /* n images; h,w = INPUT spatial size of the FORWARD op; cin/cout of the forward op (multiples of 64). */
@@ -45,8 +46,8 @@ typedef struct { int kind, n, h, w, cin, cout; } lsps_conv_shape;
 /* Optional extras of lsps_conv_{fwd,dgrad}_ex; zero-initialise, set what is used.
      grouped launch : images [0, n_split) use (w, bias), images [n_split, n) use (w2, bias2)   (see lsps_conv_fwd_grouped)
      LSPS_EP_STATS  : sums  f32 [n][2][cout]  (zeroed by the call, then red.add'ed by the kernel)
-     LSPS_EP_INBWD  : in_h bf16 [n,h,w,cin] = the conv output that was normalised, in_stats f32 [n][2][cin] = its (mean, rstd)
-                      rows, bsums f32 [n][2][cin] (zeroed by the call)
+     LSPS_EP_INBWD  : in_a bf16 [n,h,w,cin] = lrelu(IN(h)), the activation the gradient lands on; bsums f32 [n][2][cin]
+                      (zeroed by the call)
      split          : "bf16x3" operands for layers whose bf16 rounding shows in the losses (the discriminator stack,
                       lsps_nets.py:102-126): activations are stored as [n,h,w,2c] = (bf16 hi | bf16 lo) channel halves with
                       hi + lo carrying 16 mantissa bits, weights as two tensors (w = hi, w_lo = lo, same layout); the GEMM
@@ -55,7 +56,7 @@ typedef struct { int kind, n, h, w, cin, cout; } lsps_conv_shape;
 typedef struct {
   const void* w2; const float* bias2; int n_split;
   float* sums;
-  const void* in_h; const float* in_stats; float* bsums;
+  const void* in_a; float* bsums;
   const void* w_lo; int split;
 } lsps_conv_ext;
 
@@ -87,6 +88,8 @@ int lsps_conv_dgrad_ex(lsps_ctx*, const lsps_conv_shape*, const void* dy, const 
                        const void* add, int flags, float slope, const lsps_conv_ext* ext, lsps_stream);
 /* dw[tap][cout][cin] += conv_backward_weight(x, dy)   (fp32, accumulating; split-K over pixels with red.add) */
 int lsps_conv_wgrad(lsps_ctx*, const lsps_conv_shape*, const void* x, const void* dy, float* dw, lsps_stream);
+/* same with split-bf16 operands: x [n,h,w,2cin], dy [n,ho,wo,2cout] as (hi | lo) halves; dy_hi*x_hi + dy_hi*x_lo + dy_lo*x_hi */
+int lsps_conv_wgrad_split(lsps_ctx*, const lsps_conv_shape*, const void* x, const void* dy, float* dw, lsps_stream);
 /* db[c] += sum over rows of dy[rows][c]   (bias gradients; dy bf16) */
 int lsps_colsum_bf16(lsps_ctx*, const void* dy, long long rows, int c, float* db, lsps_stream);
 
@@ -99,6 +102,15 @@ int lsps_stem_wgrad(lsps_ctx*, const float* img, const void* dy, float* dw, floa
 /* dimg (+)= conv_backward_data(dy, w); accumulate != 0 adds into dimg */
 int lsps_stem_dgrad(lsps_ctx*, const void* dy, const float* w, float* dimg, int n, int h, int wd, int stride,
                     int accumulate, lsps_stream);
+
+/* split-bf16 ("bf16x3") variants: y / dy are [n,ho,wo,128] = (bf16 hi | bf16 lo) channel halves, the weights are split
+   inside the kernels.  Tensor-core kernels only: output width 64 or 128. */
+int lsps_stem_fwd_split(lsps_ctx*, const float* img, const float* w, const float* bias, void* y, int n, int h, int wd,
+                        int stride, float slope, lsps_stream);
+int lsps_stem_wgrad_split(lsps_ctx*, const float* img, const void* dy, float* dw, float* db, int n, int h, int wd,
+                          int stride, lsps_stream);
+int lsps_stem_dgrad_split(lsps_ctx*, const void* dy, const float* w, float* dimg, int n, int h, int wd, int stride,
+                          int accumulate, lsps_stream);
 
 /* ---- decoder head ConvTranspose2d(64,1,1)+Tanh (lsps_nets.py:226-229): x bf16 [npix,64] -> out f32 [npix] */
 int lsps_head_fwd(lsps_ctx*, const void* x, const float* w, const float* bias, float* out, long long npix, lsps_stream);
@@ -119,8 +131,36 @@ int lsps_instnorm_bwd(lsps_ctx*, const void* dy, const void* h, const float* sta
 int lsps_instnorm_bwd_grouped(lsps_ctx*, const void* dy, const void* h, const float* stats, void* dh, int n, int hw, int c,
                               int mode, float slope, float* db, float* db2, int n_split, lsps_stream);
 
+/* ---- norms whose statistics were taken in the producing conv's epilogue (LSPS_EP_STATS): ONE streaming pass each.
+   InstanceNorm2d(affine=False) of LeakyINSResBlock (common_net.py:168,171): per_image = 1, sums/stats/bsums are
+   [n][2][c] rows; BatchNorm2d(affine=False) of the BN wrappers (common_net.py:187,190,274,...): per_image = 0, ONE
+   [2][c] row (lsps_norm_reduce_images adds the per-image rows up), count = n*hw.
+   forward : mode 0 y = lrelu(xhat), 1 y = res + xhat, 2 y = xhat ; xhat = (h - mean)*rstd from sums = (sum, sum of squares);
+             stats_out (may be NULL) receives the (mean, rstd) rows the backward pass reads */
+int lsps_norm_apply_fwd(lsps_ctx*, const void* h, const void* res, void* y, const float* sums, float* stats_out, int n,
+                        int hw, int c, int mode, int per_image, float eps, float slope, lsps_stream);
+/* bsums (zeroed by the call) += (sum g, sum g*xhat), g = dy (mode 1) or dy*lrelu'(xhat) (mode 0) -- only needed when the
+   gradient's producer could not take the sums itself (LSPS_EP_INBWD) */
+int lsps_norm_bwd_stats(lsps_ctx*, const void* dy, const void* h, const float* stats, float* bsums, int n, int hw, int c,
+                        int mode, int per_image, float slope, lsps_stream);
+/* dh = rstd*(g - mean(g) - xhat*mean(g*xhat)); gmode 0: g is the raw gradient w.r.t. lrelu(xhat) (masked here),
+   gmode 1: g is used as is (the gradient w.r.t. res + xhat), gmode 2: g was pre-masked by LSPS_EP_INBWD and `h` is the
+   ACTIVATION a = lrelu(xhat) (xhat recovered from it; only the rstd row of stats is read).  The bias of the conv that
+   produced h gets NO gradient from here: it is exactly zero (the norm subtracts the mean). */
+int lsps_norm_bwd_apply(lsps_ctx*, const void* g, const void* h, const float* stats, const float* bsums, void* dh, int n,
+                        int hw, int c, int gmode, int per_image, float slope, lsps_stream);
+/* out[2][c] = sum over images of sums[n][2][c]  (BatchNorm batch statistics; the row a data-parallel run all-reduces) */
+int lsps_norm_reduce_images(lsps_ctx*, const float* sums, float* out, int n, int c, lsps_stream);
+
 /* ---- GaussianNoiseLayer + KL term (common_net.py:36-40; lsps_trainer.py:55-58): z = x + noise, acc[0] += sum z^2 */
 int lsps_noise_kl_fwd(lsps_ctx*, const void* x, const float* noise, void* z, float* acc, long long n, lsps_stream);
+/* same with the noise drawn inside the kernel (Philox4x32-10, counter = (seed, 16-byte chunk index, offset)): the
+   device-RNG mode -- statistically, not bitwise, the reference's layer; no noise tensor touches HBM */
+int lsps_noise_kl_philox(lsps_ctx*, const void* x, void* z, float* acc, long long n, unsigned long long seed,
+                         unsigned long long offset, lsps_stream);
+/* stream-ordered fill / device-to-device copy (cudaMemsetAsync / cudaMemcpyAsync; capturable) */
+int lsps_memset(lsps_ctx*, void* dst, int value, long long bytes, lsps_stream);
+int lsps_memcpy(lsps_ctx*, void* dst, const void* src, long long bytes, lsps_stream);
 /* out = a + alpha * b  (bf16 tensors; a may be NULL) */
 int lsps_axpy_bf16(lsps_ctx*, const void* a, const void* b, float alpha, void* out, long long n, lsps_stream);
 
@@ -148,9 +188,21 @@ int lsps_dhead_bwd(lsps_ctx*, const void* f, const float* w, const float* dlogit
                    long long rows, int c, lsps_stream);
 /* trunk-feature gradient f32 -> bf16 with the LeakyReLU mask of the features: out = df * lrelu'(f) */
 int lsps_mask_to_bf16(lsps_ctx*, const float* df, const void* f, void* out, float slope, long long n, lsps_stream);
+/* the same four on split-bf16 feature tensors f [rows][hi c | lo c] (df / logits stay plain f32 [rows][c]) */
+int lsps_l1_feat_split(lsps_ctx*, const void* a, const void* b, float* da, float* db, float scale, float* acc,
+                       long long n, int c, lsps_stream);
+int lsps_dhead_fwd_split(lsps_ctx*, const void* f, const float* w, const float* bias, float* logits, long long rows,
+                         int c, lsps_stream);
+int lsps_dhead_bwd_split(lsps_ctx*, const void* f, const float* w, const float* dlogits, float* df, float* dw,
+                         float* db, long long rows, int c, lsps_stream);
+int lsps_mask_to_bf16_split(lsps_ctx*, const float* df, const void* f, void* out, float slope, long long n, int c,
+                            lsps_stream);
+/* db[c] += column sums of a split tensor dy [rows][hi c | lo c] */
+int lsps_colsum_bf16_split(lsps_ctx*, const void* dy, long long rows, int c, float* db, lsps_stream);
 
 /* ---- small dense layers (Post head = FC 8192->20, lsps_nets.py:123,135-145; poseVAE MLP, lsps_nets.py:34-83) */
-/* y[m,n] = act(x[m,k] . w[n,k]^T + b[n]) ; act 0 none, 1 lrelu, 2 softplus.  x is bf16 if x_bf16 else f32 */
+/* y[m,n] = act(x[m,k] . w[n,k]^T + b[n]) ; act 0 none, 1 lrelu, 2 softplus.  x_bf16: 0 = f32 rows, 1 = bf16 rows,
+   c > 1 = split-bf16 rows laid out [pixels][hi c | lo c] (k a multiple of c; the row holds k/c pixels) */
 int lsps_linear_fwd(lsps_ctx*, const void* x, int x_bf16, const float* w, const float* b, float* y, int m, int n, int k,
                     int act, float slope, lsps_stream);
 /* dy is the gradient w.r.t. the pre-activation.  dx[m,k] (+)= dy.w ; dw[n,k] += dy^T.x ; db[n] += sum dy. NULL skips. */
@@ -176,6 +228,17 @@ int lsps_adam(lsps_ctx*, float* p, const float* g, float* m, float* v, void* w16
               float beta2, float eps, float wd, int step, float grad_scale, const float* hyper, lsps_stream);
 /* wt[tap][cin][cout] (bf16) = transpose of w[tap][cout][cin] (f32 master) : the dgrad operand */
 int lsps_pack_dgrad(lsps_ctx*, const float* w, void* wt, int taps, int cout, int cin, lsps_stream);
+/* every conv weight of a flat store in ONE launch.  desc: device array of (count + 1) x 6 int64 = {w_off, wt_off, taps,
+   cout, cin, tile0} -- element offsets from w_base / wt_base, tile0 = index of the entry's first 32x32 tile (the extra
+   last row carries tile0 = total_tiles).  wt_lo_base (may be NULL): bf16 remainders for the split-bf16 operands. */
+int lsps_pack_dgrad_multi(lsps_ctx*, const float* w_base, void* wt_base, void* wt_lo_base, const long long* desc,
+                          int count, int total_tiles, lsps_stream);
+/* lsps_adam with a second bf16 copy: w16_lo = bf16(p - float(w16)) (split-bf16 forward operands; may be NULL) */
+int lsps_adam_ex(lsps_ctx*, float* p, const float* g, float* m, float* v, void* w16, void* w16_lo, long long n, float lr,
+                 float beta1, float beta2, float eps, float wd, int step, float grad_scale, const float* hyper,
+                 lsps_stream);
+/* hi = bf16(x), lo = bf16(x - hi) */
+int lsps_f32_split_bf16(lsps_ctx*, const float* x, void* hi, void* lo, long long n, lsps_stream);
 int lsps_f32_to_bf16(lsps_ctx*, const float* x, void* y, long long n, lsps_stream);
 /* ---- evaluation sweep on device (src/depth_train.py:229-237; src/utils/handpose_evaluation.py:92-97,197-203):
    per frame i: e_j = || (gt[i,j,:] - pred[i,j,:]) * (sx,sy,sz) ||  over joints j in joint_idx (NULL = first nj joints);

@@ -12,12 +12,19 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "liblsps_b200.so")
 
 CONV_S1, CONV_S2, DECONV_S2, DECONV4_S2 = 0, 1, 2, 3
-EP_BIAS, EP_LRELU, EP_MASK, EP_ADD = 1, 2, 4, 8
+EP_BIAS, EP_LRELU, EP_MASK, EP_ADD, EP_STATS, EP_INBWD = 1, 2, 4, 8, 16, 32
 ACT_NONE, ACT_LRELU, ACT_SOFTPLUS = 0, 1, 2
 
 
 class ConvShape(C.Structure):
     _fields_ = [(k, C.c_int) for k in ("kind", "n", "h", "w", "cin", "cout")]
+
+
+class ConvExt(C.Structure):
+    """lsps_conv_ext (include/lsps_b200.h): optional extras of lsps_conv_{fwd,dgrad}_ex"""
+    _fields_ = [("w2", C.c_void_p), ("bias2", C.c_void_p), ("n_split", C.c_int), ("sums", C.c_void_p),
+                ("in_a", C.c_void_p), ("bsums", C.c_void_p), ("w_lo", C.c_void_p),
+                ("split", C.c_int)]
 
 
 _vp, _i, _f, _ll = C.c_void_p, C.c_int, C.c_float, C.c_longlong
@@ -28,7 +35,25 @@ _SIGS = {
     "lsps_conv_dgrad": [_SH, _vp, _vp, _vp, _vp, _vp, _i, _f],
     "lsps_conv_fwd_grouped": [_SH, _vp, _vp, _vp, _vp, _vp, _i, _vp, _i, _f],
     "lsps_conv_dgrad_grouped": [_SH, _vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _f],
+    "lsps_conv_fwd_ex": [_SH, _vp, _vp, _vp, _vp, _i, _f, _vp],
+    "lsps_conv_dgrad_ex": [_SH, _vp, _vp, _vp, _vp, _vp, _i, _f, _vp],
     "lsps_conv_wgrad": [_SH, _vp, _vp, _vp],
+    "lsps_conv_wgrad_split": [_SH, _vp, _vp, _vp],
+    "lsps_stem_fwd_split": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _f],
+    "lsps_stem_wgrad_split": [_vp, _vp, _vp, _vp, _i, _i, _i, _i],
+    "lsps_stem_dgrad_split": [_vp, _vp, _vp, _i, _i, _i, _i, _i],
+    "lsps_l1_feat_split": [_vp, _vp, _vp, _vp, _f, _vp, _ll, _i],
+    "lsps_dhead_fwd_split": [_vp, _vp, _vp, _vp, _ll, _i],
+    "lsps_dhead_bwd_split": [_vp, _vp, _vp, _vp, _vp, _vp, _ll, _i],
+    "lsps_mask_to_bf16_split": [_vp, _vp, _vp, _f, _ll, _i],
+    "lsps_colsum_bf16_split": [_vp, _ll, _i, _vp],
+    "lsps_pack_dgrad_multi": [_vp, _vp, _vp, _vp, _i, _i],
+    "lsps_adam_ex": [_vp, _vp, _vp, _vp, _vp, _vp, _ll, _f, _f, _f, _f, _f, _i, _f, _vp],
+    "lsps_f32_split_bf16": [_vp, _vp, _vp, _ll],
+    "lsps_norm_apply_fwd": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _f],
+    "lsps_norm_bwd_stats": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f],
+    "lsps_norm_bwd_apply": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f],
+    "lsps_norm_reduce_images": [_vp, _vp, _i, _i],
     "lsps_colsum_bf16": [_vp, _ll, _i, _vp],
     "lsps_stem_fwd": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _f],
     "lsps_stem_wgrad": [_vp, _vp, _vp, _vp, _i, _i, _i, _i],
@@ -39,6 +64,9 @@ _SIGS = {
     "lsps_instnorm_bwd": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _vp],
     "lsps_instnorm_bwd_grouped": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _vp, _vp, _i],
     "lsps_noise_kl_fwd": [_vp, _vp, _vp, _vp, _ll],
+    "lsps_noise_kl_philox": [_vp, _vp, _vp, _ll, C.c_ulonglong, C.c_ulonglong],
+    "lsps_memset": [_vp, _i, _ll],
+    "lsps_memcpy": [_vp, _vp, _ll],
     "lsps_axpy_bf16": [_vp, _vp, _f, _vp, _ll],
     "lsps_l2_bf16": [_vp, _vp, _vp, _f, _vp, _ll],
     "lsps_l1_f32": [_vp, _vp, _vp, _f, _i, _vp, _ll],
@@ -77,6 +105,20 @@ def _load():
             raise ImportError("lsps_b200: %s is missing and could not be built (%r); there is no fallback path"
                               % (LIB_PATH, e))
     lib = C.CDLL(LIB_PATH)
+    missing = [n for n in _SIGS if not hasattr(lib, n)]
+    if missing:
+        # a stale library from an older source tree: rebuild once (nvcc cross-compiles without a GPU), load the new
+        # file under a fresh handle; still missing -> fail loudly
+        from . import build as _build
+        _build.build(force=True)
+        import shutil
+        import tempfile
+        tmp = os.path.join(tempfile.mkdtemp(prefix="lsps_lib_"), "liblsps_b200.so")
+        shutil.copy(LIB_PATH, tmp)
+        lib = C.CDLL(tmp)
+        missing = [n for n in _SIGS if not hasattr(lib, n)]
+        if missing:
+            raise ImportError("lsps_b200: %s lacks %s even after a rebuild" % (LIB_PATH, missing[:4]))
     lib.lsps_last_error.restype = C.c_char_p
     lib.lsps_last_error.argtypes = [_vp]
     lib.lsps_ctx_create.argtypes = [C.POINTER(_vp), _i]

@@ -8,6 +8,8 @@
 //                     /root/reference/src/trainers/lsps_trainer.py:26-34,42-60,107-121,171-192,241-250
 #include <stdlib.h>
 
+#include <curand_kernel.h>
+
 #include "common.h"
 #include "ptx.cuh"
 
@@ -44,6 +46,13 @@ __device__ __forceinline__ uint4 pack8(const float* f) {
   u.x = pack_bf16x2(f[0], f[1]); u.y = pack_bf16x2(f[2], f[3]);
   u.z = pack_bf16x2(f[4], f[5]); u.w = pack_bf16x2(f[6], f[7]);
   return u;
+}
+// element i of a logical [pixels][sc] tensor stored split as [pixels][hi sc | lo sc] (sc = 0: plain bf16 tensor)
+__device__ __forceinline__ float ld_bf16_maybe_split(const bf16* t, long long i, int sc) {
+  if (sc == 0) return __bfloat162float(t[i]);
+  const long long px = i / sc;
+  const bf16* q = t + px * 2 * sc + (i - px * sc);
+  return __bfloat162float(q[0]) + __bfloat162float(q[sc]);
 }
 inline int grid_for(long long n, int block, int cap) {
   long long g = (n + block - 1) / block;
@@ -617,7 +626,8 @@ __global__ void __launch_bounds__(256) norm_bwd_stats_kernel(const bf16* __restr
 
 // dh = rstd * (g - mean(g) - xhat * mean(g*xhat)), the means from bsums (taken by the dgrad epilogue, LSPS_EP_INBWD, or
 // by norm_bwd_stats_kernel).  GMODE 0: `g` is the raw gradient w.r.t. lrelu(xhat) (mask applied here); 1: g is used as is
-// (already masked by the dgrad epilogue, or the gradient w.r.t. res + xhat).
+// (the gradient w.r.t. res + xhat); 2: g was masked by the dgrad epilogue and `h` holds a = lrelu(xhat), from which
+// xhat is recovered.
 template <int GMODE>
 __global__ void __launch_bounds__(256) norm_bwd_apply_kernel(const bf16* __restrict__ g_, const bf16* __restrict__ h,
                                                             const float* __restrict__ stats,
@@ -629,6 +639,7 @@ __global__ void __launch_bounds__(256) norm_bwd_apply_kernel(const bf16* __restr
   const int n = blockIdx.y, p0 = blockIdx.x * ppb;
   const float* st = stats + n * stat_stride + oct * 8;
   const float* bs = bsums + n * bsum_stride + oct * 8;
+  const float inv_slope = 1.f / slope;
   float mean[8], rstd[8], mg[8], mgx[8];
   {
     const float4 a0 = __ldg(reinterpret_cast<const float4*>(st)), a1 = __ldg(reinterpret_cast<const float4*>(st) + 1);
@@ -651,7 +662,7 @@ __global__ void __launch_bounds__(256) norm_bwd_apply_kernel(const bf16* __restr
     unpack8(__ldg(reinterpret_cast<const uint4*>(g_ + base + (long long)p * c)), g);
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-      const float xh = (f[k] - mean[k]) * rstd[k];
+      const float xh = GMODE == 2 ? (f[k] > 0.f ? f[k] : f[k] * inv_slope) : (f[k] - mean[k]) * rstd[k];
       const float gg = (GMODE == 0 && !(xh > 0.f)) ? g[k] * slope : g[k];
       f[k] = rstd[k] * (gg - mg[k] - xh * mgx[k]);
     }
@@ -680,6 +691,29 @@ __global__ void __launch_bounds__(256) noise_kl_kernel(const bf16* __restrict__ 
     unpack8(__ldg(reinterpret_cast<const uint4*>(x) + i), f);
     const float4 a = __ldg(reinterpret_cast<const float4*>(noise) + 2 * i);
     const float4 b = __ldg(reinterpret_cast<const float4*>(noise) + 2 * i + 1);
+    f[0] += a.x; f[1] += a.y; f[2] += a.z; f[3] += a.w; f[4] += b.x; f[5] += b.y; f[6] += b.z; f[7] += b.w;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += f[k] * f[k];
+    reinterpret_cast<uint4*>(z)[i] = pack8(f);
+  }
+  const float t = block_sum(s, sm);
+  if (threadIdx.x == 0) atomicAdd(acc, t);
+}
+
+// Device-RNG form of the GaussianNoiseLayer (the timed mode): z = x + N(0,1) drawn in the kernel from Philox4x32-10 --
+// counter = (seed, subsequence = 16-byte chunk index, offset), two normal4 draws per chunk -- so no noise tensor is ever
+// written to or read from HBM (the host-RNG parity mode keeps noise_kl_kernel above, which consumes the reference's draws).
+__global__ void __launch_bounds__(256) noise_kl_philox_kernel(const bf16* __restrict__ x, bf16* __restrict__ z,
+                                                             float* __restrict__ acc, long long n8,
+                                                             unsigned long long seed, unsigned long long offset) {
+  __shared__ float sm[8];
+  float s = 0.f;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n8; i += (long long)gridDim.x * 256) {
+    curandStatePhilox4_32_10_t st;
+    curand_init(seed, (unsigned long long)i, offset, &st);
+    const float4 a = curand_normal4(&st), b = curand_normal4(&st);
+    float f[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(x) + i), f);
     f[0] += a.x; f[1] += a.y; f[2] += a.z; f[3] += a.w; f[4] += b.x; f[5] += b.y; f[6] += b.z; f[7] += b.w;
 #pragma unroll
     for (int k = 0; k < 8; ++k) s += f[k] * f[k];
@@ -742,11 +776,11 @@ __global__ void __launch_bounds__(256) l1_f32_kernel(const float* __restrict__ x
 
 __global__ void __launch_bounds__(256) l1_feat_kernel(const bf16* __restrict__ a, const bf16* __restrict__ b,
                                                      float* __restrict__ da, float* __restrict__ db, float scale,
-                                                     float* __restrict__ acc, long long n) {
+                                                     float* __restrict__ acc, long long n, int sc) {
   __shared__ float sm[8];
   float s = 0.f;
   for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
-    const float d = __bfloat162float(a[i]) - __bfloat162float(b[i]);
+    const float d = ld_bf16_maybe_split(a, i, sc) - ld_bf16_maybe_split(b, i, sc);
     s += fabsf(d);
     const float g = d > 0.f ? scale : (d < 0.f ? -scale : 0.f);
     if (da) da[i] += g;
@@ -759,14 +793,21 @@ __global__ void __launch_bounds__(256) l1_feat_kernel(const bf16* __restrict__ a
 // one warp per row
 __global__ void __launch_bounds__(256) dhead_fwd_kernel(const bf16* __restrict__ f, const float* __restrict__ w,
                                                        const float* __restrict__ bias, float* __restrict__ logits,
-                                                       long long rows, int c) {
+                                                       long long rows, int c, int split) {
   const int lane = threadIdx.x & 31;
   const long long r = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (r >= rows) return;
+  const long long pitch = split ? 2LL * c : c;
   float s = 0.f;
   for (int j = lane; j < c / 8; j += 32) {
     float v[8];
-    unpack8(__ldg(reinterpret_cast<const uint4*>(f + r * c) + j), v);
+    unpack8(__ldg(reinterpret_cast<const uint4*>(f + r * pitch) + j), v);
+    if (split) {
+      float l[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(f + r * pitch + c) + j), l);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] += l[k];
+    }
     const float4 a = __ldg(reinterpret_cast<const float4*>(w) + 2 * j), b = __ldg(reinterpret_cast<const float4*>(w) + 2 * j + 1);
     s += v[0] * a.x + v[1] * a.y + v[2] * a.z + v[3] * a.w + v[4] * b.x + v[5] * b.y + v[6] * b.z + v[7] * b.w;
   }
@@ -796,9 +837,10 @@ __global__ void __launch_bounds__(256) bce_logits_kernel(const float* __restrict
 __global__ void __launch_bounds__(256) dhead_bwd_kernel(const bf16* __restrict__ f, const float* __restrict__ w,
                                                        const float* __restrict__ dl, float* __restrict__ df,
                                                        float* __restrict__ dw, float* __restrict__ db, long long rows,
-                                                       int c, int rows_per_block) {
+                                                       int c, int rows_per_block, int split) {
   const int col = blockIdx.x * 256 + threadIdx.x;
   if (col >= c) return;
+  const long long pitch = split ? 2LL * c : c;
   const long long r0 = (long long)blockIdx.y * rows_per_block;
   const long long r1 = r0 + rows_per_block < rows ? r0 + rows_per_block : rows;
   const float wc = __ldg(w + col);
@@ -806,7 +848,7 @@ __global__ void __launch_bounds__(256) dhead_bwd_kernel(const bf16* __restrict__
   for (long long r = r0; r < r1; ++r) {
     const float d = __ldg(dl + r);
     if (df) df[r * c + col] += d * wc;
-    aw += d * __bfloat162float(f[r * c + col]);
+    aw += d * (__bfloat162float(f[r * pitch + col]) + (split ? __bfloat162float(f[r * pitch + c + col]) : 0.f));
     ab += d;
   }
   if (dw) atomicAdd(dw + col, aw);
@@ -814,15 +856,24 @@ __global__ void __launch_bounds__(256) dhead_bwd_kernel(const bf16* __restrict__
 }
 
 __global__ void __launch_bounds__(256) mask_to_bf16_kernel(const float* __restrict__ df, const bf16* __restrict__ f,
-                                                          bf16* __restrict__ out, float slope, long long n) {
+                                                          bf16* __restrict__ out, float slope, long long n, int sc) {
   for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
-    const float v = __bfloat162float(f[i]);
-    out[i] = __float2bfloat16(df[i] * (v > 0.f ? 1.f : slope));
+    if (sc == 0) {
+      const float v = __bfloat162float(f[i]);
+      out[i] = __float2bfloat16(df[i] * (v > 0.f ? 1.f : slope));
+    } else {   // split tensors: the hi half carries the sign; the result is written as hi | lo
+      const long long px = i / sc, o = px * 2 * sc + (i - px * sc);
+      const float v = __bfloat162float(f[o]);
+      const float g = df[i] * (v > 0.f ? 1.f : slope);
+      const bf16 hi = __float2bfloat16(g);
+      out[o] = hi;
+      out[o + sc] = __float2bfloat16(g - __bfloat162float(hi));
+    }
   }
 }
 
 __global__ void __launch_bounds__(256) colsum_kernel(const bf16* __restrict__ dy, long long rows, int c,
-                                                    float* __restrict__ db, int row_lanes) {
+                                                    float* __restrict__ db, int row_lanes, int fold) {
   // block = (octets of 8 channels) x (row lanes); grid.x strides over rows, grid.y over 2048-channel slabs
   __shared__ float red[256 * 8];
   const int octs_blk = 256 / row_lanes;
@@ -848,22 +899,23 @@ __global__ void __launch_bounds__(256) colsum_kernel(const bf16* __restrict__ dy
     float s = 0.f;
     for (int j = 0; j < row_lanes; ++j) s += red[j * nch + ch];
     const int gc = blockIdx.y * nch + ch;
-    if (gc < c) atomicAdd(db + gc, s);
+    if (gc < c) atomicAdd(db + ((fold && gc >= fold) ? gc - fold : gc), s);   // fold: columns [fold, 2 fold) are lo halves
   }
 }
 
 // =============================================================================================== small dense layers
+// XBF16: x is bf16; sc > 0 additionally says x rows are split tensors with sc channels per pixel half
 template <bool XBF16>
 __global__ void __launch_bounds__(256) linear_fwd_kernel(const void* __restrict__ x_, const float* __restrict__ w,
                                                         const float* __restrict__ b, float* __restrict__ y, int m,
-                                                        int n, int k, int act, float slope) {
+                                                        int n, int k, int act, float slope, int sc) {
   const int lane = threadIdx.x & 31;
   const long long o = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (o >= (long long)m * n) return;
   const int i = (int)(o / n), j = (int)(o % n);
   float s = 0.f;
   for (int q = lane; q < k; q += 32) {
-    const float xv = XBF16 ? __bfloat162float(static_cast<const bf16*>(x_)[(long long)i * k + q])
+    const float xv = XBF16 ? ld_bf16_maybe_split(static_cast<const bf16*>(x_), (long long)i * k + q, sc)
                            : static_cast<const float*>(x_)[(long long)i * k + q];
     s += xv * __ldg(w + (long long)j * k + q);
   }
@@ -878,13 +930,13 @@ __global__ void __launch_bounds__(256) linear_fwd_kernel(const void* __restrict_
 
 template <bool XBF16>
 __global__ void __launch_bounds__(256) linear_bwd_dw_kernel(const void* __restrict__ x_, const float* __restrict__ dy,
-                                                           float* __restrict__ dw, int m, int n, int k) {
+                                                           float* __restrict__ dw, int m, int n, int k, int sc) {
   const long long o = (long long)blockIdx.x * 256 + threadIdx.x;
   if (o >= (long long)n * k) return;
   const int j = (int)(o / k), q = (int)(o % k);
   float s = 0.f;
   for (int i = 0; i < m; ++i) {
-    const float xv = XBF16 ? __bfloat162float(static_cast<const bf16*>(x_)[(long long)i * k + q])
+    const float xv = XBF16 ? ld_bf16_maybe_split(static_cast<const bf16*>(x_), (long long)i * k + q, sc)
                            : static_cast<const float*>(x_)[(long long)i * k + q];
     s += __ldg(dy + (long long)i * n + j) * xv;
   }
@@ -955,8 +1007,8 @@ __global__ void vae_reparam_bwd_kernel(const float* __restrict__ mu, const float
 // =============================================================================================== optimiser / packing
 __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g,
                                                   float* __restrict__ m, float* __restrict__ v, bf16* __restrict__ w16,
-                                                  long long n, float step_size, float beta1, float beta2, float eps,
-                                                  float wd, float inv_sqrt_bc2, float grad_scale,
+                                                  bf16* __restrict__ w16lo, long long n, float step_size, float beta1,
+                                                  float beta2, float eps, float wd, float inv_sqrt_bc2, float grad_scale,
                                                   const float* __restrict__ hyper) {
   if (hyper) { step_size = hyper[0]; inv_sqrt_bc2 = hyper[1]; }  // CUDA-graph replays: step-dependent factors from memory
   for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
@@ -967,7 +1019,11 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
     m[i] = mm; v[i] = vv;
     const float np = pv - step_size * mm / (sqrtf(vv) * inv_sqrt_bc2 + eps);
     p[i] = np;
-    if (w16) w16[i] = __float2bfloat16(np);
+    if (w16) {
+      const bf16 hi = __float2bfloat16(np);
+      w16[i] = hi;
+      if (w16lo) w16lo[i] = __float2bfloat16(np - __bfloat162float(hi));   // bf16x3 operands: hi + lo = 16 mantissa bits
+    }
   }
 }
 
@@ -985,6 +1041,54 @@ __global__ void pack_dgrad_kernel(const float* __restrict__ w, bf16* __restrict_
   for (int r = threadIdx.y; r < 32; r += blockDim.y) {
     const int ci = ci0 + r, co = co0 + threadIdx.x;
     if (ci < cin && co < cout) dst[(long long)ci * cout + co] = __float2bfloat16(tile[threadIdx.x][r]);
+  }
+}
+
+// every conv weight of a store in ONE launch: desc[e] = {w_off, wt_off, taps, cout, cin, tile0} (int64 each; offsets in
+// elements from the bases; tile0 = index of the entry's first 32x32 tile, desc[count].tile0 = total).  wt_lo (may be NULL)
+// receives the bf16 remainder w - float(bf16(w)) for the split-bf16 ("bf16x3") operands.
+__global__ void pack_dgrad_multi_kernel(const float* __restrict__ w, bf16* __restrict__ wt, bf16* __restrict__ wt_lo,
+                                        const long long* __restrict__ desc, int count) {
+  __shared__ float tile[32][33];
+  __shared__ int s_e;
+  if (threadIdx.x == 0 && threadIdx.y == 0) {
+    int e = 0;
+    while (e + 1 < count && desc[(e + 1) * 6 + 5] <= (long long)blockIdx.x) ++e;
+    s_e = e;
+  }
+  __syncthreads();
+  const long long* d = desc + s_e * 6;
+  const int cout = (int)d[3], cin = (int)d[4];
+  const int tx = (cin + 31) / 32, ty = (cout + 31) / 32;
+  int local = blockIdx.x - (int)d[5];
+  const int tap = local / (tx * ty);
+  local -= tap * tx * ty;
+  const int ci0 = (local % tx) * 32, co0 = (local / tx) * 32;
+  const float* src = w + d[0] + (long long)tap * cout * cin;
+  const long long dbase = d[1] + (long long)tap * cout * cin;
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int co = co0 + r, ci = ci0 + threadIdx.x;
+    tile[r][threadIdx.x] = (co < cout && ci < cin) ? src[(long long)co * cin + ci] : 0.f;
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int ci = ci0 + r, co = co0 + threadIdx.x;
+    if (ci < cin && co < cout) {
+      const float v = tile[threadIdx.x][r];
+      const bf16 hi = __float2bfloat16(v);
+      wt[dbase + (long long)ci * cout + co] = hi;
+      if (wt_lo) wt_lo[dbase + (long long)ci * cout + co] = __float2bfloat16(v - __bfloat162float(hi));
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) f32_split_bf16_kernel(const float* __restrict__ x, bf16* __restrict__ hi,
+                                                            bf16* __restrict__ lo, long long n) {
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
+    const float v = x[i];
+    const bf16 h = __float2bfloat16(v);
+    hi[i] = h;
+    lo[i] = __float2bfloat16(v - __bfloat162float(h));
   }
 }
 
@@ -1021,11 +1125,11 @@ __global__ void bf16_to_f32_kernel(const bf16* __restrict__ x, float* __restrict
 
 // tensor-core stems (stem_tc.cu); LSPS_STEM_SIMT=1 keeps the direct fp32 kernels of this file
 int lsps_stem_fwd_tc(lsps_ctx* ctx, const float* img, const float* w, const float* bias, void* y, int n, int h, int wd,
-                     int stride, float slope, cudaStream_t st);
+                     int stride, float slope, int split, cudaStream_t st);
 int lsps_stem_wgrad_tc(lsps_ctx* ctx, const float* img, const void* dy, float* dw, float* db, int n, int h, int wd,
-                       int stride, cudaStream_t st);
+                       int stride, int split, cudaStream_t st);
 int lsps_stem_dgrad_tc(lsps_ctx* ctx, const void* dy, const float* w, float* dimg, int n, int h, int wd, int stride,
-                       int accumulate, cudaStream_t st);
+                       int accumulate, int split, cudaStream_t st);
 static bool stem_use_tc(int wd, int stride) {
   static int simt = -1;
   if (simt < 0) { const char* e = getenv("LSPS_STEM_SIMT"); simt = (e && e[0] == '1') ? 1 : 0; }
@@ -1050,7 +1154,7 @@ extern "C" int lsps_stem_fwd(lsps_ctx* ctx, const float* img, const float* w, co
   REQUIRE(ctx, (stride == 1 || stride == 2) && h % (ST * stride) == 0 && wd % (ST * stride) == 0 && n > 0, LSPS_E_SHAPE,
           "stem_fwd: h,w must be multiples of 16*stride");
   if (stem_use_tc(wd, stride) && (h / stride) % (128 / (wd / stride)) == 0)
-    return lsps_stem_fwd_tc(ctx, img, w, bias, y, n, h, wd, stride, slope, ST_(st));
+    return lsps_stem_fwd_tc(ctx, img, w, bias, y, n, h, wd, stride, slope, 0, ST_(st));
   dim3 grid(wd / stride / ST, h / stride / ST, n);
   if (stride == 1) stem_fwd_kernel<1><<<grid, 256, 0, ST_(st)>>>(img, w, bias, static_cast<bf16*>(y), h, wd, slope);
   else stem_fwd_kernel<2><<<grid, 256, 0, ST_(st)>>>(img, w, bias, static_cast<bf16*>(y), h, wd, slope);
@@ -1064,7 +1168,7 @@ extern "C" int lsps_stem_wgrad(lsps_ctx* ctx, const float* img, const void* dy, 
   REQUIRE(ctx, (stride == 1 || stride == 2) && h % (ST * stride) == 0 && wd % (ST * stride) == 0 && n > 0, LSPS_E_SHAPE,
           "stem_wgrad: shape");
   if (stem_use_tc(wd, stride) && (h / stride) % (128 / (wd / stride)) == 0)
-    return lsps_stem_wgrad_tc(ctx, img, dy, dw, db, n, h, wd, stride, ST_(st));
+    return lsps_stem_wgrad_tc(ctx, img, dy, dw, db, n, h, wd, stride, 0, ST_(st));
   const int total = (wd / stride / ST) * (h / stride / ST) * n;
   const int grid = total < 2 * ctx->num_sms ? total : 2 * ctx->num_sms;
   if (stride == 1) stem_wgrad_kernel<1><<<grid, 256, 0, ST_(st)>>>(img, static_cast<const bf16*>(dy), dw, db, n, h, wd);
@@ -1078,7 +1182,7 @@ extern "C" int lsps_stem_dgrad(lsps_ctx* ctx, const void* dy, const float* w, fl
   REQUIRE(ctx, dy && w && dimg, LSPS_E_ARG, "stem_dgrad: null");
   REQUIRE(ctx, (stride == 1 || stride == 2) && h % (ST * stride) == 0 && wd % (ST * stride) == 0 && n > 0, LSPS_E_SHAPE,
           "stem_dgrad: shape");
-  if (stem_use_tc(wd, stride)) return lsps_stem_dgrad_tc(ctx, dy, w, dimg, n, h, wd, stride, accumulate, ST_(st));
+  if (stem_use_tc(wd, stride)) return lsps_stem_dgrad_tc(ctx, dy, w, dimg, n, h, wd, stride, accumulate, 0, ST_(st));
   dim3 grid(wd / ST, h / ST, n);
   const int de = stride == 1 ? ST + 6 : (ST + 6) / 2 + 1;
   const int smem = 49 * 64 * 4 + de * de * 128;
@@ -1091,6 +1195,32 @@ extern "C" int lsps_stem_dgrad(lsps_ctx* ctx, const void* dy, const float* w, fl
   }
   LSPS_CHECK_LAUNCH(ctx, "stem_dgrad");
   return LSPS_OK;
+}
+
+// bf16x3 variants (tensor-core kernels only: output width 64 or 128): y / dy are [n,ho,wo,128] = (hi | lo) halves
+extern "C" int lsps_stem_fwd_split(lsps_ctx* ctx, const float* img, const float* w, const float* bias, void* y, int n,
+                                   int h, int wd, int stride, float slope, lsps_stream st) {
+  REQUIRE(ctx, img && w && bias && y, LSPS_E_ARG, "stem_fwd_split: null");
+  const int wo = wd / stride;
+  REQUIRE(ctx, (stride == 1 || stride == 2) && n > 0 && (wo == 64 || wo == 128) && (h / stride) % (128 / wo) == 0,
+          LSPS_E_SHAPE, "stem_fwd_split: output width must be 64 or 128");
+  return lsps_stem_fwd_tc(ctx, img, w, bias, y, n, h, wd, stride, slope, 1, ST_(st));
+}
+extern "C" int lsps_stem_wgrad_split(lsps_ctx* ctx, const float* img, const void* dy, float* dw, float* db, int n, int h,
+                                     int wd, int stride, lsps_stream st) {
+  REQUIRE(ctx, img && dy && dw, LSPS_E_ARG, "stem_wgrad_split: null");
+  const int wo = wd / stride;
+  REQUIRE(ctx, (stride == 1 || stride == 2) && n > 0 && (wo == 64 || wo == 128) && (h / stride) % (128 / wo) == 0,
+          LSPS_E_SHAPE, "stem_wgrad_split: output width must be 64 or 128");
+  return lsps_stem_wgrad_tc(ctx, img, dy, dw, db, n, h, wd, stride, 1, ST_(st));
+}
+extern "C" int lsps_stem_dgrad_split(lsps_ctx* ctx, const void* dy, const float* w, float* dimg, int n, int h, int wd,
+                                     int stride, int accumulate, lsps_stream st) {
+  REQUIRE(ctx, dy && w && dimg, LSPS_E_ARG, "stem_dgrad_split: null");
+  const int wo = wd / stride;
+  REQUIRE(ctx, (stride == 1 || stride == 2) && n > 0 && (wo == 64 || wo == 128) && h % 8 == 0 && wd % 16 == 0, LSPS_E_SHAPE,
+          "stem_dgrad_split: output width must be 64 or 128");
+  return lsps_stem_dgrad_tc(ctx, dy, w, dimg, n, h, wd, stride, accumulate, 1, ST_(st));
 }
 
 extern "C" int lsps_head_fwd(lsps_ctx* ctx, const void* x, const float* w, const float* bias, float* out,
@@ -1146,6 +1276,71 @@ extern "C" int lsps_instnorm_bwd_grouped(lsps_ctx* ctx, const void* dy, const vo
   return LSPS_OK;
 }
 
+// ---- norm from epilogue statistics (InstanceNorm: per_image = 1, rows [n][2][c]; BatchNorm: per_image = 0, ONE row)
+static bool norm_shape_ok(int n, int hw, int c) { return n > 0 && hw > 0 && c >= 64 && c <= 2048 && (c & (c - 1)) == 0; }
+static int norm_ppb(int hw, int c) {
+  const int lanes = 256 / (c / 8);
+  int ppb = lanes * 8;
+  return ppb > hw ? hw : ppb;
+}
+extern "C" int lsps_norm_apply_fwd(lsps_ctx* ctx, const void* h, const void* res, void* y, const float* sums,
+                                   float* stats_out, int n, int hw, int c, int mode, int per_image, float eps,
+                                   float slope, lsps_stream st) {
+  REQUIRE(ctx, h && y && sums && (mode != 1 || res), LSPS_E_ARG, "norm_apply_fwd: null");
+  REQUIRE(ctx, norm_shape_ok(n, hw, c) && mode >= 0 && mode <= 2, LSPS_E_SHAPE, "norm_apply_fwd: c must be a power of two in [64, 2048]");
+  const int ppb = norm_ppb(hw, c);
+  const dim3 grid((hw + ppb - 1) / ppb, n);
+  const long long stride = per_image ? 2LL * c : 0;
+  const float inv = 1.f / (per_image ? (float)hw : (float)hw * (float)n);
+  const bf16 *hh = static_cast<const bf16*>(h), *rr = static_cast<const bf16*>(res);
+  bf16* yy = static_cast<bf16*>(y);
+  float* so = stats_out;
+  if (mode == 0) norm_apply_fwd_kernel<0><<<grid, 256, 0, ST_(st)>>>(hh, rr, yy, sums, so, hw, c, ppb, stride, inv, eps, slope);
+  else if (mode == 1) norm_apply_fwd_kernel<1><<<grid, 256, 0, ST_(st)>>>(hh, rr, yy, sums, so, hw, c, ppb, stride, inv, eps, slope);
+  else norm_apply_fwd_kernel<2><<<grid, 256, 0, ST_(st)>>>(hh, rr, yy, sums, so, hw, c, ppb, stride, inv, eps, slope);
+  LSPS_CHECK_LAUNCH(ctx, "norm_apply_fwd");
+  return LSPS_OK;
+}
+extern "C" int lsps_norm_bwd_stats(lsps_ctx* ctx, const void* dy, const void* h, const float* stats, float* bsums, int n,
+                                   int hw, int c, int mode, int per_image, float slope, lsps_stream st) {
+  REQUIRE(ctx, dy && h && stats && bsums, LSPS_E_ARG, "norm_bwd_stats: null");
+  REQUIRE(ctx, norm_shape_ok(n, hw, c) && (mode == 0 || mode == 1), LSPS_E_SHAPE, "norm_bwd_stats: shape");
+  const int lanes = 256 / (c / 8);
+  int ppb = lanes * 16;
+  if (ppb > hw) ppb = hw;
+  const dim3 grid((hw + ppb - 1) / ppb, n);
+  const long long stride = per_image ? 2LL * c : 0;
+  if (cudaMemsetAsync(bsums, 0, (size_t)(per_image ? n : 1) * 2 * c * sizeof(float), ST_(st)) != cudaSuccess)
+    return lsps_set_error(ctx, LSPS_E_CUDA, "norm_bwd_stats: memset");
+  const int smem = 2 * lanes * c * (int)sizeof(float);
+  const bf16 *gg = static_cast<const bf16*>(dy), *hh = static_cast<const bf16*>(h);
+  if (mode == 0) norm_bwd_stats_kernel<0><<<grid, 256, smem, ST_(st)>>>(gg, hh, stats, bsums, hw, c, ppb, stride, stride, slope);
+  else norm_bwd_stats_kernel<1><<<grid, 256, smem, ST_(st)>>>(gg, hh, stats, bsums, hw, c, ppb, stride, stride, slope);
+  LSPS_CHECK_LAUNCH(ctx, "norm_bwd_stats");
+  return LSPS_OK;
+}
+extern "C" int lsps_norm_bwd_apply(lsps_ctx* ctx, const void* g, const void* h, const float* stats, const float* bsums,
+                                   void* dh, int n, int hw, int c, int gmode, int per_image, float slope, lsps_stream st) {
+  REQUIRE(ctx, g && h && stats && bsums && dh, LSPS_E_ARG, "norm_bwd_apply: null");
+  REQUIRE(ctx, norm_shape_ok(n, hw, c) && gmode >= 0 && gmode <= 2 && slope > 0.f, LSPS_E_SHAPE, "norm_bwd_apply: shape");
+  const int ppb = norm_ppb(hw, c);
+  const dim3 grid((hw + ppb - 1) / ppb, n);
+  const long long stride = per_image ? 2LL * c : 0;
+  const float inv = 1.f / (per_image ? (float)hw : (float)hw * (float)n);
+  const bf16 *gg = static_cast<const bf16*>(g), *hh = static_cast<const bf16*>(h);
+  if (gmode == 0) norm_bwd_apply_kernel<0><<<grid, 256, 0, ST_(st)>>>(gg, hh, stats, bsums, static_cast<bf16*>(dh), hw, c, ppb, stride, stride, inv, slope);
+  else if (gmode == 1) norm_bwd_apply_kernel<1><<<grid, 256, 0, ST_(st)>>>(gg, hh, stats, bsums, static_cast<bf16*>(dh), hw, c, ppb, stride, stride, inv, slope);
+  else norm_bwd_apply_kernel<2><<<grid, 256, 0, ST_(st)>>>(gg, hh, stats, bsums, static_cast<bf16*>(dh), hw, c, ppb, stride, stride, inv, slope);
+  LSPS_CHECK_LAUNCH(ctx, "norm_bwd_apply");
+  return LSPS_OK;
+}
+extern "C" int lsps_norm_reduce_images(lsps_ctx* ctx, const float* sums, float* out, int n, int c, lsps_stream st) {
+  REQUIRE(ctx, sums && out && n > 0 && c > 0, LSPS_E_ARG, "norm_reduce_images: arg");
+  norm_reduce_images_kernel<<<(2 * c + 255) / 256, 256, 0, ST_(st)>>>(sums, out, n, 2 * c);
+  LSPS_CHECK_LAUNCH(ctx, "norm_reduce_images");
+  return LSPS_OK;
+}
+
 extern "C" int lsps_noise_kl_fwd(lsps_ctx* ctx, const void* x, const float* noise, void* z, float* acc, long long n,
                                  lsps_stream st) {
   REQUIRE(ctx, x && noise && z && acc, LSPS_E_ARG, "noise_kl: null");
@@ -1153,6 +1348,27 @@ extern "C" int lsps_noise_kl_fwd(lsps_ctx* ctx, const void* x, const float* nois
   noise_kl_kernel<<<grid_for(n / 8, 256, 8 * ctx->num_sms), 256, 0, ST_(st)>>>(static_cast<const bf16*>(x), noise,
                                                                              static_cast<bf16*>(z), acc, n / 8);
   LSPS_CHECK_LAUNCH(ctx, "noise_kl");
+  return LSPS_OK;
+}
+extern "C" int lsps_noise_kl_philox(lsps_ctx* ctx, const void* x, void* z, float* acc, long long n,
+                                    unsigned long long seed, unsigned long long offset, lsps_stream st) {
+  REQUIRE(ctx, x && z && acc, LSPS_E_ARG, "noise_kl_philox: null");
+  REQUIRE(ctx, n > 0 && n % 8 == 0, LSPS_E_SHAPE, "noise_kl_philox: n % 8");
+  noise_kl_philox_kernel<<<grid_for(n / 8, 256, 16 * ctx->num_sms), 256, 0, ST_(st)>>>(
+      static_cast<const bf16*>(x), static_cast<bf16*>(z), acc, n / 8, seed, offset);
+  LSPS_CHECK_LAUNCH(ctx, "noise_kl_philox");
+  return LSPS_OK;
+}
+// plain stream-ordered fills / copies (graph-capturable; no kernel of any library involved)
+extern "C" int lsps_memset(lsps_ctx* ctx, void* dst, int value, long long bytes, lsps_stream st) {
+  REQUIRE(ctx, dst && bytes >= 0, LSPS_E_ARG, "memset: arg");
+  if (bytes && cudaMemsetAsync(dst, value, (size_t)bytes, ST_(st)) != cudaSuccess) return lsps_set_error(ctx, LSPS_E_CUDA, "memset failed");
+  return LSPS_OK;
+}
+extern "C" int lsps_memcpy(lsps_ctx* ctx, void* dst, const void* src, long long bytes, lsps_stream st) {
+  REQUIRE(ctx, dst && src && bytes >= 0, LSPS_E_ARG, "memcpy: arg");
+  if (bytes && cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyDeviceToDevice, ST_(st)) != cudaSuccess)
+    return lsps_set_error(ctx, LSPS_E_CUDA, "memcpy failed");
   return LSPS_OK;
 }
 extern "C" int lsps_axpy_bf16(lsps_ctx* ctx, const void* a, const void* b, float alpha, void* out, long long n,
@@ -1180,21 +1396,38 @@ extern "C" int lsps_l1_f32(lsps_ctx* ctx, const float* x, const float* t, float*
   LSPS_CHECK_LAUNCH(ctx, "l1_f32");
   return LSPS_OK;
 }
+static int run_l1_feat(lsps_ctx* ctx, const void* a, const void* b, float* da, float* db, float scale, float* acc,
+                       long long n, int sc, lsps_stream st) {
+  REQUIRE(ctx, a && b && acc && n > 0 && (sc == 0 || n % sc == 0), LSPS_E_ARG, "l1_feat: arg");
+  l1_feat_kernel<<<grid_for(n, 256, 4 * ctx->num_sms), 256, 0, ST_(st)>>>(static_cast<const bf16*>(a),
+                                                                        static_cast<const bf16*>(b), da, db, scale, acc, n, sc);
+  LSPS_CHECK_LAUNCH(ctx, "l1_feat");
+  return LSPS_OK;
+}
 extern "C" int lsps_l1_feat(lsps_ctx* ctx, const void* a, const void* b, float* da, float* db, float scale, float* acc,
                             long long n, lsps_stream st) {
-  REQUIRE(ctx, a && b && acc && n > 0, LSPS_E_ARG, "l1_feat: null");
-  l1_feat_kernel<<<grid_for(n, 256, 4 * ctx->num_sms), 256, 0, ST_(st)>>>(static_cast<const bf16*>(a),
-                                                                        static_cast<const bf16*>(b), da, db, scale, acc, n);
-  LSPS_CHECK_LAUNCH(ctx, "l1_feat");
+  return run_l1_feat(ctx, a, b, da, db, scale, acc, n, 0, st);
+}
+extern "C" int lsps_l1_feat_split(lsps_ctx* ctx, const void* a, const void* b, float* da, float* db, float scale,
+                                  float* acc, long long n, int c, lsps_stream st) {
+  REQUIRE(ctx, c > 0, LSPS_E_ARG, "l1_feat_split: c");
+  return run_l1_feat(ctx, a, b, da, db, scale, acc, n, c, st);
+}
+static int run_dhead_fwd(lsps_ctx* ctx, const void* f, const float* w, const float* bias, float* logits, long long rows,
+                         int c, int split, lsps_stream st) {
+  REQUIRE(ctx, f && w && bias && logits && rows > 0, LSPS_E_ARG, "dhead_fwd: null");
+  REQUIRE(ctx, c % 8 == 0, LSPS_E_SHAPE, "dhead_fwd: c % 8");
+  dhead_fwd_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, ST_(st)>>>(static_cast<const bf16*>(f), w, bias, logits, rows, c, split);
+  LSPS_CHECK_LAUNCH(ctx, "dhead_fwd");
   return LSPS_OK;
 }
 extern "C" int lsps_dhead_fwd(lsps_ctx* ctx, const void* f, const float* w, const float* bias, float* logits,
                               long long rows, int c, lsps_stream st) {
-  REQUIRE(ctx, f && w && bias && logits && rows > 0, LSPS_E_ARG, "dhead_fwd: null");
-  REQUIRE(ctx, c % 8 == 0, LSPS_E_SHAPE, "dhead_fwd: c % 8");
-  dhead_fwd_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, ST_(st)>>>(static_cast<const bf16*>(f), w, bias, logits, rows, c);
-  LSPS_CHECK_LAUNCH(ctx, "dhead_fwd");
-  return LSPS_OK;
+  return run_dhead_fwd(ctx, f, w, bias, logits, rows, c, 0, st);
+}
+extern "C" int lsps_dhead_fwd_split(lsps_ctx* ctx, const void* f, const float* w, const float* bias, float* logits,
+                                    long long rows, int c, lsps_stream st) {
+  return run_dhead_fwd(ctx, f, w, bias, logits, rows, c, 1, st);
 }
 extern "C" int lsps_bce_logits(lsps_ctx* ctx, const float* logits, float target, float scale, float* dlogits,
                                float* acc, long long rows, lsps_stream st) {
@@ -1203,24 +1436,49 @@ extern "C" int lsps_bce_logits(lsps_ctx* ctx, const float* logits, float target,
   LSPS_CHECK_LAUNCH(ctx, "bce_logits");
   return LSPS_OK;
 }
-extern "C" int lsps_dhead_bwd(lsps_ctx* ctx, const void* f, const float* w, const float* dlogits, float* df, float* dw,
-                              float* db, long long rows, int c, lsps_stream st) {
+static int run_dhead_bwd(lsps_ctx* ctx, const void* f, const float* w, const float* dlogits, float* df, float* dw,
+                         float* db, long long rows, int c, int split, lsps_stream st) {
   REQUIRE(ctx, f && w && dlogits && rows > 0, LSPS_E_ARG, "dhead_bwd: null");
   const int rpb = 32;
   dim3 grid((c + 255) / 256, (unsigned)((rows + rpb - 1) / rpb));
-  dhead_bwd_kernel<<<grid, 256, 0, ST_(st)>>>(static_cast<const bf16*>(f), w, dlogits, df, dw, db, rows, c, rpb);
+  dhead_bwd_kernel<<<grid, 256, 0, ST_(st)>>>(static_cast<const bf16*>(f), w, dlogits, df, dw, db, rows, c, rpb, split);
   LSPS_CHECK_LAUNCH(ctx, "dhead_bwd");
+  return LSPS_OK;
+}
+extern "C" int lsps_dhead_bwd(lsps_ctx* ctx, const void* f, const float* w, const float* dlogits, float* df, float* dw,
+                              float* db, long long rows, int c, lsps_stream st) {
+  return run_dhead_bwd(ctx, f, w, dlogits, df, dw, db, rows, c, 0, st);
+}
+extern "C" int lsps_dhead_bwd_split(lsps_ctx* ctx, const void* f, const float* w, const float* dlogits, float* df,
+                                    float* dw, float* db, long long rows, int c, lsps_stream st) {
+  return run_dhead_bwd(ctx, f, w, dlogits, df, dw, db, rows, c, 1, st);
+}
+static int run_mask_to_bf16(lsps_ctx* ctx, const float* df, const void* f, void* out, float slope, long long n, int sc,
+                            lsps_stream st) {
+  REQUIRE(ctx, df && f && out && n > 0 && (sc == 0 || n % sc == 0), LSPS_E_ARG, "mask_to_bf16: arg");
+  mask_to_bf16_kernel<<<grid_for(n, 256, 8 * ctx->num_sms), 256, 0, ST_(st)>>>(df, static_cast<const bf16*>(f),
+                                                                             static_cast<bf16*>(out), slope, n, sc);
+  LSPS_CHECK_LAUNCH(ctx, "mask_to_bf16");
   return LSPS_OK;
 }
 extern "C" int lsps_mask_to_bf16(lsps_ctx* ctx, const float* df, const void* f, void* out, float slope, long long n,
                                  lsps_stream st) {
-  REQUIRE(ctx, df && f && out && n > 0, LSPS_E_ARG, "mask_to_bf16: null");
-  mask_to_bf16_kernel<<<grid_for(n, 256, 8 * ctx->num_sms), 256, 0, ST_(st)>>>(df, static_cast<const bf16*>(f),
-                                                                             static_cast<bf16*>(out), slope, n);
-  LSPS_CHECK_LAUNCH(ctx, "mask_to_bf16");
-  return LSPS_OK;
+  return run_mask_to_bf16(ctx, df, f, out, slope, n, 0, st);
 }
+extern "C" int lsps_mask_to_bf16_split(lsps_ctx* ctx, const float* df, const void* f, void* out, float slope, long long n,
+                                       int c, lsps_stream st) {
+  REQUIRE(ctx, c > 0, LSPS_E_ARG, "mask_to_bf16_split: c");
+  return run_mask_to_bf16(ctx, df, f, out, slope, n, c, st);
+}
+static int run_colsum(lsps_ctx* ctx, const void* dy, long long rows, int c, float* db, int fold, lsps_stream st);
 extern "C" int lsps_colsum_bf16(lsps_ctx* ctx, const void* dy, long long rows, int c, float* db, lsps_stream st) {
+  return run_colsum(ctx, dy, rows, c, db, 0, st);
+}
+// dy split [rows][hi c | lo c]: db[c] += column sums of hi + lo
+extern "C" int lsps_colsum_bf16_split(lsps_ctx* ctx, const void* dy, long long rows, int c, float* db, lsps_stream st) {
+  return run_colsum(ctx, dy, rows, 2 * c, db, c, st);
+}
+static int run_colsum(lsps_ctx* ctx, const void* dy, long long rows, int c, float* db, int fold, lsps_stream st) {
   REQUIRE(ctx, dy && db && rows > 0, LSPS_E_ARG, "colsum: null");
   REQUIRE(ctx, c % 8 == 0 && (c / 8 >= 256 ? (c / 8) % 256 == 0 : 256 % (c / 8) == 0), LSPS_E_SHAPE, "colsum: c");
   const int octs = c / 8;
@@ -1229,7 +1487,7 @@ extern "C" int lsps_colsum_bf16(lsps_ctx* ctx, const void* dy, long long rows, i
   long long gx = (rows + row_lanes - 1) / row_lanes;
   const long long cap = (2LL * ctx->num_sms + gy - 1) / gy;
   if (gx > cap) gx = cap;
-  colsum_kernel<<<dim3((unsigned)gx, gy), 256, 0, ST_(st)>>>(static_cast<const bf16*>(dy), rows, c, db, row_lanes);
+  colsum_kernel<<<dim3((unsigned)gx, gy), 256, 0, ST_(st)>>>(static_cast<const bf16*>(dy), rows, c, db, row_lanes, fold);
   LSPS_CHECK_LAUNCH(ctx, "colsum");
   return LSPS_OK;
 }
@@ -1238,8 +1496,11 @@ extern "C" int lsps_linear_fwd(lsps_ctx* ctx, const void* x, int x_bf16, const f
                                int n, int k, int act, float slope, lsps_stream st) {
   REQUIRE(ctx, x && w && y && m > 0 && n > 0 && k > 0, LSPS_E_ARG, "linear_fwd: arg");
   const unsigned grid = (unsigned)(((long long)m * n + 7) / 8);
-  if (x_bf16) linear_fwd_kernel<true><<<grid, 256, 0, ST_(st)>>>(x, w, b, y, m, n, k, act, slope);
-  else linear_fwd_kernel<false><<<grid, 256, 0, ST_(st)>>>(x, w, b, y, m, n, k, act, slope);
+  // x_bf16: 0 = f32 rows, 1 = bf16 rows, c > 1 = split-bf16 rows ([pixels][hi c | lo c], k a multiple of c)
+  const int sc = x_bf16 > 1 ? x_bf16 : 0;
+  REQUIRE(ctx, sc == 0 || k % sc == 0, LSPS_E_SHAPE, "linear_fwd: k must be a multiple of the split channel count");
+  if (x_bf16) linear_fwd_kernel<true><<<grid, 256, 0, ST_(st)>>>(x, w, b, y, m, n, k, act, slope, sc);
+  else linear_fwd_kernel<false><<<grid, 256, 0, ST_(st)>>>(x, w, b, y, m, n, k, act, slope, 0);
   LSPS_CHECK_LAUNCH(ctx, "linear_fwd");
   return LSPS_OK;
 }
@@ -1249,8 +1510,9 @@ extern "C" int lsps_linear_bwd(lsps_ctx* ctx, const void* x, int x_bf16, const f
   if (dw) {
     REQUIRE(ctx, x, LSPS_E_ARG, "linear_bwd: dw needs x");
     const unsigned grid = (unsigned)(((long long)n * k + 255) / 256);
-    if (x_bf16) linear_bwd_dw_kernel<true><<<grid, 256, 0, ST_(st)>>>(x, dy, dw, m, n, k);
-    else linear_bwd_dw_kernel<false><<<grid, 256, 0, ST_(st)>>>(x, dy, dw, m, n, k);
+    const int sc = x_bf16 > 1 ? x_bf16 : 0;
+    if (x_bf16) linear_bwd_dw_kernel<true><<<grid, 256, 0, ST_(st)>>>(x, dy, dw, m, n, k, sc);
+    else linear_bwd_dw_kernel<false><<<grid, 256, 0, ST_(st)>>>(x, dy, dw, m, n, k, 0);
     LSPS_CHECK_LAUNCH(ctx, "linear_bwd_dw");
   }
   if (dx) {
@@ -1293,12 +1555,21 @@ extern "C" int lsps_vae_reparam_bwd(lsps_ctx* ctx, const float* mu, const float*
   return LSPS_OK;
 }
 
+extern "C" int lsps_adam_ex(lsps_ctx* ctx, float* p, const float* g, float* m, float* v, void* w16, void* w16_lo,
+                            long long n, float lr, float beta1, float beta2, float eps, float wd, int step,
+                            float grad_scale, const float* hyper, lsps_stream st);
 extern "C" int lsps_adam(lsps_ctx* ctx, float* p, const float* g, float* m, float* v, void* w16, long long n, float lr,
                          float beta1, float beta2, float eps, float wd, int step, float grad_scale, const float* hyper,
                          lsps_stream st) {
+  return lsps_adam_ex(ctx, p, g, m, v, w16, nullptr, n, lr, beta1, beta2, eps, wd, step, grad_scale, hyper, st);
+}
+extern "C" int lsps_adam_ex(lsps_ctx* ctx, float* p, const float* g, float* m, float* v, void* w16, void* w16_lo,
+                            long long n, float lr, float beta1, float beta2, float eps, float wd, int step,
+                            float grad_scale, const float* hyper, lsps_stream st) {
   REQUIRE(ctx, p && g && m && v && n > 0 && step > 0, LSPS_E_ARG, "adam: arg");
   const double bc1 = 1.0 - pow((double)beta1, step), bc2 = 1.0 - pow((double)beta2, step);
-  adam_kernel<<<grid_for(n, 256, 8 * ctx->num_sms), 256, 0, ST_(st)>>>(p, g, m, v, static_cast<bf16*>(w16), n,
+  adam_kernel<<<grid_for(n, 256, 8 * ctx->num_sms), 256, 0, ST_(st)>>>(p, g, m, v, static_cast<bf16*>(w16),
+                                                                     static_cast<bf16*>(w16_lo), n,
                                                                      (float)(lr / bc1), beta1, beta2, eps, wd,
                                                                      (float)(1.0 / sqrt(bc2)), grad_scale, hyper);
   LSPS_CHECK_LAUNCH(ctx, "adam");
@@ -1308,6 +1579,21 @@ extern "C" int lsps_pack_dgrad(lsps_ctx* ctx, const float* w, void* wt, int taps
   REQUIRE(ctx, w && wt && taps > 0 && cout > 0 && cin > 0, LSPS_E_ARG, "pack_dgrad: arg");
   pack_dgrad_kernel<<<dim3((cin + 31) / 32, (cout + 31) / 32, taps), dim3(32, 8), 0, ST_(st)>>>(w, static_cast<bf16*>(wt), cout, cin);
   LSPS_CHECK_LAUNCH(ctx, "pack_dgrad");
+  return LSPS_OK;
+}
+extern "C" int lsps_pack_dgrad_multi(lsps_ctx* ctx, const float* w_base, void* wt_base, void* wt_lo_base,
+                                     const long long* desc, int count, int total_tiles, lsps_stream st) {
+  REQUIRE(ctx, w_base && wt_base && desc && count > 0 && total_tiles > 0, LSPS_E_ARG, "pack_dgrad_multi: arg");
+  pack_dgrad_multi_kernel<<<total_tiles, dim3(32, 8), 0, ST_(st)>>>(w_base, static_cast<bf16*>(wt_base),
+                                                                    static_cast<bf16*>(wt_lo_base), desc, count);
+  LSPS_CHECK_LAUNCH(ctx, "pack_dgrad_multi");
+  return LSPS_OK;
+}
+extern "C" int lsps_f32_split_bf16(lsps_ctx* ctx, const float* x, void* hi, void* lo, long long n, lsps_stream st) {
+  REQUIRE(ctx, x && hi && lo && n > 0, LSPS_E_ARG, "f32_split_bf16: arg");
+  f32_split_bf16_kernel<<<grid_for(n, 256, 8 * ctx->num_sms), 256, 0, ST_(st)>>>(x, static_cast<bf16*>(hi),
+                                                                               static_cast<bf16*>(lo), n);
+  LSPS_CHECK_LAUNCH(ctx, "f32_split_bf16");
   return LSPS_OK;
 }
 extern "C" int lsps_f32_to_bf16(lsps_ctx* ctx, const float* x, void* y, long long n, lsps_stream st) {

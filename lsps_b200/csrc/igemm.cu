@@ -127,14 +127,16 @@ struct IgemmParams {
   //   into sums[nimg][2][nc_total] -- the InstanceNorm / BatchNorm statistics of the NEXT layer, taken while the values
   //   are still in registers (one streaming apply pass is all that is left of the norm).
   float* sums;
-  // LSPS_EP_INBWD (data gradient that lands on lrelu(IN(h))): `mask` points at h, in_stats[nimg][2][nc_total] holds its
-  //   (mean, rstd); the epilogue stores g = acc * lrelu'(xhat) and accumulates sum g, sum g*xhat into bsums[nimg][2][nc]
-  const float* in_stats;
+  // LSPS_EP_INBWD (data gradient that lands on a = lrelu(xhat), xhat = IN(h)): `mask` points at a, from which
+  //   xhat = a > 0 ? a : a / slope is recovered (no statistics loads in the epilogue); the epilogue stores
+  //   g = acc * lrelu'(xhat) and accumulates sum g, sum g*xhat into bsums[nimg][2][nc_total]
   float* bsums;
+  float inv_slope;
   int nc_total;     // output channels of the GEMM (row pitch of sums / in_stats / bsums, lo-half offset of split outputs)
   // split-bf16 ("bf16x3") operands: A tensor channels are [hi | lo] (lo half a_lo channels in), the weights come as two
   // tensors (tmB hi, tmBlo lo); K-steps per (tap, chunk): hi*hi, hi*lo, lo*hi; the output is written as [hi | lo] too
   int split, a_lo, kch_eff;
+  int gpb;          // multi-phase launches: M groups per block of the block-major tile order (0 = phase-major)
   Phase ph[4];
   Tap taps[16];
 };
@@ -159,16 +161,36 @@ struct IgemmCfg {
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256 + BIAS_BYTES + KTAB_BYTES;
 };
 
-// tile index -> (phase, n tile, m tile, pixel origin); the M grid dims are powers of two
+// tile index -> (phase, n tile, m tile, pixel origin); the M grid dims are powers of two.
+// Multi-phase (2x up-sampling) launches walk the M groups in blocks of gpb groups (a few images): all phases of one
+// block before the next block, so the block's input (read by every phase) is fetched from DRAM once and then hit in L2,
+// while concurrently running CTAs still sit in the same phase (no interleaved partial-line writes between neighbours).
 struct TileCoord { int pi, nt, mt, x0, y0, ti; };
+__device__ __forceinline__ void decode_phase(const IgemmParams& p, int t, int per_phase, int groups_m, int& pi, int& r,
+                                             int& gcount, int& gbase) {
+  pi = 0; r = t; gcount = groups_m; gbase = 0;
+  if (p.nphases > 1) {
+    if (p.gpb > 0) {
+      const int blk_tiles = p.nphases * p.gpb * p.tiles_n;
+      const int blk = t / blk_tiles;
+      const int rb = t - blk * blk_tiles;
+      gbase = blk * p.gpb;
+      gcount = groups_m - gbase < p.gpb ? groups_m - gbase : p.gpb;
+      pi = rb / (gcount * p.tiles_n);
+      r = rb - pi * gcount * p.tiles_n;
+    } else {
+      pi = t / per_phase; r = t - pi * per_phase;
+    }
+  }
+}
 __device__ __forceinline__ TileCoord decode_tile(const IgemmParams& p, int t, int per_phase, int groups_m, int cg, int rank) {
   TileCoord c;
-  int r = t;
-  c.pi = 0;
-  if (p.nphases > 1) { c.pi = t / per_phase; r = t - c.pi * per_phase; }
+  int r, gcount, gbase;
+  decode_phase(p, t, per_phase, groups_m, c.pi, r, gcount, gbase);
   c.nt = 0;
   int mg = r;
-  if (p.tiles_n > 1) { c.nt = r / groups_m; mg = r - c.nt * groups_m; }
+  if (p.tiles_n > 1) { c.nt = r / gcount; mg = r - c.nt * gcount; }
+  mg += gbase;
   c.mt = mg * cg + rank;
   const int tx = c.mt & (p.tiles_x - 1), ty = (c.mt >> p.txl) & (p.tiles_y - 1);
   c.ti = c.mt >> (p.txl + p.tyl);
@@ -310,22 +332,17 @@ __device__ __forceinline__ void epilogue_role(const IgemmParams& p, const float*
           }
         }
         if (inbwd) {
-          // f = dL/d lrelu(IN(h)); h in cm.  g = f * lrelu'(xhat); per-(image, channel) sums of g and g*xhat
-          const float4* mu4 = reinterpret_cast<const float4*>(p.in_stats + srow + c0);
-          const float4* rs4 = reinterpret_cast<const float4*>(p.in_stats + srow + p.nc_total + c0);
+          // f = dL/da with a = lrelu(xhat) in cm.  g = f * lrelu'(xhat); per-(image, channel) sums of g and g*xhat
           float gx[32];
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const uint32_t w[4] = {cm[j].x, cm[j].y, cm[j].z, cm[j].w};
-            const float4 m0 = __ldg(mu4 + 2 * j), m1 = __ldg(mu4 + 2 * j + 1);
-            const float4 r0 = __ldg(rs4 + 2 * j), r1 = __ldg(rs4 + 2 * j + 1);
-            const float mu[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
-            const float rs[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
-              const float hv = (k & 1) ? bf16hi(w[k >> 1]) : bf16lo(w[k >> 1]);
-              const float xh = (hv - mu[k]) * rs[k];
-              float g = xh > 0.f ? f[8 * j + k] : f[8 * j + k] * p.slope;
+              const float av = (k & 1) ? bf16hi(w[k >> 1]) : bf16lo(w[k >> 1]);
+              const bool pos = av > 0.f;
+              const float xh = pos ? av : av * p.inv_slope;
+              float g = pos ? f[8 * j + k] : f[8 * j + k] * p.slope;
               g = valid ? g : 0.f;
               f[8 * j + k] = g;
               gx[8 * j + k] = g * xh;
@@ -482,7 +499,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const uint32_t sA_u32 = smem_u32(sA), sB_u32 = smem_u32(sB);
       int stage = 0; uint32_t ph = 0; int it = 0;
       for (int t = worker; t < total; t += nworkers, ++it) {
-        const int pi = p.nphases > 1 ? t / per_phase : 0;
+        int pi, r_, gc_, gb_;
+        decode_phase(p, t, per_phase, groups_m, pi, r_, gc_, gb_);
         const int nks = p.ph[pi].ntaps * p.kch_eff;
         const int acc = it & 1; const uint32_t accph = (it >> 1) & 1;
         mbar_wait(&tempty[acc], accph ^ 1);
@@ -525,6 +543,9 @@ struct WgradParams {
   int ntaps, co_tiles, ci_tiles, splits;   // co_tiles counts tiles of 128*CG output channels
   int cout, cin;
   int dbg;
+  // split-bf16 operands (dy and x stored as [hi | lo] channel halves): three passes per pixel tile into the same
+  // accumulator -- dy_hi x x_hi, dy_hi x x_lo (x channels + n_lo), dy_lo (dy channels + m_lo) x x_hi
+  int nvar, m_lo, n_lo;
   float* dw;
   WTap taps[16];
 };
@@ -592,7 +613,10 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ CU
     const WTap T = p.taps[tap];
     int stage = 0; uint32_t ph = 0;
     const int nboxes = nA + Cfg::NB_BOXES;
-    for (int pt = pt0; pt < pt1; ++pt) {
+    const int niter = (pt1 - pt0) * p.nvar;
+    for (int i = 0; i < niter; ++i) {
+      const int pt = pt0 + i / p.nvar, var = i - (i / p.nvar) * p.nvar;
+      const int m_off = var == 2 ? p.m_lo : 0, n_off = var == 1 ? p.n_lo : 0;
       const int tx = pt % p.tiles_x, ty = (pt / p.tiles_x) % p.tiles_y, ti = pt / (p.tiles_x * p.tiles_y);
       const int x0 = tx << p.twl, y0 = ty << p.thl, n0 = ti * p.nb;
       uint8_t* s = base + stage * Cfg::STAGE_BYTES;
@@ -605,11 +629,11 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ CU
       __syncwarp();
       if (p.dbg & 2) {
       } else if (lane < nA) {
-        if (CG == 2) tma_load_5d_cg2(s + lane * W_BOX_BYTES, &tmM, &full[stage], cot * 128 + lane * 64 + T.mc, x0 + T.mx, T.mp, y0 + T.my, n0);
-        else tma_load_5d(s + lane * W_BOX_BYTES, &tmM, &full[stage], cot * 128 + lane * 64 + T.mc, x0 + T.mx, T.mp, y0 + T.my, n0);
+        if (CG == 2) tma_load_5d_cg2(s + lane * W_BOX_BYTES, &tmM, &full[stage], cot * 128 + lane * 64 + T.mc + m_off, x0 + T.mx, T.mp, y0 + T.my, n0);
+        else tma_load_5d(s + lane * W_BOX_BYTES, &tmM, &full[stage], cot * 128 + lane * 64 + T.mc + m_off, x0 + T.mx, T.mp, y0 + T.my, n0);
       } else if (lane < nboxes) {
         const int j = lane - nA;
-        const int cbase = cit * BN + (rank * Cfg::NB_BOXES + j) * 64 + T.nc;
+        const int cbase = cit * BN + (rank * Cfg::NB_BOXES + j) * 64 + T.nc + n_off;
         if (CG == 2) tma_load_5d_cg2(s + (2 + j) * W_BOX_BYTES, &tmN, &full[stage], cbase, x0 + T.nx, T.np, y0 + T.ny, n0);
         else tma_load_5d(s + (2 + j) * W_BOX_BYTES, &tmN, &full[stage], cbase, x0 + T.nx, T.np, y0 + T.ny, n0);
       }
@@ -619,7 +643,8 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ CU
     if (lane == 0 && leader) {
       constexpr uint32_t idesc = umma_idesc_bf16(128 * CG, BN, 1, 1);
       int stage = 0; uint32_t ph = 0;
-      for (int pt = pt0; pt < pt1; ++pt) {
+      const int niter = (pt1 - pt0) * p.nvar;
+      for (int pt = 0; pt < niter; ++pt) {
         mbar_wait(&full[stage], ph);
         tc_fence_after();
         const uint32_t a_addr = smem_u32(base + stage * Cfg::STAGE_BYTES);
@@ -629,8 +654,8 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ CU
           if (p.dbg & 1) break;
           const uint64_t ad = umma_smem_desc(a_addr + k * 2048, W_BOX_BYTES, 1024);
           const uint64_t bd = umma_smem_desc(b_addr + k * 2048, W_BOX_BYTES, 1024);
-          if (CG == 2) umma_bf16_cg2(tmem_base, ad, bd, idesc, (pt > pt0 || k > 0) ? 1u : 0u);
-          else umma_bf16(tmem_base, ad, bd, idesc, (pt > pt0 || k > 0) ? 1u : 0u);
+          if (CG == 2) umma_bf16_cg2(tmem_base, ad, bd, idesc, (pt > 0 || k > 0) ? 1u : 0u);
+          else umma_bf16(tmem_base, ad, bd, idesc, (pt > 0 || k > 0) ? 1u : 0u);
         }
         if (CG == 2) umma_commit_cg2(&empty[stage]); else umma_commit(&empty[stage]);
         if (++stage == STAGES) { stage = 0; ph ^= 1; }
@@ -726,6 +751,11 @@ inline int lsps_dbg() {
   if (v < 0) { const char* e = getenv("LSPS_DBG"); v = e ? atoi(e) : 0; }
   return v;
 }
+inline bool lsps_phase_major() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("LSPS_PHASE_MAJOR"); v = (e && e[0] == '1') ? 1 : 0; }
+  return v == 1;
+}
 inline bool lsps_use_pairs() {
   static int v = -1;
   if (v < 0) { const char* e = getenv("LSPS_NO_PAIRS"); v = (e && e[0] == '1') ? 0 : 1; }
@@ -777,9 +807,9 @@ int run_igemm(lsps_ctx* ctx, const lsps_conv_shape* s, Dir dir, const void* in, 
   if (split && (!ext->w_lo || nsplit > 0 || (flags & (LSPS_EP_ADD | LSPS_EP_STATS | LSPS_EP_INBWD))))
     return lsps_set_error(ctx, LSPS_E_ARG, "split-bf16 conv: needs w_lo; not combinable with grouped / add / stats");
   if ((flags & LSPS_EP_STATS) && !ext->sums) return lsps_set_error(ctx, LSPS_E_ARG, "stats flag without sums");
-  if ((flags & LSPS_EP_INBWD) && (!ext->in_h || !ext->in_stats || !ext->bsums || (flags & LSPS_EP_MASK)))
-    return lsps_set_error(ctx, LSPS_E_ARG, "inbwd flag needs in_h, in_stats, bsums and excludes mask");
-  if (flags & LSPS_EP_INBWD) mask = ext->in_h;
+  if ((flags & LSPS_EP_INBWD) && (!ext->in_a || !ext->bsums || (flags & LSPS_EP_MASK) || !(slope > 0.f)))
+    return lsps_set_error(ctx, LSPS_E_ARG, "inbwd flag needs in_a, bsums, a positive slope and excludes mask");
+  if (flags & LSPS_EP_INBWD) mask = ext->in_a;
   const int kind = s->kind, n = s->n, h = s->h, w = s->w, cin = s->cin, cout = s->cout;
   if (kind < 0 || kind > 3 || n <= 0 || !is_pow2(h) || !is_pow2(w) || cin % 64 || cout % 64 || cin <= 0 || cout <= 0)
     return lsps_set_error(ctx, LSPS_E_SHAPE, "conv shape kind %d n %d h %d w %d cin %d cout %d", kind, n, h, w, cin, cout);
@@ -815,7 +845,7 @@ int run_igemm(lsps_ctx* ctx, const lsps_conv_shape* s, Dir dir, const void* in, 
   p.nimg = n; p.kchunks = kc / 64; p.ntaps_all = ks * ks;
   p.split = split ? 1 : 0; p.a_lo = kc; p.kch_eff = split ? 3 * p.kchunks : p.kchunks; p.nc_total = nc;
   if (p.ntaps_all * p.kch_eff > 1024) return lsps_set_error(ctx, LSPS_E_SHAPE, "K-step table overflow (%d steps)", p.ntaps_all * p.kch_eff);
-  p.sums = ext->sums; p.in_stats = ext->in_stats; p.bsums = ext->bsums;
+  p.sums = ext->sums; p.bsums = ext->bsums; p.inv_slope = slope > 0.f ? 1.f / slope : 0.f;
   const int kct = split ? 2 * kc : kc, nct = split ? 2 * nc : nc;     // channels of the `in` / `out` TENSORS
   if ((flags & (LSPS_EP_STATS | LSPS_EP_INBWD)) && hg * wg < 32)
     return lsps_set_error(ctx, LSPS_E_SHAPE, "fused statistics need >= 32 GEMM pixels per image");
@@ -893,6 +923,14 @@ int run_igemm(lsps_ctx* ctx, const lsps_conv_shape* s, Dir dir, const void* in, 
   const int force = lsps_force_cg();
   int cg = (lsps_use_pairs() && tiles_m >= 2 && nk_min >= 27 && (long long)tiles_m * p.tiles_n >= 2 * ctx->num_sms) ? 2 : 1;
   if (force && tiles_m >= 2) cg = force;
+  if (p.nphases > 1 && !lsps_phase_major()) {
+    // ~512 tiles per phase and block: enough to fill every SM twice, small enough that the block's input stays in L2
+    const int tiles_img = p.tiles_x * p.tiles_y;
+    int imgs = (512 + tiles_img - 1) / tiles_img;
+    if (imgs < 1) imgs = 1;
+    const long long groups = ((long long)imgs * tiles_img) / g.nb / cg;     // tiles_i counts groups of nb images
+    p.gpb = groups < 1 ? 1 : (int)groups;
+  }
   CUtensorMap tmA, tmB, tmBlo;
   int rc = act_tmap(ctx, in, n, ih, iw, kct, down, g, &tmA);
   if (rc) return rc;
@@ -986,9 +1024,18 @@ extern "C" int lsps_conv_dgrad_grouped(lsps_ctx* ctx, const lsps_conv_shape* s, 
                    static_cast<cudaStream_t>(st), &ext);
 }
 
+static int run_wgrad(lsps_ctx* ctx, const lsps_conv_shape* s, const void* x, const void* dy, float* dw, int split,
+                     cudaStream_t st);
 extern "C" int lsps_conv_wgrad(lsps_ctx* ctx, const lsps_conv_shape* s, const void* x, const void* dy, float* dw,
                                lsps_stream st_) {
-  cudaStream_t st = static_cast<cudaStream_t>(st_);
+  return run_wgrad(ctx, s, x, dy, dw, 0, static_cast<cudaStream_t>(st_));
+}
+extern "C" int lsps_conv_wgrad_split(lsps_ctx* ctx, const lsps_conv_shape* s, const void* x, const void* dy, float* dw,
+                                     lsps_stream st_) {
+  return run_wgrad(ctx, s, x, dy, dw, 1, static_cast<cudaStream_t>(st_));
+}
+static int run_wgrad(lsps_ctx* ctx, const lsps_conv_shape* s, const void* x, const void* dy, float* dw, int split,
+                     cudaStream_t st) {
   if (!ctx || !s || !x || !dy || !dw) return lsps_set_error(ctx, LSPS_E_ARG, "null argument");
   const int kind = s->kind, n = s->n, h = s->h, w = s->w, cin = s->cin, cout = s->cout;
   if (kind < 0 || kind > 3 || n <= 0 || !is_pow2(h) || !is_pow2(w) || cin % 64 || cout % 64 || cin <= 0 || cout <= 0)
@@ -1007,6 +1054,8 @@ extern "C" int lsps_conv_wgrad(lsps_ctx* ctx, const lsps_conv_shape* s, const vo
   const bool k4 = kind == LSPS_DECONV4_S2;
   const int ks = k4 ? 4 : 3;
   p.ntaps = ks * ks; p.cout = cout; p.cin = cin; p.dw = dw; p.dbg = lsps_dbg();
+  p.nvar = split ? 3 : 1; p.m_lo = cout; p.n_lo = cin;
+  const int cout_t = split ? 2 * cout : cout, cin_t = split ? 2 * cin : cin;   // channels of the dy / x TENSORS
   p.co_tiles = (cout + 128 * cg - 1) / (128 * cg);
   p.ci_tiles = cin / bn;
   for (int r = 0; r < ks; ++r)
@@ -1014,16 +1063,16 @@ extern "C" int lsps_conv_wgrad(lsps_ctx* ctx, const lsps_conv_shape* s, const vo
       WTap& T = p.taps[r * ks + c];
       T = WTap{0, 0, 0, 0, 0, 0, 0, 0};
       if (k4) {  // dy pair view at parity ((r+1)&1, (c+1)&1); x shifted by +1 (tap 0), 0 (taps 1, 2), -1 (tap 3)
-        T.mp = (r + 1) & 1; T.mc = ((c + 1) & 1) * cout;
+        T.mp = (r + 1) & 1; T.mc = ((c + 1) & 1) * cout_t;
         T.ny = r == 0 ? 1 : (r == 3 ? -1 : 0); T.nx = c == 0 ? 1 : (c == 3 ? -1 : 0);
       } else if (kind == LSPS_CONV_S1) { T.ny = r - 1; T.nx = c - 1; }
       else if (kind == LSPS_CONV_S2) {
         int dy_, py, dx_, px;
         s2_axis(r, &dy_, &py); s2_axis(c, &dx_, &px);
-        T.ny = dy_; T.np = py; T.nx = dx_; T.nc = px * cin;
+        T.ny = dy_; T.np = py; T.nx = dx_; T.nc = px * cin_t;
       } else {  // deconv: dy pair view at parity (a,b); x shifted by (di,dj)
         const int a = r == 1 ? 0 : 1, b = c == 1 ? 0 : 1;
-        T.mp = a; T.mc = b * cout;
+        T.mp = a; T.mc = b * cout_t;
         T.ny = r == 0 ? 1 : 0; T.nx = c == 0 ? 1 : 0;
       }
     }
@@ -1035,9 +1084,9 @@ extern "C" int lsps_conv_wgrad(lsps_ctx* ctx, const lsps_conv_shape* s, const vo
   p.splits = splits;
   CUtensorMap tmM, tmN;
   // M side: dy (cout channels) ; N side: x (cin channels)
-  int rc = act_tmap(ctx, dy, n, ho, wo, cout, kind == LSPS_DECONV_S2 || k4, g, &tmM);
+  int rc = act_tmap(ctx, dy, n, ho, wo, cout_t, kind == LSPS_DECONV_S2 || k4, g, &tmM);
   if (rc) return rc;
-  rc = act_tmap(ctx, x, n, h, w, cin, kind == LSPS_CONV_S2, g, &tmN);
+  rc = act_tmap(ctx, x, n, h, w, cin_t, kind == LSPS_CONV_S2, g, &tmN);
   if (rc) return rc;
   if (cg == 2) rc = bn == 256 ? launch_wgrad<256, 2>(ctx, tmM, tmN, p, st) : launch_wgrad<128, 2>(ctx, tmM, tmN, p, st);
   else rc = bn == 256 ? launch_wgrad<256, 1>(ctx, tmM, tmN, p, st)

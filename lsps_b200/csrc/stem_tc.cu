@@ -61,7 +61,9 @@ __device__ __forceinline__ void load_patch(float* patch, int pw, int prow, const
 }
 
 // ------------------------------------------------------------------------------------------------ forward
-template <int S>
+// SPLIT: the weights are split into bf16 hi + lo as well (third MMA pass: taps_hi x w_lo) and the output is written as
+// [hi | lo] channel halves (128 channels per pixel) -- the "bf16x3" discriminator path.
+template <int S, bool SPLIT>
 __global__ void __launch_bounds__(128) stem_fwd_tc_kernel(const float* __restrict__ img, const float* __restrict__ w,
                                                          const float* __restrict__ bias, bf16* __restrict__ y, int n,
                                                          int h, int wd, float slope) {
@@ -69,8 +71,8 @@ __global__ void __launch_bounds__(128) stem_fwd_tc_kernel(const float* __restric
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* a_hi = base;
   uint8_t* a_lo = base + A_BYTES;
-  uint8_t* wt = base + 2 * A_BYTES;                   // [64 co][64 taps] bf16, K-major, swizzled: 8 KB
-  float* patch = reinterpret_cast<float*>(wt + 8192);
+  uint8_t* wt = base + 2 * A_BYTES;                   // [64 co][64 taps] bf16, K-major, swizzled: 8 KB (+ 8 KB lo)
+  float* patch = reinterpret_cast<float*>(wt + 16384);
   const int wo = wd / S, ho = h / S;
   const int tr = TILE_PX / wo;                        // output rows per tile (1 or 2)
   const int prow = (tr - 1) * S + 7, pw = wd + 8;
@@ -86,20 +88,25 @@ __global__ void __launch_bounds__(128) stem_fwd_tc_kernel(const float* __restric
     sbias[co] = bias[co];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      uint32_t u[4];
+      uint32_t u[4], ul[4];
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const int t0 = j * 8 + 2 * k;
-        u[k] = pack_bf16x2(t0 < 49 ? w[co * 49 + t0] : 0.f, t0 + 1 < 49 ? w[co * 49 + t0 + 1] : 0.f);
+        const float w0 = t0 < 49 ? w[co * 49 + t0] : 0.f, w1 = t0 + 1 < 49 ? w[co * 49 + t0 + 1] : 0.f;
+        u[k] = pack_bf16x2(w0, w1);
+        ul[k] = pack_bf16x2(w0 - bf16lo(u[k]), w1 - bf16hi(u[k]));
       }
       *reinterpret_cast<uint4*>(wt + co * 128 + ((j ^ (co & 7)) << 4)) = make_uint4(u[0], u[1], u[2], u[3]);
+      if (SPLIT) *reinterpret_cast<uint4*>(wt + 8192 + co * 128 + ((j ^ (co & 7)) << 4)) = make_uint4(ul[0], ul[1], ul[2], ul[3]);
     }
   }
+  fence_async_smem();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
   constexpr uint32_t idesc = umma_idesc_bf16(128, 64, 0, 0);
+  constexpr int OC = SPLIT ? 128 : 64;                // channels per output pixel
 
   const int tiles_per_img = ho / tr;
   const int total = tiles_per_img * n;
@@ -122,13 +129,18 @@ __global__ void __launch_bounds__(128) stem_fwd_tc_kernel(const float* __restric
 #pragma unroll
       for (int k = 0; k < 4; ++k)
         umma_bf16(tmem, umma_smem_desc(al + k * 32, 0, 1024), umma_smem_desc(bw + k * 32, 0, 1024), idesc, 1u);
+      if (SPLIT) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_bf16(tmem, umma_smem_desc(ah + k * 32, 0, 1024), umma_smem_desc(bw + 8192 + k * 32, 0, 1024), idesc, 1u);
+      }
       umma_commit(bar);
     }
     mbar_wait(bar, phase);
     phase ^= 1;
     tc_fence_after();
     const uint32_t taddr = tmem + (static_cast<uint32_t>(warp * 32) << 16);
-    uint4* o = reinterpret_cast<uint4*>(y + (((long long)im_i * ho + oy0 + ty) * wo + tx) * 64);
+    uint4* o = reinterpret_cast<uint4*>(y + (((long long)im_i * ho + oy0 + ty) * wo + tx) * OC);
 #pragma unroll
     for (int c0 = 0; c0 < 64; c0 += 32) {
       uint32_t v[32];
@@ -146,6 +158,12 @@ __global__ void __launch_bounds__(128) stem_fwd_tc_kernel(const float* __restric
         u.x = pack_bf16x2(f[0], f[1]); u.y = pack_bf16x2(f[2], f[3]);
         u.z = pack_bf16x2(f[4], f[5]); u.w = pack_bf16x2(f[6], f[7]);
         o[c0 / 8 + j] = u;
+        if (SPLIT) {
+          uint4 l;
+          l.x = pack_bf16x2(f[0] - bf16lo(u.x), f[1] - bf16hi(u.x)); l.y = pack_bf16x2(f[2] - bf16lo(u.y), f[3] - bf16hi(u.y));
+          l.z = pack_bf16x2(f[4] - bf16lo(u.z), f[5] - bf16hi(u.z)); l.w = pack_bf16x2(f[6] - bf16lo(u.w), f[7] - bf16hi(u.w));
+          o[8 + c0 / 8 + j] = l;
+        }
       }
     }
     tc_fence_before();
@@ -158,15 +176,16 @@ __global__ void __launch_bounds__(128) stem_fwd_tc_kernel(const float* __restric
 
 // ------------------------------------------------------------------------------------------------ wgrad
 // D[tap rows: 64 hi + 64 lo][co] accumulated in TMEM over all tiles of this CTA; one red.add epilogue at the end.
-template <int S>
+// SPLIT: dy comes as [hi | lo] channel halves (two TMA boxes); second MMA pass with the lo tile.
+template <int S, bool SPLIT>
 __global__ void __launch_bounds__(128) stem_wgrad_tc_kernel(const float* __restrict__ img,
                                                            const __grid_constant__ CUtensorMap tmDy,
                                                            float* __restrict__ dw, float* __restrict__ db, int n, int h,
                                                            int wd) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  // two buffers of {taps hi, taps lo, dy}: the MMAs of tile i run while the threads build tile i+1
-  constexpr int BUF = 3 * A_BYTES;
+  // two buffers of {taps hi, taps lo, dy [, dy lo]}: the MMAs of tile i run while the threads build tile i+1
+  constexpr int BUF = (SPLIT ? 4 : 3) * A_BYTES;
   const int wo = wd / S, ho = h / S;
   const int tr = TILE_PX / wo;
   const int prow = (tr - 1) * S + 7, pw = wd + 8;
@@ -199,8 +218,9 @@ __global__ void __launch_bounds__(128) stem_wgrad_tc_kernel(const float* __restr
     const int im_i = t / tiles_per_img, oy0 = (t - im_i * tiles_per_img) * tr;
     if (it >= 2) mbar_wait(&done[b], use ^ 1);   // MMAs that read this buffer two tiles ago have retired
     if (threadIdx.x == 0) {
-      mbar_expect_tx(&full[b], A_BYTES);
+      mbar_expect_tx(&full[b], (SPLIT ? 2 : 1) * A_BYTES);
       tma_load_2d(buf + 2 * A_BYTES, &tmDy, &full[b], 0, (im_i * ho + oy0) * wo);
+      if (SPLIT) tma_load_2d(buf + 3 * A_BYTES, &tmDy, &full[b], 64, (im_i * ho + oy0) * wo);
     }
     load_patch<S>(patch, pw, prow, img + (long long)im_i * h * wd, h, wd, oy0 * S - 3);
     __syncthreads();
@@ -216,6 +236,12 @@ __global__ void __launch_bounds__(128) stem_wgrad_tc_kernel(const float* __restr
       for (int k = 0; k < 8; ++k)  // 16 pixels per MMA; A = taps (M: hi block, lo block A_BYTES apart), B = dy (N = 64 co)
         umma_bf16(tmem, umma_smem_desc(at + k * 2048, A_BYTES, 1024), umma_smem_desc(bd + k * 2048, A_BYTES, 1024), idesc,
                   (it > 0 || k > 0) ? 1u : 0u);
+      if (SPLIT) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          umma_bf16(tmem, umma_smem_desc(at + k * 2048, A_BYTES, 1024),
+                    umma_smem_desc(bd + A_BYTES + k * 2048, A_BYTES, 1024), idesc, 1u);
+      }
       umma_commit(&done[b]);
     }
   }
@@ -250,7 +276,8 @@ __global__ void __launch_bounds__(128) stem_wgrad_tc_kernel(const float* __restr
 //   step 1 (tensor cores): G[px][tap] = dy[px][0:64] . W[0:64][tap] for every dy pixel that touches the 16x8 input tile
 //                          (one TMA box with halo, zero-filled outside the image)
 //   step 2 (gather)      : each thread owns one input pixel and adds the <= 49 G entries that map onto it.
-template <int S>
+// SPLIT: dy as [hi | lo] halves (two TMA boxes), weights split hi + lo: dy_hi x w_hi + dy_lo x w_hi + dy_hi x w_lo.
+template <int S, bool SPLIT>
 __global__ void __launch_bounds__(128) stem_dgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDy,
                                                            const float* __restrict__ w, float* __restrict__ dimg,
                                                            int n, int h, int wd, int accumulate) {
@@ -260,9 +287,10 @@ __global__ void __launch_bounds__(128) stem_dgrad_tc_kernel(const __grid_constan
   constexpr int TCOLS = MT == 1 ? 64 : 256;                   // TMEM columns: one 64-column accumulator per M tile
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* dyb = base;                                        // MT operand tiles of 128 rows
-  uint8_t* wt = base + MT * A_BYTES;                          // [64 tap rows][64 co] bf16, K-major, swizzled
-  float* G = reinterpret_cast<float*>(wt + 8192);
+  constexpr int NDY = SPLIT ? 2 : 1;
+  uint8_t* dyb = base;                                        // MT operand tiles of 128 rows (x2: lo halves behind)
+  uint8_t* wt = base + NDY * MT * A_BYTES;                    // [64 tap rows][64 co] bf16, K-major, swizzled (+ lo)
+  float* G = reinterpret_cast<float*>(wt + 16384);
   uint64_t* full = reinterpret_cast<uint64_t*>(G + MT * 128 * GP);
   uint64_t* done = full + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
@@ -274,13 +302,16 @@ __global__ void __launch_bounds__(128) stem_dgrad_tc_kernel(const __grid_constan
     const int tap = threadIdx.x;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      uint32_t u[4];
+      uint32_t u[4], ul[4];
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const int co = j * 8 + 2 * k;
-        u[k] = tap < 49 ? pack_bf16x2(w[co * 49 + tap], w[(co + 1) * 49 + tap]) : 0u;
+        const float w0 = tap < 49 ? w[co * 49 + tap] : 0.f, w1 = tap < 49 ? w[(co + 1) * 49 + tap] : 0.f;
+        u[k] = pack_bf16x2(w0, w1);
+        ul[k] = pack_bf16x2(w0 - bf16lo(u[k]), w1 - bf16hi(u[k]));
       }
       *reinterpret_cast<uint4*>(wt + tap * 128 + ((j ^ (tap & 7)) << 4)) = make_uint4(u[0], u[1], u[2], u[3]);
+      if (SPLIT) *reinterpret_cast<uint4*>(wt + 8192 + tap * 128 + ((j ^ (tap & 7)) << 4)) = make_uint4(ul[0], ul[1], ul[2], ul[3]);
     }
   }
   fence_async_smem();
@@ -297,8 +328,9 @@ __global__ void __launch_bounds__(128) stem_dgrad_tc_kernel(const __grid_constan
   auto issue_load = [&](int t) {
     const int bx = t % tiles_x, by = (t / tiles_x) % tiles_y, im_i = t / (tiles_x * tiles_y);
     const int oxb = S == 1 ? bx * 16 - 3 : bx * 8 - 1, oyb = S == 1 ? by * 8 - 3 : by * 4 - 1;
-    mbar_expect_tx(full, ROWS * 128);
+    mbar_expect_tx(full, NDY * ROWS * 128);
     tma_load_4d(dyb, &tmDy, full, 0, oxb, oyb, im_i);
+    if (SPLIT) tma_load_4d(dyb + MT * A_BYTES, &tmDy, full, 64, oxb, oyb, im_i);
   };
   if (threadIdx.x == 0 && (int)blockIdx.x < total) issue_load(blockIdx.x);
   uint32_t phase = 0;
@@ -309,11 +341,22 @@ __global__ void __launch_bounds__(128) stem_dgrad_tc_kernel(const __grid_constan
       tc_fence_after();
       const uint32_t a0 = smem_u32(dyb), bw = smem_u32(wt);
 #pragma unroll
-      for (int m = 0; m < MT; ++m)
+      for (int m = 0; m < MT; ++m) {
 #pragma unroll
         for (int k = 0; k < 4; ++k)
           umma_bf16(tmem + m * 64, umma_smem_desc(a0 + m * A_BYTES + k * 32, 0, 1024), umma_smem_desc(bw + k * 32, 0, 1024),
                     idesc, k > 0 ? 1u : 0u);
+        if (SPLIT) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_bf16(tmem + m * 64, umma_smem_desc(a0 + (MT + m) * A_BYTES + k * 32, 0, 1024),
+                      umma_smem_desc(bw + k * 32, 0, 1024), idesc, 1u);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_bf16(tmem + m * 64, umma_smem_desc(a0 + m * A_BYTES + k * 32, 0, 1024),
+                      umma_smem_desc(bw + 8192 + k * 32, 0, 1024), idesc, 1u);
+        }
+      }
       umma_commit(done);
     }
     mbar_wait(done, phase);
@@ -377,67 +420,71 @@ int set_smem(lsps_ctx* ctx, K kernel, int bytes) {
 
 }  // namespace
 
-// Called from aux.cu's lsps_stem_fwd / lsps_stem_wgrad when the shape qualifies (output width 64 or 128).
+// Called from aux.cu's lsps_stem_fwd / lsps_stem_wgrad / lsps_stem_dgrad when the shape qualifies (output width 64 or
+// 128).  split != 0: the bf16x3 variants (y / dy as [hi | lo] channel halves, weights split in the kernel).
 int lsps_stem_fwd_tc(lsps_ctx* ctx, const float* img, const float* w, const float* bias, void* y, int n, int h, int wd,
-                     int stride, float slope, cudaStream_t st) {
+                     int stride, float slope, int split, cudaStream_t st) {
   const int wo = wd / stride, ho = h / stride, tr = TILE_PX / wo;
   const int prow = (tr - 1) * stride + 7, pw = wd + 8;
-  const int smem = 1024 + 2 * A_BYTES + 8192 + (prow * pw + 64) * 4 + 64;
+  const int smem = 1024 + 2 * A_BYTES + 16384 + (prow * pw + 64) * 4 + 64;
   const int total = (ho / tr) * n;
   const int grid = total < 4 * ctx->num_sms ? total : 4 * ctx->num_sms;
   int rc;
-  if (stride == 1) {
-    if ((rc = set_smem(ctx, stem_fwd_tc_kernel<1>, smem))) return rc;
-    stem_fwd_tc_kernel<1><<<grid, 128, smem, st>>>(img, w, bias, static_cast<bf16*>(y), n, h, wd, slope);
-  } else {
-    if ((rc = set_smem(ctx, stem_fwd_tc_kernel<2>, smem))) return rc;
-    stem_fwd_tc_kernel<2><<<grid, 128, smem, st>>>(img, w, bias, static_cast<bf16*>(y), n, h, wd, slope);
-  }
+#define LSPS_STEM_FWD(S_, SP_)                                                                                      \
+  do {                                                                                                              \
+    if ((rc = set_smem(ctx, stem_fwd_tc_kernel<S_, SP_>, smem))) return rc;                                          \
+    stem_fwd_tc_kernel<S_, SP_><<<grid, 128, smem, st>>>(img, w, bias, static_cast<bf16*>(y), n, h, wd, slope);       \
+  } while (0)
+  if (stride == 1) { if (split) LSPS_STEM_FWD(1, true); else LSPS_STEM_FWD(1, false); }
+  else { if (split) LSPS_STEM_FWD(2, true); else LSPS_STEM_FWD(2, false); }
+#undef LSPS_STEM_FWD
   LSPS_CHECK_LAUNCH(ctx, "stem_fwd_tc");
   return LSPS_OK;
 }
 
 int lsps_stem_wgrad_tc(lsps_ctx* ctx, const float* img, const void* dy, float* dw, float* db, int n, int h, int wd,
-                       int stride, cudaStream_t st) {
+                       int stride, int split, cudaStream_t st) {
   const int wo = wd / stride, ho = h / stride, tr = TILE_PX / wo;
   const int prow = (tr - 1) * stride + 7, pw = wd + 8;
-  const int smem = 1024 + 6 * A_BYTES + prow * pw * 4 + 128;
+  const int smem = 1024 + (split ? 8 : 6) * A_BYTES + prow * pw * 4 + 128;
   const int total = (ho / tr) * n;
   const int grid = total < 2 * ctx->num_sms ? total : 2 * ctx->num_sms;
   CUtensorMap tm;
-  uint32_t dims[2] = {64u, (uint32_t)((long long)n * ho * wo)}, box[2] = {64u, (uint32_t)TILE_PX};
+  uint32_t dims[2] = {split ? 128u : 64u, (uint32_t)((long long)n * ho * wo)}, box[2] = {64u, (uint32_t)TILE_PX};
   int rc = lsps_get_tmap(ctx, dy, 2, dims, box, &tm);
   if (rc) return rc;
-  if (stride == 1) {
-    if ((rc = set_smem(ctx, stem_wgrad_tc_kernel<1>, smem))) return rc;
-    stem_wgrad_tc_kernel<1><<<grid, 128, smem, st>>>(img, tm, dw, db, n, h, wd);
-  } else {
-    if ((rc = set_smem(ctx, stem_wgrad_tc_kernel<2>, smem))) return rc;
-    stem_wgrad_tc_kernel<2><<<grid, 128, smem, st>>>(img, tm, dw, db, n, h, wd);
-  }
+#define LSPS_STEM_WG(S_, SP_)                                                                                       \
+  do {                                                                                                              \
+    if ((rc = set_smem(ctx, stem_wgrad_tc_kernel<S_, SP_>, smem))) return rc;                                        \
+    stem_wgrad_tc_kernel<S_, SP_><<<grid, 128, smem, st>>>(img, tm, dw, db, n, h, wd);                                \
+  } while (0)
+  if (stride == 1) { if (split) LSPS_STEM_WG(1, true); else LSPS_STEM_WG(1, false); }
+  else { if (split) LSPS_STEM_WG(2, true); else LSPS_STEM_WG(2, false); }
+#undef LSPS_STEM_WG
   LSPS_CHECK_LAUNCH(ctx, "stem_wgrad_tc");
   return LSPS_OK;
 }
 
 int lsps_stem_dgrad_tc(lsps_ctx* ctx, const void* dy, const float* w, float* dimg, int n, int h, int wd, int stride,
-                       int accumulate, cudaStream_t st) {
+                       int accumulate, int split, cudaStream_t st) {
   const int ho = h / stride, wo = wd / stride;
   const int rows = stride == 1 ? 22 * 14 : 11 * 7, mt = (rows + 127) / 128;
-  const int smem = 1024 + mt * A_BYTES + 8192 + mt * 128 * 49 * 4 + 64;
+  const int smem = 1024 + (split ? 2 : 1) * mt * A_BYTES + 16384 + mt * 128 * 49 * 4 + 64;
   const int total = (wd / 16) * (h / 8) * n;
   const int grid = total < ctx->num_sms ? total : ctx->num_sms * (stride == 1 ? 1 : 2);
   CUtensorMap tm;
-  uint32_t dims[4] = {64u, (uint32_t)wo, (uint32_t)ho, (uint32_t)n};
+  uint32_t dims[4] = {split ? 128u : 64u, (uint32_t)wo, (uint32_t)ho, (uint32_t)n};
   uint32_t box[4] = {64u, stride == 1 ? 22u : 11u, stride == 1 ? 14u : 7u, 1u};
   int rc = lsps_get_tmap(ctx, dy, 4, dims, box, &tm);
   if (rc) return rc;
-  if (stride == 1) {
-    if ((rc = set_smem(ctx, stem_dgrad_tc_kernel<1>, smem))) return rc;
-    stem_dgrad_tc_kernel<1><<<grid, 128, smem, st>>>(tm, w, dimg, n, h, wd, accumulate);
-  } else {
-    if ((rc = set_smem(ctx, stem_dgrad_tc_kernel<2>, smem))) return rc;
-    stem_dgrad_tc_kernel<2><<<grid, 128, smem, st>>>(tm, w, dimg, n, h, wd, accumulate);
-  }
+#define LSPS_STEM_DG(S_, SP_)                                                                                       \
+  do {                                                                                                              \
+    if ((rc = set_smem(ctx, stem_dgrad_tc_kernel<S_, SP_>, smem))) return rc;                                        \
+    stem_dgrad_tc_kernel<S_, SP_><<<grid, 128, smem, st>>>(tm, w, dimg, n, h, wd, accumulate);                        \
+  } while (0)
+  if (stride == 1) { if (split) LSPS_STEM_DG(1, true); else LSPS_STEM_DG(1, false); }
+  else { if (split) LSPS_STEM_DG(2, true); else LSPS_STEM_DG(2, false); }
+#undef LSPS_STEM_DG
   LSPS_CHECK_LAUNCH(ctx, "stem_dgrad_tc");
   return LSPS_OK;
 }

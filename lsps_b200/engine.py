@@ -14,7 +14,8 @@ import os
 import torch
 
 from . import _lib
-from ._lib import CONV_S1, CONV_S2, DECONV_S2, DECONV4_S2, EP_BIAS, EP_LRELU, EP_MASK, EP_ADD, ConvShape
+from ._lib import (CONV_S1, CONV_S2, DECONV_S2, DECONV4_S2, EP_BIAS, EP_LRELU, EP_MASK, EP_ADD, EP_STATS, EP_INBWD,
+                   ConvShape, ConvExt)
 
 SLOPE = 0.01   # nn.LeakyReLU() default (common_net.py:169,251)
 IN_EPS = 1e-5  # nn.InstanceNorm2d default
@@ -35,6 +36,9 @@ class Ops:
         self.side = torch.cuda.Stream(device=self.device)
         self.use_side = os.environ.get("LSPS_NO_SIDE", "0") != "1"
         self._side_refs = []
+        # InstanceNorm statistics taken in the conv epilogues + one streaming apply pass (round 2); LSPS_OLD_IN=1 keeps
+        # the stand-alone three-pass kernels for A/B runs
+        self.fused_in = os.environ.get("LSPS_OLD_IN", "0") != "1"
 
     def _on_side(self, fn, *keep):
         if not self.use_side or torch.cuda.is_current_stream_capturing():
@@ -47,6 +51,12 @@ class Ops:
             fn()
         self._side_refs.append(keep)     # keep the operands alive (and their memory unrecycled) until the join
 
+    def side_event(self):
+        """Event that completes when everything enqueued so far on the weight-gradient stream has run."""
+        ev = torch.cuda.Event()
+        ev.record(self.side if (self.use_side and self._side_refs) else torch.cuda.current_stream())
+        return ev
+
     def join_side(self):
         if self._side_refs:
             ev = torch.cuda.Event()
@@ -58,7 +68,35 @@ class Ops:
         return torch.empty(shape, dtype=dtype, device=self.device)
 
     def zeros(self, *shape, dtype=torch.float32):
-        return torch.zeros(shape, dtype=dtype, device=self.device)
+        """zero-filled tensor through a stream-ordered memset (no library fill kernel on the hot path)"""
+        t = torch.empty(shape, dtype=dtype, device=self.device)
+        self.ctx.memset(t.data_ptr(), 0, t.numel() * t.element_size())
+        return t
+
+    def cat(self, tensors):
+        """torch.cat along dim 0 of contiguous same-shaped-tail tensors as plain device-to-device copies"""
+        tensors = [t for t in tensors if t is not None]
+        if len(tensors) == 1:
+            return tensors[0]
+        out = torch.empty((sum(t.shape[0] for t in tensors),) + tuple(tensors[0].shape[1:]), dtype=tensors[0].dtype,
+                          device=self.device)
+        r = 0
+        for t in tensors:
+            self.copy_into(out[r:r + t.shape[0]], t)
+            r += t.shape[0]
+        return out
+
+    def copy_into(self, dst, src):
+        assert dst.is_contiguous() and src.is_contiguous() and dst.numel() == src.numel() and dst.dtype == src.dtype
+        self.ctx.memcpy(dst.data_ptr(), src.data_ptr(), src.numel() * src.element_size())
+
+    def noise_kl(self, x, noise, z, acc):
+        """GaussianNoiseLayer + KL sum.  noise: host-drawn fp32 tensor shaped like x (parity mode) or a
+        ("philox", seed, offset) token (device mode: drawn inside the kernel)."""
+        if isinstance(noise, tuple):
+            self.ctx.noise_kl_philox(x.data_ptr(), z.data_ptr(), acc.data_ptr(), x.numel(), noise[1], noise[2])
+        else:
+            self.ctx.noise_kl_fwd(x.data_ptr(), noise.data_ptr(), z.data_ptr(), acc.data_ptr(), x.numel())
 
     # ---- 3x3 convs on tcgen05
     @staticmethod
@@ -68,14 +106,33 @@ class Ops:
 
     # `key` may be a pair (key_a, key_b, split): images [0, split) go through conv key_a, the rest through key_b --
     # ONE grouped launch for forward / data gradient (full waves of CTA pairs instead of two half-size launches)
-    def conv_fwd(self, S, key, kind, x, lrelu, out=None):
+    def conv_fwd(self, S, key, kind, x, lrelu, out=None, sums=None, split=False):
+        """sums: optional fp32 [n,2,cout] -- the epilogue accumulates per-(image, channel) sum / sum of squares of the
+        conv result there (LSPS_EP_STATS), which is all the following InstanceNorm needs.
+        split: bf16x3 operands -- x / y are [n,h,w,2c] (hi | lo) tensors, the store carries the weight remainders."""
         n, h, w, cin = x.shape
         k0 = key[0] if isinstance(key, tuple) else key
         ci, co = self._io(S, k0, kind)
-        assert ci == cin, (key, ci, cin)
+        assert (2 * ci if split else ci) == cin, (key, ci, cin)
         ho, wo = (h, w) if kind == CONV_S1 else ((h // 2, w // 2) if kind == CONV_S2 else (2 * h, 2 * w))
-        y = out if out is not None else self.empty(n, ho, wo, co)
+        y = out if out is not None else self.empty(n, ho, wo, 2 * co if split else co)
         flags = EP_BIAS | (EP_LRELU if lrelu else 0)
+        if split:
+            ext = ConvExt()
+            ext.split, ext.w_lo = 1, S.W16L(key + ".weight").data_ptr()
+            self.ctx.conv_fwd_ex(_shape(kind, n, h, w, ci, co), x.data_ptr(), S.W16(key + ".weight").data_ptr(),
+                                 S.W(key + ".bias").data_ptr(), y.data_ptr(), flags, SLOPE, C.byref(ext))
+            return y
+        if sums is not None:
+            ext = ConvExt()
+            ext.sums = sums.data_ptr()
+            ka = key
+            if isinstance(key, tuple):
+                ka, kb, split = key
+                ext.w2, ext.bias2, ext.n_split = S.W16(kb + ".weight").data_ptr(), S.W(kb + ".bias").data_ptr(), split
+            self.ctx.conv_fwd_ex(_shape(kind, n, h, w, ci, co), x.data_ptr(), S.W16(ka + ".weight").data_ptr(),
+                                 S.W(ka + ".bias").data_ptr(), y.data_ptr(), flags | EP_STATS, SLOPE, C.byref(ext))
+            return y
         if isinstance(key, tuple):
             ka, kb, split = key
             self.ctx.conv_fwd_grouped(_shape(kind, n, h, w, ci, co), x.data_ptr(), S.W16(ka + ".weight").data_ptr(),
@@ -86,12 +143,32 @@ class Ops:
                               S.W(key + ".bias").data_ptr(), y.data_ptr(), flags, SLOPE)
         return y
 
-    def conv_dgrad(self, S, key, kind, dy, x_shape, mask=None, add=None, out=None):
+    def conv_dgrad(self, S, key, kind, dy, x_shape, mask=None, add=None, out=None, inbwd=None, split=False):
+        """inbwd = (a, bsums): the gradient lands on a = lrelu(IN(h)); the epilogue applies lrelu'(xhat) and accumulates
+        sum g / sum g*xhat per (image, channel) into bsums (LSPS_EP_INBWD; xhat is recovered from a)."""
         n, h, w, cin = x_shape
         k0 = key[0] if isinstance(key, tuple) else key
         ci, co = self._io(S, k0, kind)
-        dx = out if out is not None else self.empty(n, h, w, ci)
+        dx = out if out is not None else self.empty(n, h, w, 2 * ci if split else ci)
         flags = (EP_MASK if mask is not None else 0) | (EP_ADD if add is not None else 0)
+        if split:
+            assert add is None and inbwd is None
+            ext = ConvExt()
+            ext.split, ext.w_lo = 1, S.W16TL(key + ".weight").data_ptr()
+            self.ctx.conv_dgrad_ex(_shape(kind, n, h, w, ci, co), dy.data_ptr(), S.W16T(key + ".weight").data_ptr(),
+                                   dx.data_ptr(), _lib.ptr(mask), None, flags, SLOPE, C.byref(ext))
+            return dx
+        if inbwd is not None:
+            assert mask is None
+            ext = ConvExt()
+            ext.in_a, ext.bsums = inbwd[0].data_ptr(), inbwd[1].data_ptr()
+            ka = key
+            if isinstance(key, tuple):
+                ka, kb, split = key
+                ext.w2, ext.n_split = S.W16T(kb + ".weight").data_ptr(), split
+            self.ctx.conv_dgrad_ex(_shape(kind, n, h, w, ci, co), dy.data_ptr(), S.W16T(ka + ".weight").data_ptr(),
+                                   dx.data_ptr(), None, _lib.ptr(add), flags | EP_INBWD, SLOPE, C.byref(ext))
+            return dx
         if isinstance(key, tuple):
             ka, kb, split = key
             self.ctx.conv_dgrad_grouped(_shape(kind, n, h, w, ci, co), dy.data_ptr(), S.W16T(ka + ".weight").data_ptr(),
@@ -102,16 +179,22 @@ class Ops:
                                 dx.data_ptr(), _lib.ptr(mask), _lib.ptr(add), flags, SLOPE)
         return dx
 
-    def conv_wgrad(self, S, key, kind, x, dy, bias=True):
+    def conv_wgrad(self, S, key, kind, x, dy, bias=True, split=False):
         if isinstance(key, tuple):       # weight gradients stay per conv: one launch per half
-            ka, kb, split = key
-            self.conv_wgrad(S, ka, kind, x[:split], dy[:split], bias)
-            self.conv_wgrad(S, kb, kind, x[split:], dy[split:], bias)
+            ka, kb, nsplit = key
+            self.conv_wgrad(S, ka, kind, x[:nsplit], dy[:nsplit], bias)
+            self.conv_wgrad(S, kb, kind, x[nsplit:], dy[nsplit:], bias)
             return
         n, h, w, cin = x.shape
         ci, co = self._io(S, key, kind)
 
         def launch():
+            if split:
+                self.ctx.conv_wgrad_split(_shape(kind, n, h, w, ci, co), x.data_ptr(), dy.data_ptr(),
+                                          S.G(key + ".weight").data_ptr())
+                if bias:
+                    self.ctx.colsum_bf16_split(dy.data_ptr(), dy.numel() // (2 * co), co, S.G(key + ".bias").data_ptr())
+                return
             self.ctx.conv_wgrad(_shape(kind, n, h, w, ci, co), x.data_ptr(), dy.data_ptr(), S.G(key + ".weight").data_ptr())
             if bias:
                 self.ctx.colsum_bf16(dy.data_ptr(), dy.numel() // co, co, S.G(key + ".bias").data_ptr())
@@ -148,6 +231,52 @@ class Ops:
         return key + suffix
 
     def res_fwd(self, S, key, x, save, out=None):
+        if not self.fused_in:
+            return self._res_fwd_old(S, key, x, save, out)
+        n, hh, ww, c = x.shape
+        ctx = self.ctx
+        sums = self.empty(2, n, 2, c, dtype=torch.float32)         # epilogue accumulators of the two convs
+        stats = self.empty(2, n, 2, c, dtype=torch.float32)        # (mean, rstd) rows, kept for the backward pass
+        h1 = self.conv_fwd(S, self._sub(key, ".model.0"), CONV_S1, x, False, sums=sums[0])
+        a1 = torch.empty_like(h1)
+        ctx.norm_apply_fwd(h1.data_ptr(), None, a1.data_ptr(), sums[0].data_ptr(), stats[0].data_ptr(), n, hh * ww, c, 0, 1,
+                           IN_EPS, SLOPE)
+        h2 = self.conv_fwd(S, self._sub(key, ".model.3"), CONV_S1, a1, False, sums=sums[1])
+        y = out if out is not None else torch.empty_like(h2)
+        ctx.norm_apply_fwd(h2.data_ptr(), x.data_ptr(), y.data_ptr(), sums[1].data_ptr(), stats[1].data_ptr(), n, hh * ww, c,
+                           1, 1, IN_EPS, SLOPE)
+        if save is not None:
+            save.append((key, x, None, stats[0], a1, h2, stats[1]))     # h1 is not needed: xhat1 is recovered from a1
+        return y
+
+    def res_bwd(self, S, saved, dout, wgrad=True, mask=None, out=None):
+        """The biases of both convs feed an InstanceNorm: their gradient is exactly zero and is left at zero (the
+        reference accumulates fp32 rounding noise there)."""
+        if not self.fused_in:
+            return self._res_bwd_old(S, saved, dout, wgrad, mask, out)
+        key, x, h1, st1, a1, h2, st2 = saved
+        k0, k3 = self._sub(key, ".model.0"), self._sub(key, ".model.3")
+        n, hh, ww, c = x.shape
+        ctx, hw = self.ctx, hh * ww
+        bs = self.empty(2, n, 2, c, dtype=torch.float32)
+        # IN #2 (res + xhat): the gradient is dout itself; its two sums need one reduction pass
+        ctx.norm_bwd_stats(dout.data_ptr(), h2.data_ptr(), st2.data_ptr(), bs[1].data_ptr(), n, hw, c, 1, 1, SLOPE)
+        dh2 = torch.empty_like(h2)
+        ctx.norm_bwd_apply(dout.data_ptr(), h2.data_ptr(), st2.data_ptr(), bs[1].data_ptr(), dh2.data_ptr(), n, hw, c, 1, 1,
+                           SLOPE)
+        if wgrad:
+            self.conv_wgrad(S, k3, CONV_S1, a1, dh2, bias=False)
+        # IN #1 (lrelu(xhat)): mask + sums in the data-gradient epilogue, then one apply pass
+        g1 = self.conv_dgrad(S, k3, CONV_S1, dh2, a1.shape, inbwd=(a1, bs[0]))
+        dh1 = torch.empty_like(a1)
+        ctx.norm_bwd_apply(g1.data_ptr(), a1.data_ptr(), st1.data_ptr(), bs[0].data_ptr(), dh1.data_ptr(), n, hw, c, 2, 1,
+                           SLOPE)
+        if wgrad:
+            self.conv_wgrad(S, k0, CONV_S1, x, dh1, bias=False)
+        return self.conv_dgrad(S, k0, CONV_S1, dh1, x.shape, mask=mask, add=dout, out=out)
+
+    # -- the stand-alone InstanceNorm kernels (round 1), kept for A/B runs (LSPS_OLD_IN=1)
+    def _res_fwd_old(self, S, key, x, save, out=None):
         h1 = self.conv_fwd(S, self._sub(key, ".model.0"), CONV_S1, x, False)
         a1, st1 = self.in_fwd(h1, 0)
         h2 = self.conv_fwd(S, self._sub(key, ".model.3"), CONV_S1, a1, False)
@@ -156,7 +285,7 @@ class Ops:
             save.append((key, x, h1, st1, a1, h2, st2))
         return y
 
-    def res_bwd(self, S, saved, dout, wgrad=True, mask=None, out=None):
+    def _res_bwd_old(self, S, saved, dout, wgrad=True, mask=None, out=None):
         key, x, h1, st1, a1, h2, st2 = saved
         k0, k3 = self._sub(key, ".model.0"), self._sub(key, ".model.3")
 
@@ -176,22 +305,24 @@ class Ops:
         return self.conv_dgrad(S, k0, CONV_S1, dh1, x.shape, mask=mask, add=dout, out=out)
 
     # ---- stems / head
-    def stem_fwd(self, S, key, img, stride, out=None):
+    def stem_fwd(self, S, key, img, stride, out=None, split=False):
         n, h, w = img.shape
-        y = out if out is not None else self.empty(n, h // stride, w // stride, 64)
-        self.ctx.stem_fwd(img.data_ptr(), S.W(key + ".weight").data_ptr(), S.W(key + ".bias").data_ptr(), y.data_ptr(),
-                          n, h, w, stride, SLOPE)
+        y = out if out is not None else self.empty(n, h // stride, w // stride, 128 if split else 64)
+        fn = self.ctx.stem_fwd_split if split else self.ctx.stem_fwd
+        fn(img.data_ptr(), S.W(key + ".weight").data_ptr(), S.W(key + ".bias").data_ptr(), y.data_ptr(), n, h, w, stride,
+           SLOPE)
         return y
 
-    def stem_wgrad(self, S, key, img, dy, stride):
+    def stem_wgrad(self, S, key, img, dy, stride, split=False):
         n, h, w = img.shape
-        self._on_side(lambda: self.ctx.stem_wgrad(img.data_ptr(), dy.data_ptr(), S.G(key + ".weight").data_ptr(),
-                                                  S.G(key + ".bias").data_ptr(), n, h, w, stride), img, dy)
+        fn = self.ctx.stem_wgrad_split if split else self.ctx.stem_wgrad
+        self._on_side(lambda: fn(img.data_ptr(), dy.data_ptr(), S.G(key + ".weight").data_ptr(),
+                                 S.G(key + ".bias").data_ptr(), n, h, w, stride), img, dy)
 
-    def stem_dgrad(self, S, key, dy, dimg, stride, accumulate):
+    def stem_dgrad(self, S, key, dy, dimg, stride, accumulate, split=False):
         n, h, w = dimg.shape
-        self.ctx.stem_dgrad(dy.data_ptr(), S.W(key + ".weight").data_ptr(), dimg.data_ptr(), n, h, w, stride,
-                            1 if accumulate else 0)
+        fn = self.ctx.stem_dgrad_split if split else self.ctx.stem_dgrad
+        fn(dy.data_ptr(), S.W(key + ".weight").data_ptr(), dimg.data_ptr(), n, h, w, stride, 1 if accumulate else 0)
 
 
 class Generator:
@@ -318,7 +449,7 @@ class Generator:
             x = o.res_fwd(S, "enc_shared.%d" % i, x, eb)
         if noise is not None:
             z = torch.empty_like(x)
-            o.ctx.noise_kl_fwd(x.data_ptr(), noise.data_ptr(), z.data_ptr(), kl_acc.data_ptr(), x.numel())
+            o.noise_kl(x, noise, z, kl_acc)
         else:
             z = x
         db = [] if save is not None else None
@@ -380,9 +511,10 @@ class Generator:
         return dx
 
     # -- full forward (lsps_nets.py:250-258): returns images (x_aa|x_ba) and (x_ab|x_bb) as [2n,128,128] tensors
-    def forward(self, xa, xb, noise, kl_acc, save=None):
+    def forward(self, xa, xb, noise, kl_acc, save=None, out_a=None, out_b=None):
         """xa [na,128,128] / xb [nb,128,128] (either may be None).  Returns decode_A and decode_B of ALL na+nb
-        latents: oa = (x_aa | x_ba), ob = (x_ab | x_bb), plus the noised shared latent."""
+        latents: oa = (x_aa | x_ba), ob = (x_ab | x_bb), plus the noised shared latent.  out_a / out_b: optional
+        [na+nb,128,128] fp32 destinations (slices of the discriminator's input batch: no concatenation copy)."""
         o = self.ops
         na = xa.shape[0] if xa is not None else 0
         nb = xb.shape[0] if xb is not None else 0
@@ -398,8 +530,8 @@ class Generator:
         ss = [] if save is not None else None
         y, z = self.shared_fwd(h, noise, kl_acc, ss)
         sd = [] if save is not None else None
-        oa = self.dec_fwd("A", y, sd)
-        ob = self.dec_fwd("B", y, sd)
+        oa = self.dec_fwd("A", y, sd, out=out_a)
+        ob = self.dec_fwd("B", y, sd, out=out_b)
         if save is not None:
             save.update(enc=se, shared=ss[0], dec=sd, na=na, nb=nb)
         return oa, ob, z
@@ -485,9 +617,12 @@ class Generator:
         for i in range(self.p["n_enc_shared_blk"]):
             x = o.res_fwd(S, "enc_shared.%d" % i, x, eb)
         z = torch.empty_like(x)
-        half = x[:n].numel()
-        o.ctx.noise_kl_fwd(x[:n].data_ptr(), noise[:n].data_ptr(), z[:n].data_ptr(), acc0.data_ptr(), half)
-        o.ctx.noise_kl_fwd(x[n:].data_ptr(), noise[n:].data_ptr(), z[n:].data_ptr(), acc1.data_ptr(), half)
+        if isinstance(noise, tuple):     # device mode: two draws with distinct Philox offsets
+            o.noise_kl(x[:n], noise, z[:n], acc0)
+            o.noise_kl(x[n:], (noise[0], noise[1], noise[2] + 1), z[n:], acc1)
+        else:
+            o.noise_kl(x[:n], noise[:n], z[:n], acc0)
+            o.noise_kl(x[n:], noise[n:], z[n:], acc1)
         db = [] if save is not None else None
         y = z
         for i in range(self.p["n_gen_shared_blk"]):
@@ -570,12 +705,22 @@ class Mapping:
 
 
 class Discriminator:
-    """SharedDis forward/backward (lsps_nets.py:86-160)."""
+    """SharedDis forward/backward (lsps_nets.py:86-160).
+
+    With a split store (ParamStore(split=True)) the whole stack runs on the bf16x3 kernels: every activation and
+    gradient tensor is [.., 2c] = (bf16 hi | bf16 lo) channel halves, every GEMM accumulates hi*hi + hi*lo + lo*hi.  The
+    discriminator is ~1 % of the step's FLOPs but its bf16 rounding is ~80 % of the adversarial-loss deviation from the
+    fp32 reference (profiles/r02_precision_ablation.json), so this is where the extra tensor-core passes go."""
 
     def __init__(self, ops, store, hp):
         self.ops, self.S, self.p = ops, store, hp
         assert hp["n_front_layer"] == 2 and hp["ch"] == 64, "kernel set covers the reference configs"
         self.training = True
+        self.split = bool(getattr(store, "split", False))
+        self.cf = hp["ch"] * 2 ** (hp["n_front_layer"] - 1 + hp["n_shared_layer"])   # trunk feature channels (2048)
+        # called with the conv key right after the LAST trunk layer's weight gradient (75 MB of the 101 MB gradient
+        # buffer, the first one the backward pass finishes) has been enqueued: the trainer starts its allreduce there
+        self.on_tail_wgrad = None
 
     def train(self, mode=True):
         self.training = mode
@@ -584,10 +729,13 @@ class Discriminator:
     def eval(self):
         return self.train(False)
 
+    def _c(self, c):
+        return 2 * c if self.split else c
+
     def front_fwd(self, dom, img, save, out=None):
         o, S, m = self.ops, self.S, "model_%s" % dom
-        f0 = o.stem_fwd(S, m + ".0.model.0", img, 2)
-        f1 = o.conv_fwd(S, m + ".1.model.0", CONV_S2, f0, True, out=out)
+        f0 = o.stem_fwd(S, m + ".0.model.0", img, 2, split=self.split)
+        f1 = o.conv_fwd(S, m + ".1.model.0", CONV_S2, f0, True, out=out, split=self.split)
         if save is not None:
             save.append(dict(dom=dom, img=img, f0=f0))
         return f1
@@ -595,19 +743,20 @@ class Discriminator:
     def front_bwd(self, sv, d1, wgrad, dimg=None, f1=None):
         o, S, m = self.ops, self.S, "model_%s" % sv["dom"]
         f0 = sv["f0"]
+        n, h, w, _ = f0.shape
         if wgrad:
-            o.conv_wgrad(S, m + ".1.model.0", CONV_S2, f0, d1)
-        d0 = o.conv_dgrad(S, m + ".1.model.0", CONV_S2, d1, f0.shape, mask=f0)
+            o.conv_wgrad(S, m + ".1.model.0", CONV_S2, f0, d1, split=self.split)
+        d0 = o.conv_dgrad(S, m + ".1.model.0", CONV_S2, d1, (n, h, w, self.p["ch"]), mask=f0, split=self.split)
         if wgrad:
-            o.stem_wgrad(S, m + ".0.model.0", sv["img"], d0, 2)
+            o.stem_wgrad(S, m + ".0.model.0", sv["img"], d0, 2, split=self.split)
         if dimg is not None:
-            o.stem_dgrad(S, m + ".0.model.0", d0, dimg, 2, accumulate=False)
+            o.stem_dgrad(S, m + ".0.model.0", d0, dimg, 2, accumulate=False, split=self.split)
 
     def trunk_fwd(self, x, save):
         o, S = self.ops, self.S
         acts = [x]
         for i in range(self.p["n_shared_layer"]):
-            x = o.conv_fwd(S, "model_S.%d.model.0" % i, CONV_S2, x, True)
+            x = o.conv_fwd(S, "model_S.%d.model.0" % i, CONV_S2, x, True, split=self.split)
             acts.append(x)
         if save is not None:
             save["acts"] = acts
@@ -620,8 +769,11 @@ class Discriminator:
         for i in range(self.p["n_shared_layer"] - 1, -1, -1):
             key = "model_S.%d.model.0" % i
             if wgrad:
-                o.conv_wgrad(S, key, CONV_S2, acts[i], d)
-            d = o.conv_dgrad(S, key, CONV_S2, d, acts[i].shape, mask=acts[i])
+                o.conv_wgrad(S, key, CONV_S2, acts[i], d, split=self.split)
+                if i == self.p["n_shared_layer"] - 1 and self.on_tail_wgrad is not None:
+                    self.on_tail_wgrad(key)
+            n, h, w, c = acts[i].shape
+            d = o.conv_dgrad(S, key, CONV_S2, d, (n, h, w, c // 2 if self.split else c), mask=acts[i], split=self.split)
         return d
 
     def features(self, imgs_a, imgs_b, save=None):
@@ -629,7 +781,7 @@ class Discriminator:
         o = self.ops
         na = imgs_a.shape[0] if imgs_a is not None else 0
         nb = imgs_b.shape[0] if imgs_b is not None else 0
-        x = o.empty(na + nb, 32, 32, 2 * self.p["ch"])
+        x = o.empty(na + nb, 32, 32, self._c(2 * self.p["ch"]))
         fr = [] if save is not None else None
         if na:
             self.front_fwd("A", imgs_a, fr, out=x[:na])
@@ -648,24 +800,65 @@ class Discriminator:
         if save["nb"]:
             self.front_bwd(save["fronts"][i], d[na:], wgrad, dimg=dimg_b)
 
+    # ---- heads and feature losses on the trunk features F [n, 2, 2, cf] (split: [n, 2, 2, 2 cf]).  Gradients w.r.t. F
+    #      are accumulated in a plain fp32 [n, 4 cf] buffer (dF) and masked / packed once by mask_grad().
+    def rows(self, F):
+        return F.shape[0] * F.shape[1] * F.shape[2]
+
+    def _fptr(self, F, img):
+        return F.data_ptr() + img * F[0].numel() * F.element_size()
+
     def logits(self, F):
         o, S = self.ops, self.S
-        rows = F.numel() // F.shape[-1]
-        lg = o.empty(rows, dtype=torch.float32)
-        o.ctx.dhead_fwd(F.data_ptr(), S.W("D.weight").data_ptr(), S.W("D.bias").data_ptr(), lg.data_ptr(), rows,
-                        F.shape[-1])
+        lg = o.empty(self.rows(F), dtype=torch.float32)
+        fn = o.ctx.dhead_fwd_split if self.split else o.ctx.dhead_fwd
+        fn(F.data_ptr(), S.W("D.weight").data_ptr(), S.W("D.bias").data_ptr(), lg.data_ptr(), self.rows(F), self.cf)
         return lg
 
-    def post(self, F):
+    def logits_bwd(self, F, dlg, dF, wgrad):
+        o, S = self.ops, self.S
+        fn = o.ctx.dhead_bwd_split if self.split else o.ctx.dhead_bwd
+        fn(F.data_ptr(), S.W("D.weight").data_ptr(), dlg.data_ptr(), dF.data_ptr(),
+           S.G("D.weight").data_ptr() if wgrad else None, S.G("D.bias").data_ptr() if wgrad else None, self.rows(F), self.cf)
+
+    def l1_feat(self, F, img_a, img_b, nimg, dF, scale, acc):
+        """acc += sum |F[img_a:img_a+nimg] - F[img_b:img_b+nimg]| ; dF rows get +-scale*sign (lsps_trainer.py:171-177)."""
+        o = self.ops
+        per = 4 * self.cf
+        args = (self._fptr(F, img_a), self._fptr(F, img_b), dF[img_a:].data_ptr(), dF[img_b:].data_ptr(), scale,
+                acc.data_ptr(), nimg * per)
+        if self.split:
+            o.ctx.l1_feat_split(*args, self.cf)
+        else:
+            o.ctx.l1_feat(*args)
+
+    def mask_grad(self, dF, F):
+        """dF fp32 [n, 4 cf] -> gradient w.r.t. the pre-activation of the last trunk conv, in F's storage format."""
+        o = self.ops
+        out = torch.empty_like(F)
+        if self.split:
+            o.ctx.mask_to_bf16_split(dF.data_ptr(), F.data_ptr(), out.data_ptr(), SLOPE, dF.numel(), self.cf)
+        else:
+            o.ctx.mask_to_bf16(dF.data_ptr(), F.data_ptr(), out.data_ptr(), SLOPE, dF.numel())
+        return out
+
+    def post(self, F, img0=0, nimg=None):
         """Post = Conv2d(2048, post_dim, 2) on the 2x2 map == FC 8192 -> post_dim (lsps_nets.py:123,135-145)."""
         o, S = self.ops, self.S
-        n = F.shape[0]
-        k = F.numel() // n
+        n = F.shape[0] - img0 if nimg is None else nimg
+        k = 4 * self.cf
         pd = self.p["post_dim"]
         out = o.empty(n, pd, dtype=torch.float32)
-        o.ctx.linear_fwd(F.data_ptr(), 1, S.W("Post.weight").data_ptr(), S.W("Post.bias").data_ptr(), out.data_ptr(),
-                         n, pd, k, 0, SLOPE)
+        o.ctx.linear_fwd(self._fptr(F, img0), self.cf if self.split else 1, S.W("Post.weight").data_ptr(),
+                         S.W("Post.bias").data_ptr(), out.data_ptr(), n, pd, k, 0, SLOPE)
         return out
+
+    def post_bwd(self, F, img0, nimg, dp, dF):
+        """dF[img0:img0+nimg] = dp . W_post (overwrites those rows) ; Post weight / bias gradients accumulate."""
+        o, S = self.ops, self.S
+        o.ctx.linear_bwd(self._fptr(F, img0), self.cf if self.split else 1, S.W("Post.weight").data_ptr(), dp.data_ptr(),
+                         dF[img0:].data_ptr(), 0, S.G("Post.weight").data_ptr(), S.G("Post.bias").data_ptr(), nimg,
+                         self.p["post_dim"], 4 * self.cf)
 
     # public inference API used by the drivers (depth_train.py:197-206)
     def _regress(self, dom, x):

@@ -65,8 +65,11 @@ class ParamStore:
     """entries: list of (key, shape, kind, law, fan_in).
     kind in conv3|deconv3|deconv4|map0|stem|head|dhead|post|linear|bias."""
 
-    def __init__(self, entries, device, lr, weight_decay, betas=(0.5, 0.999), eps=1e-8):
+    def __init__(self, entries, device, lr, weight_decay, betas=(0.5, 0.999), eps=1e-8, split=False):
+        """split: keep a second bf16 copy of every operand tensor holding the rounding remainder (w - bf16(w)), for the
+        split-bf16 ("bf16x3") kernels -- hi + lo carry 16 mantissa bits."""
         self.device = torch.device(device)
+        self.split = bool(split)
         self.entries = OrderedDict()
         off = dg = 0
         for e in entries:
@@ -87,6 +90,20 @@ class ParamStore:
         self.v = torch.zeros(off, dtype=torch.float32, **kw)
         self.w16 = torch.zeros(off, dtype=torch.bfloat16, **kw)           # forward operands [tap][co][ci]
         self.w16t = torch.zeros(max(dg, 8), dtype=torch.bfloat16, **kw)   # dgrad operands  [tap][ci][co]
+        self.w16l = torch.zeros(off, dtype=torch.bfloat16, **kw) if self.split else None
+        self.w16tl = torch.zeros(max(dg, 8), dtype=torch.bfloat16, **kw) if self.split else None
+        # one-launch transposition of every conv weight (lsps_pack_dgrad_multi): {w_off, wt_off, taps, cout, cin, tile0}
+        rows, tile0 = [], 0
+        for ent in self.entries.values():
+            if ent.dg_off < 0:
+                continue
+            co, ci = (ent.shape[0], ent.shape[1]) if ent.kind == "conv3" else (ent.shape[1], ent.shape[0])
+            taps = 16 if ent.kind == "deconv4" else 9
+            rows.append([ent.off, ent.dg_off, taps, co, ci, tile0])
+            tile0 += taps * ((ci + 31) // 32) * ((co + 31) // 32)
+        self._pack_count, self._pack_tiles = len(rows), tile0
+        rows.append([0, 0, 0, 0, 0, tile0])
+        self._pack_desc = torch.tensor(rows, dtype=torch.int64).to(self.device) if self._pack_count else None
         self.lr, self.base_lr, self.wd, self.betas, self.eps = lr, lr, weight_decay, betas, eps
         self.ctx = _lib.context(self.device.index if self.device.index is not None else torch.cuda.current_device())
 
@@ -107,6 +124,13 @@ class ParamStore:
     def W16T(self, key):
         e = self.entries[key]
         return self.w16t[e.dg_off:e.dg_off + e.numel]
+
+    def W16L(self, key):
+        return self._view(self.w16l, key)
+
+    def W16TL(self, key):
+        e = self.entries[key]
+        return self.w16tl[e.dg_off:e.dg_off + e.numel]
 
     # --- reference-compatible (de)serialisation
     def state_dict(self):
@@ -146,22 +170,22 @@ class ParamStore:
 
     def refresh_operands(self):
         """bf16 forward copy of everything + transposed dgrad copies of the 3x3 (de)conv weights."""
-        self.ctx.f32_to_bf16(self.w.data_ptr(), self.w16.data_ptr(), self.size)
+        if self.split:
+            self.ctx.f32_split_bf16(self.w.data_ptr(), self.w16.data_ptr(), self.w16l.data_ptr(), self.size)
+        else:
+            self.ctx.f32_to_bf16(self.w.data_ptr(), self.w16.data_ptr(), self.size)
         self.refresh_dgrad_operands()
 
-    def refresh_dgrad_operands(self, keys=None):
-        for k, e in self.entries.items():
-            if e.dg_off < 0 or (keys is not None and k not in keys):
-                continue
-            if e.kind == "conv3":
-                co, ci = e.shape[0], e.shape[1]
-            else:
-                ci, co = e.shape[0], e.shape[1]
-            self.ctx.pack_dgrad(self.W(k).data_ptr(), self.W16T(k).data_ptr(), 16 if e.kind == "deconv4" else 9, co, ci)
+    def refresh_dgrad_operands(self):
+        """[tap][ci][co] bf16 copies of every conv weight (and their remainders for a split store): ONE launch."""
+        if self._pack_count:
+            self.ctx.pack_dgrad_multi(self.w.data_ptr(), self.w16t.data_ptr(),
+                                      self.w16tl.data_ptr() if self.split else None, self._pack_desc.data_ptr(),
+                                      self._pack_count, self._pack_tiles)
 
     # --- optimiser
     def zero_grad(self):
-        self.gbuf.zero_()
+        self.ctx.memset(self.gbuf.data_ptr(), 0, self.gbuf.numel() * 4)
 
     def _segments(self, active):
         """Maximal runs of consecutive active tensors with equal step counts -> [(first, last)] entry indices."""
@@ -199,9 +223,10 @@ class ParamStore:
             hp = None
             if hyper is not None:
                 hp = hyper[2 * si:].data_ptr()
-            self.ctx.adam(self.w[lo:].data_ptr(), self.g[lo:].data_ptr(), self.m[lo:].data_ptr(),
-                          self.v[lo:].data_ptr(), self.w16[lo:].data_ptr(), hi - lo, float(self.lr), self.betas[0],
-                          self.betas[1], self.eps, float(self.wd), step, float(grad_scale), hp)
+            self.ctx.adam_ex(self.w[lo:].data_ptr(), self.g[lo:].data_ptr(), self.m[lo:].data_ptr(),
+                             self.v[lo:].data_ptr(), self.w16[lo:].data_ptr(),
+                             self.w16l[lo:].data_ptr() if self.split else None, hi - lo, float(self.lr), self.betas[0],
+                             self.betas[1], self.eps, float(self.wd), step, float(grad_scale), hp)
         return segs
 
     def segments_consistent(self, segs):

@@ -5,6 +5,7 @@ reference builds by concatenating `groups` per-domain blocks along batch (e.g. t
 gen.forward = [domain-a block | domain-b block]) are sharded block-wise so that every rank sees exactly the rows
 of its own samples."""
 import torch
+import torch.distributed as dist
 
 
 def shard_rows(t, groups, world, rank):
@@ -29,3 +30,24 @@ def global_count(local, world):
     """Every loss mean is normalised by the global element count so that sum-allreduced gradients equal the
     single-process gradients of the global batch."""
     return local * world
+
+
+def world_rank():
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_world_size(), dist.get_rank()
+    return 1, 0
+
+
+def allreduce_sum_(flat):
+    """The step's one collective: in-place sum over ranks of a flat buffer (gradients + loss sums).  NCCL on the GPUs,
+    gloo in the CPU tests; a no-op for a single process."""
+    if world_rank()[0] > 1:
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+    return flat
+
+
+def feature_sources(n_a, n_b, world, rank):
+    """(ka, kb, idx): the source images of post_update's feature-matching sub-graph this rank runs the generator on, and
+    their rows in the reference's (n_a + n_b)-row latent-noise draw (domain-a rows first)."""
+    ka, kb = source_assignment(n_a, n_b, world, rank)
+    return ka, kb, ka + [n_a + i for i in kb]

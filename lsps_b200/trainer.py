@@ -16,7 +16,7 @@ import torch.distributed as dist
 
 from . import _lib
 from .engine import Ops, Generator, Discriminator, PoseVAE, Mapping, SLOPE
-from .sharding import shard_rows, source_assignment
+from .sharding import shard_rows, feature_sources, allreduce_sum_, world_rank
 from .params import ParamStore, MultiStepLR, Optimizer, gen_entries, dis_entries, vae_entries, map_entries
 
 _LATENT = 256 * 32 * 32
@@ -24,9 +24,7 @@ _NPIX = 128 * 128
 
 
 def _world():
-    if dist.is_available() and dist.is_initialized():
-        return dist.get_world_size(), dist.get_rank()
-    return 1, 0
+    return world_rank()
 
 
 def _img(t, dev):
@@ -52,8 +50,14 @@ class _JointSchedule:
 
 
 class LSPSTrainerB200(object):
-    def __init__(self, hyperparameters, device=None, seed=0, noise="host", graphs=False):
+    def __init__(self, hyperparameters, device=None, seed=0, noise="host", graphs=False, precision=None):
+        """precision: "mixed" (default) runs the discriminator stack on the split-bf16 ("bf16x3") kernels -- ~1 % of the
+        step's FLOPs, ~80 % of the adversarial-loss deviation from the fp32 reference when run in plain bf16
+        (profiles/r02_precision_ablation.json); "bf16" runs every conv with plain bf16 operands.  LSPS_PRECISION
+        overrides the default."""
         hp = hyperparameters
+        self.precision = precision or os.environ.get("LSPS_PRECISION", "mixed")
+        assert self.precision in ("mixed", "bf16"), self.precision
         if device is None:
             device = torch.cuda.current_device() if torch.cuda.is_available() else 0
         self.device = torch.device("cuda", device if isinstance(device, int) else torch.device(device).index)
@@ -67,7 +71,7 @@ class LSPSTrainerB200(object):
         lr = hp["lr"]
         # lsps_trainer.py:26-31 -- Adam betas (0.5, 0.999); weight decay 1e-4 (dis, gen) / 1e-3 (vae); vae lr = 10*lr
         self.gen_store = ParamStore(gen_entries(hp["gen"]), self.device, lr, 1e-4)
-        self.dis_store = ParamStore(dis_entries(hp["dis"]), self.device, lr, 1e-4)
+        self.dis_store = ParamStore(dis_entries(hp["dis"]), self.device, lr, 1e-4, split=self.precision == "mixed")
         self.vae_store = ParamStore(vae_entries(hp["vae"]), self.device, lr * 10.0, 1e-3)
         self.gen_store.init_(seed + 1)
         self.dis_store.init_(seed + 2)
@@ -94,6 +98,15 @@ class LSPSTrainerB200(object):
         self.vae_sch = MultiStepLR(self.vae_store, [125, 175], 0.1)
         self._scratch = torch.zeros(8, dtype=torch.float32, device=self.device)
         self.last_outputs = None
+        self._comm = torch.cuda.Stream(device=self.device)
+        self._early = {}
+        self.dis.on_tail_wgrad = lambda key: self._allreduce_early(self.dis_store, key)
+        # device-noise mode: Philox counters of the in-kernel draws; every rank gets its own stream (its samples differ)
+        world, rank = _world()
+        self._rng_seed = (int(seed) * 7919 + 1000003 * rank + 12345) & 0x7FFFFFFFFFFFFFFF
+        self._rng_offset = 0
+        if noise == "device":
+            torch.cuda.manual_seed(self._rng_seed & 0x7FFFFFFF)     # the torch.randn draws that remain (pose-VAE, graphs)
 
     # ------------------------------------------------------------------ plumbing
     def cuda(self, gpu=None):
@@ -112,7 +125,10 @@ class LSPSTrainerB200(object):
             else:
                 t = shard_rows(torch.randn(n * world, 256, 32, 32), groups, world, rank)
             return t.to(self.device).permute(0, 2, 3, 1).contiguous()
-        return torch.randn(n, 32, 32, 256, device=self.device)
+        if torch.cuda.is_current_stream_capturing():
+            return torch.randn(n, 32, 32, 256, device=self.device)   # graph-safe generator state; a baked counter is not
+        self._rng_offset += 2
+        return ("philox", self._rng_seed, self._rng_offset)
 
     def _vae_noise(self, shape):
         """poseVAE.encode draw (lsps_nets.py:77): torch.normal(zeros, std=0.05) on the host."""
@@ -125,9 +141,38 @@ class LSPSTrainerB200(object):
         return torch.randn(shape, device=self.device) * 0.05
 
     def _allreduce(self, store):
+        """The update's ONE exchange: sum-allreduce of the flat gradient buffer (+ loss sums in its tail).  When a slice
+        of it was already started on the communication stream (_allreduce_early), only the rest goes now and the
+        compute stream then waits for the early part."""
         world, _ = _world()
-        if world > 1:
-            dist.all_reduce(store.gbuf, op=dist.ReduceOp.SUM)
+        if world <= 1:
+            return
+        early = self._early.pop(id(store), None)
+        if early is None:
+            allreduce_sum_(store.gbuf)
+            return
+        lo, hi, ev = early
+        if lo > 0:
+            dist.all_reduce(store.gbuf[:lo], op=dist.ReduceOp.SUM)
+        dist.all_reduce(store.gbuf[hi:], op=dist.ReduceOp.SUM)
+        torch.cuda.current_stream().wait_event(ev)
+
+    def _allreduce_early(self, store, key):
+        """Starts the allreduce of one conv's gradient slice (weight + bias) on the communication stream as soon as the
+        kernels that produce it have been enqueued, so that it overlaps the rest of the backward pass."""
+        world, _ = _world()
+        if world <= 1 or torch.cuda.is_current_stream_capturing() or os.environ.get("LSPS_NO_EARLY_AR", "0") == "1":
+            return
+        from .params import _round_up
+        ew, eb = store.entries[key + ".weight"], store.entries[key + ".bias"]
+        lo, hi = ew.off, eb.off + _round_up(eb.numel)
+        assert hi > lo and eb.off == ew.off + _round_up(ew.numel)
+        self._comm.wait_event(self.ops.side_event())
+        with torch.cuda.stream(self._comm):
+            dist.all_reduce(store.gbuf[lo:hi], op=dist.ReduceOp.SUM)
+            done = torch.cuda.Event()
+            done.record(self._comm)
+        self._early[id(store)] = (lo, hi, done)
 
     def _p(self, t):
         return t.data_ptr()
@@ -188,42 +233,42 @@ class LSPSTrainerB200(object):
         Bg = B * world
         D.zero_grad()
         noise = self._latent_noise(2 * B, groups=2)
-        oa, ob, _ = self.gen.forward(ia, ib, noise, self._scratch)           # no activations kept: gen gets no grads
-        x_aa, x_ba, x_ab, x_bb = oa[:B], oa[B:], ob[:B], ob[B:]
         train_map = bool(hp.get("train_map", False))
+        ndiv = 4 if train_map else 3
+        # discriminator input batches, by group: a = (ia | x_aa | x_ba [| dec_a]), b = (ib | x_ab | x_bb [| dec_b]).  The
+        # reference concatenates (ia, x_ba, x_aa) (lsps_trainer.py:156-165); the order of the groups inside the batch is
+        # immaterial (every layer is per-sample), and this one lets both decoders write straight into the batch.
+        o = self.ops
+        imgs_a, imgs_b = o.empty(ndiv * B, 128, 128, dtype=torch.float32), o.empty(ndiv * B, 128, 128, dtype=torch.float32)
+        o.copy_into(imgs_a[:B], ia)
+        o.copy_into(imgs_b[:B], ib)
+        self.gen.forward(ia, ib, noise, self._scratch, out_a=imgs_a[B:3 * B], out_b=imgs_b[B:3 * B])   # gen gets no grads
         if train_map:                                                        # :147-158, no activations kept either
             _, dec_a, dec_b = self._map_decode(labels_a, labels_b, hp)
-            imgs_a, imgs_b, ndiv = torch.cat((ia, x_ba, x_aa, dec_a), 0), torch.cat((ib, x_ab, x_bb, dec_b), 0), 4
-        elif feat_mat:
-            imgs_a, imgs_b, ndiv = torch.cat((ia, x_ba, x_aa), 0), torch.cat((ib, x_ab, x_bb), 0), 3
-        else:
-            imgs_a, imgs_b, ndiv = torch.cat((ia, x_ba), 0), torch.cat((ib, x_ab), 0), 2
+            o.copy_into(imgs_a[3 * B:], dec_a)
+            o.copy_into(imgs_b[3 * B:], dec_b)
         sv = {}
-        F = dis.features(imgs_a, imgs_b, sv)                                 # [2*ndiv*B, 2, 2, 2048]
-        cf = F.shape[-1]
+        F = dis.features(imgs_a, imgs_b, sv)                                 # [2*ndiv*B, 2, 2, 2048] (split: 2 x 2048)
+        cf = dis.cf
         lg = dis.logits(F)
-        dlg = torch.zeros_like(lg)
+        dlg = o.zeros(lg.numel())
         r = 4 * B                                                            # logits per group
         scale = hp["gan_w"] / float(4 * Bg)
-        for off in (0, ndiv * r):                                            # domain a, domain b
-            ctx.bce_logits(lg[off:].data_ptr(), 1.0, scale, dlg[off:].data_ptr(), D.acc[0:].data_ptr(), r)
-            ctx.bce_logits(lg[off + r:].data_ptr(), 0.0, scale, dlg[off + r:].data_ptr(), D.acc[2:].data_ptr(), r)
-            if train_map:                                                    # ad_fake_dec (:201-204): 4th group vs zeros
-                ctx.bce_logits(lg[off + 3 * r:].data_ptr(), 0.0, scale, dlg[off + 3 * r:].data_ptr(),
-                               D.acc[8:].data_ptr(), r)
-        dF = torch.zeros(F.numel(), dtype=torch.float32, device=self.device)
-        ctx.dhead_bwd(F.data_ptr(), D.W("D.weight").data_ptr(), dlg.data_ptr(), dF.data_ptr(),
-                      D.G("D.weight").data_ptr(), D.G("D.bias").data_ptr(), lg.numel(), cf)
+        A_REAL, A_XAA, A_XBA, B_REAL, B_XAB, B_XBB = 0, 1, 2, ndiv, ndiv + 1, ndiv + 2
+        for real, fake in ((A_REAL, A_XBA), (B_REAL, B_XAB)):
+            ctx.bce_logits(lg[real * r:].data_ptr(), 1.0, scale, dlg[real * r:].data_ptr(), D.acc[0:].data_ptr(), r)
+            ctx.bce_logits(lg[fake * r:].data_ptr(), 0.0, scale, dlg[fake * r:].data_ptr(), D.acc[2:].data_ptr(), r)
+        if train_map:                                                        # ad_fake_dec (:201-204): 4th group vs zeros
+            for dec in (3, ndiv + 3):
+                ctx.bce_logits(lg[dec * r:].data_ptr(), 0.0, scale, dlg[dec * r:].data_ptr(), D.acc[8:].data_ptr(), r)
+        dF = o.zeros(F.shape[0], 4 * cf)
+        dis.logits_bwd(F, dlg, dF, wgrad=True)
         if feat_mat:
-            fs = B * 4 * cf
-            Ff = F.reshape(-1)
             fscale = hp["feature_w"] / float(Bg * 4 * cf)
-            # mean|F_b(x_ab) - F_a(x_aa)| + mean|F_a(x_ba) - F_b(x_bb)|   groups: a=(ia,x_ba,x_aa[,dec]) b=(ib,x_ab,x_bb[,dec])
-            for ga, gb in ((ndiv + 1, 2), (1, ndiv + 2)):
-                ctx.l1_feat(Ff[ga * fs:].data_ptr(), Ff[gb * fs:].data_ptr(), dF[ga * fs:].data_ptr(),
-                            dF[gb * fs:].data_ptr(), fscale, D.acc[4:].data_ptr(), fs)
-        dFm = torch.empty_like(F)
-        ctx.mask_to_bf16(dF.data_ptr(), F.data_ptr(), dFm.data_ptr(), SLOPE, F.numel())
+            # mean|F_b(x_ab) - F_a(x_aa)| + mean|F_a(x_ba) - F_b(x_bb)|      (lsps_trainer.py:171-177)
+            for ga, gb in ((B_XAB, A_XAA), (A_XBA, B_XBB)):
+                dis.l1_feat(F, ga * B, gb * B, B, dF, fscale, D.acc[4:])
+        dFm = dis.mask_grad(dF, F)
         dis.features_bwd(sv, dFm, wgrad=True)
         self.ops.join_side()
         del sv
@@ -258,7 +303,8 @@ class LSPSTrainerB200(object):
         oa, ob, shared = gen.forward(ia, ib, n2, G.acc[2:], s1)
         x_aa, x_ba, x_ab, x_bb = oa[:B], oa[B:], ob[:B], ob[B:]
         s2 = {}
-        x_bab, x_aba = gen.forward_cycle(x_ba, x_ab, torch.cat((n3, n4), 0), G.acc[3:], G.acc[4:], s2)
+        x_bab, x_aba = gen.forward_cycle(x_ba, x_ab, n3 if isinstance(n3, tuple) else torch.cat((n3, n4), 0), G.acc[3:],
+                                         G.acc[4:], s2)
         del n2, n3, n4
         dec_a, dec_b, nd = x_ba, x_ab, 1
         if train_map:                        # :84-99 (the vae.encode draw comes after the three latent draws, as there)
@@ -267,23 +313,21 @@ class LSPSTrainerB200(object):
             nd = 2
         # adversarial term through the discriminator (data gradient only)
         sd = {}
-        F = dis.features(torch.cat((x_ba, dec_a), 0) if train_map else x_ba,
-                         torch.cat((x_ab, dec_b), 0) if train_map else x_ab, sd)
+        F = dis.features(self.ops.cat((x_ba, dec_a)) if train_map else x_ba,
+                         self.ops.cat((x_ab, dec_b)) if train_map else x_ab, sd)
         lg = dis.logits(F)
         dlg = torch.empty_like(lg)
         ctx.bce_logits(lg.data_ptr(), 1.0, hp["gan_w"] / float(4 * nd * Bg), dlg.data_ptr(), G.acc[0:].data_ptr(), lg.numel())
-        dF = torch.zeros(F.numel(), dtype=torch.float32, device=self.device)
-        ctx.dhead_bwd(F.data_ptr(), D.W("D.weight").data_ptr(), dlg.data_ptr(), dF.data_ptr(), None, None, lg.numel(),
-                      F.shape[-1])
-        dFm = torch.empty_like(F)
-        ctx.mask_to_bf16(dF.data_ptr(), F.data_ptr(), dFm.data_ptr(), SLOPE, F.numel())
+        dF = self.ops.zeros(F.shape[0], 4 * dis.cf)
+        dis.logits_bwd(F, dlg, dF, wgrad=False)
+        dFm = dis.mask_grad(dF, F)
         doa = torch.empty_like(oa)           # d/d(x_aa | x_ba)
         dob = torch.empty_like(ob)           # d/d(x_ab | x_bb)
         if train_map:
             dia, dib = torch.empty(2 * B, 128, 128, device=self.device), torch.empty(2 * B, 128, 128, device=self.device)
             dis.features_bwd(sd, dFm, wgrad=False, dimg_a=dia, dimg_b=dib)
-            doa[B:].copy_(dia[:B])
-            dob[:B].copy_(dib[:B])
+            self.ops.copy_into(doa[B:], dia[:B])
+            self.ops.copy_into(dob[:B], dib[:B])
             d_dec_a, d_dec_b = dia[B:], dib[B:]
         else:
             dis.features_bwd(sd, dFm, wgrad=False, dimg_a=doa[B:], dimg_b=dob[:B])
@@ -375,12 +419,11 @@ class LSPSTrainerB200(object):
             # per-sample ops make it exact to give source image a_i to rank i % world and b_i to rank (4+i) % world
             n4 = src_a.shape[0]
             noise = self._latent_noise(src_a.shape[0] + src_b.shape[0], shard=False)
-            ka, kb = source_assignment(src_a.shape[0], src_b.shape[0], world, rank)
+            ka, kb, idx = feature_sources(src_a.shape[0], src_b.shape[0], world, rank)
             if ka or kb:
                 xa = (src_a if len(ka) == src_a.shape[0] else src_a[ka]) if ka else None
                 xb = (src_b if len(kb) == src_b.shape[0] else src_b[kb]) if kb else None
-                idx = ka + [src_a.shape[0] + i for i in kb]
-                nz = noise if len(idx) == noise.shape[0] else noise[idx].contiguous()
+                nz = noise if (isinstance(noise, tuple) or len(idx) == noise.shape[0]) else noise[idx].contiguous()
                 oa, ob, _ = self.gen.forward(xa, xb, nz, self._scratch)     # (x_aa|x_ba), (x_ab|x_bb)
                 na, nb = len(ka), len(kb)
                 nf = na + nb
@@ -388,30 +431,25 @@ class LSPSTrainerB200(object):
                 outs = (oa[:na], oa[na:], ob[:na], ob[na:])
         imgs_a = [t for t in (fa_extra, ia if reg_a else None) if t is not None]
         imgs_b = [t for t in (fb_extra, ib if reg_b else None) if t is not None]
-        imgs_a = torch.cat(imgs_a, 0) if len(imgs_a) > 1 else (imgs_a[0] if imgs_a else None)
-        imgs_b = torch.cat(imgs_b, 0) if len(imgs_b) > 1 else (imgs_b[0] if imgs_b else None)
+        imgs_a = self.ops.cat(imgs_a) if imgs_a else None
+        imgs_b = self.ops.cat(imgs_b) if imgs_b else None
         sv = {}
         F = dis.features(imgs_a, imgs_b, sv)
-        cf = F.shape[-1]
+        cf = dis.cf
         per = 4 * cf
         n_a = imgs_a.shape[0] if imgs_a is not None else 0
-        Ff = F.reshape(F.shape[0], per)
-        dF = torch.zeros(F.shape[0], per, dtype=torch.float32, device=self.device)
+        dF = self.ops.zeros(F.shape[0], per)
         pd = hp["dis"]["post_dim"]
         preds = []
         for dom, on, row0, labels, slot in (("a", reg_a, nf, la, 5), ("b", reg_b, n_a + nf, lb, 6)):
             if not on:
                 continue
-            Fr = Ff[row0:row0 + B]
-            p = self.ops.empty(B, pd, dtype=torch.float32)
-            ctx.linear_fwd(Fr.data_ptr(), 1, D.W("Post.weight").data_ptr(), D.W("Post.bias").data_ptr(), p.data_ptr(),
-                           B, pd, per, 0, SLOPE)
+            p = dis.post(F, row0, B)
             e = self.vae.encode(labels)[0]
             dp = torch.empty_like(p)
             ctx.mse(p.data_ptr(), e.data_ptr(), dp.data_ptr(), 2.0 * hp["reg_w"] / float(Bg * pd), D.acc[slot:].data_ptr(),
                     p.numel())
-            ctx.linear_bwd(Fr.data_ptr(), 1, D.W("Post.weight").data_ptr(), dp.data_ptr(), dF[row0:].data_ptr(), 0,
-                           D.G("Post.weight").data_ptr(), D.G("Post.bias").data_ptr(), B, pd, per)
+            dis.post_bwd(F, row0, B, dp, dF)
             preds.append(p)
         if nf:
             na = outs[0].shape[0]
@@ -419,13 +457,10 @@ class LSPSTrainerB200(object):
             fscale = hp["feature_w_reg"] / float(n4 * per)
             # rows: FA part = (x_aa[na] | x_ba[nb]) ; FB part (offset n_a) = (x_ab[na] | x_bb[nb])
             if na:   # mean|f_ab - f_aa|
-                ctx.l1_feat(Ff[n_a:].data_ptr(), Ff[0:].data_ptr(), dF[n_a:].data_ptr(), dF[0:].data_ptr(), fscale,
-                            D.acc[7:].data_ptr(), na * per)
+                dis.l1_feat(F, n_a, 0, na, dF, fscale, D.acc[7:])
             if nb:   # mean|f_ba - f_bb|
-                ctx.l1_feat(Ff[na:].data_ptr(), Ff[n_a + na:].data_ptr(), dF[na:].data_ptr(), dF[n_a + na:].data_ptr(),
-                            fscale, D.acc[7:].data_ptr(), nb * per)
-        dFm = torch.empty_like(F)
-        ctx.mask_to_bf16(dF.data_ptr(), F.data_ptr(), dFm.data_ptr(), SLOPE, F.numel())
+                dis.l1_feat(F, na, n_a + na, nb, dF, fscale, D.acc[7:])
+        dFm = dis.mask_grad(dF, F)
         dis.features_bwd(sv, dFm, wgrad=True)
         self.ops.join_side()
         return dict(outs=outs, preds=preds, Bg=Bg, pd=pd, per=per, n4=n4, feat=feat)

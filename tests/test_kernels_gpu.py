@@ -371,3 +371,263 @@ def test_pack_dgrad(ctx):
     wt = torch.empty(9, 64, 128, device="cuda", dtype=torch.bfloat16)
     ctx.pack_dgrad(w.data_ptr(), wt.data_ptr(), 9, 128, 64)
     assert torch.equal(wt, w.transpose(1, 2).bfloat16())
+
+
+# ------------------------------------------------------------------ round 2: statistics in the conv epilogues
+@pytest.mark.parametrize("n,cin,cout,hw,grouped", [(3, 256, 256, 32, False), (40, 256, 256, 32, False),
+                                                    (80, 256, 256, 32, True), (2, 64, 128, 16, False)])
+def test_conv_epilogue_statistics_and_norm_apply(ctx, n, cin, cout, hw, grouped):
+    """LSPS_EP_STATS: per-(image, channel) sum / sum of squares of the fp32 conv result from the epilogue, then
+    lsps_norm_apply_fwd (lrelu / residual) against F.instance_norm on the fp32 conv output of torch."""
+    from lsps_b200._lib import ConvShape, ConvExt
+    g = gen(300 + n)
+    x = torch.randn(n, cin, hw, hw, device="cuda", generator=g).bfloat16().float()
+    ws = [(torch.randn(cout, cin, 3, 3, device="cuda", generator=g) * 0.05).bfloat16().float() for _ in range(2)]
+    bs = [torch.randn(cout, device="cuda", generator=g) for _ in range(2)]
+    pack = lambda t: t.permute(2, 3, 0, 1).reshape(9, cout, cin)
+    flat = torch.cat([pack(w_).reshape(-1) for w_ in ws]).bfloat16().contiguous()
+    per = 9 * cout * cin
+    split = n // 2 if grouped else 0
+    if grouped:
+        ref = torch.cat((F.conv2d(x[:split], ws[0], bs[0], padding=1), F.conv2d(x[split:], ws[1], bs[1], padding=1)), 0)
+    else:
+        ref = F.conv2d(x, ws[0], bs[0], padding=1)
+    xb = nhwc16(x)
+    yb = torch.empty(n, hw, hw, cout, device="cuda", dtype=torch.bfloat16)
+    sums = torch.full((n, 2, cout), 7.0, device="cuda")            # the call must zero it
+    ext = ConvExt()
+    ext.sums = sums.data_ptr()
+    if grouped:
+        ext.w2, ext.bias2, ext.n_split = flat[per:].data_ptr(), bs[1].data_ptr(), split
+    ctx.conv_fwd_ex(C.byref(ConvShape(0, n, hw, hw, cin, cout)), xb.data_ptr(), flat.data_ptr(), bs[0].data_ptr(),
+                    yb.data_ptr(), 1 | 16, SLOPE, C.byref(ext))
+    assert rel_l2(nchw32(yb), ref) < BF16_L2
+    s1, s2 = ref.sum((2, 3)), (ref * ref).sum((2, 3))
+    assert (sums[:, 0] - s1).abs().max().item() < 2e-3 * (ref.std().item() * hw)      # sqrt(hw*hw) random-walk scale
+    assert rel_l2(sums[:, 1], s2) < 1e-4
+    # forward apply, both modes, against instance_norm of the STORED (bf16) conv output with the epilogue's statistics
+    hs = nchw32(yb)
+    res = torch.randn(n, cout, hw, hw, device="cuda", generator=g).bfloat16()
+    stats = torch.empty(n, 2, cout, device="cuda")
+    y0, y1 = torch.empty_like(yb), torch.empty_like(yb)
+    ctx.norm_apply_fwd(yb.data_ptr(), None, y0.data_ptr(), sums.data_ptr(), stats.data_ptr(), n, hw * hw, cout, 0, 1, 1e-5, SLOPE)
+    resb = res.permute(0, 2, 3, 1).contiguous()
+    ctx.norm_apply_fwd(yb.data_ptr(), resb.data_ptr(), y1.data_ptr(), sums.data_ptr(), stats.data_ptr(), n, hw * hw, cout, 1, 1,
+                       1e-5, SLOPE)
+    xn = F.instance_norm(ref, eps=1e-5)
+    assert rel_l2(nchw32(y0), F.leaky_relu(xn, SLOPE)) < 2 * BF16_L2
+    assert rel_l2(nchw32(y1), res.float() + xn) < 2 * BF16_L2
+    mean, var = ref.mean((2, 3)), ref.var((2, 3), unbiased=False)
+    assert (stats[:, 0] - mean).abs().max().item() < 2e-3 * ref.std().item()
+    assert rel_l2(stats[:, 1], torch.rsqrt(var + 1e-5)) < 1e-3
+    del hs
+
+
+@pytest.mark.parametrize("n,grouped", [(3, False), (40, False), (80, True)])
+def test_instnorm_backward_through_dgrad_epilogue(ctx, n, grouped):
+    """A whole LeakyINSResBlock backward front half on the new kernels: norm_bwd_stats + norm_bwd_apply for `res + IN(h2)`,
+    the data gradient with LSPS_EP_INBWD for lrelu(IN(h1)), norm_bwd_apply -- against torch autograd in fp32."""
+    from lsps_b200._lib import ConvShape, ConvExt
+    g = gen(400 + n)
+    c, hw = 256, 32
+    split = n // 2 if grouped else 0
+    h1 = torch.randn(n, c, hw, hw, device="cuda", generator=g).bfloat16().float().requires_grad_(True)
+    ws = [(torch.randn(c, c, 3, 3, device="cuda", generator=g) * 0.05).bfloat16().float() for _ in range(2)]
+    a1 = F.leaky_relu(F.instance_norm(h1, eps=1e-5), SLOPE)
+    a1r = a1.detach().bfloat16().float().requires_grad_(True)           # the stored activation the convs read
+    if grouped:
+        h2 = torch.cat((F.conv2d(a1r[:split], ws[0], None, padding=1), F.conv2d(a1r[split:], ws[1], None, padding=1)), 0)
+    else:
+        h2 = F.conv2d(a1r, ws[0], None, padding=1)
+    h2r = h2.detach().bfloat16().float().requires_grad_(True)
+    out = F.instance_norm(h2r, eps=1e-5)
+    dout = torch.randn(n, c, hw, hw, device="cuda", generator=g).bfloat16().float()
+    out.backward(dout)
+    dh2_ref = h2r.grad
+    h2.backward(dh2_ref.bfloat16().float())
+    da1_ref = a1r.grad
+    a1.backward(da1_ref)
+    dh1_ref = h1.grad
+    # --- kernels
+    def stats_of(t):
+        return torch.stack((t.mean((2, 3)), torch.rsqrt(t.var((2, 3), unbiased=False) + 1e-5)), 1).contiguous()
+    st1, st2 = stats_of(h1.detach()), stats_of(h2r.detach())
+    h1b, h2b, doutb = nhwc16(h1.detach()), nhwc16(h2r.detach()), nhwc16(dout)
+    bs = torch.full((2, n, 2, c), 3.0, device="cuda")
+    ctx.norm_bwd_stats(doutb.data_ptr(), h2b.data_ptr(), st2.data_ptr(), bs[1].data_ptr(), n, hw * hw, c, 1, 1, SLOPE)
+    dh2b = torch.empty_like(h2b)
+    ctx.norm_bwd_apply(doutb.data_ptr(), h2b.data_ptr(), st2.data_ptr(), bs[1].data_ptr(), dh2b.data_ptr(), n, hw * hw, c, 1, 1, SLOPE)
+    assert rel_l2(nchw32(dh2b), dh2_ref) < BF16_L2
+    pack = lambda t: t.permute(2, 3, 0, 1).reshape(9, c, c)
+    flat_d = torch.cat([pack(w_).transpose(1, 2).reshape(-1) for w_ in ws]).bfloat16().contiguous()
+    ext = ConvExt()
+    a1b = nhwc16(a1.detach())
+    ext.in_a, ext.bsums = a1b.data_ptr(), bs[0].data_ptr()
+    if grouped:
+        ext.w2, ext.n_split = flat_d[9 * c * c:].data_ptr(), split
+    g1 = torch.empty_like(h1b)
+    dh2in = nhwc16(dh2_ref)                     # feed the reference gradient so that errors do not compound
+    ctx.conv_dgrad_ex(C.byref(ConvShape(0, n, hw, hw, c, c)), dh2in.data_ptr(), flat_d.data_ptr(), g1.data_ptr(), None, None,
+                      32, SLOPE, C.byref(ext))
+    xh1 = F.instance_norm(h1.detach(), eps=1e-5)
+    g_ref = da1_ref * torch.where(xh1 > 0, 1.0, SLOPE)
+    assert rel_l2(nchw32(g1), g_ref) < BF16_L2
+    assert rel_l2(bs[0][:, 0], g_ref.sum((2, 3))) < 2e-3 and rel_l2(bs[0][:, 1], (g_ref * xh1).sum((2, 3))) < 2e-3
+    dh1b = torch.empty_like(h1b)
+    ctx.norm_bwd_apply(g1.data_ptr(), a1b.data_ptr(), st1.data_ptr(), bs[0].data_ptr(), dh1b.data_ptr(), n, hw * hw, c, 2, 1, SLOPE)
+    assert rel_l2(nchw32(dh1b), dh1_ref) < 1.5 * BF16_L2
+    # un-fused fallback of the same thing: stats kernel in mode 0 + apply with gmode 0 on the raw gradient
+    da1b = nhwc16(da1_ref)
+    ctx.norm_bwd_stats(da1b.data_ptr(), h1b.data_ptr(), st1.data_ptr(), bs[0].data_ptr(), n, hw * hw, c, 0, 1, SLOPE)
+    ctx.norm_bwd_apply(da1b.data_ptr(), h1b.data_ptr(), st1.data_ptr(), bs[0].data_ptr(), dh1b.data_ptr(), n, hw * hw, c, 0, 1, SLOPE)
+    assert rel_l2(nchw32(dh1b), dh1_ref) < 1.5 * BF16_L2
+
+
+# ------------------------------------------------------------------ round 2: split-bf16 ("bf16x3") kernels
+SPLIT_L2 = 1e-4     # hi + lo carry 16 mantissa bits; the dropped lo*lo term and the output split are ~2^-17
+
+
+def split16(t):
+    """fp32 -> (hi, lo) bf16 pair and the value hi + lo they represent."""
+    hi = t.bfloat16()
+    lo = (t - hi.float()).bfloat16()
+    return hi, lo, hi.float() + lo.float()
+
+
+def nhwc_split(t):
+    """NCHW fp32 -> NHWC [.., 2c] = (hi | lo) bf16"""
+    hi, lo, _ = split16(t.permute(0, 2, 3, 1).contiguous())
+    return torch.cat((hi, lo), 3).contiguous()
+
+
+def unsplit(t):
+    c = t.shape[-1] // 2
+    return (t[..., :c].float() + t[..., c:].float()).permute(0, 3, 1, 2)
+
+
+@pytest.mark.parametrize("kind,n,h,w,cin,cout", [(1, 6, 64, 64, 64, 128), (1, 5, 32, 32, 128, 256), (1, 40, 4, 4, 1024, 2048),
+                                                 (1, 297, 16, 16, 256, 512), (0, 3, 32, 32, 256, 256), (2, 2, 32, 32, 256, 128)])
+def test_split_bf16_conv_fwd_dgrad_wgrad(ctx, kind, n, h, w, cin, cout):
+    from lsps_b200._lib import ConvShape, ConvExt
+    g = gen(500 + n)
+    x = split16(torch.randn(n, cin, h, w, device="cuda", generator=g))[2].requires_grad_(True)
+    if kind == 2:
+        wt = split16(torch.randn(cin, cout, 3, 3, device="cuda", generator=g) * 0.05)[2].requires_grad_(True)
+        pack = lambda t: t.permute(2, 3, 1, 0).reshape(9, cout, cin)
+        y = F.conv_transpose2d(x, wt, None, stride=2, padding=1, output_padding=1)
+    else:
+        wt = split16(torch.randn(cout, cin, 3, 3, device="cuda", generator=g) * 0.05)[2].requires_grad_(True)
+        pack = lambda t: t.permute(2, 3, 0, 1).reshape(9, cout, cin)
+        y = F.conv2d(x, wt, None, stride=1 if kind == 0 else 2, padding=1)
+    bias = torch.randn(cout, device="cuda", generator=g)
+    dy = split16(torch.randn(y.shape, device="cuda", generator=g))[2]
+    y.backward(dy)
+    sh = C.byref(ConvShape(kind, n, h, w, cin, cout))
+    xs, dys = nhwc_split(x.detach()), nhwc_split(dy)
+    wf_hi, wf_lo, _ = split16(pack(wt.detach()).contiguous())
+    wd_hi, wd_lo, _ = split16(pack(wt.detach()).transpose(1, 2).contiguous())
+    ys = torch.empty(n, y.shape[2], y.shape[3], 2 * cout, device="cuda", dtype=torch.bfloat16)
+    ext = ConvExt()
+    ext.split, ext.w_lo = 1, wf_lo.data_ptr()
+    ctx.conv_fwd_ex(sh, xs.data_ptr(), wf_hi.data_ptr(), bias.data_ptr(), ys.data_ptr(), 3, SLOPE, C.byref(ext))
+    assert rel_l2(unsplit(ys), F.leaky_relu(y.detach() + bias[None, :, None, None], SLOPE)) < SPLIT_L2
+    mask = torch.randn(n, cin, h, w, device="cuda", generator=g)
+    masks = nhwc_split(mask)
+    dxs = torch.empty(n, h, w, 2 * cin, device="cuda", dtype=torch.bfloat16)
+    ext.w_lo = wd_lo.data_ptr()
+    ctx.conv_dgrad_ex(sh, dys.data_ptr(), wd_hi.data_ptr(), dxs.data_ptr(), masks.data_ptr(), None, 4, SLOPE, C.byref(ext))
+    ref = x.grad * torch.where(mask.bfloat16().float() > 0, 1.0, SLOPE)
+    assert rel_l2(unsplit(dxs), ref) < SPLIT_L2
+    dw = torch.zeros(9, cout, cin, device="cuda")
+    ctx.conv_wgrad_split(sh, xs.data_ptr(), dys.data_ptr(), dw.data_ptr())
+    assert rel_l2(dw, pack(wt.grad)) < SPLIT_L2
+    db = torch.zeros(cout, device="cuda")
+    ctx.colsum_bf16_split(dys.data_ptr(), dys.numel() // (2 * cout), cout, db.data_ptr())
+    assert rel_l2(db, dy.sum((0, 2, 3))) < 1e-4
+
+
+@pytest.mark.parametrize("stride,n", [(2, 5), (1, 3)])
+def test_split_bf16_stems(ctx, stride, n):
+    g = gen(600 + stride)
+    img = (torch.rand(n, 1, 128, 128, device="cuda", generator=g) * 2 - 1).requires_grad_(True)
+    w = (torch.randn(64, 1, 7, 7, device="cuda", generator=g) * 0.05).requires_grad_(True)
+    b = torch.randn(64, device="cuda", generator=g)
+    pre = F.conv2d(img, w, b, stride=stride, padding=3)
+    y = F.leaky_relu(pre, SLOPE)
+    ho = 128 // stride
+    dy = split16(torch.randn(n, 64, ho, ho, device="cuda", generator=g))[2]
+    pre.backward(dy)
+    ys = torch.empty(n, ho, ho, 128, device="cuda", dtype=torch.bfloat16)
+    i3 = img.detach().reshape(n, 128, 128).contiguous()
+    wk = w.detach().reshape(64, 49).contiguous()
+    ctx.stem_fwd_split(i3.data_ptr(), wk.data_ptr(), b.data_ptr(), ys.data_ptr(), n, 128, 128, stride, SLOPE)
+    assert rel_l2(unsplit(ys), y.detach()) < SPLIT_L2
+    dys = nhwc_split(dy)
+    dw, db = torch.zeros(64, 49, device="cuda"), torch.zeros(64, device="cuda")
+    ctx.stem_wgrad_split(i3.data_ptr(), dys.data_ptr(), dw.data_ptr(), db.data_ptr(), n, 128, 128, stride)
+    assert rel_l2(dw, w.grad.reshape(64, 49)) < SPLIT_L2 and rel_l2(db, dy.sum((0, 2, 3))) < SPLIT_L2
+    dimg = torch.zeros(n, 128, 128, device="cuda")
+    ctx.stem_dgrad_split(dys.data_ptr(), wk.data_ptr(), dimg.data_ptr(), n, 128, 128, stride, 0)
+    assert rel_l2(dimg, img.grad.reshape(n, 128, 128)) < SPLIT_L2
+
+
+def test_split_bf16_heads_and_feature_losses(ctx):
+    """dhead fwd/bwd, l1_feat, mask_to_bf16 and the Post FC on split feature tensors against their plain-tensor forms."""
+    g = gen(700)
+    n, cf = 6, 2048
+    Ff = torch.randn(n, 2, 2, cf, device="cuda", generator=g)
+    hi, lo, Fv = split16(Ff)
+    Fs = torch.cat((hi, lo), 3).contiguous()
+    w, b = torch.randn(cf, device="cuda", generator=g) * 0.02, torch.randn(1, device="cuda", generator=g)
+    rows = n * 4
+    lg = torch.empty(rows, device="cuda")
+    ctx.dhead_fwd_split(Fs.data_ptr(), w.data_ptr(), b.data_ptr(), lg.data_ptr(), rows, cf)
+    assert rel_l2(lg, Fv.reshape(rows, cf) @ w + b) < 1e-5
+    dl = torch.randn(rows, device="cuda", generator=g)
+    dF, dw, db = torch.zeros(rows, cf, device="cuda"), torch.zeros(cf, device="cuda"), torch.zeros(1, device="cuda")
+    ctx.dhead_bwd_split(Fs.data_ptr(), w.data_ptr(), dl.data_ptr(), dF.data_ptr(), dw.data_ptr(), db.data_ptr(), rows, cf)
+    assert rel_l2(dF, dl[:, None] * w[None]) < 1e-6 and rel_l2(dw, dl @ Fv.reshape(rows, cf)) < 1e-5
+    acc = torch.zeros(2, device="cuda")
+    dF2 = torch.zeros(n, 4 * cf, device="cuda")
+    per = 4 * cf
+    ctx.l1_feat_split(Fs.data_ptr(), Fs[3:].data_ptr(), dF2.data_ptr(), dF2[3:].data_ptr(), 0.5, acc.data_ptr(), 3 * per, cf)
+    d = Fv[:3] - Fv[3:]
+    assert abs(acc[0].item() - d.abs().sum().item()) < 1e-4 * d.abs().sum().item()
+    assert torch.equal(dF2[:3].reshape(3, 2, 2, cf), 0.5 * torch.sign(d)) and torch.equal(dF2[3:], -dF2[:3])
+    out = torch.empty_like(Fs)
+    dFr = torch.randn(n, per, device="cuda", generator=g)
+    ctx.mask_to_bf16_split(dFr.data_ptr(), Fs.data_ptr(), out.data_ptr(), SLOPE, dFr.numel(), cf)
+    ref = dFr.reshape(n, 2, 2, cf) * torch.where(hi.float() > 0, 1.0, SLOPE)
+    assert rel_l2(out[..., :cf].float() + out[..., cf:].float(), ref) < SPLIT_L2
+    wp, bp = torch.randn(20, per, device="cuda", generator=g) * 0.01, torch.randn(20, device="cuda", generator=g)
+    p = torch.empty(n, 20, device="cuda")
+    ctx.linear_fwd(Fs.data_ptr(), cf, wp.data_ptr(), bp.data_ptr(), p.data_ptr(), n, 20, per, 0, SLOPE)
+    assert rel_l2(p, Fv.reshape(n, per) @ wp.t() + bp) < 1e-5
+    dp = torch.randn(n, 20, device="cuda", generator=g)
+    dwp, dbp, dx = torch.zeros(20, per, device="cuda"), torch.zeros(20, device="cuda"), torch.empty(n, per, device="cuda")
+    ctx.linear_bwd(Fs.data_ptr(), cf, wp.data_ptr(), dp.data_ptr(), dx.data_ptr(), 0, dwp.data_ptr(), dbp.data_ptr(), n, 20, per)
+    assert rel_l2(dwp, dp.t() @ Fv.reshape(n, per)) < 1e-5 and rel_l2(dx, dp @ wp) < 1e-5
+
+
+def test_pack_dgrad_multi_and_split_store(ctx):
+    """ParamStore(split=True): one-launch transposed copies + remainders; Adam refreshes hi and lo forward copies."""
+    from lsps_b200.params import ParamStore
+    ents = [("a.weight", (128, 64, 3, 3), "conv3", "conv", 576), ("a.bias", (128,), "bias", "bias", 576),
+            ("t.weight", (128, 64, 3, 3), "deconv3", "conv", 576), ("m.weight", (64, 128, 4, 4), "deconv4", "conv", 1024),
+            ("z.weight", (256, 128, 3, 3), "conv3", "conv", 1152)]
+    S = ParamStore(ents, "cuda:0", 1e-3, 1e-4, split=True)
+    S.init_(3)
+    for k, e in S.entries.items():
+        if e.dg_off < 0:
+            continue
+        taps = 16 if e.kind == "deconv4" else 9
+        co, ci = (e.shape[0], e.shape[1]) if e.kind == "conv3" else (e.shape[1], e.shape[0])
+        wk = S.W(k).reshape(taps, co, ci)
+        hi, lo, _ = split16(wk.transpose(1, 2).contiguous())
+        assert torch.equal(S.W16T(k).reshape(taps, ci, co), hi) and torch.equal(S.W16TL(k).reshape(taps, ci, co), lo), k
+        hi, lo, _ = split16(wk)
+        assert torch.equal(S.W16(k).reshape(taps, co, ci), hi) and torch.equal(S.W16L(k).reshape(taps, co, ci), lo), k
+    S.g.normal_(generator=gen(9))
+    S.adam_step()
+    hi, lo, _ = split16(S.w)
+    assert torch.equal(S.w16, hi) and torch.equal(S.w16l, lo)
