@@ -29,7 +29,9 @@ enum { LSPS_OK = 0, LSPS_E_ARG = -1, LSPS_E_SHAPE = -2, LSPS_E_ARCH = -3, LSPS_E
 
 /* conv kinds: 3x3 stride-1 pad-1 Conv2d | 3x3 stride-2 pad-1 Conv2d | 3x3 stride-2 pad-1 output_padding-1 ConvTranspose2d
    | 4x4 stride-2 pad-1 ConvTranspose2d (Mapping net, lsps_nets.py:17-23; 16 taps, tap = r*4+s) */
-enum { LSPS_CONV_S1 = 0, LSPS_CONV_S2 = 1, LSPS_DECONV_S2 = 2, LSPS_DECONV4_S2 = 3 };
+enum { LSPS_CONV_S1 = 0, LSPS_CONV_S2 = 1, LSPS_DECONV_S2 = 2, LSPS_DECONV4_S2 = 3,
+       /* 1x1 stride-1 Conv2d (LeakyINSResNeXtBlock, common_net.py:116,122): one tap, weights [Cout][Cin] */
+       LSPS_CONV1X1 = 4 };
 /* epilogue flags of the implicit-GEMM kernels, applied in this order: +bias, LeakyReLU, +add, *lrelu'(mask) */
 enum { LSPS_EP_BIAS = 1, LSPS_EP_LRELU = 2, LSPS_EP_MASK = 4, LSPS_EP_ADD = 8,
        /* forward: accumulate per-(image, channel) sum / sum of squares of the fp32 result (after bias) -- the statistics of
@@ -58,6 +60,9 @@ typedef struct {
   float* sums;
   const void* in_a; float* bsums;
   const void* w_lo; int split;
+  int groups;   /* > 1: grouped 3x3 stride-1 conv (ResNeXt cardinality, common_net.py:118): cin == cout, group width
+                   cin/groups in {64, 128}; weights [tap][Cout][cin/groups] (forward) and [tap][Cin][cout/groups]
+                   (data gradient).  lsps_conv_wgrad_grouped is the matching weight gradient. */
 } lsps_conv_ext;
 
 int lsps_ctx_create(lsps_ctx** out, int device);
@@ -88,6 +93,9 @@ int lsps_conv_dgrad_ex(lsps_ctx*, const lsps_conv_shape*, const void* dy, const 
                        const void* add, int flags, float slope, const lsps_conv_ext* ext, lsps_stream);
 /* dw[tap][cout][cin] += conv_backward_weight(x, dy)   (fp32, accumulating; split-K over pixels with red.add) */
 int lsps_conv_wgrad(lsps_ctx*, const lsps_conv_shape*, const void* x, const void* dy, float* dw, lsps_stream);
+/* grouped 3x3 stride-1 conv: dw[tap][cout][cin/groups] += ... (only the block-diagonal of the dense gradient) */
+int lsps_conv_wgrad_grouped(lsps_ctx*, const lsps_conv_shape*, const void* x, const void* dy, float* dw, int groups,
+                            lsps_stream);
 /* same with split-bf16 operands: x [n,h,w,2cin], dy [n,ho,wo,2cout] as (hi | lo) halves; dy_hi*x_hi + dy_hi*x_lo + dy_lo*x_hi */
 int lsps_conv_wgrad_split(lsps_ctx*, const lsps_conv_shape*, const void* x, const void* dy, float* dw, lsps_stream);
 /* db[c] += sum over rows of dy[rows][c]   (bias gradients; dy bf16) */
@@ -138,17 +146,29 @@ int lsps_instnorm_bwd_grouped(lsps_ctx*, const void* dy, const void* h, const fl
    forward : mode 0 y = lrelu(xhat), 1 y = res + xhat, 2 y = xhat ; xhat = (h - mean)*rstd from sums = (sum, sum of squares);
              stats_out (may be NULL) receives the (mean, rstd) rows the backward pass reads */
 int lsps_norm_apply_fwd(lsps_ctx*, const void* h, const void* res, void* y, const float* sums, float* stats_out, int n,
-                        int hw, int c, int mode, int per_image, float eps, float slope, lsps_stream);
+                        int hw, int c, int mode, int per_image, float eps, float slope, const float* gamma,
+                        const float* beta, lsps_stream);
+/* gamma / beta (f32 [c], either may be NULL = 1 / 0) in the three norm calls: the affine part of BatchNorm2d(affine=True)
+   (LeakyReLUBNConv2d, common_net.py:270-281) or the Bias2d that follows BatchNorm2d(affine=False) in the BNNS wrappers
+   (common_net.py:294-322): the value handed to the activation is gamma*xhat + beta.  With them the two rows of bsums are
+   exactly d beta = sum g and d gamma = sum g*xhat. */
 /* bsums (zeroed by the call) += (sum g, sum g*xhat), g = dy (mode 1) or dy*lrelu'(xhat) (mode 0) -- only needed when the
    gradient's producer could not take the sums itself (LSPS_EP_INBWD) */
 int lsps_norm_bwd_stats(lsps_ctx*, const void* dy, const void* h, const float* stats, float* bsums, int n, int hw, int c,
-                        int mode, int per_image, float slope, lsps_stream);
+                        int mode, int per_image, float slope, const float* gamma, const float* beta, lsps_stream);
 /* dh = rstd*(g - mean(g) - xhat*mean(g*xhat)); gmode 0: g is the raw gradient w.r.t. lrelu(xhat) (masked here),
    gmode 1: g is used as is (the gradient w.r.t. res + xhat), gmode 2: g was pre-masked by LSPS_EP_INBWD and `h` is the
    ACTIVATION a = lrelu(xhat) (xhat recovered from it; only the rstd row of stats is read).  The bias of the conv that
    produced h gets NO gradient from here: it is exactly zero (the norm subtracts the mean). */
 int lsps_norm_bwd_apply(lsps_ctx*, const void* g, const void* h, const float* stats, const float* bsums, void* dh, int n,
-                        int hw, int c, int gmode, int per_image, float slope, lsps_stream);
+                        int hw, int c, int gmode, int per_image, float slope, const float* gamma, const float* beta,
+                        lsps_stream);
+/* BatchNorm2d running statistics: momentum update from a batch row of sums (unbiased variance, like torch), and a sums
+   row that makes lsps_norm_apply_fwd normalise with the running statistics (eval mode) */
+int lsps_bn_running_update(lsps_ctx*, const float* sums, float* running_mean, float* running_var, int c, float count,
+                           float momentum, lsps_stream);
+int lsps_bn_running_to_sums(lsps_ctx*, const float* running_mean, const float* running_var, float* sums, int c,
+                            float count, lsps_stream);
 /* out[2][c] = sum over images of sums[n][2][c]  (BatchNorm batch statistics; the row a data-parallel run all-reduces) */
 int lsps_norm_reduce_images(lsps_ctx*, const float* sums, float* out, int n, int c, lsps_stream);
 
@@ -186,6 +206,15 @@ int lsps_bce_logits(lsps_ctx*, const float* logits, float target, float scale, f
 /* df[r,:] += dlogits[r]*w (f32) ; dw[c] += sum_r dlogits[r]*f[r,c] ; db += sum dlogits  (dw/db may be NULL) */
 int lsps_dhead_bwd(lsps_ctx*, const void* f, const float* w, const float* dlogits, float* df, float* dw, float* db,
                    long long rows, int c, lsps_stream);
+/* D head + sigmoid + BCE + the backward of all three, one launch (the GAN loss fused into the head it follows).
+   f bf16 [rows,c] (split != 0: [rows][hi c | lo c]); rows are grouped by image group: group g = row / rows_per_group has
+   the constant target targets[g] (HOST array of ngroups <= 8 floats; < 0: the group takes no part, its df rows are zero)
+   and adds (sum bce, #correct) to acc[slots[g]], acc[slots[g]+1] (slots: HOST int array).  dlogit = scale*(sigmoid - t);
+   df[r,:] = dlogit*w is WRITTEN (no zero fill needed); dw[c] += sum_r dlogit*f[r,c]; db += sum dlogit.
+   logits / df / dw / db may be NULL. */
+int lsps_dhead_bce(lsps_ctx*, const void* f, const float* w, const float* bias, long long rows, int c, int split,
+                   long long rows_per_group, int ngroups, const float* targets, const int* slots, float scale,
+                   float* logits, float* df, float* dw, float* db, float* acc, lsps_stream);
 /* trunk-feature gradient f32 -> bf16 with the LeakyReLU mask of the features: out = df * lrelu'(f) */
 int lsps_mask_to_bf16(lsps_ctx*, const float* df, const void* f, void* out, float slope, long long n, lsps_stream);
 /* the same four on split-bf16 feature tensors f [rows][hi c | lo c] (df / logits stay plain f32 [rows][c]) */

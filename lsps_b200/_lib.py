@@ -11,7 +11,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "liblsps_b200.so")
 
-CONV_S1, CONV_S2, DECONV_S2, DECONV4_S2 = 0, 1, 2, 3
+CONV_S1, CONV_S2, DECONV_S2, DECONV4_S2, CONV1X1 = 0, 1, 2, 3, 4
 EP_BIAS, EP_LRELU, EP_MASK, EP_ADD, EP_STATS, EP_INBWD = 1, 2, 4, 8, 16, 32
 ACT_NONE, ACT_LRELU, ACT_SOFTPLUS = 0, 1, 2
 
@@ -24,7 +24,7 @@ class ConvExt(C.Structure):
     """lsps_conv_ext (include/lsps_b200.h): optional extras of lsps_conv_{fwd,dgrad}_ex"""
     _fields_ = [("w2", C.c_void_p), ("bias2", C.c_void_p), ("n_split", C.c_int), ("sums", C.c_void_p),
                 ("in_a", C.c_void_p), ("bsums", C.c_void_p), ("w_lo", C.c_void_p),
-                ("split", C.c_int)]
+                ("split", C.c_int), ("groups", C.c_int)]
 
 
 _vp, _i, _f, _ll = C.c_void_p, C.c_int, C.c_float, C.c_longlong
@@ -39,6 +39,7 @@ _SIGS = {
     "lsps_conv_dgrad_ex": [_SH, _vp, _vp, _vp, _vp, _vp, _i, _f, _vp],
     "lsps_conv_wgrad": [_SH, _vp, _vp, _vp],
     "lsps_conv_wgrad_split": [_SH, _vp, _vp, _vp],
+    "lsps_conv_wgrad_grouped": [_SH, _vp, _vp, _vp, _i],
     "lsps_stem_fwd_split": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _f],
     "lsps_stem_wgrad_split": [_vp, _vp, _vp, _vp, _i, _i, _i, _i],
     "lsps_stem_dgrad_split": [_vp, _vp, _vp, _i, _i, _i, _i, _i],
@@ -50,9 +51,11 @@ _SIGS = {
     "lsps_pack_dgrad_multi": [_vp, _vp, _vp, _vp, _i, _i],
     "lsps_adam_ex": [_vp, _vp, _vp, _vp, _vp, _vp, _ll, _f, _f, _f, _f, _f, _i, _f, _vp],
     "lsps_f32_split_bf16": [_vp, _vp, _vp, _ll],
-    "lsps_norm_apply_fwd": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _f],
-    "lsps_norm_bwd_stats": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f],
-    "lsps_norm_bwd_apply": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f],
+    "lsps_norm_apply_fwd": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _f, _vp, _vp],
+    "lsps_norm_bwd_stats": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _vp, _vp],
+    "lsps_norm_bwd_apply": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _vp, _vp],
+    "lsps_bn_running_update": [_vp, _vp, _vp, _i, _f, _f],
+    "lsps_bn_running_to_sums": [_vp, _vp, _vp, _i, _f],
     "lsps_norm_reduce_images": [_vp, _vp, _i, _i],
     "lsps_colsum_bf16": [_vp, _ll, _i, _vp],
     "lsps_stem_fwd": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _f],
@@ -74,6 +77,8 @@ _SIGS = {
     "lsps_dhead_fwd": [_vp, _vp, _vp, _vp, _ll, _i],
     "lsps_bce_logits": [_vp, _f, _f, _vp, _vp, _ll],
     "lsps_dhead_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _ll, _i],
+    "lsps_dhead_bce": [_vp, _vp, _vp, _ll, _i, _i, _ll, _i, C.POINTER(C.c_float), C.POINTER(C.c_int), _f, _vp, _vp, _vp, _vp,
+                       _vp],
     "lsps_mask_to_bf16": [_vp, _vp, _vp, _f, _ll],
     "lsps_linear_fwd": [_vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _f],
     "lsps_linear_bwd": [_vp, _i, _vp, _vp, _vp, _i, _vp, _vp, _i, _i, _i],

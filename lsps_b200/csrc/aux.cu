@@ -535,12 +535,18 @@ __global__ void __launch_bounds__(256) norm_apply_fwd_kernel(const bf16* __restr
                                                             bf16* __restrict__ y, const float* __restrict__ sums,
                                                             float* __restrict__ stats_out, int hw, int c, int ppb,
                                                             long long img_stride, float inv_count, float eps,
-                                                            float slope) {
+                                                            float slope, const float* __restrict__ gamma,
+                                                            const float* __restrict__ beta) {
   const int octs = c >> 3, lanes = 256 / octs;
   const int oct = threadIdx.x % octs, pl = threadIdx.x / octs;
   const int n = blockIdx.y, p0 = blockIdx.x * ppb;
   const float* sr = sums + n * img_stride + oct * 8;
-  float mean[8], rstd[8];
+  float mean[8], rstd[8], ga[8], be[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {   // BatchNorm2d(affine=True) weight / bias, or Bias2d alone (common_net.py:92-103,274,297)
+    ga[k] = gamma ? __ldg(gamma + oct * 8 + k) : 1.f;
+    be[k] = beta ? __ldg(beta + oct * 8 + k) : 0.f;
+  }
   {
     const float4 a0 = __ldg(reinterpret_cast<const float4*>(sr)), a1 = __ldg(reinterpret_cast<const float4*>(sr) + 1);
     const float4 b0 = __ldg(reinterpret_cast<const float4*>(sr + c)), b1 = __ldg(reinterpret_cast<const float4*>(sr + c) + 1);
@@ -554,7 +560,7 @@ __global__ void __launch_bounds__(256) norm_apply_fwd_kernel(const bf16* __restr
     }
   }
   if (stats_out && blockIdx.x == 0 && pl == 0) {
-    float* so = stats_out + (long long)n * 2 * c + oct * 8;
+    float* so = stats_out + n * img_stride + oct * 8;      // BatchNorm (img_stride 0): every image writes the same row
     reinterpret_cast<float4*>(so)[0] = make_float4(mean[0], mean[1], mean[2], mean[3]);
     reinterpret_cast<float4*>(so)[1] = make_float4(mean[4], mean[5], mean[6], mean[7]);
     reinterpret_cast<float4*>(so + c)[0] = make_float4(rstd[0], rstd[1], rstd[2], rstd[3]);
@@ -569,7 +575,7 @@ __global__ void __launch_bounds__(256) norm_apply_fwd_kernel(const bf16* __restr
     if (MODE == 1) unpack8(__ldg(reinterpret_cast<const uint4*>(res + base + (long long)p * c)), r);
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-      const float v = (f[k] - mean[k]) * rstd[k];
+      const float v = (f[k] - mean[k]) * rstd[k] * ga[k] + be[k];
       f[k] = MODE == 1 ? r[k] + v : (MODE == 0 ? (v > 0.f ? v : v * slope) : v);
     }
     *reinterpret_cast<uint4*>(y + base + (long long)p * c) = pack8(f);
@@ -582,7 +588,9 @@ template <int MODE>
 __global__ void __launch_bounds__(256) norm_bwd_stats_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ h,
                                                             const float* __restrict__ stats, float* __restrict__ bsums,
                                                             int hw, int c, int ppb, long long stat_stride,
-                                                            long long bsum_stride, float slope) {
+                                                            long long bsum_stride, float slope,
+                                                            const float* __restrict__ gamma,
+                                                            const float* __restrict__ beta) {
   extern __shared__ float nred[];   // [lanes][c] x 2
   const int octs = c >> 3, lanes = 256 / octs;
   const int oct = threadIdx.x % octs, pl = threadIdx.x / octs;
@@ -595,8 +603,13 @@ __global__ void __launch_bounds__(256) norm_bwd_stats_kernel(const bf16* __restr
     mean[0] = a0.x; mean[1] = a0.y; mean[2] = a0.z; mean[3] = a0.w; mean[4] = a1.x; mean[5] = a1.y; mean[6] = a1.z; mean[7] = a1.w;
     rstd[0] = b0.x; rstd[1] = b0.y; rstd[2] = b0.z; rstd[3] = b0.w; rstd[4] = b1.x; rstd[5] = b1.y; rstd[6] = b1.z; rstd[7] = b1.w;
   }
+  float ga[8], be[8];
 #pragma unroll
-  for (int k = 0; k < 8; ++k) { sg[k] = 0.f; sgx[k] = 0.f; }
+  for (int k = 0; k < 8; ++k) {
+    sg[k] = 0.f; sgx[k] = 0.f;
+    ga[k] = gamma ? __ldg(gamma + oct * 8 + k) : 1.f;
+    be[k] = beta ? __ldg(beta + oct * 8 + k) : 0.f;
+  }
   const long long base = (long long)n * hw * c + oct * 8;
   const int pend = min(p0 + ppb, hw);
 #pragma unroll 4
@@ -607,8 +620,8 @@ __global__ void __launch_bounds__(256) norm_bwd_stats_kernel(const bf16* __restr
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       const float xh = (f[k] - mean[k]) * rstd[k];
-      const float gg = (MODE == 0 && !(xh > 0.f)) ? g[k] * slope : g[k];
-      sg[k] += gg; sgx[k] += gg * xh;
+      const float gg = (MODE == 0 && !(xh * ga[k] + be[k] > 0.f)) ? g[k] * slope : g[k];   // lrelu'(gamma*xhat + beta)
+      sg[k] += gg; sgx[k] += gg * xh;          // = d beta, d gamma of an affine norm
     }
   }
   float* r1 = nred;
@@ -633,14 +646,21 @@ __global__ void __launch_bounds__(256) norm_bwd_apply_kernel(const bf16* __restr
                                                             const float* __restrict__ stats,
                                                             const float* __restrict__ bsums, bf16* __restrict__ dh,
                                                             int hw, int c, int ppb, long long stat_stride,
-                                                            long long bsum_stride, float inv_count, float slope) {
+                                                            long long bsum_stride, float inv_count, float slope,
+                                                            const float* __restrict__ gamma,
+                                                            const float* __restrict__ beta) {
   const int octs = c >> 3, lanes = 256 / octs;
   const int oct = threadIdx.x % octs, pl = threadIdx.x / octs;
   const int n = blockIdx.y, p0 = blockIdx.x * ppb;
   const float* st = stats + n * stat_stride + oct * 8;
   const float* bs = bsums + n * bsum_stride + oct * 8;
   const float inv_slope = 1.f / slope;
-  float mean[8], rstd[8], mg[8], mgx[8];
+  float mean[8], rstd[8], mg[8], mgx[8], ga[8], be[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    ga[k] = gamma ? __ldg(gamma + oct * 8 + k) : 1.f;
+    be[k] = beta ? __ldg(beta + oct * 8 + k) : 0.f;
+  }
   {
     const float4 a0 = __ldg(reinterpret_cast<const float4*>(st)), a1 = __ldg(reinterpret_cast<const float4*>(st) + 1);
     const float4 b0 = __ldg(reinterpret_cast<const float4*>(st + c)), b1 = __ldg(reinterpret_cast<const float4*>(st + c) + 1);
@@ -663,11 +683,30 @@ __global__ void __launch_bounds__(256) norm_bwd_apply_kernel(const bf16* __restr
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       const float xh = GMODE == 2 ? (f[k] > 0.f ? f[k] : f[k] * inv_slope) : (f[k] - mean[k]) * rstd[k];
-      const float gg = (GMODE == 0 && !(xh > 0.f)) ? g[k] * slope : g[k];
-      f[k] = rstd[k] * (gg - mg[k] - xh * mgx[k]);
+      const float gg = (GMODE == 0 && !(xh * ga[k] + be[k] > 0.f)) ? g[k] * slope : g[k];
+      f[k] = rstd[k] * ga[k] * (gg - mg[k] - xh * mgx[k]);
     }
     *reinterpret_cast<uint4*>(dh + base + (long long)p * c) = pack8(f);
   }
+}
+
+// BatchNorm2d running statistics (momentum update with the unbiased variance, as torch) from a batch row of sums,
+// and the inverse: a sums row that makes norm_apply_fwd normalise with the running statistics (eval mode).
+__global__ void bn_running_update_kernel(const float* __restrict__ sums, float* __restrict__ rmean,
+                                         float* __restrict__ rvar, int c, float count, float momentum) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= c) return;
+  const float mean = sums[j] / count;
+  const float var = fmaxf(sums[c + j] / count - mean * mean, 0.f);
+  rmean[j] = (1.f - momentum) * rmean[j] + momentum * mean;
+  rvar[j] = (1.f - momentum) * rvar[j] + momentum * var * (count > 1.f ? count / (count - 1.f) : 1.f);
+}
+__global__ void bn_running_to_sums_kernel(const float* __restrict__ rmean, const float* __restrict__ rvar,
+                                          float* __restrict__ sums, int c, float count) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= c) return;
+  sums[j] = rmean[j] * count;
+  sums[c + j] = (rvar[j] + rmean[j] * rmean[j]) * count;
 }
 
 // BatchNorm: per-channel batch statistics = the per-image rows of `sums` added up (tiny: n x 2c floats).
@@ -831,6 +870,93 @@ __global__ void __launch_bounds__(256) bce_logits_kernel(const float* __restrict
   const float r = block_sum(s, sm);
   const float c2 = block_sum(cnt, sm);
   if (threadIdx.x == 0) { atomicAdd(acc, r); atomicAdd(acc + 1, c2); }
+}
+
+// D head, sigmoid, binary cross-entropy and the backward of all three in ONE kernel (the GAN BCE fused into the head it
+// follows).  One warp per row of f (a 2x2-map pixel of an image): logit = f.w + b, p = sigmoid(logit), BCE vs the
+// constant target of the row's group (torch semantics: log clamped at -100), dlogit = scale*(p - t); then
+// df[r,:] = dlogit*w (written, so df needs no zero fill), dw += dlogit*f[r,:], db += dlogit.  Rows are grouped by image
+// group (real / generated / decoded batches): group g = r / rows_per_group has target tgt[g] (< 0: the group takes no
+// part: its df rows are zero) and adds (loss sum, #correct) to acc[slot[g]], acc[slot[g] + 1].
+struct DheadGroups { float tgt[8]; int slot[8]; };
+__global__ void __launch_bounds__(256) dhead_bce_kernel(const bf16* __restrict__ f, const float* __restrict__ w,
+                                                       const float* __restrict__ bias, long long rows, int c, int split,
+                                                       long long rows_per_group, DheadGroups G, float scale,
+                                                       float* __restrict__ logits, float* __restrict__ df,
+                                                       float* __restrict__ dw, float* __restrict__ db,
+                                                       float* __restrict__ acc, int rows_per_warp) {
+  const int lane = threadIdx.x & 31;
+  const long long wid = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const long long r0 = wid * rows_per_warp;
+  const long long pitch = split ? 2LL * c : c;
+  const int noct = c / 8;                 // <= 256: at most 8 octets per lane
+  float aw[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int k = 0; k < 8; ++k) aw[i][k] = 0.f;
+  float ab = 0.f;
+  const float b0 = __ldg(bias);
+  for (long long r = r0; r < r0 + rows_per_warp && r < rows; ++r) {
+    float fv[8][8];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int j = lane + 32 * i;
+      if (j < noct) {
+        unpack8(__ldg(reinterpret_cast<const uint4*>(f + r * pitch) + j), fv[i]);
+        if (split) {
+          float l[8];
+          unpack8(__ldg(reinterpret_cast<const uint4*>(f + r * pitch + c) + j), l);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) fv[i][k] += l[k];
+        }
+        const float4 a = __ldg(reinterpret_cast<const float4*>(w) + 2 * j), b = __ldg(reinterpret_cast<const float4*>(w) + 2 * j + 1);
+        s += fv[i][0] * a.x + fv[i][1] * a.y + fv[i][2] * a.z + fv[i][3] * a.w + fv[i][4] * b.x + fv[i][5] * b.y + fv[i][6] * b.z + fv[i][7] * b.w;
+      }
+    }
+    s = warp_sum(s);
+    const float z = s + b0;
+    const int g = (int)(r / rows_per_group);
+    const float t = G.tgt[g < 8 ? g : 7];
+    float dl = 0.f;
+    if (t >= 0.f) {
+      const float p = 1.f / (1.f + expf(-z));
+      dl = scale * (p - t);
+      if (lane == 0) {
+        const float lp = fmaxf(logf(p), -100.f), lq = fmaxf(logf(1.f - p), -100.f);
+        atomicAdd(acc + G.slot[g], -(t * lp + (1.f - t) * lq));
+        atomicAdd(acc + G.slot[g] + 1, t > 0.5f ? (p >= 0.5f ? 1.f : 0.f) : (p <= 0.5f ? 1.f : 0.f));
+      }
+    }
+    if (lane == 0 && logits) logits[r] = z;
+    ab += dl;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int j = lane + 32 * i;
+      if (j < noct) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(w) + 2 * j), b = __ldg(reinterpret_cast<const float4*>(w) + 2 * j + 1);
+        if (df) {
+          float4* o = reinterpret_cast<float4*>(df + r * c) + 2 * j;
+          o[0] = make_float4(dl * a.x, dl * a.y, dl * a.z, dl * a.w);
+          o[1] = make_float4(dl * b.x, dl * b.y, dl * b.z, dl * b.w);
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) aw[i][k] += dl * fv[i][k];
+      }
+    }
+  }
+  if (dw) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int j = lane + 32 * i;
+      if (j < noct) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) atomicAdd(dw + 8 * j + k, aw[i][k]);
+      }
+    }
+  }
+  if (db && lane == 0 && r0 < rows) atomicAdd(db, ab);
 }
 
 // thread per column, block.y = row chunk
@@ -1285,7 +1411,7 @@ static int norm_ppb(int hw, int c) {
 }
 extern "C" int lsps_norm_apply_fwd(lsps_ctx* ctx, const void* h, const void* res, void* y, const float* sums,
                                    float* stats_out, int n, int hw, int c, int mode, int per_image, float eps,
-                                   float slope, lsps_stream st) {
+                                   float slope, const float* gamma, const float* beta, lsps_stream st) {
   REQUIRE(ctx, h && y && sums && (mode != 1 || res), LSPS_E_ARG, "norm_apply_fwd: null");
   REQUIRE(ctx, norm_shape_ok(n, hw, c) && mode >= 0 && mode <= 2, LSPS_E_SHAPE, "norm_apply_fwd: c must be a power of two in [64, 2048]");
   const int ppb = norm_ppb(hw, c);
@@ -1295,14 +1421,15 @@ extern "C" int lsps_norm_apply_fwd(lsps_ctx* ctx, const void* h, const void* res
   const bf16 *hh = static_cast<const bf16*>(h), *rr = static_cast<const bf16*>(res);
   bf16* yy = static_cast<bf16*>(y);
   float* so = stats_out;
-  if (mode == 0) norm_apply_fwd_kernel<0><<<grid, 256, 0, ST_(st)>>>(hh, rr, yy, sums, so, hw, c, ppb, stride, inv, eps, slope);
-  else if (mode == 1) norm_apply_fwd_kernel<1><<<grid, 256, 0, ST_(st)>>>(hh, rr, yy, sums, so, hw, c, ppb, stride, inv, eps, slope);
-  else norm_apply_fwd_kernel<2><<<grid, 256, 0, ST_(st)>>>(hh, rr, yy, sums, so, hw, c, ppb, stride, inv, eps, slope);
+  if (mode == 0) norm_apply_fwd_kernel<0><<<grid, 256, 0, ST_(st)>>>(hh, rr, yy, sums, so, hw, c, ppb, stride, inv, eps, slope, gamma, beta);
+  else if (mode == 1) norm_apply_fwd_kernel<1><<<grid, 256, 0, ST_(st)>>>(hh, rr, yy, sums, so, hw, c, ppb, stride, inv, eps, slope, gamma, beta);
+  else norm_apply_fwd_kernel<2><<<grid, 256, 0, ST_(st)>>>(hh, rr, yy, sums, so, hw, c, ppb, stride, inv, eps, slope, gamma, beta);
   LSPS_CHECK_LAUNCH(ctx, "norm_apply_fwd");
   return LSPS_OK;
 }
 extern "C" int lsps_norm_bwd_stats(lsps_ctx* ctx, const void* dy, const void* h, const float* stats, float* bsums, int n,
-                                   int hw, int c, int mode, int per_image, float slope, lsps_stream st) {
+                                   int hw, int c, int mode, int per_image, float slope, const float* gamma,
+                                   const float* beta, lsps_stream st) {
   REQUIRE(ctx, dy && h && stats && bsums, LSPS_E_ARG, "norm_bwd_stats: null");
   REQUIRE(ctx, norm_shape_ok(n, hw, c) && (mode == 0 || mode == 1), LSPS_E_SHAPE, "norm_bwd_stats: shape");
   const int lanes = 256 / (c / 8);
@@ -1314,24 +1441,40 @@ extern "C" int lsps_norm_bwd_stats(lsps_ctx* ctx, const void* dy, const void* h,
     return lsps_set_error(ctx, LSPS_E_CUDA, "norm_bwd_stats: memset");
   const int smem = 2 * lanes * c * (int)sizeof(float);
   const bf16 *gg = static_cast<const bf16*>(dy), *hh = static_cast<const bf16*>(h);
-  if (mode == 0) norm_bwd_stats_kernel<0><<<grid, 256, smem, ST_(st)>>>(gg, hh, stats, bsums, hw, c, ppb, stride, stride, slope);
-  else norm_bwd_stats_kernel<1><<<grid, 256, smem, ST_(st)>>>(gg, hh, stats, bsums, hw, c, ppb, stride, stride, slope);
+  if (mode == 0) norm_bwd_stats_kernel<0><<<grid, 256, smem, ST_(st)>>>(gg, hh, stats, bsums, hw, c, ppb, stride, stride, slope, gamma, beta);
+  else norm_bwd_stats_kernel<1><<<grid, 256, smem, ST_(st)>>>(gg, hh, stats, bsums, hw, c, ppb, stride, stride, slope, gamma, beta);
   LSPS_CHECK_LAUNCH(ctx, "norm_bwd_stats");
   return LSPS_OK;
 }
 extern "C" int lsps_norm_bwd_apply(lsps_ctx* ctx, const void* g, const void* h, const float* stats, const float* bsums,
-                                   void* dh, int n, int hw, int c, int gmode, int per_image, float slope, lsps_stream st) {
+                                   void* dh, int n, int hw, int c, int gmode, int per_image, float slope,
+                                   const float* gamma, const float* beta, lsps_stream st) {
   REQUIRE(ctx, g && h && stats && bsums && dh, LSPS_E_ARG, "norm_bwd_apply: null");
-  REQUIRE(ctx, norm_shape_ok(n, hw, c) && gmode >= 0 && gmode <= 2 && slope > 0.f, LSPS_E_SHAPE, "norm_bwd_apply: shape");
+  REQUIRE(ctx, norm_shape_ok(n, hw, c) && gmode >= 0 && gmode <= 2 && (gmode != 2 || slope > 0.f), LSPS_E_SHAPE,
+          "norm_bwd_apply: shape (gmode 2 recovers xhat from the activation and needs slope > 0)");
   const int ppb = norm_ppb(hw, c);
   const dim3 grid((hw + ppb - 1) / ppb, n);
   const long long stride = per_image ? 2LL * c : 0;
   const float inv = 1.f / (per_image ? (float)hw : (float)hw * (float)n);
   const bf16 *gg = static_cast<const bf16*>(g), *hh = static_cast<const bf16*>(h);
-  if (gmode == 0) norm_bwd_apply_kernel<0><<<grid, 256, 0, ST_(st)>>>(gg, hh, stats, bsums, static_cast<bf16*>(dh), hw, c, ppb, stride, stride, inv, slope);
-  else if (gmode == 1) norm_bwd_apply_kernel<1><<<grid, 256, 0, ST_(st)>>>(gg, hh, stats, bsums, static_cast<bf16*>(dh), hw, c, ppb, stride, stride, inv, slope);
-  else norm_bwd_apply_kernel<2><<<grid, 256, 0, ST_(st)>>>(gg, hh, stats, bsums, static_cast<bf16*>(dh), hw, c, ppb, stride, stride, inv, slope);
+  if (gmode == 0) norm_bwd_apply_kernel<0><<<grid, 256, 0, ST_(st)>>>(gg, hh, stats, bsums, static_cast<bf16*>(dh), hw, c, ppb, stride, stride, inv, slope, gamma, beta);
+  else if (gmode == 1) norm_bwd_apply_kernel<1><<<grid, 256, 0, ST_(st)>>>(gg, hh, stats, bsums, static_cast<bf16*>(dh), hw, c, ppb, stride, stride, inv, slope, gamma, beta);
+  else norm_bwd_apply_kernel<2><<<grid, 256, 0, ST_(st)>>>(gg, hh, stats, bsums, static_cast<bf16*>(dh), hw, c, ppb, stride, stride, inv, slope, gamma, beta);
   LSPS_CHECK_LAUNCH(ctx, "norm_bwd_apply");
+  return LSPS_OK;
+}
+extern "C" int lsps_bn_running_update(lsps_ctx* ctx, const float* sums, float* running_mean, float* running_var, int c,
+                                      float count, float momentum, lsps_stream st) {
+  REQUIRE(ctx, sums && running_mean && running_var && c > 0 && count > 0.f, LSPS_E_ARG, "bn_running_update: arg");
+  bn_running_update_kernel<<<(c + 127) / 128, 128, 0, ST_(st)>>>(sums, running_mean, running_var, c, count, momentum);
+  LSPS_CHECK_LAUNCH(ctx, "bn_running_update");
+  return LSPS_OK;
+}
+extern "C" int lsps_bn_running_to_sums(lsps_ctx* ctx, const float* running_mean, const float* running_var, float* sums,
+                                       int c, float count, lsps_stream st) {
+  REQUIRE(ctx, sums && running_mean && running_var && c > 0 && count > 0.f, LSPS_E_ARG, "bn_running_to_sums: arg");
+  bn_running_to_sums_kernel<<<(c + 127) / 128, 128, 0, ST_(st)>>>(running_mean, running_var, sums, c, count);
+  LSPS_CHECK_LAUNCH(ctx, "bn_running_to_sums");
   return LSPS_OK;
 }
 extern "C" int lsps_norm_reduce_images(lsps_ctx* ctx, const float* sums, float* out, int n, int c, lsps_stream st) {
@@ -1459,6 +1602,23 @@ static int run_mask_to_bf16(lsps_ctx* ctx, const float* df, const void* f, void*
   mask_to_bf16_kernel<<<grid_for(n, 256, 8 * ctx->num_sms), 256, 0, ST_(st)>>>(df, static_cast<const bf16*>(f),
                                                                              static_cast<bf16*>(out), slope, n, sc);
   LSPS_CHECK_LAUNCH(ctx, "mask_to_bf16");
+  return LSPS_OK;
+}
+extern "C" int lsps_dhead_bce(lsps_ctx* ctx, const void* f, const float* w, const float* bias, long long rows, int c,
+                              int split, long long rows_per_group, int ngroups, const float* targets, const int* slots,
+                              float scale, float* logits, float* df, float* dw, float* db, float* acc, lsps_stream st) {
+  REQUIRE(ctx, f && w && bias && acc && targets && slots && rows > 0, LSPS_E_ARG, "dhead_bce: null");
+  REQUIRE(ctx, c % 8 == 0 && c <= 2048 && ngroups >= 1 && ngroups <= 8 && rows_per_group > 0 &&
+               rows_per_group * ngroups >= rows, LSPS_E_SHAPE, "dhead_bce: c <= 2048, <= 8 row groups covering all rows");
+  DheadGroups G;
+  for (int i = 0; i < 8; ++i) { G.tgt[i] = i < ngroups ? targets[i] : -1.f; G.slot[i] = i < ngroups ? slots[i] : 0; }
+  // few rows per warp keeps the dw atomics count down (rows/rpw x c) while still filling the machine
+  int rpw = (int)((rows + 8LL * 2 * ctx->num_sms - 1) / (8LL * 2 * ctx->num_sms));
+  if (rpw < 1) rpw = 1;
+  const long long warps = (rows + rpw - 1) / rpw;
+  dhead_bce_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, ST_(st)>>>(static_cast<const bf16*>(f), w, bias, rows, c, split,
+                                                                   rows_per_group, G, scale, logits, df, dw, db, acc, rpw);
+  LSPS_CHECK_LAUNCH(ctx, "dhead_bce");
   return LSPS_OK;
 }
 extern "C" int lsps_mask_to_bf16(lsps_ctx* ctx, const float* df, const void* f, void* out, float slope, long long n,

@@ -136,6 +136,7 @@ struct IgemmParams {
   // split-bf16 ("bf16x3") operands: A tensor channels are [hi | lo] (lo half a_lo channels in), the weights come as two
   // tensors (tmB hi, tmBlo lo); K-steps per (tap, chunk): hi*hi, hi*lo, lo*hi; the output is written as [hi | lo] too
   int split, a_lo, kch_eff;
+  int a_group;      // grouped conv: N tile nt reads A channels [nt * a_group, (nt + 1) * a_group); 0 = dense
   int gpb;          // multi-phase launches: M groups per block of the block-major tile order (0 = phase-major)
   Phase ph[4];
   Tap taps[16];
@@ -219,17 +220,24 @@ __device__ __forceinline__ void red_add_f32(float* addr, float v) {
 
 // Epilogue role (4 warps): TMEM -> registers -> (+bias, statistics, LeakyReLU, +residual gradient, *lrelu'(mask) or the
 // InstanceNorm-backward front half) -> bf16 (or split hi|lo) -> global.
-template <int BN, int CG>
+// EG = epilogue warp groups.  EG == 2 (short-K layers, where one tile's MMAs are done before four warps have drained
+// the previous tile): warps 2-5 take the tiles of accumulator buffer 0, warps 6-9 those of buffer 1, so every group has
+// two tile periods per epilogue; this variant compiles the plain bias / LeakyReLU / mask / add epilogue only (the
+// statistics, InstanceNorm-backward and split-output paths stay in the EG == 1 kernels, which keeps it under 204 registers).
+template <int BN, int CG, int EG>
 __device__ __forceinline__ void epilogue_role(const IgemmParams& p, const float* sbias, uint32_t tmem_base,
                                               uint64_t* tfull, uint64_t* tempty, int warp, int lane, int rank,
                                               int worker, int nworkers, int groups_m, int per_phase, int total) {
+    constexpr bool FULL = EG == 1;
     const int q = warp & 3;  // TMEM lane quarter this warp may read
+    const int egroup = (warp - 2) >> 2;
     const int row = q * 32 + lane;
     const int tw_mask = (1 << p.twl) - 1, th_mask = (1 << p.thl) - 1;
     const int xl = row & tw_mask, yl = (row >> p.twl) & th_mask, nl = row >> (p.twl + p.thl);
-    const bool inbwd = (p.flags & LSPS_EP_INBWD) != 0;
+    const bool inbwd = FULL && (p.flags & LSPS_EP_INBWD) != 0;
     int it = 0;
     for (int t = worker; t < total; t += nworkers, ++it) {
+      if (EG == 2 && (it & 1) != egroup) continue;
       const TileCoord tc = decode_tile(p, t, per_phase, groups_m, CG, rank);
       const int nt = tc.nt, x0 = tc.x0, y0 = tc.y0, n = tc.ti * p.nb + nl;
       const Phase P = p.ph[tc.pi];
@@ -292,7 +300,7 @@ __device__ __forceinline__ void epilogue_role(const IgemmParams& p, const float*
             f[4 * j] += b.x; f[4 * j + 1] += b.y; f[4 * j + 2] += b.z; f[4 * j + 3] += b.w;
           }
         }
-        if (p.flags & LSPS_EP_STATS) {   // warp-uniform branch; invalid (phantom) rows contribute zeros
+        if (FULL && (p.flags & LSPS_EP_STATS)) {   // warp-uniform branch; invalid (phantom) rows contribute zeros
           float s[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) s[j] = valid ? f[j] : 0.f;
@@ -358,7 +366,7 @@ __device__ __forceinline__ void epilogue_role(const IgemmParams& p, const float*
           }
         }
         if (valid) {
-          if (p.split) {
+          if (FULL && p.split) {
             // 16 mantissa bits: hi = bf16(f), lo = bf16(f - hi); the lo half sits nc_total channels further
             uint4* o4l = reinterpret_cast<uint4*>(p.out + off + p.nc_total);
 #pragma unroll
@@ -390,8 +398,8 @@ __device__ __forceinline__ void epilogue_role(const IgemmParams& p, const float*
 }
 
 // warp 0: TMA producer | warp 1: TMEM owner + MMA issuer | warps 2-5: epilogue (TMEM -> regs -> global)
-template <int BN, int CG, int KCH>
-__global__ void __launch_bounds__(192, 1)
+template <int BN, int CG, int KCH, int EG>
+__global__ void __launch_bounds__(64 + 128 * EG, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const __grid_constant__ CUtensorMap tmBlo, const __grid_constant__ IgemmParams p) {
   using Cfg = IgemmCfg<BN, CG, KCH>;
@@ -461,6 +469,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         // K-steps (tap, 64-channel chunk) are flattened; a stage carries up to KCH consecutive ones
         const int nks = P.ntaps * p.kch_eff;
         const int4* kt = ktab + P.tap0 * p.kch_eff;
+        const int a_goff = nt * p.a_group;
         const int brow_off = nt * BN + rank * (BN / 2) * (CG - 1) + ((p.nsplit && n0 >= p.nsplit) ? p.brow1 : p.brow0);
         for (int i0 = 0; i0 < nks; i0 += KCH) {
           const int cnt = nks - i0 < KCH ? nks - i0 : KCH;
@@ -479,10 +488,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 const int ap = e.z & 7, kcol = e.z >> 4;
                 const CUtensorMap* tb = (e.z & 8) ? &tmBlo : &tmB;
                 if (CG == 2) {
-                  tma_load_5d_cg2(da, &tmA, &full[stage], e.x, x0 + ax, ap, y0 + ay, n0);
+                  tma_load_5d_cg2(da, &tmA, &full[stage], e.x + a_goff, x0 + ax, ap, y0 + ay, n0);
                   tma_load_2d_cg2(db, tb, &full[stage], kcol, e.w + brow_off);
                 } else {
-                  tma_load_5d(da, &tmA, &full[stage], e.x, x0 + ax, ap, y0 + ay, n0);
+                  tma_load_5d(da, &tmA, &full[stage], e.x + a_goff, x0 + ax, ap, y0 + ay, n0);
                   tma_load_2d(db, tb, &full[stage], kcol, e.w + brow_off);
                 }
               }
@@ -528,12 +537,202 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       }
     }
   } else {
-    epilogue_role<BN, CG>(p, sbias, tmem_base, tfull, tempty, warp, lane, rank, worker, nworkers, groups_m, per_phase, total);
+    epilogue_role<BN, CG, EG>(p, sbias, tmem_base, tfull, tempty, warp, lane, rank, worker, nworkers, groups_m, per_phase, total);
   }
   tc_fence_before();
   if (CG == 2) cluster_sync_all(); else __syncthreads();
   if (warp == 1) { if (CG == 2) tmem_dealloc_cg2(tmem_base, Cfg::TMEM_COLS); else tmem_dealloc(tmem_base, Cfg::TMEM_COLS); }
 }
+
+// ------------------------------------------------------------------------------------------------ 2x up-sampling, N = 64
+// ConvTranspose2d(3x3, s2, p1, op1) forward and the data gradient of Conv2d(3x3, s2, p1) write a 2x finer grid: output
+// pixel (2i+a, 2j+b) ("phase" (a,b)) is a sum over 1/2/2/4 of the 9 taps of input pixels (i+dy, j+dx), dy,dx in {0,1}.
+// The generic kernel runs the four phases as four GEMMs (9 A-tile loads and 9 weight-tile loads per 64-channel chunk,
+// one pipeline handshake each, the input re-read from DRAM once per phase).  For the two widest such layers of the
+// generator (128 -> 64 channels at 64x64 -> 128x128, N = 64) that is handshake- and L2-bound (ncu: 13-17 % tensor pipe,
+// 2 GB of L2->SM traffic for 0.4 GB of algorithmic bytes).  Here ONE CTA computes all four phases of its 128 input
+// pixels: the whole weight tensor (9 taps x K <= 128 x 64 = 144 KB) is loaded into shared memory once per CTA, each
+// of the 4 shifted A tiles is loaded once per chunk and feeds every tap that uses it (4/2/2/1 MMAs groups), the four
+// 128x64 accumulators live side by side in TMEM (256 columns, double-buffered).
+struct Up64Params {
+  int tiles_x, tiles_y, tiles_i, twl, thl, nb, txl, tyl, nimg, kchunks;
+  long long o_n, o_y, o_x;     // OUTPUT strides (elements); output pixel = (2y + a, 2x + b)
+  __nv_bfloat16* out;
+  const float* bias;
+  const __nv_bfloat16* mask;
+  float slope;
+  int flags;
+  int nc;                      // = 64: weight rows per tap
+};
+constexpr int UP64_W_TILE = 64 * 128;          // one (tap, chunk) weight tile: 64 rows x 64 bf16
+constexpr int UP64_A_SLOTS = 3;
+// taps of each A shift s = dy*2 + dx: (tap index r*3+c, phase a*2+b); see t2_axis()
+__constant__ int c_up64_ntaps[4] = {4, 2, 2, 1};
+__constant__ int c_up64_tap[4][4] = {{4, 5, 7, 8}, {3, 6, 0, 0}, {1, 2, 0, 0}, {0, 0, 0, 0}};
+__constant__ int c_up64_phase[4][4] = {{0, 1, 2, 3}, {1, 3, 0, 0}, {2, 3, 0, 0}, {3, 0, 0, 0}};
+
+__global__ void __launch_bounds__(320, 1)
+conv_up64_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const __grid_constant__ Up64Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int wtiles = 9 * p.kchunks;
+  uint8_t* sW = base;                                   // [tap][chunk] weight tiles, resident
+  uint8_t* sA = base + 18 * UP64_W_TILE;                // ring of A tiles
+  uint64_t* full = reinterpret_cast<uint64_t*>(sA + UP64_A_SLOTS * A_STAGE_BYTES);
+  uint64_t* empty = full + UP64_A_SLOTS;
+  uint64_t* wfull = empty + UP64_A_SLOTS;
+  uint64_t* tfull = wfull + 1;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  float* sbias = reinterpret_cast<float*>(tmem_slot + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if ((p.flags & LSPS_EP_BIAS) && threadIdx.x < 64) sbias[threadIdx.x] = p.bias[threadIdx.x];
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < UP64_A_SLOTS; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    mbar_init(wfull, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
+    fence_barrier_init();
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int total = p.tiles_x * p.tiles_y * p.tiles_i;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(wfull, wtiles * UP64_W_TILE);
+      for (int tap = 0; tap < 9; ++tap)
+        for (int kc = 0; kc < p.kchunks; ++kc)
+          tma_load_2d(sW + (tap * p.kchunks + kc) * UP64_W_TILE, &tmB, wfull, kc * 64, tap * p.nc);
+      int slot = 0; uint32_t ph = 0;
+      for (int t = blockIdx.x; t < total; t += gridDim.x) {
+        const int tx = t & (p.tiles_x - 1), ty = (t >> p.txl) & (p.tiles_y - 1), ti = t >> (p.txl + p.tyl);
+        const int x0 = tx << p.twl, y0 = ty << p.thl, n0 = ti * p.nb;
+        for (int kc = 0; kc < p.kchunks; ++kc)
+          for (int sft = 0; sft < 4; ++sft) {
+            mbar_wait(&empty[slot], ph ^ 1);
+            mbar_expect_tx(&full[slot], A_STAGE_BYTES);
+            tma_load_5d(sA + slot * A_STAGE_BYTES, &tmA, &full[slot], kc * 64, x0 + (sft & 1), 0, y0 + (sft >> 1), n0);
+            if (++slot == UP64_A_SLOTS) { slot = 0; ph ^= 1; }
+          }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(128, 64, 0, 0);
+      constexpr uint64_t dbase = umma_desc_base(0, 1024);
+      const uint32_t sA_u32 = smem_u32(sA), sW_u32 = smem_u32(sW);
+      mbar_wait(wfull, 0);
+      tc_fence_after();
+      int slot = 0; uint32_t ph = 0; int it = 0;
+      for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
+        const int acc = it & 1; const uint32_t accph = (it >> 1) & 1;
+        mbar_wait(&tempty[acc], accph ^ 1);
+        tc_fence_after();
+        const uint32_t d0 = tmem_base + acc * 256;
+        for (int kc = 0; kc < p.kchunks; ++kc)
+          for (int sft = 0; sft < 4; ++sft) {
+            mbar_wait(&full[slot], ph);
+            tc_fence_after();
+            const uint64_t a_base = dbase | ((sA_u32 + slot * A_STAGE_BYTES) >> 4);
+            const int nt = c_up64_ntaps[sft];
+            for (int j = 0; j < nt; ++j) {
+              const uint64_t b_base = dbase | ((sW_u32 + (c_up64_tap[sft][j] * p.kchunks + kc) * UP64_W_TILE) >> 4);
+              const uint32_t d = d0 + c_up64_phase[sft][j] * 64;
+#pragma unroll
+              for (int k = 0; k < 4; ++k)      // the first chunk's shift-0 taps open the four accumulators
+                umma_bf16(d, a_base + k * 2, b_base + k * 2, idesc, (kc | sft | k) != 0 ? 1u : 0u);
+            }
+            umma_commit(&empty[slot]);
+            if (++slot == UP64_A_SLOTS) { slot = 0; ph ^= 1; }
+          }
+        umma_commit(&tfull[acc]);
+      }
+    }
+  } else {
+    // two epilogue warp groups (warps 2-5: accumulator set 0, warps 6-9: set 1): a tile's 8 TMEM chunks with their
+    // global mask loads and strided stores take longer than its 36-72 MMAs, so each group gets two tile periods
+    const int q = warp & 3;
+    const int egroup = (warp - 2) >> 2;
+    const int row = q * 32 + lane;
+    const int tw_mask = (1 << p.twl) - 1, th_mask = (1 << p.thl) - 1;
+    const int xl = row & tw_mask, yl = (row >> p.twl) & th_mask, nl = row >> (p.twl + p.thl);
+    int it = 0;
+    for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
+      if ((it & 1) != egroup) continue;
+      const int tx = t & (p.tiles_x - 1), ty = (t >> p.txl) & (p.tiles_y - 1), ti = t >> (p.txl + p.tyl);
+      const int x0 = tx << p.twl, y0 = ty << p.thl, n = ti * p.nb + nl;
+      const bool valid = n < p.nimg;
+      const int acc = it & 1; const uint32_t accph = (it >> 1) & 1;
+      mbar_wait(&tfull[acc], accph);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * 256;
+#pragma unroll 1
+      for (int c8 = 0; c8 < 8; ++c8) {          // 4 phases x 2 chunks of 32 columns
+        const int phs = c8 >> 1, c0 = (c8 & 1) * 32;
+        const long long off = (long long)n * p.o_n + (long long)((y0 + yl) * 2 + (phs >> 1)) * p.o_y +
+                              (long long)((x0 + xl) * 2 + (phs & 1)) * p.o_x + c0;
+        uint4 gm[4];
+        if (valid && (p.flags & LSPS_EP_MASK)) {
+          const uint4* m4 = reinterpret_cast<const uint4*>(p.mask + off);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) gm[j] = __ldg(m4 + j);
+        }
+        uint32_t v[32];
+        tmem_ld32(taddr + phs * 64 + c0, v);
+        tmem_ld_wait();
+        if (c8 == 7) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty[acc]);
+        }
+        if (!valid) continue;
+        float f[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+        if (p.flags & LSPS_EP_BIAS) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] += sbias[c0 + j];
+        }
+        if (p.flags & LSPS_EP_LRELU) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = f[j] > 0.f ? f[j] : f[j] * p.slope;
+        }
+        if (p.flags & LSPS_EP_MASK) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint32_t w[4] = {gm[j].x, gm[j].y, gm[j].z, gm[j].w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              if (!(bf16lo(w[k]) > 0.f)) f[8 * j + 2 * k] *= p.slope;
+              if (!(bf16hi(w[k]) > 0.f)) f[8 * j + 2 * k + 1] *= p.slope;
+            }
+          }
+        }
+        uint4* o4 = reinterpret_cast<uint4*>(p.out + off);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          uint4 o;
+          o.x = pack_bf16x2(f[8 * j], f[8 * j + 1]);
+          o.y = pack_bf16x2(f[8 * j + 2], f[8 * j + 3]);
+          o.z = pack_bf16x2(f[8 * j + 4], f[8 * j + 5]);
+          o.w = pack_bf16x2(f[8 * j + 6], f[8 * j + 7]);
+          o4[j] = o;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+constexpr int UP64_SMEM = 18 * UP64_W_TILE + UP64_A_SLOTS * A_STAGE_BYTES + 1024 + 512;
 
 // ------------------------------------------------------------------------------------------------ wgrad
 struct WTap { short mc, mx, mp, my, nc, nx, np, ny; };  // tap offsets in the dy (M side) / x (N side) maps
@@ -546,6 +745,9 @@ struct WgradParams {
   // split-bf16 operands (dy and x stored as [hi | lo] channel halves): three passes per pixel tile into the same
   // accumulator -- dy_hi x x_hi, dy_hi x x_lo (x channels + n_lo), dy_lo (dy channels + m_lo) x x_hi
   int nvar, m_lo, n_lo;
+  // grouped conv (gw = group width, 0 = dense): only the diagonal (co tile, ci tile) pairs are computed, the x channels
+  // are those of the dy tile, and the epilogue keeps the gw x gw blocks on the diagonal: dw[tap][cout][gw]
+  int gw;
   float* dw;
   WTap taps[16];
 };
@@ -584,6 +786,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ CU
   const int split = b % p.splits; b /= p.splits;
   const int cit = b % p.ci_tiles; b /= p.ci_tiles;
   const int cot = (b % p.co_tiles) * CG + rank;   // this CTA's 128-channel tile of dy
+  const int nbase = p.gw ? (b % p.co_tiles) * CG * 128 : cit * BN;   // first x channel of the N tile
   const int tap = b / p.co_tiles;
   const int ptiles = p.tiles_x * p.tiles_y * p.tiles_i;
   const int pt0 = (int)((long long)ptiles * split / p.splits);
@@ -633,7 +836,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ CU
         else tma_load_5d(s + lane * W_BOX_BYTES, &tmM, &full[stage], cot * 128 + lane * 64 + T.mc + m_off, x0 + T.mx, T.mp, y0 + T.my, n0);
       } else if (lane < nboxes) {
         const int j = lane - nA;
-        const int cbase = cit * BN + (rank * Cfg::NB_BOXES + j) * 64 + T.nc + n_off;
+        const int cbase = nbase + (rank * Cfg::NB_BOXES + j) * 64 + T.nc + n_off;
         if (CG == 2) tma_load_5d_cg2(s + (2 + j) * W_BOX_BYTES, &tmN, &full[stage], cbase, x0 + T.nx, T.np, y0 + T.ny, n0);
         else tma_load_5d(s + (2 + j) * W_BOX_BYTES, &tmN, &full[stage], cbase, x0 + T.nx, T.np, y0 + T.ny, n0);
       }
@@ -667,7 +870,8 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ CU
     const int co = cot * 128 + q * 32 + lane;
     mbar_wait(tfull, 0);
     tc_fence_after();
-    float* dst = p.dw + ((long long)tap * p.cout + co) * p.cin + cit * BN;
+    float* dst = p.gw ? p.dw + ((long long)tap * p.cout + co) * p.gw - (co / p.gw) * p.gw + nbase
+                      : p.dw + ((long long)tap * p.cout + co) * p.cin + cit * BN;
     const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     uint32_t v[32];
     tmem_ld32(taddr, v);
@@ -678,7 +882,8 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ CU
 #pragma unroll
       for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
       if (c0 + 32 < BN) tmem_ld32(taddr + c0 + 32, v);
-      if (co < p.cout) {
+      // grouped: x channel nbase + c0 must lie in the group of output channel co (dst then indexes it within the group)
+      if (co < p.cout && (p.gw == 0 || (nbase + c0) / p.gw == co / p.gw)) {
 #pragma unroll
         for (int j = 0; j < 8; ++j)
           asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + c0 + 4 * j), "f"(f[4 * j]),
@@ -756,6 +961,16 @@ inline bool lsps_phase_major() {
   if (v < 0) { const char* e = getenv("LSPS_PHASE_MAJOR"); v = (e && e[0] == '1') ? 1 : 0; }
   return v == 1;
 }
+inline bool lsps_one_epi_group() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("LSPS_ONE_EPI_GROUP"); v = (e && e[0] == '1') ? 1 : 0; }
+  return v == 1;
+}
+inline bool lsps_no_up64() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("LSPS_NO_UP64"); v = (e && e[0] == '1') ? 1 : 0; }
+  return v == 1;
+}
 inline bool lsps_use_pairs() {
   static int v = -1;
   if (v < 0) { const char* e = getenv("LSPS_NO_PAIRS"); v = (e && e[0] == '1') ? 0 : 1; }
@@ -763,9 +978,9 @@ inline bool lsps_use_pairs() {
 }
 
 template <typename K, typename... Args>
-cudaError_t launch_maybe_cluster(K kernel, int grid, int smem, int cg, cudaStream_t st, Args... args) {
+cudaError_t launch_maybe_cluster(K kernel, int grid, int smem, int cg, cudaStream_t st, int threads, Args... args) {
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(192); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(threads); cfg.dynamicSmemBytes = smem; cfg.stream = st;
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeClusterDimension;
   at[0].val.clusterDim.x = cg; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
@@ -773,20 +988,21 @@ cudaError_t launch_maybe_cluster(K kernel, int grid, int smem, int cg, cudaStrea
   return cudaLaunchKernelEx(&cfg, kernel, args...);
 }
 
-template <int BN, int CG, int KCH = 1>
+template <int BN, int CG, int KCH = 1, int EG = 1>
 int launch_igemm(lsps_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmBlo, const IgemmParams& p,
                  cudaStream_t st) {
   using Cfg = IgemmCfg<BN, CG, KCH>;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(conv_igemm_kernel<BN, CG, KCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(conv_igemm_kernel<BN, CG, KCH, EG>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return lsps_set_error(ctx, LSPS_E_CUDA, "igemm smem attr: %s", cudaGetErrorString(e));
     configured = true;
   }
   const int tiles_m = p.tiles_x * p.tiles_y * p.tiles_i;
   const int total = ((tiles_m + CG - 1) / CG) * p.tiles_n * p.nphases;
   const int workers = total < ctx->num_sms / CG ? total : ctx->num_sms / CG;
-  cudaError_t e = launch_maybe_cluster(conv_igemm_kernel<BN, CG, KCH>, workers * CG, Cfg::SMEM_BYTES, CG, st, tmA, tmB, tmBlo, p);
+  cudaError_t e = launch_maybe_cluster(conv_igemm_kernel<BN, CG, KCH, EG>, workers * CG, Cfg::SMEM_BYTES, CG, st, 64 + 128 * EG,
+                                       tmA, tmB, tmBlo, p);
   if (e != cudaSuccess) return lsps_set_error(ctx, LSPS_E_CUDA, "conv_igemm launch: %s", cudaGetErrorString(e));
   LSPS_CHECK_LAUNCH(ctx, "conv_igemm");
   return LSPS_OK;
@@ -811,21 +1027,28 @@ int run_igemm(lsps_ctx* ctx, const lsps_conv_shape* s, Dir dir, const void* in, 
     return lsps_set_error(ctx, LSPS_E_ARG, "inbwd flag needs in_a, bsums, a positive slope and excludes mask");
   if (flags & LSPS_EP_INBWD) mask = ext->in_a;
   const int kind = s->kind, n = s->n, h = s->h, w = s->w, cin = s->cin, cout = s->cout;
-  if (kind < 0 || kind > 3 || n <= 0 || !is_pow2(h) || !is_pow2(w) || cin % 64 || cout % 64 || cin <= 0 || cout <= 0)
+  if (kind < 0 || kind > 4 || n <= 0 || !is_pow2(h) || !is_pow2(w) || cin % 64 || cout % 64 || cin <= 0 || cout <= 0)
     return lsps_set_error(ctx, LSPS_E_SHAPE, "conv shape kind %d n %d h %d w %d cin %d cout %d", kind, n, h, w, cin, cout);
-  if (kind != LSPS_CONV_S1 && (h < 2 || w < 2)) return lsps_set_error(ctx, LSPS_E_SHAPE, "stride-2 op needs h,w >= 2");
+  const bool k1 = kind == LSPS_CONV1X1;
+  if (kind != LSPS_CONV_S1 && !k1 && (h < 2 || w < 2)) return lsps_set_error(ctx, LSPS_E_SHAPE, "stride-2 op needs h,w >= 2");
+  // grouped 3x3 stride-1 conv (ResNeXt, common_net.py:118): every N tile is one group and reads only its own K channels
+  const int groups = ext->groups > 1 ? ext->groups : 1;
+  const int gw = cin / groups;
+  if (groups > 1 && (kind != LSPS_CONV_S1 || cin != cout || cin % groups || (gw != 64 && gw != 128) || split || nsplit))
+    return lsps_set_error(ctx, LSPS_E_SHAPE, "grouped conv: 3x3 stride 1, cin == cout, group width 64 or 128 (got %d)", gw);
   if (cin > 2048 || cout > 2048) return lsps_set_error(ctx, LSPS_E_SHAPE, "channels > 2048 (bias / K-step tables are sized for 2048)");
   if ((flags & LSPS_EP_BIAS) && !bias) return lsps_set_error(ctx, LSPS_E_ARG, "bias flag without bias");
   if ((flags & LSPS_EP_MASK) && !mask) return lsps_set_error(ctx, LSPS_E_ARG, "mask flag without mask");
   if ((flags & LSPS_EP_ADD) && !add) return lsps_set_error(ctx, LSPS_E_ARG, "add flag without add");
 
   // forward-op output dims
-  const int ho = kind == LSPS_CONV_S1 ? h : (kind == LSPS_CONV_S2 ? h / 2 : 2 * h);
-  const int wo = kind == LSPS_CONV_S1 ? w : (kind == LSPS_CONV_S2 ? w / 2 : 2 * w);
+  const int ho = (kind == LSPS_CONV_S1 || k1) ? h : (kind == LSPS_CONV_S2 ? h / 2 : 2 * h);
+  const int wo = (kind == LSPS_CONV_S1 || k1) ? w : (kind == LSPS_CONV_S2 ? w / 2 : 2 * w);
   const bool k4 = kind == LSPS_DECONV4_S2;
-  const int ks = k4 ? 4 : 3;
-  // GEMM dims: K channels (of `in`), N channels (of `out`)
-  const int kc = dir == FWD ? cin : cout, nc = dir == FWD ? cout : cin;
+  const int ks = k4 ? 4 : (k1 ? 1 : 3);
+  // GEMM dims: K channels (of `in`; per group), N channels (of `out`)
+  const int kten = dir == FWD ? cin : cout;            // channels of the `in` tensor
+  const int kc = groups > 1 ? gw : kten, nc = dir == FWD ? cout : cin;
   // `in` / `out` tensor dims
   const int ih = dir == FWD ? h : ho, iw = dir == FWD ? w : wo;
   const int oh = dir == FWD ? ho : h, ow = dir == FWD ? wo : w;
@@ -833,7 +1056,7 @@ int run_igemm(lsps_ctx* ctx, const lsps_conv_shape* s, Dir dir, const void* in, 
   //   plain  : out grid == in grid, 9 shifted taps                       (S1 fwd, S1 dgrad)
   //   down   : out grid = in grid / 2, pair view on `in`                 (S2 fwd, DECONV dgrad)
   //   up     : out grid = 2 * in grid, 4 phases, strided store           (DECONV fwd, S2 dgrad)
-  const bool plain = kind == LSPS_CONV_S1;
+  const bool plain = kind == LSPS_CONV_S1 || k1;
   const bool down = (kind == LSPS_CONV_S2 && dir == FWD) || ((kind == LSPS_DECONV_S2 || k4) && dir == DGRAD);
   const int hg = down ? ih / 2 : ih, wg = down ? iw / 2 : iw;  // GEMM pixel grid
   const Geo g = geo_for(hg, wg, 128);
@@ -846,7 +1069,8 @@ int run_igemm(lsps_ctx* ctx, const lsps_conv_shape* s, Dir dir, const void* in, 
   p.split = split ? 1 : 0; p.a_lo = kc; p.kch_eff = split ? 3 * p.kchunks : p.kchunks; p.nc_total = nc;
   if (p.ntaps_all * p.kch_eff > 1024) return lsps_set_error(ctx, LSPS_E_SHAPE, "K-step table overflow (%d steps)", p.ntaps_all * p.kch_eff);
   p.sums = ext->sums; p.bsums = ext->bsums; p.inv_slope = slope > 0.f ? 1.f / slope : 0.f;
-  const int kct = split ? 2 * kc : kc, nct = split ? 2 * nc : nc;     // channels of the `in` / `out` TENSORS
+  const int kct = split ? 2 * kten : kten, nct = split ? 2 * nc : nc;     // channels of the `in` / `out` TENSORS
+  p.a_group = groups > 1 ? gw : 0;
   if ((flags & (LSPS_EP_STATS | LSPS_EP_INBWD)) && hg * wg < 32)
     return lsps_set_error(ctx, LSPS_E_SHAPE, "fused statistics need >= 32 GEMM pixels per image");
   p.o_n = (long long)oh * ow * nct; p.o_y = (long long)ow * nct; p.o_x = nct;
@@ -855,7 +1079,11 @@ int run_igemm(lsps_ctx* ctx, const lsps_conv_shape* s, Dir dir, const void* in, 
   p.slope = slope; p.flags = flags; p.dbg = lsps_dbg();
 
   int nt = 0;
-  if (plain) {
+  if (k1) {
+    p.nphases = 1; p.o_sy = p.o_sx = 1;
+    p.ph[0] = Phase{0, 1, 0, 0};
+    p.taps[nt++] = Tap{0, 0, 0, 0, 0};
+  } else if (plain) {
     p.nphases = 1; p.o_sy = p.o_sx = 1;
     p.ph[0] = Phase{0, 9, 0, 0};
     for (int r = 0; r < 3; ++r)
@@ -895,7 +1123,7 @@ int run_igemm(lsps_ctx* ctx, const lsps_conv_shape* s, Dir dir, const void* in, 
     }
   }
 
-  const int bn = nc % 256 == 0 ? 256 : (nc % 128 == 0 ? 128 : 64);
+  const int bn = groups > 1 ? gw : (nc % 256 == 0 ? 256 : (nc % 128 == 0 ? 128 : 64));
   p.tiles_n = nc / bn;
   // grouped launch: one tensor map over both weight sets (they live in one flat buffer)
   const char* wbase = static_cast<const char*>(wpk);
@@ -923,6 +1151,30 @@ int run_igemm(lsps_ctx* ctx, const lsps_conv_shape* s, Dir dir, const void* in, 
   const int force = lsps_force_cg();
   int cg = (lsps_use_pairs() && tiles_m >= 2 && nk_min >= 27 && (long long)tiles_m * p.tiles_n >= 2 * ctx->num_sms) ? 2 : 1;
   if (force && tiles_m >= 2) cg = force;
+  // the two N = 64, K <= 128 up-sampling layers of the generator: all four phases in one pass, resident weights
+  if (!plain && !down && !k4 && nc == 64 && p.kchunks <= 2 && !split && nsplit == 0 && tiles_m >= 1 &&
+      !(flags & (LSPS_EP_ADD | LSPS_EP_STATS | LSPS_EP_INBWD)) && !lsps_no_up64()) {
+    static bool configured = false;
+    if (!configured) {
+      cudaError_t e = cudaFuncSetAttribute(conv_up64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, UP64_SMEM);
+      if (e != cudaSuccess) return lsps_set_error(ctx, LSPS_E_CUDA, "up64 smem attr: %s", cudaGetErrorString(e));
+      configured = true;
+    }
+    Up64Params u{};
+    u.tiles_x = p.tiles_x; u.tiles_y = p.tiles_y; u.tiles_i = p.tiles_i; u.twl = p.twl; u.thl = p.thl; u.nb = p.nb;
+    u.txl = p.txl; u.tyl = p.tyl; u.nimg = n; u.kchunks = p.kchunks;
+    u.o_n = p.o_n; u.o_y = p.o_y; u.o_x = p.o_x; u.out = p.out; u.bias = bias; u.mask = p.mask; u.slope = slope;
+    u.flags = flags; u.nc = nc;
+    CUtensorMap tA, tB;
+    int rc2 = act_tmap(ctx, in, n, ih, iw, kct, false, g, &tA);
+    if (rc2) return rc2;
+    uint32_t wd2[2] = {(uint32_t)kc, (uint32_t)(9 * nc)}, wb2[2] = {64, 64};
+    if ((rc2 = lsps_get_tmap(ctx, wpk, 2, wd2, wb2, &tB))) return rc2;
+    const int grid = tiles_m < ctx->num_sms ? tiles_m : ctx->num_sms;
+    conv_up64_kernel<<<grid, 320, UP64_SMEM, st>>>(tA, tB, u);
+    LSPS_CHECK_LAUNCH(ctx, "conv_up64");
+    return LSPS_OK;
+  }
   if (p.nphases > 1 && !lsps_phase_major()) {
     // ~512 tiles per phase and block: enough to fill every SM twice, small enough that the block's input stays in L2
     const int tiles_img = p.tiles_x * p.tiles_y;
@@ -952,9 +1204,11 @@ int run_igemm(lsps_ctx* ctx, const lsps_conv_shape* s, Dir dir, const void* in, 
     return launch_igemm<64, 2>(ctx, tmA, tmB, tmBlo, p, st);
   }
   if (bn == 256) return launch_igemm<256, 1>(ctx, tmA, tmB, tmBlo, p, st);
-  // single-CTA BN <= 128 kernels stage one 64-channel chunk per pipeline stage (2 and 3 chunks measured slower, r01 probes)
-  if (bn == 128) return launch_igemm<128, 1>(ctx, tmA, tmB, tmBlo, p, st);
-  return launch_igemm<64, 1>(ctx, tmA, tmB, tmBlo, p, st);
+  // single-CTA BN <= 128 kernels stage one 64-channel chunk per pipeline stage (2 and 3 chunks measured slower, r01 probes);
+  // with a plain epilogue they run two epilogue warp groups (these short-K tiles are epilogue-bound with one)
+  const bool light = !split && !(flags & (LSPS_EP_STATS | LSPS_EP_INBWD)) && !lsps_one_epi_group();
+  if (bn == 128) return light ? launch_igemm<128, 1, 1, 2>(ctx, tmA, tmB, tmBlo, p, st) : launch_igemm<128, 1>(ctx, tmA, tmB, tmBlo, p, st);
+  return light ? launch_igemm<64, 1, 1, 2>(ctx, tmA, tmB, tmBlo, p, st) : launch_igemm<64, 1>(ctx, tmA, tmB, tmBlo, p, st);
 }
 
 template <int BN, int CG>
@@ -967,7 +1221,7 @@ int launch_wgrad(lsps_ctx* ctx, const CUtensorMap& tmM, const CUtensorMap& tmN, 
     configured = true;
   }
   const int grid = p.ntaps * p.co_tiles * p.ci_tiles * p.splits * CG;
-  cudaError_t e = launch_maybe_cluster(wgrad_kernel<BN, CG>, grid, Cfg::SMEM_BYTES, CG, st, tmM, tmN, p);
+  cudaError_t e = launch_maybe_cluster(wgrad_kernel<BN, CG>, grid, Cfg::SMEM_BYTES, CG, st, 192, tmM, tmN, p);
   if (e != cudaSuccess) return lsps_set_error(ctx, LSPS_E_CUDA, "wgrad launch: %s", cudaGetErrorString(e));
   LSPS_CHECK_LAUNCH(ctx, "wgrad");
   return LSPS_OK;
@@ -1025,7 +1279,7 @@ extern "C" int lsps_conv_dgrad_grouped(lsps_ctx* ctx, const lsps_conv_shape* s, 
 }
 
 static int run_wgrad(lsps_ctx* ctx, const lsps_conv_shape* s, const void* x, const void* dy, float* dw, int split,
-                     cudaStream_t st);
+                     cudaStream_t st, int groups = 1);
 extern "C" int lsps_conv_wgrad(lsps_ctx* ctx, const lsps_conv_shape* s, const void* x, const void* dy, float* dw,
                                lsps_stream st_) {
   return run_wgrad(ctx, s, x, dy, dw, 0, static_cast<cudaStream_t>(st_));
@@ -1034,30 +1288,38 @@ extern "C" int lsps_conv_wgrad_split(lsps_ctx* ctx, const lsps_conv_shape* s, co
                                      lsps_stream st_) {
   return run_wgrad(ctx, s, x, dy, dw, 1, static_cast<cudaStream_t>(st_));
 }
+extern "C" int lsps_conv_wgrad_grouped(lsps_ctx* ctx, const lsps_conv_shape* s, const void* x, const void* dy,
+                                       float* dw, int groups, lsps_stream st_) {
+  return run_wgrad(ctx, s, x, dy, dw, 0, static_cast<cudaStream_t>(st_), groups);
+}
 static int run_wgrad(lsps_ctx* ctx, const lsps_conv_shape* s, const void* x, const void* dy, float* dw, int split,
-                     cudaStream_t st) {
+                     cudaStream_t st, int groups) {
   if (!ctx || !s || !x || !dy || !dw) return lsps_set_error(ctx, LSPS_E_ARG, "null argument");
   const int kind = s->kind, n = s->n, h = s->h, w = s->w, cin = s->cin, cout = s->cout;
-  if (kind < 0 || kind > 3 || n <= 0 || !is_pow2(h) || !is_pow2(w) || cin % 64 || cout % 64 || cin <= 0 || cout <= 0)
+  if (kind < 0 || kind > 4 || n <= 0 || !is_pow2(h) || !is_pow2(w) || cin % 64 || cout % 64 || cin <= 0 || cout <= 0)
     return lsps_set_error(ctx, LSPS_E_SHAPE, "wgrad shape kind %d n %d h %d w %d cin %d cout %d", kind, n, h, w, cin, cout);
-  const int ho = kind == LSPS_CONV_S1 ? h : (kind == LSPS_CONV_S2 ? h / 2 : 2 * h);
-  const int wo = kind == LSPS_CONV_S1 ? w : (kind == LSPS_CONV_S2 ? w / 2 : 2 * w);
+  const bool k1 = kind == LSPS_CONV1X1;
+  const int gw = groups > 1 ? cin / groups : 0;
+  if (groups > 1 && (kind != LSPS_CONV_S1 || cin != cout || cin % groups || (gw != 64 && gw != 128) || cout % 128 || split))
+    return lsps_set_error(ctx, LSPS_E_SHAPE, "grouped wgrad: 3x3 stride 1, cin == cout, group width 64 or 128 (got %d)", gw);
+  const int ho = (kind == LSPS_CONV_S1 || k1) ? h : (kind == LSPS_CONV_S2 ? h / 2 : 2 * h);
+  const int wo = (kind == LSPS_CONV_S1 || k1) ? w : (kind == LSPS_CONV_S2 ? w / 2 : 2 * w);
   // reduction grid: the coarser of the two spatial grids
   const int hg = kind == LSPS_CONV_S2 ? ho : h, wg = kind == LSPS_CONV_S2 ? wo : w;
-  const int bn = cin % 256 == 0 ? 256 : (cin % 128 == 0 ? 128 : 64);
+  const int bn = gw ? 128 : (cin % 256 == 0 ? 256 : (cin % 128 == 0 ? 128 : 64));
   // CTA pairs: 256 output channels per pair, each CTA stages half of the x tile (needs >= 128 input channels)
-  const int cg = (lsps_use_pairs() && cout % 256 == 0 && bn >= 128) ? 2 : 1;
+  const int cg = (!gw && lsps_use_pairs() && cout % 256 == 0 && bn >= 128) ? 2 : 1;
   const Geo g = geo_for(hg, wg, (cg == 2 || bn <= 128) ? 128 : 64);
   WgradParams p{};
   p.tiles_x = wg / g.tw; p.tiles_y = hg / g.th; p.tiles_i = (n + g.nb - 1) / g.nb;
   p.twl = g.twl; p.thl = g.thl; p.nb = g.nb;
   const bool k4 = kind == LSPS_DECONV4_S2;
-  const int ks = k4 ? 4 : 3;
+  const int ks = k4 ? 4 : (k1 ? 1 : 3);
   p.ntaps = ks * ks; p.cout = cout; p.cin = cin; p.dw = dw; p.dbg = lsps_dbg();
-  p.nvar = split ? 3 : 1; p.m_lo = cout; p.n_lo = cin;
+  p.nvar = split ? 3 : 1; p.m_lo = cout; p.n_lo = cin; p.gw = gw;
   const int cout_t = split ? 2 * cout : cout, cin_t = split ? 2 * cin : cin;   // channels of the dy / x TENSORS
   p.co_tiles = (cout + 128 * cg - 1) / (128 * cg);
-  p.ci_tiles = cin / bn;
+  p.ci_tiles = gw ? 1 : cin / bn;
   for (int r = 0; r < ks; ++r)
     for (int c = 0; c < ks; ++c) {
       WTap& T = p.taps[r * ks + c];
@@ -1065,6 +1327,7 @@ static int run_wgrad(lsps_ctx* ctx, const lsps_conv_shape* s, const void* x, con
       if (k4) {  // dy pair view at parity ((r+1)&1, (c+1)&1); x shifted by +1 (tap 0), 0 (taps 1, 2), -1 (tap 3)
         T.mp = (r + 1) & 1; T.mc = ((c + 1) & 1) * cout_t;
         T.ny = r == 0 ? 1 : (r == 3 ? -1 : 0); T.nx = c == 0 ? 1 : (c == 3 ? -1 : 0);
+      } else if (k1) {
       } else if (kind == LSPS_CONV_S1) { T.ny = r - 1; T.nx = c - 1; }
       else if (kind == LSPS_CONV_S2) {
         int dy_, py, dx_, px;

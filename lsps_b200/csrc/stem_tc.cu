@@ -184,12 +184,14 @@ __global__ void __launch_bounds__(128) stem_wgrad_tc_kernel(const float* __restr
                                                            int wd) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  // two buffers of {taps hi, taps lo, dy [, dy lo]}: the MMAs of tile i run while the threads build tile i+1
+  // two buffers of {taps hi, taps lo, dy}: the MMAs of tile i run while the threads build tile i+1.  The split variant
+  // carries a fourth tile (dy lo) and keeps ONE buffer: two would be 132 KB and halve the CTAs per SM (measured slower).
   constexpr int BUF = (SPLIT ? 4 : 3) * A_BYTES;
+  constexpr int NBUF = SPLIT ? 1 : 2;
   const int wo = wd / S, ho = h / S;
   const int tr = TILE_PX / wo;
   const int prow = (tr - 1) * S + 7, pw = wd + 8;
-  float* patch = reinterpret_cast<float*>(base + 2 * BUF);
+  float* patch = reinterpret_cast<float*>(base + NBUF * BUF);
   uint64_t* full = reinterpret_cast<uint64_t*>(patch + prow * pw);   // dy tile landed (per buffer)
   uint64_t* done = full + 2;                                          // MMAs of the buffer retired
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 2);
@@ -212,11 +214,11 @@ __global__ void __launch_bounds__(128) stem_wgrad_tc_kernel(const float* __restr
   const int row = threadIdx.x, ty = row / wo, tx = row - ty * wo;
   int it = 0;
   for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
-    const int b = it & 1;
-    const uint32_t use = (it >> 1) & 1;
+    const int b = it % NBUF;
+    const uint32_t use = (it / NBUF) & 1;
     uint8_t* buf = base + b * BUF;
     const int im_i = t / tiles_per_img, oy0 = (t - im_i * tiles_per_img) * tr;
-    if (it >= 2) mbar_wait(&done[b], use ^ 1);   // MMAs that read this buffer two tiles ago have retired
+    if (it >= NBUF) mbar_wait(&done[b], use ^ 1);   // MMAs that read this buffer NBUF tiles ago have retired
     if (threadIdx.x == 0) {
       mbar_expect_tx(&full[b], (SPLIT ? 2 : 1) * A_BYTES);
       tma_load_2d(buf + 2 * A_BYTES, &tmDy, &full[b], 0, (im_i * ho + oy0) * wo);
@@ -248,7 +250,7 @@ __global__ void __launch_bounds__(128) stem_wgrad_tc_kernel(const float* __restr
   // drain: the last commit covers every MMA issued before it
   if (it > 0) {
     const int last = it - 1;
-    mbar_wait(&done[last & 1], (last >> 1) & 1);
+    mbar_wait(&done[last % NBUF], (last / NBUF) & 1);
     tc_fence_after();
     const int tap = (row & 63);
     const uint32_t taddr = tmem + (static_cast<uint32_t>(warp * 32) << 16);
@@ -446,9 +448,10 @@ int lsps_stem_wgrad_tc(lsps_ctx* ctx, const float* img, const void* dy, float* d
                        int stride, int split, cudaStream_t st) {
   const int wo = wd / stride, ho = h / stride, tr = TILE_PX / wo;
   const int prow = (tr - 1) * stride + 7, pw = wd + 8;
-  const int smem = 1024 + (split ? 8 : 6) * A_BYTES + prow * pw * 4 + 128;
+  const int smem = 1024 + (split ? 4 : 6) * A_BYTES + prow * pw * 4 + 128;
   const int total = (ho / tr) * n;
-  const int grid = total < 2 * ctx->num_sms ? total : 2 * ctx->num_sms;
+  const int per_sm = split ? 3 : 2;
+  const int grid = total < per_sm * ctx->num_sms ? total : per_sm * ctx->num_sms;
   CUtensorMap tm;
   uint32_t dims[2] = {split ? 128u : 64u, (uint32_t)((long long)n * ho * wo)}, box[2] = {64u, (uint32_t)TILE_PX};
   int rc = lsps_get_tmap(ctx, dy, 2, dims, box, &tm);

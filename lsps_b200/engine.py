@@ -14,7 +14,7 @@ import os
 import torch
 
 from . import _lib
-from ._lib import (CONV_S1, CONV_S2, DECONV_S2, DECONV4_S2, EP_BIAS, EP_LRELU, EP_MASK, EP_ADD, EP_STATS, EP_INBWD,
+from ._lib import (CONV_S1, CONV_S2, DECONV_S2, DECONV4_S2, CONV1X1, EP_BIAS, EP_LRELU, EP_MASK, EP_ADD, EP_STATS, EP_INBWD,
                    ConvShape, ConvExt)
 
 SLOPE = 0.01   # nn.LeakyReLU() default (common_net.py:169,251)
@@ -101,8 +101,16 @@ class Ops:
     # ---- 3x3 convs on tcgen05
     @staticmethod
     def _io(S, key, kind):
-        sh = S.entries[key + ".weight"].shape
+        e = S.entries[key + ".weight"]
+        sh = e.shape
+        if e.kind == "gconv3":           # grouped conv: (cout, cin / groups, 3, 3), cin == cout
+            return sh[0], sh[0]
         return (sh[1], sh[0]) if kind not in (DECONV_S2, DECONV4_S2) else (sh[0], sh[1])  # (cin, cout)
+
+    @staticmethod
+    def _groups(S, key):
+        e = S.entries[key + ".weight"]
+        return e.shape[0] // e.shape[1] if e.kind == "gconv3" else 1
 
     # `key` may be a pair (key_a, key_b, split): images [0, split) go through conv key_a, the rest through key_b --
     # ONE grouped launch for forward / data gradient (full waves of CTA pairs instead of two half-size launches)
@@ -114,7 +122,7 @@ class Ops:
         k0 = key[0] if isinstance(key, tuple) else key
         ci, co = self._io(S, k0, kind)
         assert (2 * ci if split else ci) == cin, (key, ci, cin)
-        ho, wo = (h, w) if kind == CONV_S1 else ((h // 2, w // 2) if kind == CONV_S2 else (2 * h, 2 * w))
+        ho, wo = (h, w) if kind in (CONV_S1, CONV1X1) else ((h // 2, w // 2) if kind == CONV_S2 else (2 * h, 2 * w))
         y = out if out is not None else self.empty(n, ho, wo, 2 * co if split else co)
         flags = EP_BIAS | (EP_LRELU if lrelu else 0)
         if split:
@@ -130,6 +138,8 @@ class Ops:
             if isinstance(key, tuple):
                 ka, kb, split = key
                 ext.w2, ext.bias2, ext.n_split = S.W16(kb + ".weight").data_ptr(), S.W(kb + ".bias").data_ptr(), split
+            else:
+                ext.groups = self._groups(S, key)
             self.ctx.conv_fwd_ex(_shape(kind, n, h, w, ci, co), x.data_ptr(), S.W16(ka + ".weight").data_ptr(),
                                  S.W(ka + ".bias").data_ptr(), y.data_ptr(), flags | EP_STATS, SLOPE, C.byref(ext))
             return y
@@ -166,6 +176,8 @@ class Ops:
             if isinstance(key, tuple):
                 ka, kb, split = key
                 ext.w2, ext.n_split = S.W16T(kb + ".weight").data_ptr(), split
+            else:
+                ext.groups = self._groups(S, key)
             self.ctx.conv_dgrad_ex(_shape(kind, n, h, w, ci, co), dy.data_ptr(), S.W16T(ka + ".weight").data_ptr(),
                                    dx.data_ptr(), None, _lib.ptr(add), flags | EP_INBWD, SLOPE, C.byref(ext))
             return dx
@@ -188,7 +200,13 @@ class Ops:
         n, h, w, cin = x.shape
         ci, co = self._io(S, key, kind)
 
+        groups = self._groups(S, key)
+
         def launch():
+            if groups > 1:
+                self.ctx.conv_wgrad_grouped(_shape(kind, n, h, w, ci, co), x.data_ptr(), dy.data_ptr(),
+                                            S.G(key + ".weight").data_ptr(), groups)
+                return
             if split:
                 self.ctx.conv_wgrad_split(_shape(kind, n, h, w, ci, co), x.data_ptr(), dy.data_ptr(),
                                           S.G(key + ".weight").data_ptr())
@@ -231,6 +249,8 @@ class Ops:
         return key + suffix
 
     def res_fwd(self, S, key, x, save, out=None):
+        if not isinstance(key, tuple) and (key + ".model.6.weight") in S.entries:
+            return self.resx_fwd(S, key, x, save, out)
         if not self.fused_in:
             return self._res_fwd_old(S, key, x, save, out)
         n, hh, ww, c = x.shape
@@ -240,11 +260,11 @@ class Ops:
         h1 = self.conv_fwd(S, self._sub(key, ".model.0"), CONV_S1, x, False, sums=sums[0])
         a1 = torch.empty_like(h1)
         ctx.norm_apply_fwd(h1.data_ptr(), None, a1.data_ptr(), sums[0].data_ptr(), stats[0].data_ptr(), n, hh * ww, c, 0, 1,
-                           IN_EPS, SLOPE)
+                           IN_EPS, SLOPE, None, None)
         h2 = self.conv_fwd(S, self._sub(key, ".model.3"), CONV_S1, a1, False, sums=sums[1])
         y = out if out is not None else torch.empty_like(h2)
         ctx.norm_apply_fwd(h2.data_ptr(), x.data_ptr(), y.data_ptr(), sums[1].data_ptr(), stats[1].data_ptr(), n, hh * ww, c,
-                           1, 1, IN_EPS, SLOPE)
+                           1, 1, IN_EPS, SLOPE, None, None)
         if save is not None:
             save.append((key, x, None, stats[0], a1, h2, stats[1]))     # h1 is not needed: xhat1 is recovered from a1
         return y
@@ -252,6 +272,8 @@ class Ops:
     def res_bwd(self, S, saved, dout, wgrad=True, mask=None, out=None):
         """The biases of both convs feed an InstanceNorm: their gradient is exactly zero and is left at zero (the
         reference accumulates fp32 rounding noise there)."""
+        if saved[0] == "resx":
+            return self.resx_bwd(S, saved, dout, wgrad, mask, out)
         if not self.fused_in:
             return self._res_bwd_old(S, saved, dout, wgrad, mask, out)
         key, x, h1, st1, a1, h2, st2 = saved
@@ -260,20 +282,70 @@ class Ops:
         ctx, hw = self.ctx, hh * ww
         bs = self.empty(2, n, 2, c, dtype=torch.float32)
         # IN #2 (res + xhat): the gradient is dout itself; its two sums need one reduction pass
-        ctx.norm_bwd_stats(dout.data_ptr(), h2.data_ptr(), st2.data_ptr(), bs[1].data_ptr(), n, hw, c, 1, 1, SLOPE)
+        ctx.norm_bwd_stats(dout.data_ptr(), h2.data_ptr(), st2.data_ptr(), bs[1].data_ptr(), n, hw, c, 1, 1, SLOPE, None, None)
         dh2 = torch.empty_like(h2)
         ctx.norm_bwd_apply(dout.data_ptr(), h2.data_ptr(), st2.data_ptr(), bs[1].data_ptr(), dh2.data_ptr(), n, hw, c, 1, 1,
-                           SLOPE)
+                           SLOPE, None, None)
         if wgrad:
             self.conv_wgrad(S, k3, CONV_S1, a1, dh2, bias=False)
         # IN #1 (lrelu(xhat)): mask + sums in the data-gradient epilogue, then one apply pass
         g1 = self.conv_dgrad(S, k3, CONV_S1, dh2, a1.shape, inbwd=(a1, bs[0]))
         dh1 = torch.empty_like(a1)
         ctx.norm_bwd_apply(g1.data_ptr(), a1.data_ptr(), st1.data_ptr(), bs[0].data_ptr(), dh1.data_ptr(), n, hw, c, 2, 1,
-                           SLOPE)
+                           SLOPE, None, None)
         if wgrad:
             self.conv_wgrad(S, k0, CONV_S1, x, dh1, bias=False)
         return self.conv_dgrad(S, k0, CONV_S1, dh1, x.shape, mask=mask, add=dout, out=out)
+
+    # ---- LeakyINSResNeXtBlock (common_net.py:111-132): 1x1 -> IN -> lrelu -> grouped 3x3 -> IN -> lrelu -> 1x1 -> IN, + x.
+    #      Same building blocks as the plain res block: statistics in each conv's epilogue, streaming apply passes,
+    #      the lrelu(IN) backward front halves in the data-gradient epilogues.
+    def resx_fwd(self, S, key, x, save, out=None):
+        n, hh, ww, c = x.shape
+        ctx, hw = self.ctx, hh * ww
+        k0, k3, k6 = key + ".model.0", key + ".model.3", key + ".model.6"
+        cm = S.entries[k0 + ".weight"].shape[0]                        # k * c channels inside the block
+        sums_m, stats_m = self.empty(2, n, 2, cm, dtype=torch.float32), self.empty(2, n, 2, cm, dtype=torch.float32)
+        sums_o, stats_o = self.empty(n, 2, c, dtype=torch.float32), self.empty(n, 2, c, dtype=torch.float32)
+        h1 = self.conv_fwd(S, k0, CONV1X1, x, False, sums=sums_m[0])
+        a1 = torch.empty_like(h1)
+        ctx.norm_apply_fwd(h1.data_ptr(), None, a1.data_ptr(), sums_m[0].data_ptr(), stats_m[0].data_ptr(), n, hw, cm, 0, 1,
+                           IN_EPS, SLOPE, None, None)
+        h2 = self.conv_fwd(S, k3, CONV_S1, a1, False, sums=sums_m[1])
+        a2 = torch.empty_like(h2)
+        ctx.norm_apply_fwd(h2.data_ptr(), None, a2.data_ptr(), sums_m[1].data_ptr(), stats_m[1].data_ptr(), n, hw, cm, 0, 1,
+                           IN_EPS, SLOPE, None, None)
+        h3 = self.conv_fwd(S, k6, CONV1X1, a2, False, sums=sums_o)
+        y = out if out is not None else torch.empty_like(h3)
+        ctx.norm_apply_fwd(h3.data_ptr(), x.data_ptr(), y.data_ptr(), sums_o.data_ptr(), stats_o.data_ptr(), n, hw, c, 1, 1,
+                           IN_EPS, SLOPE, None, None)
+        if save is not None:
+            save.append(("resx", key, x, a1, stats_m[0], a2, stats_m[1], h3, stats_o))
+        return y
+
+    def resx_bwd(self, S, saved, dout, wgrad=True, mask=None, out=None):
+        _, key, x, a1, st1, a2, st2, h3, st3 = saved
+        k0, k3, k6 = key + ".model.0", key + ".model.3", key + ".model.6"
+        n, hh, ww, c = x.shape
+        cm = a1.shape[-1]
+        ctx, hw = self.ctx, hh * ww
+        bs_o, bs_m = self.empty(n, 2, c, dtype=torch.float32), self.empty(2, n, 2, cm, dtype=torch.float32)
+        ctx.norm_bwd_stats(dout.data_ptr(), h3.data_ptr(), st3.data_ptr(), bs_o.data_ptr(), n, hw, c, 1, 1, SLOPE, None, None)
+        dh3 = torch.empty_like(h3)
+        ctx.norm_bwd_apply(dout.data_ptr(), h3.data_ptr(), st3.data_ptr(), bs_o.data_ptr(), dh3.data_ptr(), n, hw, c, 1, 1, SLOPE, None, None)
+        if wgrad:
+            self.conv_wgrad(S, k6, CONV1X1, a2, dh3, bias=False)
+        g2 = self.conv_dgrad(S, k6, CONV1X1, dh3, a2.shape, inbwd=(a2, bs_m[1]))
+        dh2 = torch.empty_like(a2)
+        ctx.norm_bwd_apply(g2.data_ptr(), a2.data_ptr(), st2.data_ptr(), bs_m[1].data_ptr(), dh2.data_ptr(), n, hw, cm, 2, 1, SLOPE, None, None)
+        if wgrad:
+            self.conv_wgrad(S, k3, CONV_S1, a1, dh2, bias=False)
+        g1 = self.conv_dgrad(S, k3, CONV_S1, dh2, a1.shape, inbwd=(a1, bs_m[0]))
+        dh1 = torch.empty_like(a1)
+        ctx.norm_bwd_apply(g1.data_ptr(), a1.data_ptr(), st1.data_ptr(), bs_m[0].data_ptr(), dh1.data_ptr(), n, hw, cm, 2, 1, SLOPE, None, None)
+        if wgrad:
+            self.conv_wgrad(S, k0, CONV1X1, x, dh1, bias=False)
+        return self.conv_dgrad(S, k0, CONV1X1, dh1, x.shape, mask=mask, add=dout, out=out)
 
     # -- the stand-alone InstanceNorm kernels (round 1), kept for A/B runs (LSPS_OLD_IN=1)
     def _res_fwd_old(self, S, key, x, save, out=None):
@@ -335,7 +407,7 @@ class Generator:
         self.training = True  # the reference drivers never call gen.eval()
         # encoder-A/B (and cycle decoder-B/A) res blocks as grouped launches on the concatenated batch: any split on an
         # image boundary works, the two weight sets only have to sit in one flat buffer (params.ALIGN)
-        self.grouped = os.environ.get("LSPS_NO_GROUP", "0") != "1"
+        self.grouped = os.environ.get("LSPS_NO_GROUP", "0") != "1" and hp.get("name") != "SharedResXGen"
 
     # -- encoder: 7x7 s1 stem, two 3x3 s2 convs, n_enc_res_blk res blocks
     def enc_fwd(self, dom, img, save, out=None):
@@ -442,11 +514,15 @@ class Generator:
         return dx
 
     # -- shared latent: res blocks + GaussianNoiseLayer (+ KL sum of the noised latent) ; then dec_shared
-    def shared_fwd(self, x, noise, kl_acc, save):
+    def shared_fwd(self, x, noise, kl_acc, save, pre=None):
+        """pre: optional (x_pre_noise, eb) from an earlier run of the deterministic part (see forward(front=...))."""
         o, S = self.ops, self.S
-        eb = [] if save is not None else None
-        for i in range(self.p["n_enc_shared_blk"]):
-            x = o.res_fwd(S, "enc_shared.%d" % i, x, eb)
+        if pre is not None:
+            x, eb = pre
+        else:
+            eb = []
+            for i in range(self.p["n_enc_shared_blk"]):
+                x = o.res_fwd(S, "enc_shared.%d" % i, x, eb)
         if noise is not None:
             z = torch.empty_like(x)
             o.noise_kl(x, noise, z, kl_acc)
@@ -511,15 +587,16 @@ class Generator:
         return dx
 
     # -- full forward (lsps_nets.py:250-258): returns images (x_aa|x_ba) and (x_ab|x_bb) as [2n,128,128] tensors
-    def forward(self, xa, xb, noise, kl_acc, save=None, out_a=None, out_b=None):
-        """xa [na,128,128] / xb [nb,128,128] (either may be None).  Returns decode_A and decode_B of ALL na+nb
-        latents: oa = (x_aa | x_ba), ob = (x_ab | x_bb), plus the noised shared latent.  out_a / out_b: optional
-        [na+nb,128,128] fp32 destinations (slices of the discriminator's input batch: no concatenation copy)."""
-        o = self.ops
+    def front_fwd(self, xa, xb):
+        """The deterministic front of forward(): both encoders and the enc_shared res blocks, up to (not including) the
+        GaussianNoiseLayer, with everything their backward needs.  dis_update and gen_update of one training step run
+        the generator on the SAME images with the SAME weights (only the noise draw differs, lsps_trainer.py:79,145), so
+        the trainer computes this part once per step and hands it to both (exact reuse, not an approximation)."""
+        o, S = self.ops, self.S
         na = xa.shape[0] if xa is not None else 0
         nb = xb.shape[0] if xb is not None else 0
         h = o.empty(na + nb, 32, 32, 4 * self.p["ch"])
-        se = [] if save is not None else None
+        se = []
         if na and nb and self.grouped:
             self.enc_pair_fwd(xa, xb, se, h)
         else:
@@ -527,8 +604,23 @@ class Generator:
                 self.enc_fwd("A", xa, se, out=h[:na])
             if nb:
                 self.enc_fwd("B", xb, se, out=h[na:])
+        eb = []
+        x = h
+        for i in range(self.p["n_enc_shared_blk"]):
+            x = o.res_fwd(S, "enc_shared.%d" % i, x, eb)
+        return dict(se=se, eb=eb, x=x, na=na, nb=nb)
+
+    def forward(self, xa, xb, noise, kl_acc, save=None, out_a=None, out_b=None, front=None):
+        """xa [na,128,128] / xb [nb,128,128] (either may be None).  Returns decode_A and decode_B of ALL na+nb
+        latents: oa = (x_aa | x_ba), ob = (x_ab | x_bb), plus the noised shared latent.  out_a / out_b: optional
+        [na+nb,128,128] fp32 destinations (slices of the discriminator's input batch: no concatenation copy).
+        front: result of front_fwd(xa, xb) to reuse instead of recomputing the encoders."""
+        o = self.ops
+        if front is None:
+            front = self.front_fwd(xa, xb)
+        na, nb, se = front["na"], front["nb"], front["se"]
         ss = [] if save is not None else None
-        y, z = self.shared_fwd(h, noise, kl_acc, ss)
+        y, z = self.shared_fwd(None, noise, kl_acc, ss, pre=(front["x"], front["eb"]))
         sd = [] if save is not None else None
         oa = self.dec_fwd("A", y, sd, out=out_a)
         ob = self.dec_fwd("B", y, sd, out=out_b)
@@ -820,6 +912,17 @@ class Discriminator:
         fn = o.ctx.dhead_bwd_split if self.split else o.ctx.dhead_bwd
         fn(F.data_ptr(), S.W("D.weight").data_ptr(), dlg.data_ptr(), dF.data_ptr(),
            S.G("D.weight").data_ptr() if wgrad else None, S.G("D.bias").data_ptr() if wgrad else None, self.rows(F), self.cf)
+
+    def head_bce(self, F, rows_per_group, targets, slots, scale, dF, wgrad, acc):
+        """D head + sigmoid + BCE + backward in one launch (lsps_dhead_bce): targets[g] is the constant BCE target of
+        image group g (-1: the group's logits are not used), its loss sum / correct count go to acc[slots[g]], [+1];
+        dF [n, 4 cf] fp32 is written completely (no zero fill)."""
+        o, S = self.ops, self.S
+        ng = len(targets)
+        o.ctx.dhead_bce(F.data_ptr(), S.W("D.weight").data_ptr(), S.W("D.bias").data_ptr(), self.rows(F), self.cf,
+                        1 if self.split else 0, rows_per_group, ng, (C.c_float * ng)(*targets), (C.c_int * ng)(*slots), scale,
+                        None, dF.data_ptr(), S.G("D.weight").data_ptr() if wgrad else None,
+                        S.G("D.bias").data_ptr() if wgrad else None, acc.data_ptr())
 
     def l1_feat(self, F, img_a, img_b, nimg, dF, scale, acc):
         """acc += sum |F[img_a:img_a+nimg] - F[img_b:img_b+nimg]| ; dF rows get +-scale*sign (lsps_trainer.py:171-177)."""

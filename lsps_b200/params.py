@@ -24,7 +24,7 @@ def _round_up(n, a=ALIGN):
 
 # ------------------------------------------------------------------ layout conversions (reference <-> kernel)
 def to_kernel_layout(kind, t):
-    if kind == "conv3":      # OIHW (co,ci,3,3) -> [tap][co][ci]
+    if kind in ("conv3", "gconv3"):   # OIHW (co,ci,3,3) -> [tap][co][ci]  (grouped: ci = channels of one group)
         return t.permute(2, 3, 0, 1).reshape(9, t.shape[0], t.shape[1])
     if kind == "deconv3":    # IOHW (ci,co,3,3) -> [tap][co][ci]
         return t.permute(2, 3, 1, 0).reshape(9, t.shape[1], t.shape[0])
@@ -36,7 +36,7 @@ def to_kernel_layout(kind, t):
 
 
 def from_kernel_layout(kind, flat, shape):
-    if kind == "conv3":
+    if kind in ("conv3", "gconv3"):
         co, ci = shape[0], shape[1]
         return flat.reshape(3, 3, co, ci).permute(2, 3, 0, 1).contiguous()
     if kind == "deconv3":
@@ -63,7 +63,7 @@ class Entry:
 
 class ParamStore:
     """entries: list of (key, shape, kind, law, fan_in).
-    kind in conv3|deconv3|deconv4|map0|stem|head|dhead|post|linear|bias."""
+    kind in conv3|deconv3|deconv4|conv1|gconv3|map0|stem|head|dhead|post|linear|bias."""
 
     def __init__(self, entries, device, lr, weight_decay, betas=(0.5, 0.999), eps=1e-8, split=False):
         """split: keep a second bf16 copy of every operand tensor holding the rounding remainder (w - bf16(w)), for the
@@ -76,7 +76,7 @@ class ParamStore:
             ent = Entry(*e)
             ent.off = off
             off += _round_up(ent.numel)
-            if ent.kind in ("conv3", "deconv3", "deconv4"):
+            if ent.kind in ("conv3", "deconv3", "deconv4", "conv1", "gconv3"):
                 ent.dg_off = dg
                 dg += _round_up(ent.numel)
             self.entries[ent.key] = ent
@@ -97,14 +97,17 @@ class ParamStore:
         for ent in self.entries.values():
             if ent.dg_off < 0:
                 continue
-            co, ci = (ent.shape[0], ent.shape[1]) if ent.kind == "conv3" else (ent.shape[1], ent.shape[0])
-            taps = 16 if ent.kind == "deconv4" else 9
+            co, ci = (ent.shape[0], ent.shape[1]) if ent.kind in ("conv3", "conv1", "gconv3") else (ent.shape[1], ent.shape[0])
+            taps = {"deconv4": 16, "conv1": 1}.get(ent.kind, 9)
+            if ent.kind == "gconv3":     # [tap][group][co in group][ci in group]: taps x groups square transposes
+                taps, co = taps * (co // ci), ci
             rows.append([ent.off, ent.dg_off, taps, co, ci, tile0])
             tile0 += taps * ((ci + 31) // 32) * ((co + 31) // 32)
         self._pack_count, self._pack_tiles = len(rows), tile0
         rows.append([0, 0, 0, 0, 0, tile0])
         self._pack_desc = torch.tensor(rows, dtype=torch.int64).to(self.device) if self._pack_count else None
         self.lr, self.base_lr, self.wd, self.betas, self.eps = lr, lr, weight_decay, betas, eps
+        self.version = 0     # bumped whenever the weights change (Adam step, load_state_dict): keys weight-derived caches
         self.ctx = _lib.context(self.device.index if self.device.index is not None else torch.cuda.current_device())
 
     # --- views
@@ -150,6 +153,7 @@ class ParamStore:
             if tuple(t.shape) != e.shape:
                 raise ValueError("shape mismatch for %s: %s vs %s" % (k, tuple(t.shape), e.shape))
             self.W(k).copy_(to_kernel_layout(e.kind, t).reshape(-1))
+        self.version += 1
         self.refresh_operands()
 
     def init_(self, seed):
@@ -215,6 +219,7 @@ class ParamStore:
         step-dependent factors from hyper[2*i:2*i+2]; returns the segment list so that `advance()` can replay it."""
         ents = list(self.entries.values())
         segs = self._segments(active)
+        self.version += 1
         for si, (i, j) in enumerate(segs):
             lo, hi = ents[i].off, ents[j].off + _round_up(ents[j].numel)
             step = ents[i].step + 1
@@ -237,6 +242,7 @@ class ParamStore:
         """Replay bookkeeping for a captured adam_step: bump the step counters of `segs` and write the factors the
         captured launches will read into hyper_host (pinned float tensor)."""
         ents = list(self.entries.values())
+        self.version += 1
         for si, (i, j) in enumerate(segs):
             step = ents[i].step + 1
             for q in range(i, j + 1):
@@ -300,7 +306,17 @@ def gen_entries(p):
         out.append((key + ".weight", shape, kind, "conv", fan))
         out.append((key + ".bias", (co,), "bias", "bias", fan))
 
+    resx = p.get("name") == "SharedResXGen"      # LeakyINSResNeXtBlock res blocks (lsps_nets.py:277-343)
+    rk, rc = p.get("n_resnext_k", 1), p.get("n_resnext_c", 4)
+
     def res(prefix, c):
+        if resx:
+            conv(prefix + ".model.0", rk * c, c, 1, "conv1")
+            gw = rk * c // rc
+            out.append((prefix + ".model.3.weight", (rk * c, gw, 3, 3), "gconv3", "conv", gw * 9))
+            out.append((prefix + ".model.3.bias", (rk * c,), "bias", "bias", gw * 9))
+            conv(prefix + ".model.6", c, rk * c, 1, "conv1")
+            return
         conv(prefix + ".model.0", c, c, 3, "conv3")
         conv(prefix + ".model.3", c, c, 3, "conv3")
 

@@ -98,6 +98,10 @@ class LSPSTrainerB200(object):
         self.vae_sch = MultiStepLR(self.vae_store, [125, 175], 0.1)
         self._scratch = torch.zeros(8, dtype=torch.float32, device=self.device)
         self.last_outputs = None
+        # generator front (encoders + enc_shared, deterministic) of the current step's images: computed by dis_update,
+        # reused by gen_update when images and generator weights are unchanged (LSPS_NO_FRONT_CACHE=1 disables)
+        self._front = None
+        self._front_cache_on = os.environ.get("LSPS_NO_FRONT_CACHE", "0") != "1"
         self._comm = torch.cuda.Stream(device=self.device)
         self._early = {}
         self.dis.on_tail_wgrad = lambda key: self._allreduce_early(self.dis_store, key)
@@ -177,6 +181,19 @@ class LSPSTrainerB200(object):
     def _p(self, t):
         return t.data_ptr()
 
+    def _front_key(self, ia, ib):
+        return (ia.data_ptr(), ib.data_ptr(), ia._version, ib._version, tuple(ia.shape), tuple(ib.shape),
+                self.gen_store.version)
+
+    def _gen_front(self, ia, ib, keep):
+        """front_fwd of (ia, ib), from the per-step cache when it holds exactly these tensors and weights.  keep: leave
+        the result in the cache for the next update of this step (dis_update) or drop it after use (gen_update)."""
+        key = self._front_key(ia, ib)
+        hit = self._front is not None and self._front[0] == key
+        front = self._front[1] if hit else self.gen.front_fwd(ia, ib)
+        self._front = (key, front, ia, ib) if (keep and self._front_cache_on) else None
+        return front
+
     def _map_decode(self, labels_a, labels_b, hp, save_map=None, save_dec=None):
         """lsps_trainer.py:86-93 / :148-155: cat(labels) -> vae.encode -> Mapping -> gen.decode; decode_A keeps the
         domain-a half, decode_B the domain-b half.  Returns (z_pose2depth, decode_A, decode_B)."""
@@ -242,7 +259,8 @@ class LSPSTrainerB200(object):
         imgs_a, imgs_b = o.empty(ndiv * B, 128, 128, dtype=torch.float32), o.empty(ndiv * B, 128, 128, dtype=torch.float32)
         o.copy_into(imgs_a[:B], ia)
         o.copy_into(imgs_b[:B], ib)
-        self.gen.forward(ia, ib, noise, self._scratch, out_a=imgs_a[B:3 * B], out_b=imgs_b[B:3 * B])   # gen gets no grads
+        self.gen.forward(ia, ib, noise, self._scratch, out_a=imgs_a[B:3 * B], out_b=imgs_b[B:3 * B],
+                         front=self._gen_front(ia, ib, keep=True))                                     # gen gets no grads
         if train_map:                                                        # :147-158, no activations kept either
             _, dec_a, dec_b = self._map_decode(labels_a, labels_b, hp)
             o.copy_into(imgs_a[3 * B:], dec_a)
@@ -250,19 +268,19 @@ class LSPSTrainerB200(object):
         sv = {}
         F = dis.features(imgs_a, imgs_b, sv)                                 # [2*ndiv*B, 2, 2, 2048] (split: 2 x 2048)
         cf = dis.cf
-        lg = dis.logits(F)
-        dlg = o.zeros(lg.numel())
         r = 4 * B                                                            # logits per group
         scale = hp["gan_w"] / float(4 * Bg)
         A_REAL, A_XAA, A_XBA, B_REAL, B_XAB, B_XBB = 0, 1, 2, ndiv, ndiv + 1, ndiv + 2
+        # BCE targets per image group: real -> 1 (acc[0..1]); x_ba / x_ab -> 0 (acc[2..3]); the x_aa / x_bb groups only
+        # feed the feature-matching term; train_map: decoded groups -> 0 (acc[8..9], ad_fake_dec :201-204)
+        tgt, slot = [-1.0] * (2 * ndiv), [0] * (2 * ndiv)
         for real, fake in ((A_REAL, A_XBA), (B_REAL, B_XAB)):
-            ctx.bce_logits(lg[real * r:].data_ptr(), 1.0, scale, dlg[real * r:].data_ptr(), D.acc[0:].data_ptr(), r)
-            ctx.bce_logits(lg[fake * r:].data_ptr(), 0.0, scale, dlg[fake * r:].data_ptr(), D.acc[2:].data_ptr(), r)
-        if train_map:                                                        # ad_fake_dec (:201-204): 4th group vs zeros
+            tgt[real], slot[real], tgt[fake], slot[fake] = 1.0, 0, 0.0, 2
+        if train_map:
             for dec in (3, ndiv + 3):
-                ctx.bce_logits(lg[dec * r:].data_ptr(), 0.0, scale, dlg[dec * r:].data_ptr(), D.acc[8:].data_ptr(), r)
-        dF = o.zeros(F.shape[0], 4 * cf)
-        dis.logits_bwd(F, dlg, dF, wgrad=True)
+                tgt[dec], slot[dec] = 0.0, 8
+        dF = o.empty(F.shape[0], 4 * cf, dtype=torch.float32)
+        dis.head_bce(F, r, tgt, slot, scale, dF, True, D.acc)
         if feat_mat:
             fscale = hp["feature_w"] / float(Bg * 4 * cf)
             # mean|F_b(x_ab) - F_a(x_aa)| + mean|F_a(x_ba) - F_b(x_bb)|      (lsps_trainer.py:171-177)
@@ -300,7 +318,7 @@ class LSPSTrainerB200(object):
         n3 = self._latent_noise(B)
         n4 = self._latent_noise(B)
         s1 = {}
-        oa, ob, shared = gen.forward(ia, ib, n2, G.acc[2:], s1)
+        oa, ob, shared = gen.forward(ia, ib, n2, G.acc[2:], s1, front=self._gen_front(ia, ib, keep=False))
         x_aa, x_ba, x_ab, x_bb = oa[:B], oa[B:], ob[:B], ob[B:]
         s2 = {}
         x_bab, x_aba = gen.forward_cycle(x_ba, x_ab, n3 if isinstance(n3, tuple) else torch.cat((n3, n4), 0), G.acc[3:],
@@ -315,11 +333,8 @@ class LSPSTrainerB200(object):
         sd = {}
         F = dis.features(self.ops.cat((x_ba, dec_a)) if train_map else x_ba,
                          self.ops.cat((x_ab, dec_b)) if train_map else x_ab, sd)
-        lg = dis.logits(F)
-        dlg = torch.empty_like(lg)
-        ctx.bce_logits(lg.data_ptr(), 1.0, hp["gan_w"] / float(4 * nd * Bg), dlg.data_ptr(), G.acc[0:].data_ptr(), lg.numel())
-        dF = self.ops.zeros(F.shape[0], 4 * dis.cf)
-        dis.logits_bwd(F, dlg, dF, wgrad=False)
+        dF = self.ops.empty(F.shape[0], 4 * dis.cf, dtype=torch.float32)
+        dis.head_bce(F, dis.rows(F), [1.0], [0], hp["gan_w"] / float(4 * nd * Bg), dF, False, G.acc)
         dFm = dis.mask_grad(dF, F)
         doa = torch.empty_like(oa)           # d/d(x_aa | x_ba)
         dob = torch.empty_like(ob)           # d/d(x_ab | x_bb)

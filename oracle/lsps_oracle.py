@@ -36,14 +36,24 @@ IN_EPS = 1e-5         # nn.InstanceNorm2d default eps (common_net.py:168)
 # parameter specs (shapes + init law), keyed exactly like the reference state_dicts
 # ----------------------------------------------------------------------------------------
 def gen_spec(p):
-    """SharedResGen parameter table: lsps_nets.py:164-237."""
+    """SharedResGen parameter table: lsps_nets.py:164-237; with name == "SharedResXGen" the res blocks are
+    LeakyINSResNeXtBlock (common_net.py:111-132; lsps_nets.py:277-343): 1x1 (c -> k*c), grouped 3x3 (k*c, groups =
+    cardinality), 1x1 (k*c -> c), an InstanceNorm after each."""
     ch, spec = p["ch"], OrderedDict()
+    resx = p.get("name") == "SharedResXGen"
+    rk, rc = p.get("n_resnext_k", 1), p.get("n_resnext_c", 4)
 
-    def conv(key, co, ci, k, transposed=False):
-        spec[key + ".weight"] = ((ci, co, k, k) if transposed else (co, ci, k, k), "conv", ci * k * k if not transposed else co * k * k)
-        spec[key + ".bias"] = ((co,), "bias", ci * k * k if not transposed else co * k * k)
+    def conv(key, co, ci, k, transposed=False, groups=1):
+        cig = ci // groups
+        spec[key + ".weight"] = ((ci, co, k, k) if transposed else (co, cig, k, k), "conv", cig * k * k if not transposed else co * k * k)
+        spec[key + ".bias"] = ((co,), "bias", cig * k * k if not transposed else co * k * k)
 
     def res(prefix, c):
+        if resx:
+            conv(prefix + ".model.0", rk * c, c, 1)
+            conv(prefix + ".model.3", rk * c, rk * c, 3, groups=rc)
+            conv(prefix + ".model.6", c, rk * c, 1)
+            return
         conv(prefix + ".model.0", c, c, 3)
         conv(prefix + ".model.3", c, c, 3)
 
@@ -160,7 +170,16 @@ def _conv_lrelu(P, key, x, stride, pad):
 
 
 def _res_block(P, key, x):
-    """x + IN(conv(lrelu(IN(conv(x)))))  -- common_net.py:160-181."""
+    """x + IN(conv(lrelu(IN(conv(x)))))  -- common_net.py:160-181.  A block that owns a `.model.6` conv is a
+    LeakyINSResNeXtBlock (common_net.py:111-132): 1x1 -> IN -> lrelu -> grouped 3x3 -> IN -> lrelu -> 1x1 -> IN, + x."""
+    if key + ".model.6.weight" in P:
+        w3 = P[key + ".model.3.weight"]
+        h = F.conv2d(x, P[key + ".model.0.weight"], P[key + ".model.0.bias"])
+        h = _lrelu(F.instance_norm(h, eps=IN_EPS))
+        h = F.conv2d(h, w3, P[key + ".model.3.bias"], padding=1, groups=w3.shape[0] // w3.shape[1])
+        h = _lrelu(F.instance_norm(h, eps=IN_EPS))
+        h = F.conv2d(h, P[key + ".model.6.weight"], P[key + ".model.6.bias"])
+        return x + F.instance_norm(h, eps=IN_EPS)
     h = F.conv2d(x, P[key + ".model.0.weight"], P[key + ".model.0.bias"], padding=1)
     h = _lrelu(F.instance_norm(h, eps=IN_EPS))
     h = F.conv2d(h, P[key + ".model.3.weight"], P[key + ".model.3.bias"], padding=1)

@@ -86,8 +86,10 @@ def run_case(trainers, name, hp, schedule, batch, kind="uniform", steps=2, seed=
             for k, v in _losses(tr).items():
                 rec["s%d_%s" % (s, k)] = np.float32(v)
         sd = (lambda n: getattr(tr, n).state_dict()) if who == "ref" else tr.state_dict
+        resx = hp["gen"].get("name") == "SharedResXGen"
         for net, keys in (("dis", ("model_S.3.model.0.weight", "model_A.0.model.0.weight", "D.weight", "Post.weight")),
-                          ("gen", ("encode_A.0.model.0.weight", "enc_shared.0.model.0.weight", "decode_B.5.weight")),
+                          ("gen", ("encode_A.0.model.0.weight", "enc_shared.0.model.0.weight", "decode_B.5.weight") +
+                           (("enc_shared.0.model.3.weight", "decode_A.1.model.6.weight") if resx else ())),
                           ("vae", ("en_fc1.weight", "de_fc2.bias")),
                           ("map", ("model.0.model.0.weight", "model.1.model.0.weight", "model.2.model.0.bias",
                                    "model.3.weight") if hp["train_map"] else ())):
@@ -141,6 +143,16 @@ def main(only=None):
     nnyu_map = dict(nnyu, train_map=True)
     run_case(trainers, "pretrain_map_nnyu_b1", nnyu_map, ["dis", "gen"], batch=1, steps=2)
     run_case(trainers, "pretrain_map_nnyu_b2_hand", nnyu_map, ["dis", "gen"], batch=2, steps=1, kind="hand")
+    # the ResNeXt generator (lsps_nets.py:277-387), selected from the YAML by gen.name like every net;
+    # default k = 1, cardinality 4 (64-channel groups) and the k = 2, cardinality 8 variant
+    import copy
+    resx = copy.deepcopy(nnyu)
+    resx["gen"]["name"] = "SharedResXGen"
+    run_case(trainers, "pretrain_resx_nnyu_b1", resx, ["dis", "gen"], batch=1, steps=2)
+    run_case(trainers, "estimate3_resx_nnyu_b4", resx, ["post3"], batch=4, steps=1)
+    resx2 = copy.deepcopy(resx)
+    resx2["gen"].update(n_resnext_k=2, n_resnext_c=8)
+    run_case(trainers, "pretrain_resx_k2c8_nnyu_b1", resx2, ["dis", "gen"], batch=1, steps=1)
 
 
 if __name__ == "__main__":

@@ -74,6 +74,10 @@ GOLDEN_CASES = {
     # train_map=True branches (Mapping net): config name "<yaml>:map"
     "pretrain_map_nnyu_b1": ("nnyu:map", ["dis", "gen"], 1, 2, "uniform"),
     "pretrain_map_nnyu_b2_hand": ("nnyu:map", ["dis", "gen"], 2, 1, "hand"),
+    # ResNeXt generator (gen.name = SharedResXGen; default k=1, cardinality 4, and k=2, cardinality 8)
+    "pretrain_resx_nnyu_b1": ("nnyu:resx", ["dis", "gen"], 1, 2, "uniform"),
+    "estimate3_resx_nnyu_b4": ("nnyu:resx", ["post3"], 4, 1, "uniform"),
+    "pretrain_resx_k2c8_nnyu_b1": ("nnyu:resx_k2c8", ["dis", "gen"], 1, 1, "uniform"),
 }
 
 
@@ -87,4 +91,8 @@ def load_hp(name):
         hp = yaml.safe_load(fh)["train"]["hyperparameters"]
     if opt == "map":
         hp["train_map"] = True
+    if opt.startswith("resx"):
+        hp["gen"]["name"] = "SharedResXGen"
+        if opt == "resx_k2c8":
+            hp["gen"].update(n_resnext_k=2, n_resnext_c=8)
     return hp

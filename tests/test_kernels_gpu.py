@@ -42,6 +42,8 @@ CONV_CASES = [  # kind, n, h, w, cin, cout
     (1, 2, 128, 128, 64, 128), (1, 3, 64, 64, 128, 256), (1, 5, 16, 16, 256, 512), (1, 9, 8, 8, 512, 1024),
     (1, 40, 4, 4, 1024, 2048), (1, 1, 4, 4, 1024, 2048),
     (2, 2, 32, 32, 256, 128), (2, 2, 64, 64, 128, 64), (2, 3, 8, 8, 64, 64),
+    # the fused four-phase up-sampling kernel (N = 64, K <= 128) on more than one tile per CTA and an odd image count
+    (2, 37, 64, 64, 128, 64), (1, 21, 128, 128, 64, 128), (1, 5, 32, 32, 64, 64),
     # large enough for the CTA-pair (cta_group::2) conv kernels: >= 2*148 M tiles and >= 27 K-steps per tile
     (0, 40, 32, 32, 256, 256),        # K1 shape, 320 tiles: pair kernel with 128-channel stages
     (1, 297, 16, 16, 256, 512),       # dis trunk shape, 149 M tiles (odd): the pair's phantom tile path
@@ -87,6 +89,8 @@ def test_conv_fwd_dgrad_wgrad(ctx, kind, n, h, w, cin, cout):
     ctx.conv_dgrad(sh, dyb.data_ptr(), wd.data_ptr(), dxb.data_ptr(), mask.data_ptr(), add.data_ptr(), 12, SLOPE)
     ref = (x.grad + nchw32(add)) * torch.where(nchw32(mask) > 0, 1.0, SLOPE)
     assert rel_l2(nchw32(dxb), ref) < BF16_L2
+    ctx.conv_dgrad(sh, dyb.data_ptr(), wd.data_ptr(), dxb.data_ptr(), mask.data_ptr(), None, 4, SLOPE)    # mask only
+    assert rel_l2(nchw32(dxb), x.grad * torch.where(nchw32(mask) > 0, 1.0, SLOPE)) < BF16_L2
     dw = torch.zeros(taps, cout, cin, device="cuda")
     ctx.conv_wgrad(sh, xb.data_ptr(), dyb.data_ptr(), dw.data_ptr())
     assert rel_l2(dw, pack(wt.grad)) < 1e-4
@@ -410,10 +414,10 @@ def test_conv_epilogue_statistics_and_norm_apply(ctx, n, cin, cout, hw, grouped)
     res = torch.randn(n, cout, hw, hw, device="cuda", generator=g).bfloat16()
     stats = torch.empty(n, 2, cout, device="cuda")
     y0, y1 = torch.empty_like(yb), torch.empty_like(yb)
-    ctx.norm_apply_fwd(yb.data_ptr(), None, y0.data_ptr(), sums.data_ptr(), stats.data_ptr(), n, hw * hw, cout, 0, 1, 1e-5, SLOPE)
+    ctx.norm_apply_fwd(yb.data_ptr(), None, y0.data_ptr(), sums.data_ptr(), stats.data_ptr(), n, hw * hw, cout, 0, 1, 1e-5, SLOPE, None, None)
     resb = res.permute(0, 2, 3, 1).contiguous()
     ctx.norm_apply_fwd(yb.data_ptr(), resb.data_ptr(), y1.data_ptr(), sums.data_ptr(), stats.data_ptr(), n, hw * hw, cout, 1, 1,
-                       1e-5, SLOPE)
+                       1e-5, SLOPE, None, None)
     xn = F.instance_norm(ref, eps=1e-5)
     assert rel_l2(nchw32(y0), F.leaky_relu(xn, SLOPE)) < 2 * BF16_L2
     assert rel_l2(nchw32(y1), res.float() + xn) < 2 * BF16_L2
@@ -454,9 +458,9 @@ def test_instnorm_backward_through_dgrad_epilogue(ctx, n, grouped):
     st1, st2 = stats_of(h1.detach()), stats_of(h2r.detach())
     h1b, h2b, doutb = nhwc16(h1.detach()), nhwc16(h2r.detach()), nhwc16(dout)
     bs = torch.full((2, n, 2, c), 3.0, device="cuda")
-    ctx.norm_bwd_stats(doutb.data_ptr(), h2b.data_ptr(), st2.data_ptr(), bs[1].data_ptr(), n, hw * hw, c, 1, 1, SLOPE)
+    ctx.norm_bwd_stats(doutb.data_ptr(), h2b.data_ptr(), st2.data_ptr(), bs[1].data_ptr(), n, hw * hw, c, 1, 1, SLOPE, None, None)
     dh2b = torch.empty_like(h2b)
-    ctx.norm_bwd_apply(doutb.data_ptr(), h2b.data_ptr(), st2.data_ptr(), bs[1].data_ptr(), dh2b.data_ptr(), n, hw * hw, c, 1, 1, SLOPE)
+    ctx.norm_bwd_apply(doutb.data_ptr(), h2b.data_ptr(), st2.data_ptr(), bs[1].data_ptr(), dh2b.data_ptr(), n, hw * hw, c, 1, 1, SLOPE, None, None)
     assert rel_l2(nchw32(dh2b), dh2_ref) < BF16_L2
     pack = lambda t: t.permute(2, 3, 0, 1).reshape(9, c, c)
     flat_d = torch.cat([pack(w_).transpose(1, 2).reshape(-1) for w_ in ws]).bfloat16().contiguous()
@@ -474,12 +478,12 @@ def test_instnorm_backward_through_dgrad_epilogue(ctx, n, grouped):
     assert rel_l2(nchw32(g1), g_ref) < BF16_L2
     assert rel_l2(bs[0][:, 0], g_ref.sum((2, 3))) < 2e-3 and rel_l2(bs[0][:, 1], (g_ref * xh1).sum((2, 3))) < 2e-3
     dh1b = torch.empty_like(h1b)
-    ctx.norm_bwd_apply(g1.data_ptr(), a1b.data_ptr(), st1.data_ptr(), bs[0].data_ptr(), dh1b.data_ptr(), n, hw * hw, c, 2, 1, SLOPE)
+    ctx.norm_bwd_apply(g1.data_ptr(), a1b.data_ptr(), st1.data_ptr(), bs[0].data_ptr(), dh1b.data_ptr(), n, hw * hw, c, 2, 1, SLOPE, None, None)
     assert rel_l2(nchw32(dh1b), dh1_ref) < 1.5 * BF16_L2
     # un-fused fallback of the same thing: stats kernel in mode 0 + apply with gmode 0 on the raw gradient
     da1b = nhwc16(da1_ref)
-    ctx.norm_bwd_stats(da1b.data_ptr(), h1b.data_ptr(), st1.data_ptr(), bs[0].data_ptr(), n, hw * hw, c, 0, 1, SLOPE)
-    ctx.norm_bwd_apply(da1b.data_ptr(), h1b.data_ptr(), st1.data_ptr(), bs[0].data_ptr(), dh1b.data_ptr(), n, hw * hw, c, 0, 1, SLOPE)
+    ctx.norm_bwd_stats(da1b.data_ptr(), h1b.data_ptr(), st1.data_ptr(), bs[0].data_ptr(), n, hw * hw, c, 0, 1, SLOPE, None, None)
+    ctx.norm_bwd_apply(da1b.data_ptr(), h1b.data_ptr(), st1.data_ptr(), bs[0].data_ptr(), dh1b.data_ptr(), n, hw * hw, c, 0, 1, SLOPE, None, None)
     assert rel_l2(nchw32(dh1b), dh1_ref) < 1.5 * BF16_L2
 
 
@@ -631,3 +635,67 @@ def test_pack_dgrad_multi_and_split_store(ctx):
     S.adam_step()
     hi, lo, _ = split16(S.w)
     assert torch.equal(S.w16, hi) and torch.equal(S.w16l, lo)
+
+
+# ------------------------------------------------------------------ round 2: ResNeXt building blocks
+@pytest.mark.parametrize("n,cin,cout,hw", [(3, 256, 256, 32), (5, 256, 512, 32), (40, 512, 256, 32), (2, 64, 128, 16)])
+def test_conv1x1_fwd_dgrad_wgrad(ctx, n, cin, cout, hw):
+    """LSPS_CONV1X1 (the 1x1 convs of LeakyINSResNeXtBlock, common_net.py:116,122) against F.conv2d."""
+    from lsps_b200._lib import ConvShape
+    g = gen(800 + n)
+    x = torch.randn(n, cin, hw, hw, device="cuda", generator=g).bfloat16().float().requires_grad_(True)
+    wt = (torch.randn(cout, cin, 1, 1, device="cuda", generator=g) * 0.05).bfloat16().float().requires_grad_(True)
+    bias = torch.randn(cout, device="cuda", generator=g)
+    y = F.conv2d(x, wt, None)
+    dy = torch.randn(y.shape, device="cuda", generator=g).bfloat16().float()
+    y.backward(dy)
+    sh = C.byref(ConvShape(4, n, hw, hw, cin, cout))
+    xb, dyb = nhwc16(x.detach()), nhwc16(dy)
+    wf = wt.detach().reshape(cout, cin).contiguous().bfloat16()
+    wd = wf.t().contiguous()
+    yb = torch.empty(n, hw, hw, cout, device="cuda", dtype=torch.bfloat16)
+    ctx.conv_fwd(sh, xb.data_ptr(), wf.data_ptr(), bias.data_ptr(), yb.data_ptr(), 1, SLOPE)
+    assert rel_l2(nchw32(yb), y.detach() + bias[None, :, None, None]) < BF16_L2
+    dxb = torch.empty(n, hw, hw, cin, device="cuda", dtype=torch.bfloat16)
+    add = nhwc16(torch.randn(n, cin, hw, hw, device="cuda", generator=g))
+    ctx.conv_dgrad(sh, dyb.data_ptr(), wd.data_ptr(), dxb.data_ptr(), None, add.data_ptr(), 8, SLOPE)
+    assert rel_l2(nchw32(dxb), x.grad + nchw32(add)) < BF16_L2
+    dw = torch.zeros(cout, cin, device="cuda")
+    ctx.conv_wgrad(sh, xb.data_ptr(), dyb.data_ptr(), dw.data_ptr())
+    assert rel_l2(dw, wt.grad.reshape(cout, cin)) < 1e-4
+
+
+@pytest.mark.parametrize("n,c,groups", [(3, 256, 4), (40, 256, 4), (5, 512, 8), (4, 256, 2), (3, 512, 4)])
+def test_grouped_conv3x3_fwd_dgrad_wgrad(ctx, n, c, groups):
+    """Grouped 3x3 stride-1 conv (ResNeXt cardinality, common_net.py:118): forward with epilogue statistics, data
+    gradient, and the block-diagonal weight gradient against F.conv2d(groups=...)."""
+    from lsps_b200._lib import ConvShape, ConvExt
+    g = gen(900 + n + groups)
+    gw, hw = c // groups, 32
+    x = torch.randn(n, c, hw, hw, device="cuda", generator=g).bfloat16().float().requires_grad_(True)
+    wt = (torch.randn(c, gw, 3, 3, device="cuda", generator=g) * 0.05).bfloat16().float().requires_grad_(True)
+    bias = torch.randn(c, device="cuda", generator=g)
+    y = F.conv2d(x, wt, None, padding=1, groups=groups)
+    dy = torch.randn(y.shape, device="cuda", generator=g).bfloat16().float()
+    y.backward(dy)
+    sh = C.byref(ConvShape(0, n, hw, hw, c, c))
+    xb, dyb = nhwc16(x.detach()), nhwc16(dy)
+    wk = wt.detach().permute(2, 3, 0, 1).reshape(9, c, gw).contiguous()          # [tap][co][i]
+    wf = wk.bfloat16()
+    wd = wk.reshape(9, groups, gw, gw).transpose(2, 3).reshape(9, c, gw).contiguous().bfloat16()   # [tap][ci][o]
+    yb = torch.empty(n, hw, hw, c, device="cuda", dtype=torch.bfloat16)
+    sums = torch.empty(n, 2, c, device="cuda")
+    ext = ConvExt()
+    ext.groups, ext.sums = groups, sums.data_ptr()
+    ctx.conv_fwd_ex(sh, xb.data_ptr(), wf.data_ptr(), bias.data_ptr(), yb.data_ptr(), 1 | 16, SLOPE, C.byref(ext))
+    ref = y.detach() + bias[None, :, None, None]
+    assert rel_l2(nchw32(yb), ref) < BF16_L2
+    assert rel_l2(sums[:, 1], (ref * ref).sum((2, 3))) < 1e-4
+    dxb = torch.empty_like(xb)
+    ext2 = ConvExt()
+    ext2.groups = groups
+    ctx.conv_dgrad_ex(sh, dyb.data_ptr(), wd.data_ptr(), dxb.data_ptr(), None, None, 0, SLOPE, C.byref(ext2))
+    assert rel_l2(nchw32(dxb), x.grad) < BF16_L2
+    dw = torch.zeros(9, c, gw, device="cuda")
+    ctx.conv_wgrad_grouped(sh, xb.data_ptr(), dyb.data_ptr(), dw.data_ptr(), groups)
+    assert rel_l2(dw, wt.grad.permute(2, 3, 0, 1).reshape(9, c, gw)) < 1e-4

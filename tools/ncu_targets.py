@@ -1,7 +1,7 @@
 """One launch of every kernel family at its in-step shape, inside a cudaProfilerStart/Stop range, for
    ncu --set full --clock-control none --import-source on --profile-from-start off -o gpurun_out/prof_targets python tools/ncu_targets.py
 The launch order printed on stdout is the order of the kernels in the report (tools/ncu_summary.py reads both).
-Select families with LSPS_NCU_CASES=conv,stem,head,in,adam,noise (default: all)."""
+Select families with LSPS_NCU_CASES=conv,k1,stem,head,in,adam,noise,norm,split (default: conv,stem,head,in,adam,noise)."""
 import ctypes as C
 import os
 import sys
@@ -114,6 +114,65 @@ def _sec_noise():
 
 if "noise" in want:
     _sec_noise()
+def _sec_norm():
+    from lsps_b200._lib import ConvExt
+    n, hw, c = 128, 1024, 256
+    h = torch.randn(n, hw, c, device="cuda").bfloat16()
+    res, dy, a1 = torch.randn_like(h), torch.randn_like(h), torch.randn_like(h)
+    y, dh = torch.empty_like(h), torch.empty_like(h)
+    sums = torch.zeros(n, 2, c, device="cuda")
+    sums[:, 1] = 1024.0
+    stats, bs = torch.zeros(n, 2, c, device="cuda"), torch.zeros(n, 2, c, device="cuda")
+    stats[:, 1] = 1.0
+    keep = (h, res, dy, a1, y, dh, sums, stats, bs)
+    mb = h.numel() * 2
+    cases.append(("norm_apply_fwd lrelu N=128", 2 * mb, 0, lambda: ctx.norm_apply_fwd(h.data_ptr(), None, y.data_ptr(), sums.data_ptr(), stats.data_ptr(), n, hw, c, 0, 1, 1e-5, 0.01, None, None), keep))
+    cases.append(("norm_apply_fwd residual N=128", 3 * mb, 0, lambda: ctx.norm_apply_fwd(h.data_ptr(), res.data_ptr(), y.data_ptr(), sums.data_ptr(), stats.data_ptr(), n, hw, c, 1, 1, 1e-5, 0.01, None, None), keep))
+    cases.append(("norm_bwd_stats N=128", 2 * mb, 0, lambda: ctx.norm_bwd_stats(dy.data_ptr(), h.data_ptr(), stats.data_ptr(), bs.data_ptr(), n, hw, c, 1, 1, 0.01, None, None), keep))
+    cases.append(("norm_bwd_apply N=128", 3 * mb, 0, lambda: ctx.norm_bwd_apply(dy.data_ptr(), h.data_ptr(), stats.data_ptr(), bs.data_ptr(), dh.data_ptr(), n, hw, c, 2, 1, 0.01, None, None), keep))
+    # K1 with the statistics / InstanceNorm-backward epilogues
+    x4 = h.reshape(n, 32, 32, c)
+    wf = (torch.randn(9, c, c, device="cuda") * 0.05).bfloat16()
+    b = torch.zeros(c, device="cuda")
+    sh = ConvShape(0, n, 32, 32, c, c)
+    flop = 2.0 * n * 1024 * c * c * 9
+    e1, e2 = ConvExt(), ConvExt()
+    e1.sums = sums.data_ptr()
+    e2.in_a, e2.bsums = a1.data_ptr(), bs.data_ptr()
+    keep2 = keep + (wf, b, sh, e1, e2)
+    cases.append(("K1 fwd + EP_STATS N=128", 2 * mb, flop, lambda: ctx.conv_fwd_ex(C.byref(sh), x4.data_ptr(), wf.data_ptr(), b.data_ptr(), y.data_ptr(), 1 | 16, 0.01, C.byref(e1)), keep2))
+    cases.append(("K1 dgrad + EP_INBWD N=128", 3 * mb, flop, lambda: ctx.conv_dgrad_ex(C.byref(sh), dy.data_ptr(), wf.data_ptr(), dh.data_ptr(), None, None, 32, 0.01, C.byref(e2)), keep2))
+    cases.append(("K1 dgrad plain N=128", 2 * mb, flop, lambda: ctx.conv_dgrad(C.byref(sh), dy.data_ptr(), wf.data_ptr(), dh.data_ptr(), None, None, 0, 0.01), keep2))
+
+
+if "norm" in want:
+    _sec_norm()
+
+
+def _sec_split():
+    from lsps_b200._lib import ConvExt
+    for name, n, h, cin, cout in (("split s2 64->128 @64^2 N=192", 192, 64, 64, 128), ("split s2 128->256 @32^2 N=384", 384, 32, 128, 256),
+                                  ("split s2 1024->2048 @4^2 N=384", 384, 4, 1024, 2048)):
+        x = torch.randn(n, h, h, 2 * cin, device="cuda").bfloat16()
+        dy = torch.randn(n, h // 2, h // 2, 2 * cout, device="cuda").bfloat16()
+        wf, wl = (torch.randn(9, cout, cin, device="cuda") * 0.05).bfloat16(), (torch.randn(9, cout, cin, device="cuda") * 1e-4).bfloat16()
+        b = torch.zeros(cout, device="cuda")
+        y, dx = torch.empty_like(dy), torch.empty_like(x)
+        dw = torch.zeros(9, cout, cin, device="cuda")
+        sh = ConvShape(1, n, h, h, cin, cout)
+        ext = ConvExt()
+        ext.split, ext.w_lo = 1, wl.data_ptr()
+        flop = 3 * 2.0 * n * (h // 2) ** 2 * cin * cout * 9
+        io = (x.numel() + dy.numel() + 2 * wf.numel()) * 2
+        keep = (x, dy, wf, wl, b, y, dx, dw, sh, ext)
+        cases.append((name + " fwd", io, flop, lambda sh=sh, x=x, wf=wf, b=b, y=y, ext=ext: ctx.conv_fwd_ex(C.byref(sh), x.data_ptr(), wf.data_ptr(), b.data_ptr(), y.data_ptr(), 3, 0.01, C.byref(ext)), keep))
+        cases.append((name + " dgrad+mask", io + x.numel() * 2, flop, lambda sh=sh, x=x, wf=wf, dy=dy, dx=dx, ext=ext: ctx.conv_dgrad_ex(C.byref(sh), dy.data_ptr(), wf.data_ptr(), dx.data_ptr(), x.data_ptr(), None, 4, 0.01, C.byref(ext)), keep))
+        cases.append((name + " wgrad", io, flop, lambda sh=sh, x=x, dy=dy, dw=dw: ctx.conv_wgrad_split(C.byref(sh), x.data_ptr(), dy.data_ptr(), dw.data_ptr()), keep))
+
+
+if "split" in want:
+    _sec_split()
+
 for case_ in cases:      # warm-up: sets kernel attributes, fills the tensor-map cache
     case_[3]()
 torch.cuda.synchronize()
