@@ -122,6 +122,10 @@ int lsps_stem_dgrad_split(lsps_ctx*, const void* dy, const float* w, float* dimg
 
 /* ---- decoder head ConvTranspose2d(64,1,1)+Tanh (lsps_nets.py:226-229): x bf16 [npix,64] -> out f32 [npix] */
 int lsps_head_fwd(lsps_ctx*, const void* x, const float* w, const float* bias, float* out, long long npix, lsps_stream);
+/* same with the reconstruction loss fused in (nn.L1Loss vs the input image, lsps_trainer.py:118-121): for the pixels
+   [t0, t0+tn) of the batch, acc += sum|out - target[p - t0]| and dout[p - t0] = scale*sign(out - target) (dout may be NULL) */
+int lsps_head_fwd_l1(lsps_ctx*, const void* x, const float* w, const float* bias, float* out, long long npix,
+                     const float* target, long long t0, long long tn, float scale, float* dout, float* acc, lsps_stream);
 /* dpre = dout*(1-out^2); dx = dpre*w*lrelu'(x) (bf16); dw[64] += sum dpre*x ; db += sum dpre */
 int lsps_head_bwd(lsps_ctx*, const void* x, const float* w, const float* out, const float* dout, void* dx, float* dw,
                   float* db, long long npix, float slope, lsps_stream);

@@ -62,6 +62,7 @@ _SIGS = {
     "lsps_stem_wgrad": [_vp, _vp, _vp, _vp, _i, _i, _i, _i],
     "lsps_stem_dgrad": [_vp, _vp, _vp, _i, _i, _i, _i, _i],
     "lsps_head_fwd": [_vp, _vp, _vp, _vp, _ll],
+    "lsps_head_fwd_l1": [_vp, _vp, _vp, _vp, _ll, _vp, _ll, _ll, _f, _vp, _vp],
     "lsps_head_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _ll, _f],
     "lsps_instnorm_fwd": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _f],
     "lsps_instnorm_bwd": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _vp],

@@ -240,14 +240,20 @@ __global__ void __launch_bounds__(256) stem_dgrad_kernel(const bf16* __restrict_
 }
 
 // =============================================================================================== decoder head
+// Optional fused reconstruction loss (nn.L1Loss against the input image, lsps_trainer.py:118-121): for pixels
+// [t0, t0 + tn) the kernel also accumulates sum |out - target[p - t0]| into acc and writes dout[p - t0] = scale*sign.
 __global__ void __launch_bounds__(256) head_fwd_kernel(const bf16* __restrict__ x, const float* __restrict__ w,
                                                       const float* __restrict__ bias, float* __restrict__ out,
-                                                      long long npix) {
+                                                      long long npix, const float* __restrict__ target, long long t0,
+                                                      long long tn, float scale, float* __restrict__ dout,
+                                                      float* __restrict__ acc) {
+  __shared__ float sm[8];
   const int oct = threadIdx.x & 7;
   float wr[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) wr[k] = __ldg(w + oct * 8 + k);
   const float b = __ldg(bias);
+  float l1 = 0.f;
   for (long long p = (long long)blockIdx.x * 32 + (threadIdx.x >> 3); p < npix; p += (long long)gridDim.x * 32) {
     float f[8];
     unpack8(__ldg(reinterpret_cast<const uint4*>(x + p * 64) + oct), f);
@@ -257,7 +263,19 @@ __global__ void __launch_bounds__(256) head_fwd_kernel(const bf16* __restrict__ 
     s += __shfl_xor_sync(0xffffffffu, s, 1);
     s += __shfl_xor_sync(0xffffffffu, s, 2);
     s += __shfl_xor_sync(0xffffffffu, s, 4);
-    if (oct == 0) out[p] = tanhf(s + b);
+    if (oct == 0) {
+      const float o = tanhf(s + b);
+      out[p] = o;
+      if (target && p >= t0 && p < t0 + tn) {
+        const float d = o - __ldg(target + (p - t0));
+        l1 += fabsf(d);
+        if (dout) dout[p - t0] = d > 0.f ? scale : (d < 0.f ? -scale : 0.f);
+      }
+    }
+  }
+  if (target) {           // uniform branch: every thread of every block takes it
+    const float r = block_sum(l1, sm);
+    if (threadIdx.x == 0) atomicAdd(acc, r);
   }
 }
 
@@ -1352,8 +1370,19 @@ extern "C" int lsps_stem_dgrad_split(lsps_ctx* ctx, const void* dy, const float*
 extern "C" int lsps_head_fwd(lsps_ctx* ctx, const void* x, const float* w, const float* bias, float* out,
                              long long npix, lsps_stream st) {
   REQUIRE(ctx, x && w && bias && out && npix > 0, LSPS_E_ARG, "head_fwd: null");
-  head_fwd_kernel<<<grid_for(npix, 32, 16 * ctx->num_sms), 256, 0, ST_(st)>>>(static_cast<const bf16*>(x), w, bias, out, npix);
+  head_fwd_kernel<<<grid_for(npix, 32, 16 * ctx->num_sms), 256, 0, ST_(st)>>>(static_cast<const bf16*>(x), w, bias, out, npix,
+                                                                            nullptr, 0, 0, 0.f, nullptr, nullptr);
   LSPS_CHECK_LAUNCH(ctx, "head_fwd");
+  return LSPS_OK;
+}
+extern "C" int lsps_head_fwd_l1(lsps_ctx* ctx, const void* x, const float* w, const float* bias, float* out,
+                                long long npix, const float* target, long long t0, long long tn, float scale,
+                                float* dout, float* acc, lsps_stream st) {
+  REQUIRE(ctx, x && w && bias && out && npix > 0 && target && acc && t0 >= 0 && tn > 0 && t0 + tn <= npix, LSPS_E_ARG,
+          "head_fwd_l1: arg");
+  head_fwd_kernel<<<grid_for(npix, 32, 16 * ctx->num_sms), 256, 0, ST_(st)>>>(static_cast<const bf16*>(x), w, bias, out, npix,
+                                                                            target, t0, tn, scale, dout, acc);
+  LSPS_CHECK_LAUNCH(ctx, "head_fwd_l1");
   return LSPS_OK;
 }
 extern "C" int lsps_head_bwd(lsps_ctx* ctx, const void* x, const float* w, const float* out, const float* dout,

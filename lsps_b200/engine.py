@@ -480,7 +480,7 @@ class Generator:
 
     # -- two decoders on the halves of x (doms = ("B", "A") in the cycle pass, ("A", "B") for gen.decode): grouped res
     #    blocks, then each domain's transposed convs + head on its half
-    def dec_pair_fwd(self, doms, x, save):
+    def dec_pair_fwd(self, doms, x, save, l1s=(None, None)):
         o, S = self.ops, self.S
         n = x.shape[0] // 2
         blocks = [] if save is not None else None
@@ -488,14 +488,12 @@ class Generator:
         for i in range(nres):
             x = o.res_fwd(S, ("decode_%s.%d" % (doms[0], i), "decode_%s.%d" % (doms[1], i), n), x, blocks)
         outs, tails = [], []
-        for dom, xh in ((doms[0], x[:n]), (doms[1], x[n:])):
+        for dom, xh, l1 in ((doms[0], x[:n], l1s[0]), (doms[1], x[n:], l1s[1])):
             d = "decode_%s" % dom
             g1 = o.conv_fwd(S, "%s.%d.model.0" % (d, nres), DECONV_S2, xh, True)
             g2 = o.conv_fwd(S, "%s.%d.model.0" % (d, nres + 1), DECONV_S2, g1, True)
             img = o.empty(n, g2.shape[1], g2.shape[2], dtype=torch.float32)
-            hk = "%s.%d" % (d, nres + 2)
-            o.ctx.head_fwd(g2.data_ptr(), S.W(hk + ".weight").data_ptr(), S.W(hk + ".bias").data_ptr(), img.data_ptr(),
-                           img.numel())
+            self._head("%s.%d" % (d, nres + 2), g2, img, l1)
             outs.append(img)
             tails.append(dict(dom=dom, blocks=[], x3=xh, g1=g1, g2=g2, out=img))
         if save is not None:
@@ -551,7 +549,21 @@ class Generator:
         return dz
 
     # -- decoder: res blocks, two transposed 3x3 s2 convs, 1x1 head + tanh
-    def dec_fwd(self, dom, x, save, out=None):
+    def _head(self, hk, g2, img, l1):
+        """decoder head (1x1 transposed conv + tanh); l1 = (target [nt,128,128] fp32, first image, scale, dout, acc): the
+        L1 reconstruction loss of images [first, first + nt) and its gradient are taken in the same kernel."""
+        o, S = self.ops, self.S
+        if l1 is None:
+            o.ctx.head_fwd(g2.data_ptr(), S.W(hk + ".weight").data_ptr(), S.W(hk + ".bias").data_ptr(), img.data_ptr(),
+                           img.numel())
+            return
+        target, first, scale, dout, acc = l1
+        px = img.shape[1] * img.shape[2]
+        o.ctx.head_fwd_l1(g2.data_ptr(), S.W(hk + ".weight").data_ptr(), S.W(hk + ".bias").data_ptr(), img.data_ptr(),
+                          img.numel(), target.data_ptr(), first * px, target.shape[0] * px, scale, _lib.ptr(dout),
+                          acc.data_ptr())
+
+    def dec_fwd(self, dom, x, save, out=None, l1=None):
         o, S, d = self.ops, self.S, "decode_%s" % dom
         blocks = [] if save is not None else None
         nres = self.p["n_gen_res_blk"]
@@ -561,9 +573,7 @@ class Generator:
         g2 = o.conv_fwd(S, "%s.%d.model.0" % (d, nres + 1), DECONV_S2, g1, True)
         n = g2.shape[0]
         img = out if out is not None else o.empty(n, g2.shape[1], g2.shape[2], dtype=torch.float32)
-        hk = "%s.%d" % (d, nres + 2)
-        o.ctx.head_fwd(g2.data_ptr(), S.W(hk + ".weight").data_ptr(), S.W(hk + ".bias").data_ptr(), img.data_ptr(),
-                       img.numel())
+        self._head("%s.%d" % (d, nres + 2), g2, img, l1)
         if save is not None:
             save.append(dict(dom=dom, blocks=blocks, x3=x, g1=g1, g2=g2, out=img))
         return img
@@ -610,7 +620,7 @@ class Generator:
             x = o.res_fwd(S, "enc_shared.%d" % i, x, eb)
         return dict(se=se, eb=eb, x=x, na=na, nb=nb)
 
-    def forward(self, xa, xb, noise, kl_acc, save=None, out_a=None, out_b=None, front=None):
+    def forward(self, xa, xb, noise, kl_acc, save=None, out_a=None, out_b=None, front=None, l1_a=None, l1_b=None):
         """xa [na,128,128] / xb [nb,128,128] (either may be None).  Returns decode_A and decode_B of ALL na+nb
         latents: oa = (x_aa | x_ba), ob = (x_ab | x_bb), plus the noised shared latent.  out_a / out_b: optional
         [na+nb,128,128] fp32 destinations (slices of the discriminator's input batch: no concatenation copy).
@@ -622,8 +632,8 @@ class Generator:
         ss = [] if save is not None else None
         y, z = self.shared_fwd(None, noise, kl_acc, ss, pre=(front["x"], front["eb"]))
         sd = [] if save is not None else None
-        oa = self.dec_fwd("A", y, sd, out=out_a)
-        ob = self.dec_fwd("B", y, sd, out=out_b)
+        oa = self.dec_fwd("A", y, sd, out=out_a, l1=l1_a)
+        ob = self.dec_fwd("B", y, sd, out=out_b, l1=l1_b)
         if save is not None:
             save.update(enc=se, shared=ss[0], dec=sd, na=na, nb=nb)
         return oa, ob, z
@@ -680,7 +690,7 @@ class Generator:
         return dy
 
     # -- cycle passes (lsps_nets.py:260-272), batched: first half a2b (encode_A -> decode_B), second half b2a
-    def forward_cycle(self, x_ba, x_ab, noise, kl_acc_bab, kl_acc_aba, save=None):
+    def forward_cycle(self, x_ba, x_ab, noise, kl_acc_bab, kl_acc_aba, save=None, l1s=(None, None)):
         o = self.ops
         n = x_ba.shape[0]
         h = o.empty(2 * n, 32, 32, 4 * self.p["ch"])
@@ -695,10 +705,10 @@ class Generator:
         y, z = self._shared_fwd_split(h, noise, kl_acc_bab, kl_acc_aba, n, ss)
         sd = [] if save is not None else None
         if self.grouped:
-            x_bab, x_aba = self.dec_pair_fwd(("B", "A"), y, sd)
+            x_bab, x_aba = self.dec_pair_fwd(("B", "A"), y, sd, l1s)
         else:
-            x_bab = self.dec_fwd("B", y[:n], sd)
-            x_aba = self.dec_fwd("A", y[n:], sd)
+            x_bab = self.dec_fwd("B", y[:n], sd, l1=l1s[0])
+            x_aba = self.dec_fwd("A", y[n:], sd, l1=l1s[1])
         if save is not None:
             save.update(enc=se, shared=ss[0], dec=sd, n=n)
         return x_bab, x_aba

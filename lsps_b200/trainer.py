@@ -318,11 +318,21 @@ class LSPSTrainerB200(object):
         n3 = self._latent_noise(B)
         n4 = self._latent_noise(B)
         s1 = {}
-        oa, ob, shared = gen.forward(ia, ib, n2, G.acc[2:], s1, front=self._gen_front(ia, ib, keep=False))
+        npx = float(Bg * _NPIX)
+        o = self.ops
+        doa = o.empty(2 * B, 128, 128, dtype=torch.float32)       # d/d(x_aa | x_ba)
+        dob = o.empty(2 * B, 128, 128, dtype=torch.float32)       # d/d(x_ab | x_bb)
+        d_bab, d_aba = o.empty(B, 128, 128, dtype=torch.float32), o.empty(B, 128, 128, dtype=torch.float32)
+        # the four L1 reconstruction terms (lsps_trainer.py:118-121) are taken inside the decoder-head kernels
+        oa, ob, shared = gen.forward(ia, ib, n2, G.acc[2:], s1, front=self._gen_front(ia, ib, keep=False),
+                                     l1_a=(ia, 0, hp["ll_direct_link_w"] / npx, doa[:B], G.acc[5:]),
+                                     l1_b=(ib, B, hp["ll_direct_link_w"] / npx, dob[B:], G.acc[6:]))
         x_aa, x_ba, x_ab, x_bb = oa[:B], oa[B:], ob[:B], ob[B:]
         s2 = {}
         x_bab, x_aba = gen.forward_cycle(x_ba, x_ab, n3 if isinstance(n3, tuple) else torch.cat((n3, n4), 0), G.acc[3:],
-                                         G.acc[4:], s2)
+                                         G.acc[4:], s2,
+                                         l1s=((ib, 0, hp["ll_cycle_link_w"] / npx, d_bab, G.acc[8:]),
+                                              (ia, 0, hp["ll_cycle_link_w"] / npx, d_aba, G.acc[7:])))
         del n2, n3, n4
         dec_a, dec_b, nd = x_ba, x_ab, 1
         if train_map:                        # :84-99 (the vae.encode draw comes after the three latent draws, as there)
@@ -336,8 +346,6 @@ class LSPSTrainerB200(object):
         dF = self.ops.empty(F.shape[0], 4 * dis.cf, dtype=torch.float32)
         dis.head_bce(F, dis.rows(F), [1.0], [0], hp["gan_w"] / float(4 * nd * Bg), dF, False, G.acc)
         dFm = dis.mask_grad(dF, F)
-        doa = torch.empty_like(oa)           # d/d(x_aa | x_ba)
-        dob = torch.empty_like(ob)           # d/d(x_ab | x_bb)
         if train_map:
             dia, dib = torch.empty(2 * B, 128, 128, device=self.device), torch.empty(2 * B, 128, 128, device=self.device)
             dis.features_bwd(sd, dFm, wgrad=False, dimg_a=dia, dimg_b=dib)
@@ -347,7 +355,6 @@ class LSPSTrainerB200(object):
         else:
             dis.features_bwd(sd, dFm, wgrad=False, dimg_a=doa[B:], dimg_b=dob[:B])
         del sd
-        npx = float(Bg * _NPIX)
         g_z = None
         if train_map:
             # matching losses (:97-99): ll_map_w * (L1(decode_A, images_a) + L1(decode_B, images_b)) on top of the
@@ -361,13 +368,8 @@ class LSPSTrainerB200(object):
             ctx.axpy_bf16(dzm.data_ptr(), g_z.data_ptr(), -1.0, dzm.data_ptr(), dzm.numel())
             self.map.backward(sm, dzm)
             del sdm, sm
-        d_bab, d_aba = torch.empty_like(x_bab), torch.empty_like(x_aba)
-        ctx.l1_f32(x_bab.data_ptr(), ib.data_ptr(), d_bab.data_ptr(), hp["ll_cycle_link_w"] / npx, 0, G.acc[8:].data_ptr(), x_bab.numel())
-        ctx.l1_f32(x_aba.data_ptr(), ia.data_ptr(), d_aba.data_ptr(), hp["ll_cycle_link_w"] / npx, 0, G.acc[7:].data_ptr(), x_aba.numel())
         gen.backward_cycle(s2, d_bab, d_aba, hp["kl_cycle_link_w"] / float(Bg * _LATENT), doa[B:], dob[:B])
         del s2
-        ctx.l1_f32(x_aa.data_ptr(), ia.data_ptr(), doa[:B].data_ptr(), hp["ll_direct_link_w"] / npx, 0, G.acc[5:].data_ptr(), x_aa.numel())
-        ctx.l1_f32(x_bb.data_ptr(), ib.data_ptr(), dob[B:].data_ptr(), hp["ll_direct_link_w"] / npx, 0, G.acc[6:].data_ptr(), x_bb.numel())
         # kl_direct * (enc + enc) with enc = mean over the 2B latents
         gen.backward(s1, doa, dob, 2.0 * hp["kl_direct_link_w"] / float(2 * Bg * _LATENT), dz_extra=g_z)
         self.ops.join_side()
