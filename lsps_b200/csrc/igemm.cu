@@ -966,6 +966,11 @@ inline bool lsps_one_epi_group() {
   if (v < 0) { const char* e = getenv("LSPS_ONE_EPI_GROUP"); v = (e && e[0] == '1') ? 1 : 0; }
   return v == 1;
 }
+inline bool lsps_no_small_bn() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("LSPS_NO_SMALL_BN"); v = (e && e[0] == '1') ? 1 : 0; }
+  return v == 1;
+}
 inline bool lsps_no_up64() {
   static int v = -1;
   if (v < 0) { const char* e = getenv("LSPS_NO_UP64"); v = (e && e[0] == '1') ? 1 : 0; }
@@ -1123,7 +1128,12 @@ int run_igemm(lsps_ctx* ctx, const lsps_conv_shape* s, Dir dir, const void* in, 
     }
   }
 
-  const int bn = groups > 1 ? gw : (nc % 256 == 0 ? 256 : (nc % 128 == 0 ? 128 : 64));
+  int bn = groups > 1 ? gw : (nc % 256 == 0 ? 256 : (nc % 128 == 0 ? 128 : 64));
+  // few tiles (small batches: the estimate-mode generator pass on 8 source images is 64 tiles of 128 x 256): halve the N
+  // tile so that twice as many SMs share the launch -- the K loop per CTA stays, its weight tile and epilogue halve
+  if (bn == 256 && groups == 1 && !lsps_no_small_bn() &&
+      (long long)p.tiles_x * p.tiles_y * p.tiles_i * p.nphases * (nc / 256) * 2 <= ctx->num_sms)
+    bn = 128;
   p.tiles_n = nc / bn;
   // grouped launch: one tensor map over both weight sets (they live in one flat buffer)
   const char* wbase = static_cast<const char*>(wpk);

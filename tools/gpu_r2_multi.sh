@@ -11,6 +11,7 @@ run --yaml nnyu --mode estimate3 --batch 32 --steps 40 --warmup 10 --graphs 1
 LSPS_NO_EARLY_AR=1 run --yaml nnyu --mode estimate3 --batch 32 --steps 40 --warmup 10
 # strong scaling of the same global batch 256
 run --yaml nnyu --mode estimate3 --global-batch 256 --steps 40 --warmup 10
+run --yaml nnyu --mode pretrain --batch 64 --steps 10 --warmup 4
 # config 4: nicvl hyper-parameters, 32 per rank (batch 128 over 4 GPUs), pretrain and estimate3
 run --yaml nicvl --mode pretrain --batch 32 --steps 10 --warmup 4
 run --yaml nicvl --mode estimate3 --batch 32 --steps 40 --warmup 10

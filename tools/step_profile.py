@@ -19,12 +19,18 @@ g = torch.Generator().manual_seed(1)
 ia, ib, la, lb = (t.cuda() for t in lsps_b200.synthetic_batch(B, 108, g, "hand"))
 
 
+MODE = os.environ.get("LSPS_PROFILE_MODE", "pretrain")     # pretrain | estimateN
+
+
 def step():
-    tr.dis_update(ia, la, ib, lb, None, None, hp)
-    tr.gen_update(ia, la, ib, lb, hp)
+    if MODE == "pretrain":
+        tr.dis_update(ia, la, ib, lb, None, None, hp)
+        tr.gen_update(ia, la, ib, lb, hp)
+    else:
+        tr.post_update(ia, la, ib, lb, None, None, int(MODE[len("estimate"):]), hp)
 
 
-for _ in range(8):          # long enough to reach the power-limited steady state
+for _ in range(8 if MODE == "pretrain" else 30):          # long enough to reach the power-limited steady state
     step()
 torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -43,7 +49,7 @@ for n in names:
     orig = getattr(ctx, n)
 
     def wrapped(*a, _o=orig, _n=n):
-        if _n in ("conv_fwd", "conv_dgrad", "conv_wgrad"):
+        if _n in ("conv_fwd", "conv_dgrad", "conv_wgrad", "conv_fwd_ex", "conv_dgrad_ex", "conv_wgrad_split", "conv_wgrad_grouped"):
             sh = a[0]._obj
             tag = "%s k%d %dx%d %d->%d n%d" % (_n, sh.kind, sh.h, sh.w, sh.cin, sh.cout, sh.n)
         else:
