@@ -6,7 +6,7 @@ The compute path is the in-tree CUDA library (csrc/liblsps_b200.so); importing f
 """
 from . import _lib  # noqa: F401  (loads / builds the CUDA library; raises ImportError when impossible)
 from .trainer import LSPSTrainerB200
-from .engine import Generator as SharedResGenB200, Discriminator as SharedDisB200, PoseVAE as poseVAEB200
+from .nets import SharedResGenB200, SharedResXGenB200, SharedDisB200, poseVAEB200, MappingB200
 from .data import SyntheticHandDataset, synthetic_batch
 from .config import NetConfig, load_hyperparameters
 from .evaluation import PoseEvaluator, NYU_RESTRICTED_JOINTS
@@ -14,6 +14,7 @@ from .augment import CropAugmenter
 
 LSPSTrainer = LSPSTrainerB200  # the reference's own name selects the B200 trainer as well
 
-__all__ = ["CropAugmenter", "LSPSTrainerB200", "LSPSTrainer", "SharedResGenB200", "SharedDisB200", "poseVAEB200",
+__all__ = ["CropAugmenter", "LSPSTrainerB200", "LSPSTrainer", "SharedResGenB200", "SharedResXGenB200", "SharedDisB200",
+           "poseVAEB200", "MappingB200",
            "SyntheticHandDataset", "synthetic_batch", "NetConfig", "load_hyperparameters", "PoseEvaluator",
            "NYU_RESTRICTED_JOINTS"]

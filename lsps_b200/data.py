@@ -31,9 +31,12 @@ def synthetic_batch(batch, label_dim, generator, kind="uniform", device=None):
 class SyntheticHandDataset(torch.utils.data.Dataset):
     """6-tuples like dataset_hand_NYU; deterministic per index."""
 
-    def __init__(self, specs=None, n=4096, label_dim=108, seed=23455, cube=300.0):
+    def __init__(self, specs=None, n=4096, label_dim=108, seed=23455, cube=300.0, camera_items=False):
+        """camera_items: emit a plausible centre of mass (image coordinates + depth in mm) and its crop transform M instead
+        of zeros / identity, so that the augmentation row (lsps_b200.augment.CropAugmenter) has something to move."""
         specs = specs or {}
         self.n, self.label_dim, self.seed, self.cube = n, label_dim, int(specs.get("seed", seed)), cube
+        self.camera_items = camera_items
 
     def __len__(self):
         return self.n
@@ -46,4 +49,11 @@ class SyntheticHandDataset(torch.utils.data.Dataset):
         g = torch.Generator().manual_seed(self.seed * 1000003 + i)
         ia, _, la, _ = synthetic_batch(1, self.label_dim, g, kind="hand")
         cube = torch.full((3,), self.cube)
+        if self.camera_items:
+            import numpy as np
+            from .augment import Camera, NYU_CAMERA, com_to_transform
+            com = np.array([320.0 + 40.0 * float(torch.rand(1, generator=g)) - 20.0,
+                            240.0 + 40.0 * float(torch.rand(1, generator=g)) - 20.0, 600.0 + 100.0 * float(torch.rand(1, generator=g))])
+            M = com_to_transform(com, (self.cube,) * 3, Camera(*NYU_CAMERA))
+            return ia[0], la[0], torch.from_numpy(com).float(), torch.from_numpy(np.asarray(M, np.float32)), cube, cube
         return ia[0], la[0], torch.zeros(3), torch.eye(3), cube, cube

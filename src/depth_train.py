@@ -31,6 +31,10 @@ parser.add_option('--batch', type=int, help="(new) per-GPU batch override for pr
 parser.add_option('--snapshot_prefix', type=str, help="(new) overrides the YAML snapshot_prefix", default="")
 parser.add_option('--iters', type=int, help="(new) stop after this many iterations", default=0)
 parser.add_option('--noise', type=str, help="(new) host = reference RNG stream, device = Philox", default="device")
+parser.add_option('--augment', type=int, help="(new) 1 = online crop augmentation on the GPU (lsps_augment_crops) in place "
+                  "of the DataLoader workers' augmentCrop (data/dataset_hand2.py:34-119)", default=0)
+parser.add_option('--eval_every', type=int, help="(new) estimate modes: device evaluation sweep over test_b every N "
+                  "iterations (depth_train.py:186-253 runs it every image_save_iterations)", default=0)
 
 
 def main(argv):
@@ -50,7 +54,7 @@ def main(argv):
     batch_size = hp['batch_size'] if estimate else (opts.batch or 1)       # depth_train.py:85
     max_iterations = opts.iters or hp['max_iterations']
     label_dim = hp['vae']['input_dim']
-    mk = lambda spec: SyntheticHandDataset(config.datasets[spec], label_dim=label_dim)
+    mk = lambda spec: SyntheticHandDataset(config.datasets[spec], label_dim=label_dim, camera_items=bool(opts.augment))
     dataset_a, dataset_b = mk('train_a'), mk('train_b')
     kw = dict(batch_size=batch_size, shuffle=True, num_workers=0, drop_last=True)
     sampler = lambda ds: torch.utils.data.distributed.DistributedSampler(ds) if world > 1 else None
@@ -80,9 +84,34 @@ def main(argv):
             trainer.resume(config.snapshot_prefix, idx=opts.idx, est=(mode_idx == 5))
         if 0. < opts.frac < 1. and hasattr(dataset_b, 'set_nmax'):
             dataset_b.set_nmax(opts.frac)
+    augmenters, evaluator, test_loader = None, None, None
+    if opts.augment:
+        # the reference augments per sample inside its DataLoader workers (cfg key datasets.*.augment); here the host only
+        # draws the random numbers in the reference's order and ONE kernel launch warps the whole batch on the GPU
+        from lsps_b200.augment import CropAugmenter
+        augmenters = [CropAugmenter(seed=int(config.datasets[k].get('seed', 23455)) + rank, device=local)
+                      for k in ('train_a', 'train_b')]
+    if estimate and opts.eval_every:
+        from lsps_b200.evaluation import PoseEvaluator, NYU_RESTRICTED_JOINTS
+        evaluator = PoseEvaluator(trainer, domain="b", restricted_joints=NYU_RESTRICTED_JOINTS if label_dim == 108 else None)
+        test_loader = torch.utils.data.DataLoader(mk('test_b'), batch_size=32 * batch_size, shuffle=False, num_workers=0)
+
+    def augment(aug, images, labels, com, M, cube):
+        import numpy as np
+        n = images.shape[0]
+        c = cube.numpy()
+        gt3d = [(labels[i].numpy().reshape(-1, 3) * (c[i][2] / 2.)).astype(np.float32) for i in range(n)]
+        out, labs, cubes, coms, _, _ = aug(images.cuda(local, non_blocking=True), gt3d, [com[i].numpy().astype(np.float64) for i in range(n)],
+                                           [tuple(c[i]) for i in range(n)], [M[i].numpy() for i in range(n)])
+        lab = np.stack([np.asarray(labs[i], np.float32).reshape(-1) for i in range(n)])   # already normalised by the new cube
+        return out, torch.from_numpy(lab), torch.from_numpy(np.stack([np.asarray(x, np.float32) for x in coms]))
+
     start_time = time.time()
     while iterations < max_iterations:
-        for (images_a, labels_a, com_a, _, _, _), (images_b, labels_b, com_b, _, _, _) in zip(loader_a, loader_b):
+        for (images_a, labels_a, com_a, M_a, cube_a, _), (images_b, labels_b, com_b, M_b, cube_b, _) in zip(loader_a, loader_b):
+            if augmenters is not None:
+                images_a, labels_a, com_a = augment(augmenters[0], images_a, labels_a, com_a, M_a, cube_a)
+                images_b, labels_b, com_b = augment(augmenters[1], images_b, labels_b, com_b, M_b, cube_b)
             images_a, images_b = images_a.cuda(local, non_blocking=True), images_b.cuda(local, non_blocking=True)
             labels_a, labels_b = labels_a.cuda(local, non_blocking=True), labels_b.cuda(local, non_blocking=True)
             trainer.dis.train()
@@ -102,6 +131,15 @@ def main(argv):
                 print("Iteration: %08d/%08d  %.2fs  %s" % (iterations + 1, max_iterations, time.time() - start_time,
                                                           " ".join("%s=%.4f" % (m, float(getattr(trainer, m))) for m in members)))
                 start_time = time.time()
+            if evaluator is not None and (iterations + 1) % opts.eval_every == 0:
+                evaluator.reset()                                    # depth_train.py:186-253: regress_b -> vae.decode -> mm
+                for (ti, tl, _, _, tcube, _) in test_loader:
+                    evaluator.add_batch(ti.cuda(local, non_blocking=True), tl, tcube[0])
+                    break                                            # synthetic test set: one batch of 32 x batch_size
+                mean_err, within = evaluator.summary(40.0)
+                if rank == 0:
+                    print("Mean err %.2f mm, %.1f %% of frames within 40 mm" % (mean_err, within))
+                trainer.last_eval = (mean_err, within)
             if (iterations + 1) % config.snapshot_save_iterations == 0 and rank == 0:
                 os.makedirs(os.path.dirname(config.snapshot_prefix) or ".", exist_ok=True)
                 trainer.save(config.snapshot_prefix + ('_est' if estimate else ''), iterations)

@@ -108,15 +108,17 @@ def test_100_steps_teacher_forced_pretrain_and_estimate3():
     part 1a): 100 consecutive training steps of the oracle; before each one the B200 trainer takes the oracle's
     weights and Adam moments, both run the step on the same batch and host noise, every loss is compared.
 
-    Asserted tolerances (relative; + 1e-5 absolute for the tiny estimate losses):
-      * 1e-3  reconstruction (gen_ll_loss, gen_ll_loss2), KL (gen_enc_loss, gen_enc_loss2), estimate3 dis_reg_loss;
-      * 5e-3  gen_total_loss (contains 10 x the adversarial term);
-      * 1e-2  dis_loss / dis_ad_loss and 3e-2 gen_ad_loss -- the adversarial BCE terms.  They pass through ~50
-              bf16-operand conv layers of BOTH networks and once the discriminator has trained for a few dozen steps
-              its logits react to 1e-3-level perturbations of the generated images; measured worst case over 100
-              steps: dis_ad_loss 4.2e-3, gen_ad_loss 1.3e-2 (steps 0-9 stay below 1.4e-3).  This is the bf16-operand
-              noise floor of the design the north_star prescribes (bf16 tensor-core operands, fp32 accumulation),
-              not a kernel defect: every kernel matches fp32 torch to output rounding (tests/test_kernels_gpu.py)."""
+    Asserted tolerances in the default "mixed" precision (relative; + 1e-5 absolute for the tiny estimate losses):
+      * 1e-3  reconstruction (gen_ll_loss, gen_ll_loss2), KL (gen_enc_loss, gen_enc_loss2), gen_total_loss, and BOTH
+              estimate3 losses (dis_reg_loss, dis_total_loss);
+      * 2e-3  dis_loss / dis_ad_loss (measured 1.3e-3) and 5e-3 gen_ad_loss (measured 2.9e-3): the adversarial BCE terms.
+    Where the adversarial deviation comes from is measured, not asserted by prose: tools/ablate_precision.py rounds the
+    conv operands of ONE network of the fp32 oracle to bf16 under this same protocol (profiles/r02_precision_ablation.json,
+    committed).  Discriminator-only rounding gives 7.1e-3 / 6.2e-3 (what round 1 measured on the GPU: 6.7e-3 / 1.07e-2),
+    generator-only 2.2e-3 / 1.4e-3.  The discriminator therefore runs on the split-bf16 kernels (~fp32-class operands),
+    and the test asserts that what remains is no larger than 3x the generator-only emulation curve -- i.e. it IS the
+    bf16 generator the north_star prescribes, not a kernel defect.  LSPS_PRECISION=bf16 switches the split kernels off
+    (then the round-1 tolerances 1e-2 / 3e-2 / 5e-3 apply)."""
     steps = int(os.environ.get("LSPS_TF100_STEPS", "100"))
 
     def pretrain(t, ia, la, ib, lb, hp):
@@ -126,13 +128,22 @@ def test_100_steps_teacher_forced_pretrain_and_estimate3():
     def estimate3(t, ia, la, ib, lb, hp):
         t.post_update(ia, la, ib, lb, None, None, 3, hp)
 
+    mixed = os.environ.get("LSPS_PRECISION", "mixed") == "mixed"
+    tol = ({"*": 1e-3, "dis_loss": 2e-3, "dis_ad_loss": 2e-3, "gen_ad_loss": 5e-3} if mixed else
+           {"*": 1e-3, "gen_total_loss": 5e-3, "dis_loss": 1e-2, "dis_ad_loss": 1e-2, "gen_ad_loss": 3e-2})
     w1 = _teacher_forced(pretrain, ("dis_loss", "dis_ad_loss", "gen_total_loss", "gen_ad_loss", "gen_ll_loss",
-                                    "gen_ll_loss2", "gen_enc_loss", "gen_enc_loss2"), steps, 1,
-                         {"*": 1e-3, "gen_total_loss": 5e-3, "dis_loss": 1e-2, "dis_ad_loss": 1e-2, "gen_ad_loss": 3e-2}, 0.0)
+                                    "gen_ll_loss2", "gen_enc_loss", "gen_enc_loss2"), steps, 1, tol, 0.0)
     print("pretrain   teacher-forced %d steps: max rel diff %s" % (steps, w1))
-    # dis_total_loss = 10*reg + 10*feature-matching L1 on discriminator features of generated images (two networks deep,
-    # sign-gradient loss): measured worst case 1.8e-3 over 100 steps -> 5e-3; the regression loss itself holds 1e-3
-    w2 = _teacher_forced(estimate3, ("dis_total_loss", "dis_reg_loss"), steps, 8, {"*": 1e-3, "dis_total_loss": 5e-3}, 1e-5)
+    if mixed and steps >= 100:
+        import json
+        root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+        with open(os.path.join(root, "profiles", "r02_precision_ablation.json")) as fh:
+            emu = json.load(fh)["max_rel_dev"]["gen"]        # fp32 oracle with ONLY the generator's convs in bf16
+        for k in ("dis_ad_loss", "gen_ad_loss"):
+            assert w1[k] <= 3.0 * emu[k], ("beyond the bf16-generator emulation", k, w1[k], emu[k])
+    # dis_total_loss = 10*reg + 10*feature-matching L1 on discriminator features of generated images
+    w2 = _teacher_forced(estimate3, ("dis_total_loss", "dis_reg_loss"), steps, 8,
+                         {"*": 1e-3} if mixed else {"*": 1e-3, "dis_total_loss": 5e-3}, 1e-5)
     print("estimate3  teacher-forced %d steps: max rel diff %s" % (steps, w2))
 
 
@@ -408,3 +419,37 @@ def test_device_evaluation_sweep_matches_oracle():
     d = (G - P).numpy().reshape(64, 36, 3).astype(np.float64) * np.array([150.0, 125.0, 175.0])
     e = np.sqrt(np.square(d).sum(2))
     assert np.allclose(em.cpu().numpy(), e.mean(1), rtol=1e-5) and np.allclose(ex.cpu().numpy(), e.max(1), rtol=1e-5)
+
+
+def test_standalone_nets_constructed_like_the_reference():
+    """lsps_trainer.py:21-24 builds each net as `Name(hyperparameters[...])`: the stand-alone classes take the same
+    argument, return the reference's forward tuples (NCHW fp32) and load the reference's state_dict."""
+    import lsps_b200
+    hp = _hp("nnyu")
+    oracle = O.OracleTrainer(hp, seed=0)
+    gen = lsps_b200.SharedResGenB200(hp["gen"])
+    dis = lsps_b200.SharedDisB200(hp["dis"])
+    vae = lsps_b200.poseVAEB200(hp["vae"])
+    gen.load_state_dict(oracle.state_dict("gen"))
+    dis.load_state_dict(oracle.state_dict("dis"))
+    vae.load_state_dict(oracle.state_dict("vae"))
+    g = torch.Generator().manual_seed(3)
+    xa, xb = torch.rand(3, 1, 128, 128, generator=g) * 2 - 1, torch.rand(3, 1, 128, 128, generator=g) * 2 - 1
+    gen.eval()
+    oracle.gen.training = False                      # no GaussianNoiseLayer draw on either side
+    with torch.no_grad():
+        ref = oracle.gen.forward(xa, xb)
+        ra, rb, fa, fb = oracle.dis.forward(xa, xb)
+    out = gen(xa.cuda(), xb.cuda())
+    assert [tuple(t.shape) for t in out] == [tuple(t.shape) for t in ref]
+    for a, b in zip(out[:4], ref[:4]):
+        assert (a.cpu() - b).abs().max().item() < IMG_ATOL
+    assert ((out[4].cpu() - ref[4]).norm() / ref[4].norm()).item() < 2e-2
+    oa, ob, ga, gb = dis(xa.cuda(), xb.cuda())
+    assert oa.shape == ra.shape and ga.shape == fa.shape
+    assert (oa.cpu() - ra).abs().max().item() < 1e-3 and ((ga.cpu() - fa).norm() / fa.norm()).item() < 1e-3
+    y = torch.randn(5, 108, generator=g) * 0.3
+    dec, z, mu, sd = vae(y)
+    with torch.no_grad():
+        _, _, mu_ref, sd_ref = oracle.vae.forward(y)
+    assert dec.shape == (5, 108) and (mu.cpu() - mu_ref).abs().max().item() < 1e-5 and (sd.cpu() - sd_ref).abs().max().item() < 1e-5
