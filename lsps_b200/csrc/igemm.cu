@@ -222,8 +222,8 @@ __device__ __forceinline__ void red_add_f32(float* addr, float v) {
 // InstanceNorm-backward front half) -> bf16 (or split hi|lo) -> global.
 // EG = epilogue warp groups.  EG == 2 (short-K layers, where one tile's MMAs are done before four warps have drained
 // the previous tile): warps 2-5 take the tiles of accumulator buffer 0, warps 6-9 those of buffer 1, so every group has
-// two tile periods per epilogue; this variant compiles the plain bias / LeakyReLU / mask / add epilogue only (the
-// statistics, InstanceNorm-backward and split-output paths stay in the EG == 1 kernels, which keeps it under 204 registers).
+// two tile periods per epilogue; this variant compiles the plain bias / LeakyReLU / mask / add (+ split-output) epilogue
+// only (the statistics and InstanceNorm-backward paths stay in the EG == 1 kernels, which keeps it under 204 registers).
 template <int BN, int CG, int EG>
 __device__ __forceinline__ void epilogue_role(const IgemmParams& p, const float* sbias, uint32_t tmem_base,
                                               uint64_t* tfull, uint64_t* tempty, int warp, int lane, int rank,
@@ -366,7 +366,7 @@ __device__ __forceinline__ void epilogue_role(const IgemmParams& p, const float*
           }
         }
         if (valid) {
-          if (FULL && p.split) {
+          if (p.split) {
             // 16 mantissa bits: hi = bf16(f), lo = bf16(f - hi); the lo half sits nc_total channels further
             uint4* o4l = reinterpret_cast<uint4*>(p.out + off + p.nc_total);
 #pragma unroll
@@ -1216,7 +1216,7 @@ int run_igemm(lsps_ctx* ctx, const lsps_conv_shape* s, Dir dir, const void* in, 
   if (bn == 256) return launch_igemm<256, 1>(ctx, tmA, tmB, tmBlo, p, st);
   // single-CTA BN <= 128 kernels stage one 64-channel chunk per pipeline stage (2 and 3 chunks measured slower, r01 probes);
   // with a plain epilogue they run two epilogue warp groups (these short-K tiles are epilogue-bound with one)
-  const bool light = !split && !(flags & (LSPS_EP_STATS | LSPS_EP_INBWD)) && !lsps_one_epi_group();
+  const bool light = !(flags & (LSPS_EP_STATS | LSPS_EP_INBWD)) && !lsps_one_epi_group();
   if (bn == 128) return light ? launch_igemm<128, 1, 1, 2>(ctx, tmA, tmB, tmBlo, p, st) : launch_igemm<128, 1>(ctx, tmA, tmB, tmBlo, p, st);
   return light ? launch_igemm<64, 1, 1, 2>(ctx, tmA, tmB, tmBlo, p, st) : launch_igemm<64, 1>(ctx, tmA, tmB, tmBlo, p, st);
 }

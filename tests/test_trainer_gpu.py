@@ -50,7 +50,12 @@ def test_golden(case, golden_dir):
             if k.endswith("_acc"):
                 ok = abs(float(got) - float(ref)) <= 0.26     # accuracy of ~0 logits at init flips with rounding
             else:
-                ok = abs(float(got) - float(ref)) <= LOSS_RTOL * abs(float(ref)) + 1e-5
+                # step 0 starts from identical weights; later steps of a pretrain case run free after a first Adam update
+                # (sign-like at t=1), which turns the run-to-run differences of the fp32-atomic statistics into a heavy-
+                # tailed spread: 25 repetitions of pretrain_resx_nnyu_b1 give median 2.1e-3, max 6.5e-3 on s1_gen_enc_loss2,
+                # with or without the weight-gradient stream (profiles/r02_golden_repeat.log, tools/repeat_golden.py)
+                rtol = LOSS_RTOL if k.startswith("s0_") or "pretrain" not in case else 2 * LOSS_RTOL
+                ok = abs(float(got) - float(ref)) <= rtol * abs(float(ref)) + 1e-5
             if not ok:
                 bad.append((k, float(ref), float(got)))
         else:
@@ -60,6 +65,9 @@ def test_golden(case, golden_dir):
             atol = 0.12 if "resx" in case else IMG_ATOL
             if err > atol or float(np.mean(np.abs(ref - got))) > (2.5e-2 if "resx" in case else 1e-2):
                 bad.append((k, "max abs err", err, "mean abs err", float(np.mean(np.abs(ref - got)))))
+    worst = max(((abs(float(rec[k]) - float(gold[k])) / (abs(float(gold[k])) + 1e-5), k) for k in gold.files
+                 if np.ndim(gold[k]) == 0 and not k.startswith(("meta_", "w_")) and not k.endswith("_acc")), default=(0, ""))
+    print("  %s: largest relative loss difference %.2e (%s)" % (case, worst[0], worst[1]))
     assert not bad, bad
 
 
