@@ -166,29 +166,30 @@ def test_l2_bf16(ctx):
     assert rel_l2(gr, 0.25 * d) < BF16_L2 and acc[1].item() == 0.0
 
 
-@pytest.mark.parametrize("stride,n", [(1, 3), (2, 5)])
-def test_stem(ctx, stride, n):
+@pytest.mark.parametrize("stride,n,size", [(1, 3, 128), (2, 5, 128), (1, 24, 128), (2, 40, 128), (1, 37, 64), (2, 7, 256)])
+def test_stem(ctx, stride, n, size):
+    """n = 24 / 40 / 37: several tiles per CTA (the register-prefetch pipeline and both accumulators in use)"""
     g = gen(stride)
-    img = (torch.rand(n, 1, 128, 128, device="cuda", generator=g) * 2 - 1).requires_grad_(True)
+    img = (torch.rand(n, 1, size, size, device="cuda", generator=g) * 2 - 1).requires_grad_(True)
     w = (torch.randn(64, 1, 7, 7, device="cuda", generator=g) * 0.05).requires_grad_(True)
     b = (torch.randn(64, device="cuda", generator=g) * 0.1).requires_grad_(True)
     pre = F.conv2d(img, w, b, stride=stride, padding=3)
     y = F.leaky_relu(pre, SLOPE)
-    ho = 128 // stride
+    ho = size // stride
     yb = torch.empty(n, ho, ho, 64, device="cuda", dtype=torch.bfloat16)
-    ctx.stem_fwd(img.data_ptr(), w.data_ptr(), b.data_ptr(), yb.data_ptr(), n, 128, 128, stride, SLOPE)
+    ctx.stem_fwd(img.data_ptr(), w.data_ptr(), b.data_ptr(), yb.data_ptr(), n, size, size, stride, SLOPE)
     assert rel_l2(nchw32(yb), y) < BF16_L2
     dpre = torch.randn(pre.shape, device="cuda", generator=g).bfloat16().float()
     pre.backward(dpre)
     dw, db = torch.zeros(64, 49, device="cuda"), torch.zeros(64, device="cuda")
     dyb = nhwc16(dpre)
-    ctx.stem_wgrad(img.data_ptr(), dyb.data_ptr(), dw.data_ptr(), db.data_ptr(), n, 128, 128, stride)
+    ctx.stem_wgrad(img.data_ptr(), dyb.data_ptr(), dw.data_ptr(), db.data_ptr(), n, size, size, stride)
     assert rel_l2(dw, w.grad.reshape(64, 49)) < 1e-4 and rel_l2(db, b.grad) < 1e-4
-    dimg = torch.full((n, 128, 128), 0.5, device="cuda")
+    dimg = torch.full((n, size, size), 0.5, device="cuda")
     # tensor-core dgrad: bf16 weights (like every other conv operand), fp32 accumulation -> weight-rounding noise 2^-9
-    ctx.stem_dgrad(dyb.data_ptr(), w.data_ptr(), dimg.data_ptr(), n, 128, 128, stride, 0)
+    ctx.stem_dgrad(dyb.data_ptr(), w.data_ptr(), dimg.data_ptr(), n, size, size, stride, 0)
     assert rel_l2(dimg, img.grad[:, 0]) < BF16_L2
-    ctx.stem_dgrad(dyb.data_ptr(), w.data_ptr(), dimg.data_ptr(), n, 128, 128, stride, 1)
+    ctx.stem_dgrad(dyb.data_ptr(), w.data_ptr(), dimg.data_ptr(), n, size, size, stride, 1)
     assert rel_l2(dimg, 2 * img.grad[:, 0]) < BF16_L2
 
 
@@ -550,7 +551,7 @@ def test_split_bf16_conv_fwd_dgrad_wgrad(ctx, kind, n, h, w, cin, cout):
     assert rel_l2(db, dy.sum((0, 2, 3))) < 1e-4
 
 
-@pytest.mark.parametrize("stride,n", [(2, 5), (1, 3)])
+@pytest.mark.parametrize("stride,n", [(2, 5), (1, 3), (2, 40), (1, 24)])
 def test_split_bf16_stems(ctx, stride, n):
     g = gen(600 + stride)
     img = (torch.rand(n, 1, 128, 128, device="cuda", generator=g) * 2 - 1).requires_grad_(True)
