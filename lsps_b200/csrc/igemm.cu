@@ -1154,12 +1154,13 @@ int run_igemm(lsps_ctx* ctx, const lsps_conv_shape* s, Dir dir, const void* in, 
   }
   // CTA pairs (cta_group::2) whenever there are at least two M tiles to pair up
   const int tiles_m = p.tiles_x * p.tiles_y * p.tiles_i;
-  //   ... and the tile is MMA-bound (>= 27 K-steps) and there are enough tiles to keep every SM busy in pairs;
-  //   short-K layers are issue-/latency-bound per tile and run faster as 148 independent CTAs (measured, r01 probes)
+  //   ... and the tile is MMA-bound (>= 18 K-steps: 3x3 taps x 128 input channels and up) and there are enough tiles to
+  //   keep every SM busy in pairs; shorter-K layers are issue-/latency-bound per tile and run faster as 148 independent
+  //   CTAs (measured: r01 probes; r02 microbench with LSPS_FORCE_CG=2: 128->256 stride 2 +9 %, 64->128 stride 2 -8 %)
   int nk_min = 1 << 30;
   for (int i = 0; i < p.nphases; ++i) nk_min = p.ph[i].ntaps * p.kch_eff < nk_min ? p.ph[i].ntaps * p.kch_eff : nk_min;
   const int force = lsps_force_cg();
-  int cg = (lsps_use_pairs() && tiles_m >= 2 && nk_min >= 27 && (long long)tiles_m * p.tiles_n >= 2 * ctx->num_sms) ? 2 : 1;
+  int cg = (lsps_use_pairs() && tiles_m >= 2 && nk_min >= 18 && (long long)tiles_m * p.tiles_n >= 2 * ctx->num_sms) ? 2 : 1;
   if (force && tiles_m >= 2) cg = force;
   // the two N = 64, K <= 128 up-sampling layers of the generator: all four phases in one pass, resident weights
   if (!plain && !down && !k4 && nc == 64 && p.kchunks <= 2 && !split && nsplit == 0 && tiles_m >= 1 &&

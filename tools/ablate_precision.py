@@ -22,10 +22,12 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "oracle"))
 import lsps_oracle as O  # noqa: E402
 
-SCOPE = {"cur": None, "on": set(), "mode": "bf16"}
+SCOPE = {"cur": None, "on": set(), "mode": "bf16", "what": "xwgo"}   # what: x inputs, w weights, g gradients, o outputs
 
 
-def _rnd(t):
+def _rnd(t, tag="x"):
+    if tag not in SCOPE["what"]:
+        return t
     if SCOPE["mode"] == "bf16":
         return t.to(torch.bfloat16).to(torch.float32)
     # split-bf16 (hi + lo): 16 mantissa bits
@@ -39,7 +41,7 @@ class _EmuConv(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, w, b, transposed, stride, padding, output_padding):
-        xr, wr = _rnd(x), _rnd(w)
+        xr, wr = _rnd(x, "x"), _rnd(w, "w")
         ctx.save_for_backward(xr, wr)
         ctx.cfg = (transposed, stride, padding, output_padding, b is not None)
         if transposed:
@@ -52,7 +54,7 @@ class _EmuConv(torch.autograd.Function):
     def backward(ctx, gy):
         xr, wr = ctx.saved_tensors
         transposed, stride, padding, output_padding, has_b = ctx.cfg
-        gyr = _rnd(gy)
+        gyr = _rnd(gy, "g")
         with torch.enable_grad():
             xd, wd = xr.detach().requires_grad_(True), wr.detach().requires_grad_(True)
             if transposed:
@@ -90,7 +92,7 @@ class _StoreRound(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, y):
-        return _rnd(y)
+        return _rnd(y, "o")
 
     @staticmethod
     def backward(ctx, g):
@@ -141,6 +143,7 @@ def main():
     ap.add_argument("--out", default=os.path.join(ROOT, "profiles", "r02_precision_ablation.json"))
     ap.add_argument("--variants", default="gen,dis,gen+dis")
     ap.add_argument("--mode", default="bf16")
+    ap.add_argument("--what", default="xwgo", help="which conv tensors are rounded: x inputs, w weights, g gradients, o outputs")
     args = ap.parse_args()
     install()
     import yaml
@@ -148,6 +151,7 @@ def main():
         hp = yaml.safe_load(fh)["train"]["hyperparameters"]
     torch.set_num_threads(os.cpu_count() or 1)
     SCOPE["mode"] = args.mode
+    SCOPE["what"] = args.what
     master = O.OracleTrainer(hp, seed=0)
     emu = O.OracleTrainer(hp, seed=0)
     variants = [tuple(v.split("+")) for v in args.variants.split(",")]
@@ -189,8 +193,8 @@ def main():
                 msg.append("%s: %s" % (v, {k: "%.2e" % x for k, x in w.items()}))
             print("step %d  max rel dev so far  %s" % (s, " | ".join(msg)), flush=True)
     out = {"protocol": "teacher-forced, batch %d, %d steps, uniform inputs, seeds 0/1234/42; %s rounding of conv "
-                       "operands (x, w, dy) and conv outputs in the named networks of the CPU oracle" %
-                       (args.batch, args.steps, args.mode),
+                       "tensors [%s] (x inputs, w weights, g gradients, o outputs) in the named networks of the CPU oracle" %
+                       (args.batch, args.steps, args.mode, args.what),
            "reference": ref, "emulated": curves, "max_rel_dev": {}, "per_step_rel_dev": {}}
     for v in curves:
         out["max_rel_dev"][v] = {k: max(abs(a - b) / (abs(b) + 1e-12) for a, b in zip(curves[v][k], ref[k])) for k in KEYS}
