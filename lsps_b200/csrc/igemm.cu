@@ -405,7 +405,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   using Cfg = IgemmCfg<BN, CG, KCH>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // stays a shared-space pointer: LDS/STS, not generic LD/ST
   uint8_t* sA = base;
   uint8_t* sB = base + STAGES * Cfg::A_STAGE;
   uint64_t* full = reinterpret_cast<uint64_t*>(base + STAGES * Cfg::STAGE_BYTES);
@@ -575,7 +575,7 @@ __global__ void __launch_bounds__(320, 1)
 conv_up64_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ Up64Params p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // stays a shared-space pointer: LDS/STS, not generic LD/ST
   const int wtiles = 9 * p.kchunks;
   uint8_t* sW = base;                                   // [tap][chunk] weight tiles, resident
   uint8_t* sA = base + 18 * UP64_W_TILE;                // ring of A tiles
@@ -734,6 +734,101 @@ conv_up64_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 }
 constexpr int UP64_SMEM = 18 * UP64_W_TILE + UP64_A_SLOTS * A_STAGE_BYTES + 1024 + 512;
 
+// ------------------------------------------------------------------------------------------------ resident weights, N = 128
+// 3x3 layers with 64 input channels and 128 output channels (Conv2d(64,128,3,2,1) forward, the data gradient of
+// ConvTranspose2d(128,64,3,2,1,1)) write 32 KB and read 9 x 16 KB of activations per 128-pixel tile; in the generic
+// kernel every tile also re-fetches the 9 x 16 KB weight tensor, so L2 -> SM traffic is twice what the activations need
+// and that, not HBM, bounds it (ncu r02: 0.59 of the HBM bound, 0.77x cuDNN).  Here the whole weight tensor (<= 9
+// K-steps x [128 x 64] = 144 KB) is loaded into shared memory once per CTA; the pipeline stages carry A tiles only.
+// Same tile order, accumulator hand-off and epilogue (two warp groups) as conv_igemm_kernel<128, 1, 1, 2>.
+constexpr int RESB_W_TILE = 128 * 128;         // one K-step's weight tile: 128 rows x 64 bf16
+constexpr int RESB_A_SLOTS = 5;
+constexpr int RESB_SMEM = 9 * RESB_W_TILE + RESB_A_SLOTS * A_STAGE_BYTES + 1024 + 256 + 512;
+
+__global__ void __launch_bounds__(320, 1)
+conv_resb_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const __grid_constant__ IgemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // stays a shared-space pointer: LDS/STS, not generic LD/ST
+  uint8_t* sW = base;                                   // [K-step] weight tiles, resident
+  uint8_t* sA = base + 9 * RESB_W_TILE;                 // ring of A tiles
+  uint64_t* full = reinterpret_cast<uint64_t*>(sA + RESB_A_SLOTS * A_STAGE_BYTES);
+  uint64_t* empty = full + RESB_A_SLOTS;
+  uint64_t* wfull = empty + RESB_A_SLOTS;
+  uint64_t* tfull = wfull + 1;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  float* sbias = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full) + 256);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if ((p.flags & LSPS_EP_BIAS) && threadIdx.x < 128) sbias[threadIdx.x] = p.bias[threadIdx.x];
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < RESB_A_SLOTS; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    mbar_init(wfull, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
+    fence_barrier_init();
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1) { tmem_alloc(tmem_slot, 256); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int total = p.tiles_x * p.tiles_y * p.tiles_i;  // one phase, one N tile
+  const int ntaps = p.ph[0].ntaps;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(wfull, ntaps * RESB_W_TILE);
+      for (int tp = 0; tp < ntaps; ++tp) tma_load_2d(sW + tp * RESB_W_TILE, &tmB, wfull, 0, p.taps[tp].brow);
+      int slot = 0; uint32_t ph = 0;
+      for (int t = blockIdx.x; t < total; t += gridDim.x) {
+        const TileCoord tc = decode_tile(p, t, total, total, 1, 0);
+        const int n0 = tc.ti * p.nb;
+        for (int tp = 0; tp < ntaps; ++tp) {
+          const Tap T = p.taps[tp];
+          mbar_wait(&empty[slot], ph ^ 1);
+          mbar_expect_tx(&full[slot], A_STAGE_BYTES);
+          tma_load_5d(sA + slot * A_STAGE_BYTES, &tmA, &full[slot], T.ac, tc.x0 + T.ax, T.ap, tc.y0 + T.ay, n0);
+          if (++slot == RESB_A_SLOTS) { slot = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(128, 128, 0, 0);
+      constexpr uint64_t dbase = umma_desc_base(0, 1024);
+      const uint32_t sA_u32 = smem_u32(sA), sW_u32 = smem_u32(sW);
+      mbar_wait(wfull, 0);
+      tc_fence_after();
+      int slot = 0; uint32_t ph = 0; int it = 0;
+      for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
+        const int acc = it & 1; const uint32_t accph = (it >> 1) & 1;
+        mbar_wait(&tempty[acc], accph ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * 128;
+        for (int tp = 0; tp < ntaps; ++tp) {
+          mbar_wait(&full[slot], ph);
+          tc_fence_after();
+          const uint64_t a_base = dbase | ((sA_u32 + slot * A_STAGE_BYTES) >> 4);
+          const uint64_t b_base = dbase | ((sW_u32 + tp * RESB_W_TILE) >> 4);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_bf16(d_tmem, a_base + k * 2, b_base + k * 2, idesc, (tp | k) != 0 ? 1u : 0u);
+          umma_commit(&empty[slot]);
+          if (++slot == RESB_A_SLOTS) { slot = 0; ph ^= 1; }
+        }
+        umma_commit(&tfull[acc]);
+      }
+    }
+  } else {
+    epilogue_role<128, 1, 2>(p, sbias, tmem_base, tfull, tempty, warp, lane, 0, blockIdx.x, gridDim.x, total, total, total);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 256);
+}
+
 // ------------------------------------------------------------------------------------------------ wgrad
 struct WTap { short mc, mx, mp, my, nc, nx, np, ny; };  // tap offsets in the dy (M side) / x (N side) maps
 struct WgradParams {
@@ -774,7 +869,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ CU
   constexpr int STAGES = Cfg::STAGES;
   constexpr int W_BOX_BYTES = Cfg::W_BOX_BYTES;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // stays a shared-space pointer: LDS/STS, not generic LD/ST
   uint64_t* full = reinterpret_cast<uint64_t*>(base + STAGES * Cfg::STAGE_BYTES);
   uint64_t* empty = full + STAGES;
   uint64_t* tfull = empty + STAGES;
@@ -974,6 +1069,11 @@ inline bool lsps_no_small_bn() {
 inline bool lsps_no_up64() {
   static int v = -1;
   if (v < 0) { const char* e = getenv("LSPS_NO_UP64"); v = (e && e[0] == '1') ? 1 : 0; }
+  return v == 1;
+}
+inline bool lsps_no_resb() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("LSPS_NO_RESB"); v = (e && e[0] == '1') ? 1 : 0; }
   return v == 1;
 }
 inline bool lsps_use_pairs() {
@@ -1184,6 +1284,25 @@ int run_igemm(lsps_ctx* ctx, const lsps_conv_shape* s, Dir dir, const void* in, 
     const int grid = tiles_m < ctx->num_sms ? tiles_m : ctx->num_sms;
     conv_up64_kernel<<<grid, 320, UP64_SMEM, st>>>(tA, tB, u);
     LSPS_CHECK_LAUNCH(ctx, "conv_up64");
+    return LSPS_OK;
+  }
+  // 64 -> 128 channels, one phase, <= 9 K-steps: weights resident in shared memory (conv_resb_kernel)
+  if (p.nphases == 1 && bn == 128 && nc == 128 && p.tiles_n == 1 && p.kchunks == 1 && p.ntaps_all <= 9 && !split &&
+      nsplit == 0 && p.a_group == 0 && !(flags & (LSPS_EP_STATS | LSPS_EP_INBWD)) && !lsps_no_resb() && !lsps_one_epi_group()) {
+    static bool configured = false;
+    if (!configured) {
+      cudaError_t e = cudaFuncSetAttribute(conv_resb_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RESB_SMEM);
+      if (e != cudaSuccess) return lsps_set_error(ctx, LSPS_E_CUDA, "resb smem attr: %s", cudaGetErrorString(e));
+      configured = true;
+    }
+    CUtensorMap tA, tB;
+    int rc2 = act_tmap(ctx, in, n, ih, iw, kct, down, g, &tA);
+    if (rc2) return rc2;
+    uint32_t wd2[2] = {(uint32_t)kc, (uint32_t)wrows}, wb2[2] = {64, 128};
+    if ((rc2 = lsps_get_tmap(ctx, wbase, 2, wd2, wb2, &tB))) return rc2;
+    const int grid = tiles_m < ctx->num_sms ? tiles_m : ctx->num_sms;
+    conv_resb_kernel<<<grid, 320, RESB_SMEM, st>>>(tA, tB, p);
+    LSPS_CHECK_LAUNCH(ctx, "conv_resb");
     return LSPS_OK;
   }
   if (p.nphases > 1 && !lsps_phase_major()) {

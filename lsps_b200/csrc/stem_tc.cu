@@ -162,7 +162,7 @@ __global__ void __launch_bounds__(128, 4) stem_fwd_tc_kernel(const float* __rest
                                                             const __grid_constant__ CUtensorMap tmY, int n, int h, int wd,
                                                             int wshift, float slope) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // stays a shared-space pointer: LDS/STS, not generic LD/ST
   uint8_t* a_hi = base;
   uint8_t* a_lo = base + A_BYTES;
   uint8_t* wt = base + 2 * A_BYTES;                   // [64 co][64 taps] bf16, K-major, swizzled: 8 KB (+ 8 KB lo)
@@ -261,7 +261,7 @@ __global__ void __launch_bounds__(128) stem_wgrad_tc_kernel(const float* __restr
                                                            float* __restrict__ dw, float* __restrict__ db, int n, int h,
                                                            int wd, int wshift) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // stays a shared-space pointer: LDS/STS, not generic LD/ST
   // two buffers of {taps hi, taps lo, dy}: the MMAs of tile i run while the threads build tile i+1.  The split variant
   // carries a fourth tile (dy lo) and keeps ONE buffer: two would be 132 KB and halve the CTAs per SM (measured slower).
   constexpr int BUF = (SPLIT ? 4 : 3) * A_BYTES;
@@ -382,7 +382,7 @@ __global__ void __launch_bounds__(128) stem_dgrad_tc_kernel(const __grid_constan
   constexpr int GP = 49;                                      // G row pitch (odd: conflict-free)
   constexpr int TCOLS = MT == 1 ? 64 : 256;                   // TMEM columns: one 64-column accumulator per M tile
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // stays a shared-space pointer: LDS/STS, not generic LD/ST
   constexpr int NDY = SPLIT ? 2 : 1;
   uint8_t* dyb = base;                                        // MT operand tiles of 128 rows (x2: lo halves behind)
   uint8_t* wt = base + NDY * MT * A_BYTES;                    // [64 tap rows][64 co] bf16, K-major, swizzled (+ lo)
@@ -402,7 +402,6 @@ __global__ void __launch_bounds__(128) stem_dgrad_tc_kernel(const __grid_constan
   const uint32_t tmem = *tmem_slot;
   constexpr uint32_t idesc = umma_idesc_bf16(128, 64, 0, 0);
 
-  const int ho = h / S, wo = wd / S;
   const int tiles_x = wd / 16, tiles_y = h / 8;
   const int total = tiles_x * tiles_y * n;
   const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
