@@ -573,19 +573,20 @@ __constant__ int c_up64_phase[4][4] = {{0, 1, 2, 3}, {1, 3, 0, 0}, {2, 3, 0, 0},
 
 __global__ void __launch_bounds__(320, 1)
 conv_up64_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                 const __grid_constant__ Up64Params p) {
+                 const __grid_constant__ CUtensorMap tmO, const __grid_constant__ Up64Params p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // stays a shared-space pointer: LDS/STS, not generic LD/ST
   const int wtiles = 9 * p.kchunks;
   uint8_t* sW = base;                                   // [tap][chunk] weight tiles, resident
   uint8_t* sA = base + 18 * UP64_W_TILE;                // ring of A tiles
-  uint64_t* full = reinterpret_cast<uint64_t*>(sA + UP64_A_SLOTS * A_STAGE_BYTES);
+  uint8_t* sS = sA + UP64_A_SLOTS * A_STAGE_BYTES;      // output staging: one 128 x 64 tile per epilogue group
+  uint64_t* full = reinterpret_cast<uint64_t*>(sS + 2 * A_STAGE_BYTES);
   uint64_t* empty = full + UP64_A_SLOTS;
   uint64_t* wfull = empty + UP64_A_SLOTS;
   uint64_t* tfull = wfull + 1;
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
-  float* sbias = reinterpret_cast<float*>(tmem_slot + 4);
+  float* sbias = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full) + 128);     // 16-byte aligned (float4 loads)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if ((p.flags & LSPS_EP_BIAS) && threadIdx.x < 64) sbias[threadIdx.x] = p.bias[threadIdx.x];
@@ -596,6 +597,7 @@ conv_up64_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     fence_barrier_init();
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmO);
   }
   if (warp == 1) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
   tc_fence_before();
@@ -656,83 +658,101 @@ conv_up64_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
     }
   } else {
-    // two epilogue warp groups (warps 2-5: accumulator set 0, warps 6-9: set 1): a tile's 8 TMEM chunks with their
-    // global mask loads and strided stores take longer than its 36-72 MMAs, so each group gets two tile periods
+    // two epilogue warp groups (warps 2-5: accumulator set 0, warps 6-9: set 1): a tile's 8 TMEM chunks take longer
+    // than its 36-72 MMAs, so each group gets two tile periods.  Every phase's 128 x 64 result is staged in shared memory
+    // (swizzled like an operand tile) and leaves as ONE TMA tensor store through the pair view of the output -- per-thread
+    // 16-byte global stores (32 different lines per warp instruction) kept the LSU queue full (ncu r02: long-scoreboard
+    // stalls at the top of the chunk loop).
     const int q = warp & 3;
     const int egroup = (warp - 2) >> 2;
     const int row = q * 32 + lane;
+    const bool issuer = q == 0 && lane == 0;
+    uint8_t* stage = sS + egroup * A_STAGE_BYTES;
     const int tw_mask = (1 << p.twl) - 1, th_mask = (1 << p.thl) - 1;
     const int xl = row & tw_mask, yl = (row >> p.twl) & th_mask, nl = row >> (p.twl + p.thl);
     int it = 0;
     for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
       if ((it & 1) != egroup) continue;
       const int tx = t & (p.tiles_x - 1), ty = (t >> p.txl) & (p.tiles_y - 1), ti = t >> (p.txl + p.tyl);
-      const int x0 = tx << p.twl, y0 = ty << p.thl, n = ti * p.nb + nl;
+      const int x0 = tx << p.twl, y0 = ty << p.thl, n0 = ti * p.nb, n = n0 + nl;
       const bool valid = n < p.nimg;
       const int acc = it & 1; const uint32_t accph = (it >> 1) & 1;
       mbar_wait(&tfull[acc], accph);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * 256;
 #pragma unroll 1
-      for (int c8 = 0; c8 < 8; ++c8) {          // 4 phases x 2 chunks of 32 columns
-        const int phs = c8 >> 1, c0 = (c8 & 1) * 32;
-        const long long off = (long long)n * p.o_n + (long long)((y0 + yl) * 2 + (phs >> 1)) * p.o_y +
-                              (long long)((x0 + xl) * 2 + (phs & 1)) * p.o_x + c0;
-        uint4 gm[4];
-        if (valid && (p.flags & LSPS_EP_MASK)) {
-          const uint4* m4 = reinterpret_cast<const uint4*>(p.mask + off);
+      for (int phs = 0; phs < 4; ++phs) {
+        if (issuer) bulk_wait_read();             // the previous store of this group has read the staging tile
+        named_bar_sync(1 + egroup, 128);
 #pragma unroll
-          for (int j = 0; j < 4; ++j) gm[j] = __ldg(m4 + j);
-        }
-        uint32_t v[32];
-        tmem_ld32(taddr + phs * 64 + c0, v);
-        tmem_ld_wait();
-        if (c8 == 7) {
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&tempty[acc]);
-        }
-        if (!valid) continue;
-        float f[32];
+        for (int hf = 0; hf < 2; ++hf) {
+          const int c0 = hf * 32;
+          const long long off = (long long)n * p.o_n + (long long)((y0 + yl) * 2 + (phs >> 1)) * p.o_y +
+                                (long long)((x0 + xl) * 2 + (phs & 1)) * p.o_x + c0;
+          uint4 gm[4];
+          if (valid && (p.flags & LSPS_EP_MASK)) {
+            const uint4* m4 = reinterpret_cast<const uint4*>(p.mask + off);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-        if (p.flags & LSPS_EP_BIAS) {
+            for (int j = 0; j < 4; ++j) gm[j] = __ldg(m4 + j);
+          }
+          uint32_t v[32];
+          tmem_ld32(taddr + phs * 64 + c0, v);
+          tmem_ld_wait();
+          if (phs == 3 && hf == 1) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[acc]);
+          }
+          float f[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] += sbias[c0 + j];
-        }
-        if (p.flags & LSPS_EP_LRELU) {
+          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+          if (p.flags & LSPS_EP_BIAS) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = f[j] > 0.f ? f[j] : f[j] * p.slope;
-        }
-        if (p.flags & LSPS_EP_MASK) {
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const uint32_t w[4] = {gm[j].x, gm[j].y, gm[j].z, gm[j].w};
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              if (!(bf16lo(w[k]) > 0.f)) f[8 * j + 2 * k] *= p.slope;
-              if (!(bf16hi(w[k]) > 0.f)) f[8 * j + 2 * k + 1] *= p.slope;
+            for (int j = 0; j < 8; ++j) {
+              const float4 b = *reinterpret_cast<const float4*>(sbias + c0 + 4 * j);
+              f[4 * j] += b.x; f[4 * j + 1] += b.y; f[4 * j + 2] += b.z; f[4 * j + 3] += b.w;
             }
           }
-        }
-        uint4* o4 = reinterpret_cast<uint4*>(p.out + off);
+          if (p.flags & LSPS_EP_LRELU) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          uint4 o;
-          o.x = pack_bf16x2(f[8 * j], f[8 * j + 1]);
-          o.y = pack_bf16x2(f[8 * j + 2], f[8 * j + 3]);
-          o.z = pack_bf16x2(f[8 * j + 4], f[8 * j + 5]);
-          o.w = pack_bf16x2(f[8 * j + 6], f[8 * j + 7]);
-          o4[j] = o;
+            for (int j = 0; j < 32; ++j) f[j] = f[j] > 0.f ? f[j] : f[j] * p.slope;
+          }
+          if (valid && (p.flags & LSPS_EP_MASK)) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint32_t w[4] = {gm[j].x, gm[j].y, gm[j].z, gm[j].w};
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                if (!(bf16lo(w[k]) > 0.f)) f[8 * j + 2 * k] *= p.slope;
+                if (!(bf16hi(w[k]) > 0.f)) f[8 * j + 2 * k + 1] *= p.slope;
+              }
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint4 o;
+            o.x = pack_bf16x2(f[8 * j], f[8 * j + 1]);
+            o.y = pack_bf16x2(f[8 * j + 2], f[8 * j + 3]);
+            o.z = pack_bf16x2(f[8 * j + 4], f[8 * j + 5]);
+            o.w = pack_bf16x2(f[8 * j + 6], f[8 * j + 7]);
+            *reinterpret_cast<uint4*>(stage + row * 128 + (((hf * 4 + j) ^ (row & 7)) << 4)) = o;
+          }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        named_bar_sync(1 + egroup, 128);
+        if (issuer) {                             // images past nimg (last group of a partial tile) are clipped by the map
+          tma_store_5d(&tmO, stage, (phs & 1) * 64, x0, phs >> 1, y0, n0);
+          bulk_commit();
         }
       }
     }
+    if (issuer) bulk_wait_read();
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
-constexpr int UP64_SMEM = 18 * UP64_W_TILE + UP64_A_SLOTS * A_STAGE_BYTES + 1024 + 512;
+constexpr int UP64_SMEM = 18 * UP64_W_TILE + (UP64_A_SLOTS + 2) * A_STAGE_BYTES + 1024 + 512;
 
 // ------------------------------------------------------------------------------------------------ resident weights, N = 128
 // 3x3 layers with 64 input channels and 128 output channels (Conv2d(64,128,3,2,1) forward, the data gradient of
@@ -1276,13 +1296,14 @@ int run_igemm(lsps_ctx* ctx, const lsps_conv_shape* s, Dir dir, const void* in, 
     u.txl = p.txl; u.tyl = p.tyl; u.nimg = n; u.kchunks = p.kchunks;
     u.o_n = p.o_n; u.o_y = p.o_y; u.o_x = p.o_x; u.out = p.out; u.bias = bias; u.mask = p.mask; u.slope = slope;
     u.flags = flags; u.nc = nc;
-    CUtensorMap tA, tB;
+    CUtensorMap tA, tB, tO;
     int rc2 = act_tmap(ctx, in, n, ih, iw, kct, false, g, &tA);
     if (rc2) return rc2;
     uint32_t wd2[2] = {(uint32_t)kc, (uint32_t)(9 * nc)}, wb2[2] = {64, 64};
     if ((rc2 = lsps_get_tmap(ctx, wpk, 2, wd2, wb2, &tB))) return rc2;
+    if ((rc2 = act_tmap(ctx, out, n, 2 * ih, 2 * iw, 64, true, g, &tO))) return rc2;   // output: pair view, phase = parity
     const int grid = tiles_m < ctx->num_sms ? tiles_m : ctx->num_sms;
-    conv_up64_kernel<<<grid, 320, UP64_SMEM, st>>>(tA, tB, u);
+    conv_up64_kernel<<<grid, 320, UP64_SMEM, st>>>(tA, tB, tO, u);
     LSPS_CHECK_LAUNCH(ctx, "conv_up64");
     return LSPS_OK;
   }
