@@ -286,9 +286,9 @@ def main():
         ach = tot_flop / (tot_ms * 1e-3) / 1e12
         roof = {"bound": "tensor", "kernel": "conv_igemm_kernel<256> (3x3 s1 256->256 @32x32, fwd+dgrad)",
                 "achieved": ach, "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": ach / pk["tf_sustained"],
-                "traffic": 89.1e6, "traffic_note": "dram read+write bytes per launch at N=128 images from "
-                "profiles/r01_ncu_k1_wgrad_v4.md (algorithmic: 64 MB in + 64 MB out + 1.2 MB weights; part of the "
-                "output is still in L2 at kernel end)",
+                "traffic": 87.6e6, "traffic_note": "dram read+write bytes per launch at N=128 images, forward with the "
+                "statistics epilogue, profiles/r02_ncu_targets_v2.md row 19 (68.6 MB read + 19.0 MB written; algorithmic: "
+                "64 MB in + 64 MB out + 1.2 MB weights; most of the output is still in L2 at kernel end)",
                 "launches": len(ev), "avg_launch_ms": tot_ms / max(1, len(ev)),
                 "share_of_step": tot_ms / (ms / K), "peak_source": pk["src"] + ", sustained bf16",
                 "peak_burst": pk["tf"], "frac_of_burst_peak": ach / pk["tf"],
