@@ -136,6 +136,9 @@ struct IgemmParams {
   // split-bf16 ("bf16x3") operands: A tensor channels are [hi | lo] (lo half a_lo channels in), the weights come as two
   // tensors (tmB hi, tmBlo lo); K-steps per (tap, chunk): hi*hi, hi*lo, lo*hi; the output is written as [hi | lo] too
   int split, a_lo, kch_eff;
+  // split_fused (KCH = 2 kernels): ONE stage per (tap, chunk) carries {A hi, A lo} and {B hi, B lo}; the MMA warp issues
+  // hi*hi, hi*lo, lo*hi from it -- one pipeline handshake and four TMA boxes instead of three handshakes and six boxes
+  int split_fused;
   int a_group;      // grouped conv: N tile nt reads A channels [nt * a_group, (nt + 1) * a_group); 0 = dense
   int gpb;          // multi-phase launches: M groups per block of the block-major tile order (0 = phase-major)
   Phase ph[4];
@@ -429,9 +432,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   // split-bf16: three K-steps per (tap, chunk) -- A hi x B hi, A hi x B lo (bit 3 of .z), A lo (a_lo channels in) x B hi
   for (int i = threadIdx.x; i < p.ntaps_all * p.kch_eff; i += blockDim.x) {
     const int tp = i / p.kch_eff, r = i - tp * p.kch_eff;
-    const int kc = p.split ? r / 3 : r, v = p.split ? r - kc * 3 : 0;
+    const int per = p.split ? (p.split_fused ? 2 : 3) : 1;       // table entries per (tap, chunk)
+    const int kc = r / per, v = r - kc * per;
+    const bool a_lo = p.split_fused ? v == 1 : v == 2;           // fused: entry 1 = (A lo, B lo) of the stage
     const Tap T = p.taps[tp];
-    ktab[i] = make_int4(kc * 64 + T.ac + (v == 2 ? p.a_lo : 0), (T.ax & 0xFFFF) | (T.ay << 16),
+    ktab[i] = make_int4(kc * 64 + T.ac + (a_lo ? p.a_lo : 0), (T.ax & 0xFFFF) | (T.ay << 16),
                         T.ap | (v == 1 ? 8 : 0) | ((kc * 64) << 4), T.brow);
   }
   const bool leader = rank == 0;
@@ -521,6 +526,18 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           tc_fence_after();
           const uint64_t a_base = dbase | ((sA_u32 + stage * Cfg::A_STAGE) >> 4);
           const uint64_t b_base = dbase | ((sB_u32 + stage * Cfg::B_STAGE_BYTES) >> 4);
+          if (KCH == 2 && p.split_fused) {
+#pragma unroll
+            for (int v = 0; v < 3; ++v) {          // hi*hi, hi*lo, lo*hi
+              const uint64_t av = a_base + (v == 2 ? (A_STAGE_BYTES >> 4) : 0);
+              const uint64_t bv = b_base + (v == 1 ? (Cfg::B_CHUNK_BYTES >> 4) : 0);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                if (CG == 2) umma_bf16_cg2(d_tmem, av + k * 2, bv + k * 2, idesc, (i0 | v | k) != 0 ? 1u : 0u);
+                else umma_bf16(d_tmem, av + k * 2, bv + k * 2, idesc, (i0 | v | k) != 0 ? 1u : 0u);
+              }
+            }
+          } else
 #pragma unroll
           for (int k = 0; k < 4 * KCH; ++k) {
             if ((p.dbg & 1) || (k >> 2) >= cnt) break;
@@ -1091,6 +1108,11 @@ inline bool lsps_no_up64() {
   if (v < 0) { const char* e = getenv("LSPS_NO_UP64"); v = (e && e[0] == '1') ? 1 : 0; }
   return v == 1;
 }
+inline bool lsps_no_split_fuse() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("LSPS_NO_SPLIT_FUSE"); v = (e && e[0] == '1') ? 1 : 0; }
+  return v == 1;
+}
 inline bool lsps_no_resb() {
   static int v = -1;
   if (v < 0) { const char* e = getenv("LSPS_NO_RESB"); v = (e && e[0] == '1') ? 1 : 0; }
@@ -1191,7 +1213,11 @@ int run_igemm(lsps_ctx* ctx, const lsps_conv_shape* s, Dir dir, const void* in, 
   p.twl = g.twl; p.thl = g.thl; p.nb = g.nb;
   p.txl = ilog2(p.tiles_x); p.tyl = ilog2(p.tiles_y);
   p.nimg = n; p.kchunks = kc / 64; p.ntaps_all = ks * ks;
-  p.split = split ? 1 : 0; p.a_lo = kc; p.kch_eff = split ? 3 * p.kchunks : p.kchunks; p.nc_total = nc;
+  // fused split stages pay on the wide, shallow layers (K <= 256 channels: 64->128 data gradient 256 -> 213 us, forward
+  // 134 -> 106 us); with more K chunks per tap the 2-3 stage ring of the 64 KB+ stages loses (1024->2048: 195 -> 211 us)
+  const bool fuse = split && kc <= 256 && !lsps_no_split_fuse() && !lsps_one_epi_group();
+  p.split = split ? 1 : 0; p.split_fused = fuse ? 1 : 0; p.a_lo = kc;
+  p.kch_eff = split ? (fuse ? 2 : 3) * p.kchunks : p.kchunks; p.nc_total = nc;
   if (p.ntaps_all * p.kch_eff > 1024) return lsps_set_error(ctx, LSPS_E_SHAPE, "K-step table overflow (%d steps)", p.ntaps_all * p.kch_eff);
   p.sums = ext->sums; p.bsums = ext->bsums; p.inv_slope = slope > 0.f ? 1.f / slope : 0.f;
   const int kct = split ? 2 * kten : kten, nct = split ? 2 * nc : nc;     // channels of the `in` / `out` TENSORS
@@ -1348,6 +1374,16 @@ int run_igemm(lsps_ctx* ctx, const lsps_conv_shape* s, Dir dir, const void* in, 
     return lsps_set_error(ctx, LSPS_E_CUDA, "memset sums");
   if ((flags & LSPS_EP_INBWD) && cudaMemsetAsync(ext->bsums, 0, sbytes, st) != cudaSuccess)
     return lsps_set_error(ctx, LSPS_E_CUDA, "memset bsums");
+  if (fuse) {   // split-bf16 with fused stages: the 128-channel-per-stage (KCH = 2) kernels
+    if (cg == 2) {
+      if (bn == 256) return launch_igemm<256, 2, 2>(ctx, tmA, tmB, tmBlo, p, st);
+      if (bn == 128) return launch_igemm<128, 2, 2>(ctx, tmA, tmB, tmBlo, p, st);
+      return launch_igemm<64, 2, 2>(ctx, tmA, tmB, tmBlo, p, st);
+    }
+    if (bn == 256) return launch_igemm<256, 1, 2>(ctx, tmA, tmB, tmBlo, p, st);
+    if (bn == 128) return launch_igemm<128, 1, 2, 2>(ctx, tmA, tmB, tmBlo, p, st);
+    return launch_igemm<64, 1, 2, 2>(ctx, tmA, tmB, tmBlo, p, st);
+  }
   if (cg == 2 && bn == 256 && !lsps_no_kch2()) return launch_igemm<256, 2, 2>(ctx, tmA, tmB, tmBlo, p, st);
   if (cg == 2) {
     if (bn == 256) return launch_igemm<256, 2>(ctx, tmA, tmB, tmBlo, p, st);
