@@ -61,19 +61,26 @@ class ClockSampler(threading.Thread):
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
                                           "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
             for line in self.proc.stdout:
-                self.rows.append([c.strip() for c in line.split(",")])
+                self.rows.append((time.monotonic(), [c.strip() for c in line.split(",")]))
                 if self.stop_flag:
                     break
         except Exception:  # noqa
             pass
 
-    def finish(self):
+    def finish(self, t0=None, t1=None):
+        """Samples taken inside the timed region [t0, t1]; the sampler runs from before the warm-up steps (nvidia-smi needs
+        a few hundred ms to deliver its first line), so when a short timed region caught fewer than two samples the ones
+        of the warm-up steps -- the same step, the same load -- are used as well and `window` says so."""
         self.stop_flag = True
         time.sleep(0.15)
         if self.proc:
             self.proc.terminate()
+        rows = [r for t, r in self.rows if t0 is None or t0 <= t <= t1 + 0.05]
+        window = "timed"
+        if len(rows) < 2:
+            rows, window = [r for _, r in self.rows], "warmup+timed"
         sm, reasons, smax = [], set(), None
-        for r in self.rows:
+        for r in rows:
             try:
                 sm.append(float(r[0])); smax = float(r[1])
                 for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
@@ -83,7 +90,7 @@ class ClockSampler(threading.Thread):
                 continue
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "window": window}
 
 
 def cpu_reference_rate(steps, warmup, batch):
@@ -219,15 +226,17 @@ def main():
         return ms.item()
 
     W, K = max(3, args.warmup), args.steps
-    for _ in range(W):
-        step_dev()
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
+    for _ in range(W):
+        step_dev()
     l0 = tr.ops.ctx.launch_count()
+    t_begin = time.monotonic()
     ms = timed(step_dev, K)
+    t_end = time.monotonic()
     launches = tr.ops.ctx.launch_count() - l0
-    clocks = sampler.finish() if sampler else None
+    clocks = sampler.finish(t_begin, t_end) if sampler else None
     value = world * 2 * B * K / (ms / 1e3)
     light = os.environ.get("LSPS_BENCH_LIGHT") == "1"     # profiler runs: timed loop only
     if light:
