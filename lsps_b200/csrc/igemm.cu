@@ -1391,7 +1391,8 @@ int run_igemm(lsps_ctx* ctx, const lsps_conv_shape* s, Dir dir, const void* in, 
     return launch_igemm<64, 2>(ctx, tmA, tmB, tmBlo, p, st);
   }
   if (bn == 256) return launch_igemm<256, 1>(ctx, tmA, tmB, tmBlo, p, st);
-  // single-CTA BN <= 128 kernels stage one 64-channel chunk per pipeline stage (2 and 3 chunks measured slower, r01 probes);
+  // single-CTA BN <= 128 kernels stage one 64-channel chunk per pipeline stage (2 and 3 chunks measured slower in r01,
+  // 128-channel stages re-measured in r02 with the two epilogue groups: transposed 256->128 forward 0.107 -> 0.105 ms, nil);
   // with a plain epilogue they run two epilogue warp groups (these short-K tiles are epilogue-bound with one)
   const bool light = !(flags & (LSPS_EP_STATS | LSPS_EP_INBWD)) && !lsps_one_epi_group();
   if (bn == 128) return light ? launch_igemm<128, 1, 1, 2>(ctx, tmA, tmB, tmBlo, p, st) : launch_igemm<128, 1>(ctx, tmA, tmB, tmBlo, p, st);
