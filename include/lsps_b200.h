@@ -253,6 +253,15 @@ int lsps_vae_reparam(lsps_ctx*, const float* mu, const float* sd, const float* n
 int lsps_vae_reparam_bwd(lsps_ctx*, const float* mu, const float* sd, const float* noise, const float* dz, float* dmu,
                          float* dsd, float kl_scale, long long n, lsps_stream);
 
+/* One launch for the whole pose-VAE training step before the optimiser (vae_update, lsps_trainer.py:62-74 over
+   poseVAE.forward lsps_nets.py:68-83): forward, L1 + KL losses, backward.  weights / grads: 10 device pointers in the order
+   en_fc1.{weight,bias}, en_mu.{..}, en_sigma.{..}, de_fc1.model.0.{..}, de_fc2.{..} (nn.Linear layouts [out][in]);
+   the gradients are ADDED to grads (zero them first); dec [rows][d] = reconstruction; acc[0] += sum(mu^2 + sd^2 - log sd^2),
+   acc[1] += sum|dec - y|; ll_scale / kl_scale = d(loss)/d(L1 sum) and d(loss)/d(KL sum). */
+int lsps_vae_step(lsps_ctx*, const float* y, const float* noise, const float* const* weights, float* const* grads,
+                  float* dec, float* acc, int rows, int d, int h, int z, float ll_scale, float kl_scale, float slope,
+                  lsps_stream);
+
 /* ---- optimiser (torch.optim.Adam with L2 weight decay, lsps_trainer.py:26-34) on a flat fp32 segment.
    g += wd*p ; m,v update ; p -= lr * mhat/(sqrt(vhat)+eps) ; optionally refresh the bf16 copy w16 (may be NULL).
    hyper (may be NULL): device pointer to {lr/(1-beta1^step), 1/sqrt(1-beta2^step)}; when given it overrides the values

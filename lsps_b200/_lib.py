@@ -87,6 +87,7 @@ _SIGS = {
     "lsps_mse": [_vp, _vp, _vp, _f, _vp, _ll],
     "lsps_vae_reparam": [_vp, _vp, _vp, _vp, _vp, _ll],
     "lsps_vae_reparam_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _f, _ll],
+    "lsps_vae_step": [_vp, _vp, C.POINTER(_vp), C.POINTER(_vp), _vp, _vp, _i, _i, _i, _i, _f, _f, _f],
     "lsps_adam": [_vp, _vp, _vp, _vp, _vp, _ll, _f, _f, _f, _f, _f, _i, _f, _vp],
     "lsps_pack_dgrad": [_vp, _vp, _i, _i, _i],
     "lsps_f32_to_bf16": [_vp, _vp, _ll],

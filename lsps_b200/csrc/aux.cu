@@ -1148,6 +1148,168 @@ __global__ void vae_reparam_bwd_kernel(const float* __restrict__ mu, const float
   dsd[i] = dz[i] * noise[i] + kl_scale * (2.f * d - 2.f / d);
 }
 
+// =============================================================================================== fused pose-VAE step (K11)
+// forward + losses + backward of poseVAE (lsps_nets.py:34-83, lsps_trainer.py:59-74) for a block of <= 16 rows per CTA:
+// every weight (13.8 K floats at 108/50/20) and every per-row intermediate lives in shared memory; the parameter
+// gradients of the block are added to the (zeroed) gradient buffer with atomicAdd.  Replaces 24 launches of the small
+// dense kernels by one.
+//   y -> h = lrelu(W1 y + b1) -> mu = Wmu h + bmu, sd = softplus(Wsg h + bsg) -> z = mu + sd * noise
+//     -> hd = lrelu(Wd1 z + bd1) -> dec = Wd2 hd + bd2 ;  loss = ll_scale * sum|dec - y| + kl_scale * sum(mu^2 + sd^2 - log sd^2)
+struct VaeStepParams {
+  const float* y; const float* noise;
+  const float* w[10];   // W1 b1 Wmu bmu Wsg bsg Wd1 bd1 Wd2 bd2
+  float* g[10];         // their gradient accumulators
+  float* dec;           // [rows][d]
+  float* acc;           // acc[0] += KL sum, acc[1] += L1 sum
+  int rows, d, h, z;
+  float ll_scale, kl_scale, slope;
+};
+constexpr int VAE_RPC = 16;   // rows per CTA
+
+__global__ void __launch_bounds__(256) vae_step_kernel(const __grid_constant__ VaeStepParams p) {
+  extern __shared__ float vs[];
+  const int d = p.d, h = p.h, z = p.z, R = VAE_RPC;
+  float* W1 = vs;            float* B1 = W1 + h * d;
+  float* Wmu = B1 + h;       float* Bmu = Wmu + z * h;
+  float* Wsg = Bmu + z;      float* Bsg = Wsg + z * h;
+  float* Wd1 = Bsg + z;      float* Bd1 = Wd1 + h * z;
+  float* Wd2 = Bd1 + h;      float* Bd2 = Wd2 + d * h;
+  float* Y = Bd2 + d;        float* H = Y + R * d;
+  float* MU = H + R * h;     float* SD = MU + R * z;
+  float* NZ = SD + R * z;    float* Z = NZ + R * z;
+  float* HD = Z + R * z;     float* DD = HD + R * h;
+  float* DHD = DD + R * d;   float* DMU = DHD + R * h;
+  float* DSD = DMU + R * z;  float* DH = DSD + R * z;
+  __shared__ float red[8];
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int r0 = blockIdx.x * R;
+  const int nr = p.rows - r0 < R ? p.rows - r0 : R;
+  {
+    float* dst[10] = {W1, B1, Wmu, Bmu, Wsg, Bsg, Wd1, Bd1, Wd2, Bd2};
+    const int cnt[10] = {h * d, h, z * h, z, z * h, z, h * z, h, d * h, d};
+#pragma unroll
+    for (int a = 0; a < 10; ++a)
+      for (int i = tid; i < cnt[a]; i += nt) dst[a][i] = __ldg(p.w[a] + i);
+  }
+  for (int i = tid; i < nr * d; i += nt) Y[i] = p.y[(long long)r0 * d + i];
+  for (int i = tid; i < nr * z; i += nt) NZ[i] = p.noise[(long long)r0 * z + i];
+  __syncthreads();
+  // ---- forward
+  for (int o = tid; o < nr * h; o += nt) {
+    const int r = o / h, j = o - r * h;
+    float s = B1[j];
+    for (int i = 0; i < d; ++i) s += W1[j * d + i] * Y[r * d + i];
+    H[o] = s > 0.f ? s : s * p.slope;
+  }
+  __syncthreads();
+  float kl = 0.f;
+  for (int o = tid; o < nr * z; o += nt) {
+    const int r = o / z, k = o - r * z;
+    float m = Bmu[k], q = Bsg[k];
+    for (int j = 0; j < h; ++j) { const float hv = H[r * h + j]; m += Wmu[k * h + j] * hv; q += Wsg[k * h + j] * hv; }
+    const float sd = q > 20.f ? q : log1pf(expf(q));
+    MU[o] = m; SD[o] = sd; Z[o] = m + sd * NZ[o];
+    kl += m * m + sd * sd - logf(sd * sd);
+  }
+  __syncthreads();
+  for (int o = tid; o < nr * h; o += nt) {
+    const int r = o / h, j = o - r * h;
+    float s = Bd1[j];
+    for (int k = 0; k < z; ++k) s += Wd1[j * z + k] * Z[r * z + k];
+    HD[o] = s > 0.f ? s : s * p.slope;
+  }
+  __syncthreads();
+  float l1 = 0.f;
+  for (int o = tid; o < nr * d; o += nt) {
+    const int r = o / d, i = o - r * d;
+    float s = Bd2[i];
+    for (int j = 0; j < h; ++j) s += Wd2[i * h + j] * HD[r * h + j];
+    p.dec[(long long)r0 * d + o] = s;
+    const float df = s - Y[o];
+    l1 += fabsf(df);
+    DD[o] = df > 0.f ? p.ll_scale : (df < 0.f ? -p.ll_scale : 0.f);
+  }
+  kl = block_sum(kl, red);
+  if (tid == 0) atomicAdd(p.acc, kl);
+  l1 = block_sum(l1, red);               // (block_sum ends with the values visible to every thread)
+  if (tid == 0) atomicAdd(p.acc + 1, l1);
+  __syncthreads();
+  // ---- backward: de_fc2
+  for (int o = tid; o < d * h; o += nt) {
+    const int i = o / h, j = o - i * h;
+    float s = 0.f;
+    for (int r = 0; r < nr; ++r) s += DD[r * d + i] * HD[r * h + j];
+    atomicAdd(p.g[8] + o, s);
+  }
+  for (int i = tid; i < d; i += nt) {
+    float s = 0.f;
+    for (int r = 0; r < nr; ++r) s += DD[r * d + i];
+    atomicAdd(p.g[9] + i, s);
+  }
+  for (int o = tid; o < nr * h; o += nt) {
+    const int r = o / h, j = o - r * h;
+    float s = 0.f;
+    for (int i = 0; i < d; ++i) s += Wd2[i * h + j] * DD[r * d + i];
+    DHD[o] = HD[o] > 0.f ? s : s * p.slope;
+  }
+  __syncthreads();
+  // ---- de_fc1
+  for (int o = tid; o < h * z; o += nt) {
+    const int j = o / z, k = o - j * z;
+    float s = 0.f;
+    for (int r = 0; r < nr; ++r) s += DHD[r * h + j] * Z[r * z + k];
+    atomicAdd(p.g[6] + o, s);
+  }
+  for (int j = tid; j < h; j += nt) {
+    float s = 0.f;
+    for (int r = 0; r < nr; ++r) s += DHD[r * h + j];
+    atomicAdd(p.g[7] + j, s);
+  }
+  for (int o = tid; o < nr * z; o += nt) {
+    const int r = o / z, k = o - r * z;
+    float dz = 0.f;
+    for (int j = 0; j < h; ++j) dz += Wd1[j * z + k] * DHD[r * h + j];
+    const float sd = SD[o];
+    DMU[o] = dz + p.kl_scale * 2.f * MU[o];
+    const float dsd = dz * NZ[o] + p.kl_scale * (2.f * sd - 2.f / sd);
+    DSD[o] = dsd * (sd > 20.f ? 1.f : 1.f - expf(-sd));          // softplus' = 1 - exp(-softplus)
+  }
+  __syncthreads();
+  // ---- en_mu / en_sigma
+  for (int o = tid; o < z * h; o += nt) {
+    const int k = o / h, j = o - k * h;
+    float a = 0.f, b = 0.f;
+    for (int r = 0; r < nr; ++r) { const float hv = H[r * h + j]; a += DMU[r * z + k] * hv; b += DSD[r * z + k] * hv; }
+    atomicAdd(p.g[2] + o, a);
+    atomicAdd(p.g[4] + o, b);
+  }
+  for (int k = tid; k < z; k += nt) {
+    float a = 0.f, b = 0.f;
+    for (int r = 0; r < nr; ++r) { a += DMU[r * z + k]; b += DSD[r * z + k]; }
+    atomicAdd(p.g[3] + k, a);
+    atomicAdd(p.g[5] + k, b);
+  }
+  for (int o = tid; o < nr * h; o += nt) {
+    const int r = o / h, j = o - r * h;
+    float s = 0.f;
+    for (int k = 0; k < z; ++k) s += Wmu[k * h + j] * DMU[r * z + k] + Wsg[k * h + j] * DSD[r * z + k];
+    DH[o] = H[o] > 0.f ? s : s * p.slope;
+  }
+  __syncthreads();
+  // ---- en_fc1
+  for (int o = tid; o < h * d; o += nt) {
+    const int j = o / d, i = o - j * d;
+    float s = 0.f;
+    for (int r = 0; r < nr; ++r) s += DH[r * h + j] * Y[r * d + i];
+    atomicAdd(p.g[0] + o, s);
+  }
+  for (int j = tid; j < h; j += nt) {
+    float s = 0.f;
+    for (int r = 0; r < nr; ++r) s += DH[r * h + j];
+    atomicAdd(p.g[1] + j, s);
+  }
+}
+
 // =============================================================================================== optimiser / packing
 __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g,
                                                   float* __restrict__ m, float* __restrict__ v, bf16* __restrict__ w16,
@@ -1741,6 +1903,33 @@ extern "C" int lsps_vae_reparam_bwd(lsps_ctx* ctx, const float* mu, const float*
   REQUIRE(ctx, mu && sd && noise && dz && dmu && dsd && n > 0, LSPS_E_ARG, "vae_reparam_bwd: arg");
   vae_reparam_bwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ST_(st)>>>(mu, sd, noise, dz, dmu, dsd, kl_scale, n);
   LSPS_CHECK_LAUNCH(ctx, "vae_reparam_bwd");
+  return LSPS_OK;
+}
+
+extern "C" int lsps_vae_step(lsps_ctx* ctx, const float* y, const float* noise, const float* const* weights,
+                             float* const* grads, float* dec, float* acc, int rows, int d, int h, int z, float ll_scale,
+                             float kl_scale, float slope, lsps_stream st) {
+  REQUIRE(ctx, y && noise && weights && grads && dec && acc, LSPS_E_ARG, "vae_step: null");
+  if (!(rows > 0 && d > 0 && h > 0 && z > 0 && d <= 256 && h <= 128 && z <= 64 && slope > 0.f))
+    return lsps_set_error(ctx, LSPS_E_SHAPE, "vae_step: rows %d dims %d/%d/%d (d <= 256, h <= 128, z <= 64)", rows, d, h, z);
+  VaeStepParams p{};
+  p.y = y; p.noise = noise; p.dec = dec; p.acc = acc; p.rows = rows; p.d = d; p.h = h; p.z = z;
+  p.ll_scale = ll_scale; p.kl_scale = kl_scale; p.slope = slope;
+  for (int i = 0; i < 10; ++i) {
+    if (!weights[i] || !grads[i]) return lsps_set_error(ctx, LSPS_E_ARG, "vae_step: null parameter %d", i);
+    p.w[i] = weights[i]; p.g[i] = grads[i];
+  }
+  const int nw = 2 * h * d + 3 * h * z + 2 * h + 2 * z + d;
+  const int nrow = VAE_RPC * (2 * d + 4 * h + 6 * z);
+  const int smem = (nw + nrow) * (int)sizeof(float);
+  static int configured = 0;
+  if (smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(vae_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return lsps_set_error(ctx, LSPS_E_CUDA, "vae_step smem attr: %s", cudaGetErrorString(e));
+    configured = smem;
+  }
+  vae_step_kernel<<<(rows + VAE_RPC - 1) / VAE_RPC, 256, smem, ST_(st)>>>(p);
+  LSPS_CHECK_LAUNCH(ctx, "vae_step");
   return LSPS_OK;
 }
 

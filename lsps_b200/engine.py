@@ -1058,6 +1058,29 @@ class PoseVAE:
         o.ctx.act_bwd(dh1.data_ptr(), sv["h"].data_ptr(), _lib.ACT_LRELU, SLOPE, dh1.numel())
         self._lin_bwd("en_fc1", sv["y"], dh1, False)
 
+    _KEYS = ("en_fc1", "en_mu", "en_sigma", "de_fc1.model.0", "de_fc2")
+
+    def step(self, y, ll_scale, kl_scale, acc):
+        """forward + L1 / KL losses + backward of one vae_update in ONE launch (lsps_vae_step): the parameter gradients
+        are added to the store's (zeroed) gradient buffer, acc[0] += KL sum, acc[1] += L1 sum.  Returns the
+        reconstruction.  Same arithmetic as forward() / backward() on the small dense kernels."""
+        o, S = self.ops, self.S
+        y = y.contiguous().float()
+        rows, d = y.shape
+        h, z = S.entries["en_fc1.weight"].shape[0], S.entries["en_mu.weight"].shape[0]
+        if getattr(self, "_ptrs", None) is None:
+            wp, gp = (C.c_void_p * 10)(), (C.c_void_p * 10)()
+            for i, k in enumerate(self._KEYS):
+                wp[2 * i], wp[2 * i + 1] = S.W(k + ".weight").data_ptr(), S.W(k + ".bias").data_ptr()
+                gp[2 * i], gp[2 * i + 1] = S.G(k + ".weight").data_ptr(), S.G(k + ".bias").data_ptr()
+            self._ptrs = (wp, gp)
+        wp, gp = self._ptrs
+        noise = self.noise_fn((rows, z)).contiguous().float()
+        dec = o.empty(rows, d, dtype=torch.float32)
+        o.ctx.vae_step(y.data_ptr(), noise.data_ptr(), wp, gp, dec.data_ptr(), acc.data_ptr(), rows, d, h, z,
+                       ll_scale, kl_scale, SLOPE)
+        return dec
+
     def state_dict(self):
         return self.S.state_dict()
 

@@ -89,6 +89,7 @@ class LSPSTrainerB200(object):
             self.map_store.init_(seed + 4)
             self.map = Mapping(self.ops, self.map_store, hp["map"])
         self._vae_noise_groups = 1
+        self._vae_fused = os.environ.get("LSPS_NO_VAE_FUSED", "0") != "1"
         self.dis_opt, self.gen_opt, self.vae_opt = Optimizer(self.dis_store), Optimizer(self.gen_store), Optimizer(self.vae_store)
         # lsps_trainer.py:32-34
         self.dis_sch = MultiStepLR(self.dis_store, [200, 300, 400, 450], 0.5)
@@ -221,6 +222,9 @@ class LSPSTrainerB200(object):
         def body(t):
             ctx = self.ops.ctx
             S.zero_grad()
+            if self._vae_fused:      # K11: forward + losses + backward in one launch
+                return dict(dec=self.vae.step(t["y"], hp["ll_loss_vae"] / float(rows * dim), hp["kl_loss_vae"] / float(rows),
+                                              S.acc[0:]))
             sv = {}
             dec, z, mu, sd = self.vae.forward(t["y"], kl_acc=S.acc[0:], save=sv)
             ddec = torch.empty_like(dec)

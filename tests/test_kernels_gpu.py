@@ -700,3 +700,35 @@ def test_grouped_conv3x3_fwd_dgrad_wgrad(ctx, n, c, groups):
     dw = torch.zeros(9, c, gw, device="cuda")
     ctx.conv_wgrad_grouped(sh, xb.data_ptr(), dyb.data_ptr(), dw.data_ptr(), groups)
     assert rel_l2(dw, wt.grad.permute(2, 3, 0, 1).reshape(9, c, gw)) < 1e-4
+
+
+@pytest.mark.parametrize("rows,d,h,z", [(16, 108, 50, 20), (37, 108, 50, 20), (8, 48, 50, 20), (130, 63, 40, 23)])
+def test_vae_step_fused_matches_autograd(ctx, rows, d, h, z):
+    """lsps_vae_step (K11: forward + L1/KL losses + backward of the pose-VAE in one launch) against torch autograd of
+    poseVAE.forward (lsps_nets.py:68-83) + the vae_update loss (lsps_trainer.py:59-70); several CTAs and a partial one."""
+    g = gen(900 + rows)
+    mk = lambda *s_: (torch.randn(*s_, device="cuda", generator=g) * 0.2).requires_grad_(True)
+    W1, b1, Wmu, bmu, Wsg, bsg, Wd1, bd1, Wd2, bd2 = (mk(h, d), mk(h), mk(z, h), mk(z), mk(z, h), mk(z), mk(h, z), mk(h),
+                                                       mk(d, h), mk(d))
+    params = [W1, b1, Wmu, bmu, Wsg, bsg, Wd1, bd1, Wd2, bd2]
+    y = torch.rand(rows, d, device="cuda", generator=g) * 2 - 1
+    noise = torch.randn(rows, z, device="cuda", generator=g) * 0.05
+    ll_scale, kl_scale = 1.0 / (rows * d), 0.001 / rows
+    hh = F.leaky_relu(y @ W1.t() + b1, SLOPE)
+    mu, sd = hh @ Wmu.t() + bmu, F.softplus(hh @ Wsg.t() + bsg)
+    zz = mu + sd * noise
+    dec_ref = F.leaky_relu(zz @ Wd1.t() + bd1, SLOPE) @ Wd2.t() + bd2
+    kl_ref, l1_ref = (mu * mu + sd * sd - torch.log(sd * sd)).sum(), (dec_ref - y).abs().sum()
+    (ll_scale * l1_ref + kl_scale * kl_ref).backward()
+    grads = [torch.zeros_like(p_) for p_ in params]
+    wp, gp = (C.c_void_p * 10)(), (C.c_void_p * 10)()
+    for i in range(10):
+        wp[i], gp[i] = params[i].data_ptr(), grads[i].data_ptr()
+    dec, acc = torch.empty(rows, d, device="cuda"), torch.zeros(2, device="cuda")
+    ctx.vae_step(y.data_ptr(), noise.data_ptr(), wp, gp, dec.data_ptr(), acc.data_ptr(), rows, d, h, z, ll_scale, kl_scale,
+                 SLOPE)
+    assert rel_l2(dec, dec_ref.detach()) < 1e-5
+    assert abs(acc[0].item() - kl_ref.item()) < 1e-4 * abs(kl_ref.item())
+    assert abs(acc[1].item() - l1_ref.item()) < 1e-4 * abs(l1_ref.item())
+    for p_, g_ in zip(params, grads):
+        assert rel_l2(g_, p_.grad) < 2e-4
