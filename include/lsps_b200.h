@@ -63,6 +63,14 @@ typedef struct {
   int groups;   /* > 1: grouped 3x3 stride-1 conv (ResNeXt cardinality, common_net.py:118): cin == cout, group width
                    cin/groups in {64, 128}; weights [tap][Cout][cin/groups] (forward) and [tap][Cin][cout/groups]
                    (data gradient).  lsps_conv_wgrad_grouped is the matching weight gradient. */
+  /* decoder head fused into the epilogue of the LAST transposed conv (ConvTranspose2d(128,64,3,2,1,1) + LeakyReLU ->
+     ConvTranspose2d(64,1,1) + Tanh, lsps_nets.py:222-229): with head_out != NULL the launch also writes
+     head_out[pixel] = tanh(sum_c head_w[c] * y[pixel][c] + head_b[0]) (y as stored, i.e. bf16-rounded) and, with
+     head_target != NULL, the L1 reconstruction term of lsps_head_fwd_l1 for pixels [head_t0, head_t0 + head_tn).
+     Only the fused up-sampling kernel (forward, Cout = 64, Cin <= 128, no second weight set) honours it; any other
+     shape returns LSPS_E_ARG instead of silently skipping the head. */
+  const float* head_w; const float* head_b; float* head_out;
+  const float* head_target; long long head_t0, head_tn; float head_scale; float* head_dout; float* head_acc;
 } lsps_conv_ext;
 
 int lsps_ctx_create(lsps_ctx** out, int device);

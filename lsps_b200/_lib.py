@@ -24,7 +24,10 @@ class ConvExt(C.Structure):
     """lsps_conv_ext (include/lsps_b200.h): optional extras of lsps_conv_{fwd,dgrad}_ex"""
     _fields_ = [("w2", C.c_void_p), ("bias2", C.c_void_p), ("n_split", C.c_int), ("sums", C.c_void_p),
                 ("in_a", C.c_void_p), ("bsums", C.c_void_p), ("w_lo", C.c_void_p),
-                ("split", C.c_int), ("groups", C.c_int)]
+                ("split", C.c_int), ("groups", C.c_int),
+                ("head_w", C.c_void_p), ("head_b", C.c_void_p), ("head_out", C.c_void_p), ("head_target", C.c_void_p),
+                ("head_t0", C.c_longlong), ("head_tn", C.c_longlong), ("head_scale", C.c_float),
+                ("head_dout", C.c_void_p), ("head_acc", C.c_void_p)]
 
 
 _vp, _i, _f, _ll = C.c_void_p, C.c_int, C.c_float, C.c_longlong

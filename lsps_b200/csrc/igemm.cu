@@ -580,6 +580,9 @@ struct Up64Params {
   float slope;
   int flags;
   int nc;                      // = 64: weight rows per tap
+  // fused decoder head (1x1 transposed conv 64 -> 1 + tanh, optional L1 term): see lsps_conv_ext
+  const float* head_w; const float* head_b; float* head_out;
+  const float* head_target; long long head_t0, head_tn; float head_scale; float* head_dout; float* head_acc;
 };
 constexpr int UP64_W_TILE = 64 * 128;          // one (tap, chunk) weight tile: 64 rows x 64 bf16
 constexpr int UP64_A_SLOTS = 3;
@@ -607,6 +610,8 @@ conv_up64_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if ((p.flags & LSPS_EP_BIAS) && threadIdx.x < 64) sbias[threadIdx.x] = p.bias[threadIdx.x];
+  float* shw = sbias + 64;                               // head weights
+  if (p.head_out && threadIdx.x >= 64 && threadIdx.x < 128) shw[threadIdx.x - 64] = p.head_w[threadIdx.x - 64];
   if (threadIdx.x == 0) {
     for (int i = 0; i < UP64_A_SLOTS; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
     mbar_init(wfull, 1);
@@ -687,6 +692,8 @@ conv_up64_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     uint8_t* stage = sS + egroup * A_STAGE_BYTES;
     const int tw_mask = (1 << p.twl) - 1, th_mask = (1 << p.thl) - 1;
     const int xl = row & tw_mask, yl = (row >> p.twl) & th_mask, nl = row >> (p.twl + p.thl);
+    const float head_b = p.head_out ? __ldg(p.head_b) : 0.f;
+    float head_l1 = 0.f;
     int it = 0;
     for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
       if ((it & 1) != egroup) continue;
@@ -701,6 +708,7 @@ conv_up64_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       for (int phs = 0; phs < 4; ++phs) {
         if (issuer) bulk_wait_read();             // the previous store of this group has read the staging tile
         named_bar_sync(1 + egroup, 128);
+        float hs = 0.f;                           // head: dot product of this pixel's 64 stored channels
 #pragma unroll
         for (int hf = 0; hf < 2; ++hf) {
           const int c0 = hf * 32;
@@ -753,6 +761,23 @@ conv_up64_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             o.z = pack_bf16x2(f[8 * j + 4], f[8 * j + 5]);
             o.w = pack_bf16x2(f[8 * j + 6], f[8 * j + 7]);
             *reinterpret_cast<uint4*>(stage + row * 128 + (((hf * 4 + j) ^ (row & 7)) << 4)) = o;
+            if (p.head_out) {
+              const float4 w0 = *reinterpret_cast<const float4*>(shw + c0 + 8 * j);
+              const float4 w1 = *reinterpret_cast<const float4*>(shw + c0 + 8 * j + 4);
+              hs += bf16lo(o.x) * w0.x + bf16hi(o.x) * w0.y + bf16lo(o.y) * w0.z + bf16hi(o.y) * w0.w +
+                    bf16lo(o.z) * w1.x + bf16hi(o.z) * w1.y + bf16lo(o.w) * w1.z + bf16hi(o.w) * w1.w;
+            }
+          }
+        }
+        if (p.head_out && valid) {
+          const int oy = (y0 + yl) * 2 + (phs >> 1), ox = (x0 + xl) * 2 + (phs & 1);
+          const long long px = ((long long)n * (p.tiles_y << (p.thl + 1)) + oy) * (p.tiles_x << (p.twl + 1)) + ox;
+          const float ov = tanhf(hs + head_b);
+          p.head_out[px] = ov;
+          if (p.head_target && px >= p.head_t0 && px < p.head_t0 + p.head_tn) {
+            const float df = ov - __ldg(p.head_target + (px - p.head_t0));
+            head_l1 += fabsf(df);
+            if (p.head_dout) p.head_dout[px - p.head_t0] = df > 0.f ? p.head_scale : (df < 0.f ? -p.head_scale : 0.f);
           }
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -764,12 +789,17 @@ conv_up64_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
     }
     if (issuer) bulk_wait_read();
+    if (p.head_target) {                          // one atomic per warp
+#pragma unroll
+      for (int off = 16; off >= 1; off >>= 1) head_l1 += __shfl_xor_sync(0xffffffffu, head_l1, off);
+      if (lane == 0) atomicAdd(p.head_acc, head_l1);
+    }
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
-constexpr int UP64_SMEM = 18 * UP64_W_TILE + (UP64_A_SLOTS + 2) * A_STAGE_BYTES + 1024 + 512;
+constexpr int UP64_SMEM = 18 * UP64_W_TILE + (UP64_A_SLOTS + 2) * A_STAGE_BYTES + 1024 + 1024;
 
 // ------------------------------------------------------------------------------------------------ resident weights, N = 128
 // 3x3 layers with 64 input channels and 128 output channels (Conv2d(64,128,3,2,1) forward, the data gradient of
@@ -1322,6 +1352,13 @@ int run_igemm(lsps_ctx* ctx, const lsps_conv_shape* s, Dir dir, const void* in, 
     u.txl = p.txl; u.tyl = p.tyl; u.nimg = n; u.kchunks = p.kchunks;
     u.o_n = p.o_n; u.o_y = p.o_y; u.o_x = p.o_x; u.out = p.out; u.bias = bias; u.mask = p.mask; u.slope = slope;
     u.flags = flags; u.nc = nc;
+    if (ext->head_out) {
+      if (!ext->head_w || !ext->head_b || (ext->head_target && !ext->head_acc))
+        return lsps_set_error(ctx, LSPS_E_ARG, "fused head: head_w / head_b (and head_acc with a target) required");
+      u.head_w = ext->head_w; u.head_b = ext->head_b; u.head_out = ext->head_out; u.head_target = ext->head_target;
+      u.head_t0 = ext->head_t0; u.head_tn = ext->head_tn; u.head_scale = ext->head_scale; u.head_dout = ext->head_dout;
+      u.head_acc = ext->head_acc;
+    }
     CUtensorMap tA, tB, tO;
     int rc2 = act_tmap(ctx, in, n, ih, iw, kct, false, g, &tA);
     if (rc2) return rc2;
@@ -1333,6 +1370,8 @@ int run_igemm(lsps_ctx* ctx, const lsps_conv_shape* s, Dir dir, const void* in, 
     LSPS_CHECK_LAUNCH(ctx, "conv_up64");
     return LSPS_OK;
   }
+  if (ext->head_out)
+    return lsps_set_error(ctx, LSPS_E_ARG, "fused head: only the fused up-sampling kernel (forward, Cout 64, Cin <= 128) has it");
   // 64 -> 128 channels, one phase, <= 9 K-steps: weights resident in shared memory (conv_resb_kernel)
   if (p.nphases == 1 && bn == 128 && nc == 128 && p.tiles_n == 1 && p.kchunks == 1 && p.ntaps_all <= 9 && !split &&
       nsplit == 0 && p.a_group == 0 && !(flags & (LSPS_EP_STATS | LSPS_EP_INBWD)) && !lsps_no_resb() && !lsps_one_epi_group()) {

@@ -114,10 +114,18 @@ class Ops:
 
     # `key` may be a pair (key_a, key_b, split): images [0, split) go through conv key_a, the rest through key_b --
     # ONE grouped launch for forward / data gradient (full waves of CTA pairs instead of two half-size launches)
-    def conv_fwd(self, S, key, kind, x, lrelu, out=None, sums=None, split=False):
+    @staticmethod
+    def head_fusable(kind, cin, cout):
+        """The decoder head can ride in the epilogue of the fused up-sampling kernel only (igemm.cu conv_up64_kernel)."""
+        return (kind == DECONV_S2 and cout == 64 and cin <= 128 and os.environ.get("LSPS_NO_UP64", "0") != "1"
+                and os.environ.get("LSPS_NO_HEAD_FUSE", "0") != "1")
+
+    def conv_fwd(self, S, key, kind, x, lrelu, out=None, sums=None, split=False, head=None):
         """sums: optional fp32 [n,2,cout] -- the epilogue accumulates per-(image, channel) sum / sum of squares of the
         conv result there (LSPS_EP_STATS), which is all the following InstanceNorm needs.
-        split: bf16x3 operands -- x / y are [n,h,w,2c] (hi | lo) tensors, the store carries the weight remainders."""
+        split: bf16x3 operands -- x / y are [n,h,w,2c] (hi | lo) tensors, the store carries the weight remainders.
+        head = (head key, img fp32 [n,ho,wo], l1 or None): ConvTranspose2d(64,1,1) + Tanh (+ the L1 term, l1 as in
+        Generator._head) computed in this launch's epilogue; only where head_fusable() says so."""
         n, h, w, cin = x.shape
         k0 = key[0] if isinstance(key, tuple) else key
         ci, co = self._io(S, k0, kind)
@@ -142,6 +150,18 @@ class Ops:
                 ext.groups = self._groups(S, key)
             self.ctx.conv_fwd_ex(_shape(kind, n, h, w, ci, co), x.data_ptr(), S.W16(ka + ".weight").data_ptr(),
                                  S.W(ka + ".bias").data_ptr(), y.data_ptr(), flags | EP_STATS, SLOPE, C.byref(ext))
+            return y
+        if head is not None:
+            hk, img, l1 = head
+            ext = ConvExt()
+            ext.head_w, ext.head_b, ext.head_out = S.W(hk + ".weight").data_ptr(), S.W(hk + ".bias").data_ptr(), img.data_ptr()
+            if l1 is not None:
+                target, first, scale, dout, acc = l1
+                px = img.shape[1] * img.shape[2]
+                ext.head_target, ext.head_t0, ext.head_tn = target.data_ptr(), first * px, target.shape[0] * px
+                ext.head_scale, ext.head_dout, ext.head_acc = scale, _lib.ptr(dout), acc.data_ptr()
+            self.ctx.conv_fwd_ex(_shape(kind, n, h, w, ci, co), x.data_ptr(), S.W16(key + ".weight").data_ptr(),
+                                 S.W(key + ".bias").data_ptr(), y.data_ptr(), flags, SLOPE, C.byref(ext))
             return y
         if isinstance(key, tuple):
             ka, kb, split = key
@@ -491,9 +511,8 @@ class Generator:
         for dom, xh, l1 in ((doms[0], x[:n], l1s[0]), (doms[1], x[n:], l1s[1])):
             d = "decode_%s" % dom
             g1 = o.conv_fwd(S, "%s.%d.model.0" % (d, nres), DECONV_S2, xh, True)
-            g2 = o.conv_fwd(S, "%s.%d.model.0" % (d, nres + 1), DECONV_S2, g1, True)
-            img = o.empty(n, g2.shape[1], g2.shape[2], dtype=torch.float32)
-            self._head("%s.%d" % (d, nres + 2), g2, img, l1)
+            g2, img = self._deconv_head("%s.%d.model.0" % (d, nres + 1), "%s.%d" % (d, nres + 2), g1,
+                                        lambda n_, h_, w_: o.empty(n_, h_, w_, dtype=torch.float32), l1)
             outs.append(img)
             tails.append(dict(dom=dom, blocks=[], x3=xh, g1=g1, g2=g2, out=img))
         if save is not None:
@@ -549,6 +568,19 @@ class Generator:
         return dz
 
     # -- decoder: res blocks, two transposed 3x3 s2 convs, 1x1 head + tanh
+    def _deconv_head(self, ck, hk, g1, img_of, l1):
+        """last transposed conv + decoder head: one launch where the head fits the conv's epilogue, else two.
+        img_of(g2 shape) -> the fp32 image tensor to fill.  Returns (g2, img)."""
+        o, S = self.ops, self.S
+        n, h, w, cin = g1.shape
+        _, co = o._io(S, ck, DECONV_S2)
+        img = img_of(n, 2 * h, 2 * w)
+        if o.head_fusable(DECONV_S2, cin, co):
+            return o.conv_fwd(S, ck, DECONV_S2, g1, True, head=(hk, img, l1)), img
+        g2 = o.conv_fwd(S, ck, DECONV_S2, g1, True)
+        self._head(hk, g2, img, l1)
+        return g2, img
+
     def _head(self, hk, g2, img, l1):
         """decoder head (1x1 transposed conv + tanh); l1 = (target [nt,128,128] fp32, first image, scale, dout, acc): the
         L1 reconstruction loss of images [first, first + nt) and its gradient are taken in the same kernel."""
@@ -570,10 +602,8 @@ class Generator:
         for i in range(nres):
             x = o.res_fwd(S, "%s.%d" % (d, i), x, blocks)
         g1 = o.conv_fwd(S, "%s.%d.model.0" % (d, nres), DECONV_S2, x, True)
-        g2 = o.conv_fwd(S, "%s.%d.model.0" % (d, nres + 1), DECONV_S2, g1, True)
-        n = g2.shape[0]
-        img = out if out is not None else o.empty(n, g2.shape[1], g2.shape[2], dtype=torch.float32)
-        self._head("%s.%d" % (d, nres + 2), g2, img, l1)
+        g2, img = self._deconv_head("%s.%d.model.0" % (d, nres + 1), "%s.%d" % (d, nres + 2), g1,
+                                    lambda n_, h_, w_: out if out is not None else o.empty(n_, h_, w_, dtype=torch.float32), l1)
         if save is not None:
             save.append(dict(dom=dom, blocks=blocks, x3=x, g1=g1, g2=g2, out=img))
         return img

@@ -732,3 +732,46 @@ def test_vae_step_fused_matches_autograd(ctx, rows, d, h, z):
     assert abs(acc[1].item() - l1_ref.item()) < 1e-4 * abs(l1_ref.item())
     for p_, g_ in zip(params, grads):
         assert rel_l2(g_, p_.grad) < 2e-4
+
+
+@pytest.mark.parametrize("n,h,cin", [(5, 64, 128), (3, 32, 64), (37, 64, 128)])
+def test_decoder_head_fused_into_the_upsampling_epilogue(ctx, n, h, cin):
+    """lsps_conv_ext.head_*: ConvTranspose2d(cin,64,3,2,1,1) + LeakyReLU -> ConvTranspose2d(64,1,1) + Tanh (+ L1 term) in
+    one launch == the transposed conv followed by lsps_head_fwd_l1 on its stored output."""
+    from lsps_b200._lib import ConvShape, ConvExt
+    g = gen(1000 + n)
+    x = torch.randn(n, h, h, cin, device="cuda", generator=g).bfloat16()
+    wf = (torch.randn(9, 64, cin, device="cuda", generator=g) * 0.05).bfloat16()
+    bias = torch.randn(64, device="cuda", generator=g) * 0.1
+    hw, hb = torch.randn(64, device="cuda", generator=g) * 0.2, torch.randn(1, device="cuda", generator=g) * 0.1
+    sh = C.byref(ConvShape(2, n, h, h, cin, 64))
+    px = 4 * h * h
+    first, nt = 1, n - 2                                   # L1 over images [1, n-1)
+    target = torch.rand(nt, 2 * h, 2 * h, device="cuda", generator=g) * 2 - 1
+    # reference: two launches
+    y0 = torch.empty(n, 2 * h, 2 * h, 64, device="cuda", dtype=torch.bfloat16)
+    ctx.conv_fwd(sh, x.data_ptr(), wf.data_ptr(), bias.data_ptr(), y0.data_ptr(), 3, SLOPE)
+    img0, dout0, acc0 = torch.empty(n, 2 * h, 2 * h, device="cuda"), torch.zeros_like(target), torch.zeros(1, device="cuda")
+    ctx.head_fwd_l1(y0.data_ptr(), hw.data_ptr(), hb.data_ptr(), img0.data_ptr(), img0.numel(), target.data_ptr(),
+                    first * px, nt * px, 0.25, dout0.data_ptr(), acc0.data_ptr())
+    # fused
+    y1 = torch.empty_like(y0)
+    img1, dout1, acc1 = torch.empty_like(img0), torch.zeros_like(target), torch.zeros(1, device="cuda")
+    ext = ConvExt()
+    ext.head_w, ext.head_b, ext.head_out = hw.data_ptr(), hb.data_ptr(), img1.data_ptr()
+    ext.head_target, ext.head_t0, ext.head_tn = target.data_ptr(), first * px, nt * px
+    ext.head_scale, ext.head_dout, ext.head_acc = 0.25, dout1.data_ptr(), acc1.data_ptr()
+    ctx.conv_fwd_ex(sh, x.data_ptr(), wf.data_ptr(), bias.data_ptr(), y1.data_ptr(), 3, SLOPE, C.byref(ext))
+    assert torch.equal(y0, y1)
+    assert (img0 - img1).abs().max().item() < 2e-6
+    assert abs(acc0.item() - acc1.item()) < 1e-5 * abs(acc0.item())
+    close = (img0[first:first + nt] - target).abs() > 1e-5          # sign ties apart, the gradients are identical
+    assert torch.equal(dout0[close], dout1[close])
+    # a shape the fused kernel does not take must refuse the head instead of dropping it
+    sh2 = C.byref(ConvShape(2, 2, 32, 32, 256, 128))
+    x2 = torch.randn(2, 32, 32, 256, device="cuda", generator=g).bfloat16()
+    w2 = (torch.randn(9, 128, 256, device="cuda", generator=g) * 0.05).bfloat16()
+    yb = torch.empty(2, 64, 64, 128, device="cuda", dtype=torch.bfloat16)
+    with pytest.raises(Exception):
+        ctx.conv_fwd_ex(sh2, x2.data_ptr(), w2.data_ptr(), torch.zeros(128, device="cuda").data_ptr(), yb.data_ptr(), 3, SLOPE,
+                        C.byref(ext))
