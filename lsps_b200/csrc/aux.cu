@@ -1311,24 +1311,46 @@ __global__ void __launch_bounds__(256) vae_step_kernel(const __grid_constant__ V
 }
 
 // =============================================================================================== optimiser / packing
+__device__ __forceinline__ float adam_one(float pv, float g, float& m, float& v, float step_size, float beta1, float beta2,
+                                          float eps, float wd, float inv_sqrt_bc2, float grad_scale) {
+  const float gr = g * grad_scale + wd * pv;
+  m = beta1 * m + (1.f - beta1) * gr;
+  v = beta2 * v + (1.f - beta2) * gr * gr;
+  return pv - step_size * m / (sqrtf(v) * inv_sqrt_bc2 + eps);
+}
+// four parameters per thread and iteration (16-byte loads / stores; the flat stores are 16-byte aligned), scalar tail
 __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g,
                                                   float* __restrict__ m, float* __restrict__ v, bf16* __restrict__ w16,
                                                   bf16* __restrict__ w16lo, long long n, float step_size, float beta1,
                                                   float beta2, float eps, float wd, float inv_sqrt_bc2, float grad_scale,
-                                                  const float* __restrict__ hyper) {
+                                                  const float* __restrict__ hyper, int vec) {
   if (hyper) { step_size = hyper[0]; inv_sqrt_bc2 = hyper[1]; }  // CUDA-graph replays: step-dependent factors from memory
-  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
-    const float pv = p[i];
-    const float gr = g[i] * grad_scale + wd * pv;
-    const float mm = beta1 * m[i] + (1.f - beta1) * gr;
-    const float vv = beta2 * v[i] + (1.f - beta2) * gr * gr;
-    m[i] = mm; v[i] = vv;
-    const float np = pv - step_size * mm / (sqrtf(vv) * inv_sqrt_bc2 + eps);
-    p[i] = np;
+  const long long n4 = vec ? n >> 2 : 0;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n4; i += (long long)gridDim.x * 256) {
+    const float4 pv = reinterpret_cast<const float4*>(p)[i], gv = reinterpret_cast<const float4*>(g)[i];
+    float4 mv = reinterpret_cast<const float4*>(m)[i], vv = reinterpret_cast<const float4*>(v)[i];
+    float4 np;
+    np.x = adam_one(pv.x, gv.x, mv.x, vv.x, step_size, beta1, beta2, eps, wd, inv_sqrt_bc2, grad_scale);
+    np.y = adam_one(pv.y, gv.y, mv.y, vv.y, step_size, beta1, beta2, eps, wd, inv_sqrt_bc2, grad_scale);
+    np.z = adam_one(pv.z, gv.z, mv.z, vv.z, step_size, beta1, beta2, eps, wd, inv_sqrt_bc2, grad_scale);
+    np.w = adam_one(pv.w, gv.w, mv.w, vv.w, step_size, beta1, beta2, eps, wd, inv_sqrt_bc2, grad_scale);
+    reinterpret_cast<float4*>(m)[i] = mv; reinterpret_cast<float4*>(v)[i] = vv; reinterpret_cast<float4*>(p)[i] = np;
+    if (w16) {
+      const uint32_t h0 = pack_bf16x2(np.x, np.y), h1 = pack_bf16x2(np.z, np.w);
+      reinterpret_cast<uint2*>(w16)[i] = make_uint2(h0, h1);
+      if (w16lo)   // bf16x3 operands: hi + lo = 16 mantissa bits
+        reinterpret_cast<uint2*>(w16lo)[i] = make_uint2(pack_bf16x2(np.x - bf16lo(h0), np.y - bf16hi(h0)),
+                                                        pack_bf16x2(np.z - bf16lo(h1), np.w - bf16hi(h1)));
+    }
+  }
+  for (long long i = (n4 << 2) + (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
+    float mm = m[i], vv = v[i];
+    const float np = adam_one(p[i], g[i], mm, vv, step_size, beta1, beta2, eps, wd, inv_sqrt_bc2, grad_scale);
+    m[i] = mm; v[i] = vv; p[i] = np;
     if (w16) {
       const bf16 hi = __float2bfloat16(np);
       w16[i] = hi;
-      if (w16lo) w16lo[i] = __float2bfloat16(np - __bfloat162float(hi));   // bf16x3 operands: hi + lo = 16 mantissa bits
+      if (w16lo) w16lo[i] = __float2bfloat16(np - __bfloat162float(hi));
     }
   }
 }
@@ -1354,37 +1376,44 @@ __global__ void pack_dgrad_kernel(const float* __restrict__ w, bf16* __restrict_
 // elements from the bases; tile0 = index of the entry's first 32x32 tile, desc[count].tile0 = total).  wt_lo (may be NULL)
 // receives the bf16 remainder w - float(bf16(w)) for the split-bf16 ("bf16x3") operands.
 __global__ void pack_dgrad_multi_kernel(const float* __restrict__ w, bf16* __restrict__ wt, bf16* __restrict__ wt_lo,
-                                        const long long* __restrict__ desc, int count) {
+                                        const long long* __restrict__ desc, int count, int total_tiles) {
   __shared__ float tile[32][33];
   __shared__ int s_e;
-  if (threadIdx.x == 0 && threadIdx.y == 0) {
-    int e = 0;
-    while (e + 1 < count && desc[(e + 1) * 6 + 5] <= (long long)blockIdx.x) ++e;
-    s_e = e;
-  }
-  __syncthreads();
-  const long long* d = desc + s_e * 6;
-  const int cout = (int)d[3], cin = (int)d[4];
-  const int tx = (cin + 31) / 32, ty = (cout + 31) / 32;
-  int local = blockIdx.x - (int)d[5];
-  const int tap = local / (tx * ty);
-  local -= tap * tx * ty;
-  const int ci0 = (local % tx) * 32, co0 = (local / tx) * 32;
-  const float* src = w + d[0] + (long long)tap * cout * cin;
-  const long long dbase = d[1] + (long long)tap * cout * cin;
-  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
-    const int co = co0 + r, ci = ci0 + threadIdx.x;
-    tile[r][threadIdx.x] = (co < cout && ci < cin) ? src[(long long)co * cin + ci] : 0.f;
-  }
-  __syncthreads();
-  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
-    const int ci = ci0 + r, co = co0 + threadIdx.x;
-    if (ci < cin && co < cout) {
-      const float v = tile[threadIdx.x][r];
-      const bf16 hi = __float2bfloat16(v);
-      wt[dbase + (long long)ci * cout + co] = hi;
-      if (wt_lo) wt_lo[dbase + (long long)ci * cout + co] = __float2bfloat16(v - __bfloat162float(hi));
+  // persistent blocks walk the tile list (42 K tiles of 4 KB: one short-lived block per tile was launch-bound)
+  for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+    if (threadIdx.x == 0 && threadIdx.y == 0) {   // last entry whose first tile is <= t
+      int lo = 0, hi = count - 1;
+      while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (__ldg(desc + mid * 6 + 5) <= (long long)t) lo = mid; else hi = mid - 1;
+      }
+      s_e = lo;
     }
+    __syncthreads();
+    const long long* d = desc + s_e * 6;
+    const int cout = (int)d[3], cin = (int)d[4];
+    const int tx = (cin + 31) / 32, ty = (cout + 31) / 32;
+    int local = t - (int)d[5];
+    const int tap = local / (tx * ty);
+    local -= tap * tx * ty;
+    const int ci0 = (local % tx) * 32, co0 = (local / tx) * 32;
+    const float* src = w + d[0] + (long long)tap * cout * cin;
+    const long long dbase = d[1] + (long long)tap * cout * cin;
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+      const int co = co0 + r, ci = ci0 + threadIdx.x;
+      tile[r][threadIdx.x] = (co < cout && ci < cin) ? src[(long long)co * cin + ci] : 0.f;
+    }
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+      const int ci = ci0 + r, co = co0 + threadIdx.x;
+      if (ci < cin && co < cout) {
+        const float v = tile[threadIdx.x][r];
+        const bf16 hi = __float2bfloat16(v);
+        wt[dbase + (long long)ci * cout + co] = hi;
+        if (wt_lo) wt_lo[dbase + (long long)ci * cout + co] = __float2bfloat16(v - __bfloat162float(hi));
+      }
+    }
+    __syncthreads();     // tile / s_e are rewritten by the next iteration
   }
 }
 
@@ -1946,10 +1975,12 @@ extern "C" int lsps_adam_ex(lsps_ctx* ctx, float* p, const float* g, float* m, f
                             float grad_scale, const float* hyper, lsps_stream st) {
   REQUIRE(ctx, p && g && m && v && n > 0 && step > 0, LSPS_E_ARG, "adam: arg");
   const double bc1 = 1.0 - pow((double)beta1, step), bc2 = 1.0 - pow((double)beta2, step);
-  adam_kernel<<<grid_for(n, 256, 8 * ctx->num_sms), 256, 0, ST_(st)>>>(p, g, m, v, static_cast<bf16*>(w16),
-                                                                     static_cast<bf16*>(w16_lo), n,
-                                                                     (float)(lr / bc1), beta1, beta2, eps, wd,
-                                                                     (float)(1.0 / sqrt(bc2)), grad_scale, hyper);
+  auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+  const int vec = al16(p) && al16(g) && al16(m) && al16(v) && (reinterpret_cast<uintptr_t>(w16) & 7) == 0 &&
+                  (reinterpret_cast<uintptr_t>(w16_lo) & 7) == 0;
+  adam_kernel<<<grid_for(vec ? (n + 3) / 4 : n, 256, 8 * ctx->num_sms), 256, 0, ST_(st)>>>(
+      p, g, m, v, static_cast<bf16*>(w16), static_cast<bf16*>(w16_lo), n, (float)(lr / bc1), beta1, beta2, eps, wd,
+      (float)(1.0 / sqrt(bc2)), grad_scale, hyper, vec);
   LSPS_CHECK_LAUNCH(ctx, "adam");
   return LSPS_OK;
 }
@@ -1962,8 +1993,9 @@ extern "C" int lsps_pack_dgrad(lsps_ctx* ctx, const float* w, void* wt, int taps
 extern "C" int lsps_pack_dgrad_multi(lsps_ctx* ctx, const float* w_base, void* wt_base, void* wt_lo_base,
                                      const long long* desc, int count, int total_tiles, lsps_stream st) {
   REQUIRE(ctx, w_base && wt_base && desc && count > 0 && total_tiles > 0, LSPS_E_ARG, "pack_dgrad_multi: arg");
-  pack_dgrad_multi_kernel<<<total_tiles, dim3(32, 8), 0, ST_(st)>>>(w_base, static_cast<bf16*>(wt_base),
-                                                                    static_cast<bf16*>(wt_lo_base), desc, count);
+  const int grid = total_tiles < 16 * ctx->num_sms ? total_tiles : 16 * ctx->num_sms;
+  pack_dgrad_multi_kernel<<<grid, dim3(32, 8), 0, ST_(st)>>>(w_base, static_cast<bf16*>(wt_base),
+                                                             static_cast<bf16*>(wt_lo_base), desc, count, total_tiles);
   LSPS_CHECK_LAUNCH(ctx, "pack_dgrad_multi");
   return LSPS_OK;
 }
