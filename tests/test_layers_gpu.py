@@ -1,6 +1,7 @@
 """the normalised conv wrappers of the reference's layer zoo (BatchNorm / InstanceNorm variants,
 common_net.py:137-158,183-199,270-379) on the device kernels, against the same stacks built from torch.nn in fp32
-(train-mode batch statistics, running statistics, affine / Bias2d parameters, eval mode)."""
+(train-mode batch statistics, running statistics, affine / Bias2d parameters, eval mode).  The torch.nn stacks
+themselves are pinned to the reference's own classes by tests/test_layers_ref_cpu.py."""
 import pytest
 import torch
 import torch.nn as nn
@@ -30,7 +31,7 @@ class Bias2d(nn.Module):
         return x + self.bias[None, :, None, None]
 
 
-def _ref_stack(norm, cin, cout, k, stride, transposed, slope):
+def _ref_stack(norm, cin, cout, k, stride, transposed, slope, device="cuda"):
     conv = (nn.ConvTranspose2d(cin, cout, k, stride, 1, output_padding=1, bias=norm != "bn") if transposed else
             nn.Conv2d(cin, cout, k, stride, k // 2, bias=norm != "bn"))
     layers = [conv]
@@ -41,7 +42,7 @@ def _ref_stack(norm, cin, cout, k, stride, transposed, slope):
     else:
         layers.append(nn.InstanceNorm2d(cout, affine=False))
     layers.append(nn.LeakyReLU(slope) if slope > 0 else nn.ReLU())
-    return nn.Sequential(*layers).cuda()
+    return nn.Sequential(*layers).to(device)
 
 
 @pytest.mark.parametrize("norm,k,stride,transposed,cin,cout,slope", [
